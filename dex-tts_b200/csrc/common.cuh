@@ -1,0 +1,95 @@
+// Shared device helpers: split-bf16 storage, accurate activations, warp reductions, error plumbing.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace dexb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (host) -------------------------------------------------------------------
+void set_last_error(const char* fmt, ...);
+#define DEXB_CUDA_OK(expr)                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::dexb::set_last_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return -2;                                                                                  \
+    }                                                                                             \
+  } while (0)
+#define DEXB_CHECK(cond, ...)                  \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::dexb::set_last_error(__VA_ARGS__);     \
+      return -1;                               \
+    }                                          \
+  } while (0)
+#define DEXB_TRY(expr)        \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+// ---- split-bf16 ("S" tensors) ------------------------------------------------------------------
+// A value v is stored as hi = bf16(v), lo = bf16(v - hi): hi + lo carries ~16 mantissa bits, and a GEMM on
+// (Ah*Bh + Ah*Bl + Al*Bh) with fp32 accumulation reproduces the fp32 product to ~2^-17 relative.
+// An S tensor row holds [ ... hi(C) ... | ... lo(C) ... ]; hi and lo column offsets are explicit so views
+// into channel-concatenated buffers work.
+__device__ __forceinline__ void split2(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float join2(bf16 hi, bf16 lo) { return __bfloat162float(hi) + __bfloat162float(lo); }
+
+// store 8 consecutive values as 8 hi (16 B) + 8 lo (16 B)
+__device__ __forceinline__ void store_split8(bf16* hi_ptr, bf16* lo_ptr, const float* v) {
+  __align__(16) bf16 h[8];
+  __align__(16) bf16 l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split2(v[i], h[i], l[i]);
+  *reinterpret_cast<uint4*>(hi_ptr) = *reinterpret_cast<const uint4*>(h);
+  *reinterpret_cast<uint4*>(lo_ptr) = *reinterpret_cast<const uint4*>(l);
+}
+__device__ __forceinline__ void load_split8(const bf16* hi_ptr, const bf16* lo_ptr, float* v) {
+  uint4 hq = *reinterpret_cast<const uint4*>(hi_ptr);
+  uint4 lq = *reinterpret_cast<const uint4*>(lo_ptr);
+  const bf16* h = reinterpret_cast<const bf16*>(&hq);
+  const bf16* l = reinterpret_cast<const bf16*>(&lq);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = join2(h[i], l[i]);
+}
+
+// ---- activations (accurate; never compile this project with --use_fast_math) --------------------
+// Mish(x) = x * tanh(softplus(x)); with w = e^x, tanh(log(1+w)) = w(w+2) / (w(w+2) + 2): one exp, one divide,
+// no cancellation.  torch's softplus switches to identity above 20, where tanh(x) == 1 in fp32 anyway.
+__device__ __forceinline__ float mish_f(float x) {
+  if (x > 20.f) return x;
+  float w = expf(x);
+  float n = w * (w + 2.f);
+  return x * (n / (n + 2.f));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// ---- warp reductions ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dexb

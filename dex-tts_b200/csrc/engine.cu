@@ -1,0 +1,932 @@
+// Reverse-diffusion engine: weight packing, planning and the per-step launch sequence.
+// Reference walk (DEX, one denoiser call): SURVEY.md Appendix A; DEX-TTS/model/diffusion.py:190-236.
+#include "engine.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace dexb {
+
+#define LAUNCH(expr)      \
+  do {                    \
+    expr;                 \
+    ++h->launches;        \
+  } while (0)
+#define GEMM(plan, params)                                          \
+  do {                                                              \
+    DEXB_TRY(gemm_launch((plan), (params), h->cfg.gemm_engine, st)); \
+    ++h->launches;                                                  \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+static const HostTensor* find_w(const dexb_handle* h, const std::string& name) {
+  auto it = h->w.find(name);
+  return it == h->w.end() ? nullptr : &it->second;
+}
+#define NEED_W(var, name, ...)                                                      \
+  const HostTensor* var = find_w(h, (name));                                        \
+  DEXB_CHECK(var != nullptr, "missing weight '%s'", std::string(name).c_str());    \
+  {                                                                                 \
+    const int64_t want[] = {__VA_ARGS__};                                           \
+    const size_t nd = sizeof(want) / sizeof(want[0]);                               \
+    bool ok = var->shape.size() == nd;                                              \
+    for (size_t i_ = 0; ok && i_ < nd; ++i_) ok = var->shape[i_] == want[i_];       \
+    DEXB_CHECK(ok, "weight '%s' has an unexpected shape", std::string(name).c_str()); \
+  }
+
+static int bind_block(dexb_handle* h, BlockW& b, const std::string& p, int ci, int co, Arena& ar, bool packed) {
+  NEED_W(w, p + ".block.0.weight", co, ci, 3, 3);
+  NEED_W(bi, p + ".block.0.bias", co);
+  NEED_W(g, p + ".block.1.weight", co);
+  NEED_W(be, p + ".block.1.bias", co);
+  (void)w;
+  b.ci = ci; b.co = co;
+  b.bias = bi->p; b.gamma = g->p; b.beta = be->p;
+  b.w = packed ? ar.get<bf16>(9L * co * 2 * ci) : nullptr;
+  return 0;
+}
+
+static int bind_resnet(dexb_handle* h, ResnetW& r, const std::string& p, int ci, int co, Arena& ar) {
+  const int d = h->cfg.dim;
+  r.ci = ci; r.co = co;
+  DEXB_TRY(bind_block(h, r.b1, p + ".block1", ci, co, ar, ci >= 16));
+  DEXB_TRY(bind_block(h, r.b2, p + ".block2", co, co, ar, true));
+  NEED_W(mw, p + ".mlp.1.weight", co, d);
+  NEED_W(mb, p + ".mlp.1.bias", co);
+  r.mlp_w = mw->p; r.mlp_b = mb->p;
+  r.res_w = nullptr; r.res_b = nullptr; r.rin_w = nullptr;
+  if (ci != co) {
+    NEED_W(rw, p + ".res_conv.weight", co, ci, 1, 1);
+    NEED_W(rb, p + ".res_conv.bias", co);
+    r.res_b = rb->p;
+    if (ci >= 16) r.res_w = ar.get<bf16>((long)co * 2 * ci);
+    else r.rin_w = rw->p;
+  }
+  return 0;
+}
+
+static int bind_la(dexb_handle* h, LinAttW& la, const std::string& p, int C, Arena& ar) {
+  NEED_W(qkv, p + ".fn.fn.to_qkv.weight", 384, C, 1, 1);
+  NEED_W(wo, p + ".fn.fn.to_out.weight", C, 128, 1, 1);
+  NEED_W(bo, p + ".fn.fn.to_out.bias", C);
+  NEED_W(g, p + ".fn.g", 1);
+  la.C = C;
+  la.wq = qkv->p;                       // rows 0..127
+  la.wout = wo->p; la.bout = bo->p; la.g = g->p;
+  la.kv_w = ar.get<bf16>(256L * 2 * C);
+  return 0;
+}
+
+static int layout_weights(dexb_handle* h, Arena& ar) {
+  const dexb_config& c = h->cfg;
+  const int d = c.dim, mid = 2 * c.dim, hid = c.hidden;
+  DEXB_TRY(bind_resnet(h, h->d00, "downs.0.0", 2, d, ar));
+  DEXB_TRY(bind_resnet(h, h->d01, "downs.0.1", d, d, ar));
+  DEXB_TRY(bind_la(h, h->la0, "downs.0.2", d, ar));
+  DEXB_TRY(bind_resnet(h, h->d10, "downs.1.0", d, mid, ar));
+  DEXB_TRY(bind_resnet(h, h->d11, "downs.1.1", mid, mid, ar));
+  DEXB_TRY(bind_la(h, h->la1, "downs.1.2", mid, ar));
+  DEXB_TRY(bind_resnet(h, h->u00, "ups.0.0", 2 * mid, d, ar));
+  DEXB_TRY(bind_resnet(h, h->u01, "ups.0.1", d, d, ar));
+  DEXB_TRY(bind_la(h, h->la2, "ups.0.2", d, ar));
+  DEXB_TRY(bind_block(h, h->fin, "final_block", d, d, ar, true));
+  {
+    NEED_W(w, "downs.0.0.block1.block.0.weight", d, 2, 3, 3);
+    h->conv_in_w = w->p; h->conv_in_b = h->d00.b1.bias;
+    NEED_W(dw, "downs.0.3.conv.weight", d, d, 3, 3);
+    NEED_W(db, "downs.0.3.conv.bias", d);
+    (void)dw; h->down_b = db->p; h->down_w = ar.get<bf16>(9L * d * 2 * d);
+    NEED_W(uw, "ups.0.3.conv.weight", d, d, 4, 4);
+    NEED_W(ub, "ups.0.3.conv.bias", d);
+    (void)uw; h->up_b = ub->p; h->up_w = ar.get<bf16>(16L * d * 2 * d);
+    NEED_W(fw, "final_conv.weight", 1, d, 1, 1);
+    NEED_W(fb, "final_conv.bias", 1);
+    h->fc_w = fw->p; h->fc_b = fb->p;
+  }
+  if (c.variant == 1) {
+    NEED_W(wq, "tv_adaptor.w_q.weight", mid, mid);
+    NEED_W(wk, "tv_adaptor.w_k.weight", mid, mid);
+    NEED_W(wv, "tv_adaptor.w_v.weight", mid, mid);
+    NEED_W(wl, "tv_adaptor.linear.weight", mid, mid);
+    (void)wq; h->tv_wk = wk->p; h->tv_wv = wv->p; h->tv_wl = wl->p;
+    h->wqT_s = ar.get<float>((long)mid * mid);
+    NEED_W(mw, "tiv_adaptor.mean_sap.W.weight", 1, mid);
+    NEED_W(mb, "tiv_adaptor.mean_sap.W.bias", 1);
+    NEED_W(sw, "tiv_adaptor.std_sap.W.weight", 1, mid);
+    NEED_W(sb, "tiv_adaptor.std_sap.W.bias", 1);
+    h->sap_m_w = mw->p; h->sap_m_b = mb->p; h->sap_s_w = sw->p; h->sap_s_b = sb->p;
+  }
+  // DiT
+  {
+    const int fq = (c.n_feats / 2) / c.stride;
+    NEED_W(fp, "vit.freq_new_pos_embed", 1, hid, fq, 1);
+    (void)fp; h->fpos = ar.get<float>((long)fq * hid);
+    NEED_W(dw, "vit.x_embedder.proj.0.weight", mid, 1, c.patch, c.patch);
+    NEED_W(db, "vit.x_embedder.proj.0.bias", mid);
+    h->dw_w = dw->p; h->dw_b = db->p;
+    NEED_W(pw, "vit.x_embedder.proj.2.weight", hid, mid, 1, 1);
+    NEED_W(pb, "vit.x_embedder.proj.2.bias", hid);
+    (void)pw; h->pe_b = pb->p; h->pe_w = ar.get<bf16>((long)hid * 2 * mid);
+    const int cg = hid / c.conv_pos_groups;
+    NEED_W(cw, "vit.pos_conv.0.weight", hid, cg, c.conv_pos, c.conv_pos);
+    NEED_W(cb, "vit.pos_conv.0.bias", hid);
+    (void)cw; h->posconv_b = cb->p;
+    h->posconv_w = ar.get<bf16>((long)c.conv_pos * (c.conv_pos / 2) * hid * 4 * cg);
+    NEED_W(t0, "vit.t_embedder.mlp.0.weight", hid, 256);
+    NEED_W(t2, "vit.t_embedder.mlp.2.weight", hid, hid);
+    (void)t0; (void)t2;
+    h->blocks.resize(c.depth);
+    for (int i = 0; i < c.depth; ++i) {
+      const std::string b = "vit.blocks." + std::to_string(i);
+      DitBlockW& k = h->blocks[i];
+      NEED_W(qw, b + ".attn.qkv.weight", 3 * hid, hid);
+      NEED_W(qb, b + ".attn.qkv.bias", 3 * hid);
+      NEED_W(pw2, b + ".attn.proj.weight", hid, hid);
+      NEED_W(pb2, b + ".attn.proj.bias", hid);
+      NEED_W(f1, b + ".mlp.fc1.weight", c.mlp_hidden, hid);
+      NEED_W(f1b, b + ".mlp.fc1.bias", c.mlp_hidden);
+      NEED_W(f2, b + ".mlp.fc2.weight", hid, c.mlp_hidden);
+      NEED_W(f2b, b + ".mlp.fc2.bias", hid);
+      NEED_W(aw, b + ".adaLN_modulation.1.weight", 6 * hid, hid);
+      NEED_W(ab, b + ".adaLN_modulation.1.bias", 6 * hid);
+      (void)qw; (void)pw2; (void)f1; (void)f2;
+      k.qkv_b = qb->p; k.proj_b = pb2->p; k.fc1_b = f1b->p; k.fc2_b = f2b->p; k.ada_w = aw->p; k.ada_b = ab->p;
+      k.qkv_w = ar.get<bf16>(3L * hid * 2 * hid);
+      k.proj_w = ar.get<bf16>((long)hid * 2 * hid);
+      k.fc1_w = ar.get<bf16>((long)c.mlp_hidden * 2 * hid);
+      k.fc2_w = ar.get<bf16>((long)hid * 2 * c.mlp_hidden);
+    }
+    const int nout = c.stride * c.stride * mid;
+    NEED_W(fw, "vit.final_layer.linear.weight", nout, hid);
+    NEED_W(fb, "vit.final_layer.linear.bias", nout);
+    NEED_W(faw, "vit.final_layer.adaLN_modulation.1.weight", 2 * hid, hid);
+    NEED_W(fab, "vit.final_layer.adaLN_modulation.1.bias", 2 * hid);
+    (void)fw; (void)faw; (void)fab;
+    h->final_b = fb->p; h->final_w = ar.get<bf16>((long)nout * 2 * hid);
+  }
+  return 0;
+}
+
+static void pack_block(dexb_handle* h, BlockW& b, const std::string& p, cudaStream_t st) {
+  if (b.w != nullptr) launch_pack_conv(find_w(h, p + ".block.0.weight")->p, b.w, b.co, b.ci, 3, 3, st);
+}
+static void pack_resnet(dexb_handle* h, ResnetW& r, const std::string& p, cudaStream_t st) {
+  pack_block(h, r.b1, p + ".block1", st);
+  pack_block(h, r.b2, p + ".block2", st);
+  if (r.res_w != nullptr) launch_pack_split(find_w(h, p + ".res_conv.weight")->p, r.ci, r.res_w, 2L * r.ci, r.ci, r.co, r.ci, st);
+}
+static void pack_la(dexb_handle* h, LinAttW& la, const std::string& p, cudaStream_t st) {
+  const float* qkv = find_w(h, p + ".fn.fn.to_qkv.weight")->p;
+  launch_pack_split(qkv + 128L * la.C, la.C, la.kv_w, 2L * la.C, la.C, 256, la.C, st);
+}
+
+int engine_finalize(dexb_handle* h, cudaStream_t st) {
+  const dexb_config& c = h->cfg;
+  DEXB_CHECK(c.dim == 64, "only decoder.dim == 64 is instantiated (got %d)", c.dim);
+  DEXB_CHECK(c.hidden % 128 == 0 && c.hidden <= 384, "dit.hidden_size must be 128, 256 or 384 (got %d)", c.hidden);
+  DEXB_CHECK(c.hidden % c.heads == 0 && (c.hidden / c.heads) % 64 == 0, "head dim must be a multiple of 64");
+  DEXB_CHECK(c.conv_pos % 2 == 0 && c.hidden % c.conv_pos_groups == 0, "conv_pos must be even");
+  DEXB_CHECK((c.hidden / c.conv_pos_groups) % 8 == 0, "pos-conv group width must be a multiple of 8");
+  DEXB_CHECK(c.n_feats == 80, "n_feats must be 80 (Diffusion.forward hard-codes it, diffusion.py:256)");
+  DEXB_CHECK(c.mlp_hidden % 64 == 0, "mlp hidden must be a multiple of 64");
+  engine_release_plan(h);
+  if (h->packed_base != nullptr) { cudaFree(h->packed_base); h->packed_base = nullptr; }
+  Arena m;
+  DEXB_TRY(layout_weights(h, m));
+  const size_t bytes = m.off + 1024;
+  DEXB_CUDA_OK(cudaMalloc(&h->packed_base, bytes));
+  Arena ar; ar.base = h->packed_base;
+  DEXB_TRY(layout_weights(h, ar));
+  const int d = c.dim, mid = 2 * d, hid = c.hidden;
+  pack_resnet(h, h->d00, "downs.0.0", st);
+  pack_resnet(h, h->d01, "downs.0.1", st);
+  pack_resnet(h, h->d10, "downs.1.0", st);
+  pack_resnet(h, h->d11, "downs.1.1", st);
+  pack_resnet(h, h->u00, "ups.0.0", st);
+  pack_resnet(h, h->u01, "ups.0.1", st);
+  pack_la(h, h->la0, "downs.0.2", st);
+  pack_la(h, h->la1, "downs.1.2", st);
+  pack_la(h, h->la2, "ups.0.2", st);
+  pack_block(h, h->fin, "final_block", st);
+  launch_pack_conv(find_w(h, "downs.0.3.conv.weight")->p, h->down_w, d, d, 3, 3, st);
+  launch_pack_convT(find_w(h, "ups.0.3.conv.weight")->p, h->up_w, d, d, st);
+  if (c.variant == 1)
+    launch_transpose_scale(find_w(h, "tv_adaptor.w_q.weight")->p, h->wqT_s, mid, mid, 1.f / sqrtf((float)mid), st);
+  const int fq = (c.n_feats / 2) / c.stride;
+  launch_transpose_scale(find_w(h, "vit.freq_new_pos_embed")->p, h->fpos, hid, fq, 1.f, st);
+  launch_pack_split(find_w(h, "vit.x_embedder.proj.2.weight")->p, mid, h->pe_w, 2L * mid, mid, hid, mid, st);
+  launch_pack_posconv(find_w(h, "vit.pos_conv.0.weight")->p, h->posconv_w, hid, hid / c.conv_pos_groups, c.conv_pos, st);
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string b = "vit.blocks." + std::to_string(i);
+    DitBlockW& k = h->blocks[i];
+    launch_pack_split(find_w(h, b + ".attn.qkv.weight")->p, hid, k.qkv_w, 2L * hid, hid, 3 * hid, hid, st);
+    launch_pack_split(find_w(h, b + ".attn.proj.weight")->p, hid, k.proj_w, 2L * hid, hid, hid, hid, st);
+    launch_pack_split(find_w(h, b + ".mlp.fc1.weight")->p, hid, k.fc1_w, 2L * hid, hid, c.mlp_hidden, hid, st);
+    launch_pack_split(find_w(h, b + ".mlp.fc2.weight")->p, c.mlp_hidden, k.fc2_w, 2L * c.mlp_hidden, c.mlp_hidden, hid,
+                      c.mlp_hidden, st);
+  }
+  launch_pack_split(find_w(h, "vit.final_layer.linear.weight")->p, hid, h->final_w, 2L * hid, hid, c.stride * c.stride * mid,
+                    hid, st);
+  DEXB_CUDA_OK(cudaGetLastError());
+  DEXB_CUDA_OK(cudaStreamSynchronize(st));
+  h->finalized = true;
+  return 0;
+}
+
+void engine_release_weights(dexb_handle* h) {
+  for (auto& kv : h->w)
+    if (kv.second.p != nullptr) cudaFree(kv.second.p);
+  h->w.clear();
+  if (h->packed_base != nullptr) { cudaFree(h->packed_base); h->packed_base = nullptr; }
+  h->finalized = false;
+}
+
+void engine_release_plan(dexb_handle* h) {
+  if (h->graph_exec != nullptr) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  if (h->graph != nullptr) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  if (h->ws_base != nullptr) { cudaFree(h->ws_base); h->ws_base = nullptr; }
+  h->planned = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM parameter builders
+// ------------------------------------------------------------------------------------------------
+static GemmParams gp_base(const dexb_config& c) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nz = 1; p.nheads = 1;
+  p.in_stride = 1; p.out_scale = 1; p.tap_sw = 1;
+  p.KH = 1; p.KW = 1;
+  p.nsplit = c.nsplit;
+  p.epi.alpha = 1.f;
+  p.epi.out_s_ncols = 1 << 30;
+  return p;
+}
+// input image geometry; by default output geometry == computed geometry == input geometry
+static void gp_geom(GemmParams& p, int nimg, int H, int W) {
+  p.nz = nimg;
+  p.H = H; p.W = W; p.OH = H; p.OW = W; p.CH = H; p.CW = W;
+}
+static void gp_tile(GemmParams& p) {
+  int best_bw = 128;
+  long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    const int bh = 128 / bw;
+    if (bw * p.in_stride > 256 || bh * p.in_stride > 256) continue;
+    const long tiles = (long)cdiv(p.CH, bh) * cdiv(p.CW, bw);
+    if (best < 0 || tiles < best) { best = tiles; best_bw = bw; }
+  }
+  p.BW = best_bw; p.BH = 128 / best_bw;
+}
+static void gp_a(GemmParams& p, const bf16* A, long row_stride, int hi, int lo, int K) {
+  p.A = A; p.a_row_stride = row_stride; p.a_hi = hi; p.a_lo = lo; p.K = K;
+}
+static void gp_b(GemmParams& p, const bf16* Bw, int K, int N) {      // shared packed weights [tap][N][hi(K)|lo(K)]
+  p.Bw = Bw; p.b_row_stride = 2L * K; p.b_hi = 0; p.b_lo = K; p.b_rows_per_tap = N; p.N = N; p.b_mode = 0;
+}
+static void gp_taps(GemmParams& p, int KH, int KW, int offH, int offW) { p.KH = KH; p.KW = KW; p.offH = offH; p.offW = offW; }
+static void gp_out_s(GemmParams& p, bf16* out, long stride, int hi, int lo) {
+  p.epi.out_s = out; p.epi.out_s_stride = stride; p.epi.out_s_hi = hi; p.epi.out_s_lo = lo;
+}
+static void gp_out_f(GemmParams& p, float* out, long stride) { p.epi.out_f32 = out; p.epi.out_f32_stride = stride; }
+static void gp_rowmask(GemmParams& p, const float* m, long stride) { p.epi.rowmask = m; p.epi.rowmask_stride = stride; }
+
+static int plan_shared(GemmPlan* gp, GemmParams& p) {
+  gp_tile(p);
+  return gemm_plan_init(gp, p, p.a_by_z ? p.nz : p.nz / p.nheads, (long)p.KH * p.KW * p.b_rows_per_tap, 1);
+}
+
+static int plan_block_conv(dexb_handle* h, BlockW& b, const bf16* in, long in_stride, int in_hi, int in_lo, int H, int W,
+                           float* raw) {
+  GemmParams p = gp_base(h->cfg);
+  gp_geom(p, h->B, H, W);
+  gp_a(p, in, in_stride, in_hi, in_lo, b.ci);
+  gp_b(p, b.w, b.ci, b.co);
+  gp_taps(p, 3, 3, -1, -1);
+  p.epi.bias = b.bias;
+  gp_out_f(p, raw, b.co);
+  p.epi.gn_stats = h->gn_stats + (long)b.slot * h->B * 16;
+  p.epi.gn_gs = b.co / 8;
+  return plan_shared(&b.conv, p);
+}
+
+static int plan_la(dexb_handle* h, LinAttW& la, const bf16* in, long in_stride, int in_hi, int in_lo, int H, int W,
+                   const float* mask, bf16* out, long out_stride, int out_hi, int out_lo) {
+  {
+    GemmParams p = gp_base(h->cfg);
+    gp_geom(p, h->B, H, W);
+    gp_a(p, in, in_stride, in_hi, in_lo, la.C);
+    gp_b(p, la.kv_w, la.C, 256);
+    gp_out_f(p, h->kv, 256);
+    DEXB_TRY(plan_shared(&la.kv, p));
+  }
+  {
+    GemmParams p = gp_base(h->cfg);
+    gp_geom(p, h->B, H, W);
+    gp_a(p, in, in_stride, in_hi, in_lo, la.C);
+    gp_b(p, la.weff, la.C, la.C);
+    p.b_mode = 1; p.b_mat_stride = (long)la.C * 2 * la.C;
+    p.epi.bias = la.beff; p.epi.bias_zstride = la.C;
+    gp_rowmask(p, mask, W);
+    gp_out_s(p, out, out_stride, out_hi, out_lo);
+    gp_tile(p);
+    DEXB_TRY(gemm_plan_init(&la.apply, p, h->B, la.C, h->B));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+static int layout_ws(dexb_handle* h, Arena& ar) {
+  const dexb_config& c = h->cfg;
+  const int B = h->B, d = c.dim, mid = 2 * d, hid = c.hidden, steps = h->steps;
+  const long P0 = (long)B * h->H0 * h->W0, P1 = (long)B * h->H1 * h->W1, M = (long)B * h->Ntok;
+  const bool dex = c.variant == 1;
+  h->tab = ar.get<StepScalars>(steps);
+  h->x = ar.get<float>(P0); h->mu = ar.get<float>(P0);
+  h->mask0 = ar.get<float>((long)B * h->W0); h->mask1 = ar.get<float>((long)B * h->W1);
+  // per-step zeroed region
+  const size_t z0 = (ar.off + 1023) & ~(size_t)1023;
+  h->gn_stats = ar.get<double>((long)h->n_slots * B * 16);
+  h->cstats = ar.get<double>(2L * B * mid * 2);
+  LinAttW* las[3] = {&h->la0, &h->la1, &h->la2};
+  for (LinAttW* la : las) {
+    la->kmax = ar.get<unsigned>((long)B * 128);
+    la->ctx = ar.get<float>((long)B * 4 * 32 * 32);
+    la->ssum = ar.get<float>((long)B * 128);
+  }
+  h->pe = ar.get<float>((long)B * h->Wq * hid);
+  h->zero_base = ar.base + z0;
+  h->zero_bytes = ((ar.off - z0) + 15) & ~(size_t)15;
+  for (LinAttW* la : las) {
+    la->weff = ar.get<bf16>((long)B * la->C * 2 * la->C);
+    la->beff = ar.get<float>((long)B * la->C);
+  }
+  // tables
+  h->t_init = ar.get<float>((long)steps * d); h->t_hid = ar.get<float>((long)steps * 4 * d);
+  h->t_unet = ar.get<float>((long)steps * d); h->t_hid2 = ar.get<float>((long)steps * d);
+  ResnetW* rs[6] = {&h->d00, &h->d01, &h->d10, &h->d11, &h->u00, &h->u01};
+  for (ResnetW* r : rs) r->tbias = ar.get<float>((long)steps * r->co);
+  h->temb = ar.get<float>((long)steps * 256); h->tc_hid = ar.get<float>((long)steps * hid);
+  h->tc = ar.get<float>((long)steps * hid);
+  h->mod = ar.get<float>((long)steps * c.depth * 6 * hid); h->fmod = ar.get<float>((long)steps * 2 * hid);
+  if (dex) {
+    h->t_adap = ar.get<float>((long)steps * mid); h->t_sty = ar.get<float>((long)steps * mid);
+    h->k0 = ar.get<float>((long)steps * mid); h->kw0 = ar.get<float>((long)steps * mid);
+    h->v0 = ar.get<float>((long)steps * mid); h->vl0 = ar.get<float>((long)steps * mid);
+    h->sty = ar.get<float>((long)B * mid * h->Ts); h->sty_len = ar.get<int>(B);
+    for (int i = 0; i < 6; ++i) h->refs[i] = ar.get<float>((long)B * mid * h->Ts);
+    h->ref_mean = ar.get<float>((long)B * 6 * mid); h->ref_std = ar.get<float>((long)B * 6 * mid);
+    h->tiv_shift = ar.get<float>((long)steps * B * mid); h->tiv_scale = ar.get<float>((long)steps * B * mid);
+    h->styT = ar.get<float>((long)B * h->Ts * mid);
+    h->kmat = ar.get<float>((long)B * h->Ts * mid); h->kw = ar.get<float>((long)B * h->Ts * mid);
+    h->vmat = ar.get<float>((long)B * h->Ts * mid); h->vl = ar.get<float>((long)B * h->Ts * mid);
+    h->kq = ar.get<bf16>((long)B * h->KP * 2 * mid); h->sbias = ar.get<float>((long)B * h->KP);
+    h->vlt = ar.get<bf16>((long)B * mid * 2 * h->KP);
+    h->tvscores = ar.get<float>(P1 * h->KP); h->tvP = ar.get<bf16>(P1 * 2 * h->KP);
+    h->tvout = ar.get<float>(P1 * mid);
+  }
+  // activations
+  h->raw0 = ar.get<float>(P0 * d);
+  h->A0 = ar.get<bf16>(P0 * 2 * d); h->B0 = ar.get<bf16>(P0 * 2 * d); h->C0 = ar.get<bf16>(P0 * 2 * d);
+  h->kv = ar.get<float>(P0 * 256);
+  h->raw1 = ar.get<float>(P1 * mid); h->resid1 = ar.get<float>(P1 * mid);
+  h->D1 = ar.get<bf16>(P1 * 2 * d);
+  h->A1 = ar.get<bf16>(P1 * 2 * mid); h->B1 = ar.get<bf16>(P1 * 2 * mid); h->C1 = ar.get<bf16>(P1 * 2 * mid);
+  h->cat = ar.get<bf16>(P1 * 4 * mid);
+  h->tokS = ar.get<bf16>(M * 2 * mid);
+  h->xe = ar.get<float>(M * hid);
+  h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
+  h->xtok = ar.get<float>(M * hid);
+  h->hS = ar.get<bf16>(M * 2 * hid);
+  h->qk = ar.get<bf16>(M * 4 * hid);
+  h->vT = ar.get<bf16>((long)B * hid * 2 * h->NP);
+  h->scores = ar.get<float>((long)B * c.heads * h->Ntok * h->NP);
+  h->P = ar.get<bf16>((long)B * c.heads * h->Ntok * 2 * h->NP);
+  h->attnS = ar.get<bf16>(M * 2 * hid);
+  h->h2S = ar.get<bf16>(M * 2 * c.mlp_hidden);
+  h->ytok = ar.get<float>(M * c.stride * c.stride * mid);
+  return 0;
+}
+
+static int build_plans(dexb_handle* h) {
+  const dexb_config& c = h->cfg;
+  const int B = h->B, d = c.dim, mid = 2 * d, hid = c.hidden;
+  const int H0 = h->H0, W0 = h->W0, H1 = h->H1, W1 = h->W1;
+  const bool dex = c.variant == 1;
+  // ---- level 0 ----
+  DEXB_TRY(plan_block_conv(h, h->d00.b2, h->A0, 2 * d, 0, d, H0, W0, h->raw0));
+  DEXB_TRY(plan_block_conv(h, h->d01.b1, h->B0, 2 * d, 0, d, H0, W0, h->raw0));
+  DEXB_TRY(plan_block_conv(h, h->d01.b2, h->A0, 2 * d, 0, d, H0, W0, h->raw0));
+  DEXB_TRY(plan_la(h, h->la0, h->C0, 2 * d, 0, d, H0, W0, h->mask0, h->A0, 2 * d, 0, d));
+  {
+    GemmParams p = gp_base(c);
+    gp_geom(p, B, H0, W0);
+    p.in_stride = 2; p.CH = H1; p.CW = W1; p.OH = H1; p.OW = W1;
+    gp_a(p, h->A0, 2 * d, 0, d, d);
+    gp_b(p, h->down_w, d, d);
+    gp_taps(p, 3, 3, -1, -1);
+    p.epi.bias = h->down_b;
+    gp_rowmask(p, h->mask1, W1);
+    gp_out_s(p, h->D1, 2 * d, 0, d);
+    DEXB_TRY(plan_shared(&h->g_down, p));
+  }
+  // ---- level 1 ----
+  DEXB_TRY(plan_block_conv(h, h->d10.b1, h->D1, 2 * d, 0, d, H1, W1, h->raw1));
+  DEXB_TRY(plan_block_conv(h, h->d10.b2, h->A1, 2 * mid, 0, mid, H1, W1, h->raw1));
+  {
+    GemmParams p = gp_base(c);
+    gp_geom(p, B, H1, W1);
+    gp_a(p, h->D1, 2 * d, 0, d, d);
+    gp_b(p, h->d10.res_w, d, mid);
+    p.epi.bias = h->d10.res_b;
+    gp_out_f(p, h->resid1, mid);
+    DEXB_TRY(plan_shared(&h->d10.res, p));
+  }
+  DEXB_TRY(plan_block_conv(h, h->d11.b1, h->B1, 2 * mid, 0, mid, H1, W1, h->raw1));
+  DEXB_TRY(plan_block_conv(h, h->d11.b2, h->A1, 2 * mid, 0, mid, H1, W1, h->raw1));
+  // skip / adaptor input lives in the upper half of the concat buffer: hi at col 2*mid/2.. see below
+  //   cat row = [hi(2*mid) | lo(2*mid)]: DiT output in channels [0, mid), skip in [mid, 2*mid)
+  DEXB_TRY(plan_la(h, h->la1, h->C1, 2 * mid, 0, mid, H1, W1, h->mask1, h->cat, 4 * mid, mid, 3 * mid));
+  if (dex) {
+    {
+      GemmParams p = gp_base(c);                      // S = x . KQ^T + sb      (ref_encoder.py:170)
+      gp_geom(p, B, H1, W1);
+      gp_a(p, h->cat, 4 * mid, mid, 3 * mid, mid);
+      gp_b(p, h->kq, mid, h->NK);
+      p.b_mode = 1; p.b_mat_stride = (long)h->KP * 2 * mid;
+      p.epi.bias = h->sbias; p.epi.bias_zstride = h->KP;
+      gp_out_f(p, h->tvscores, h->KP);
+      gp_tile(p);
+      DEXB_TRY(gemm_plan_init(&h->g_tvs, p, B, h->KP, B));
+    }
+    {
+      GemmParams p = gp_base(c);                      // out = P . VL + x, masked (ref_encoder.py:174-179)
+      gp_geom(p, B, H1, W1);
+      gp_a(p, h->tvP, 2L * h->KP, 0, h->KP, h->KP);
+      gp_b(p, h->vlt, h->KP, mid);
+      p.b_mode = 1; p.b_mat_stride = (long)mid * 2 * h->KP;
+      p.epi.resid_s = h->cat; p.epi.resid_s_stride = 4 * mid; p.epi.resid_s_hi = mid; p.epi.resid_s_lo = 3 * mid;
+      gp_rowmask(p, h->mask1, W1);
+      gp_out_f(p, h->tvout, mid);
+      gp_tile(p);
+      DEXB_TRY(gemm_plan_init(&h->g_tvo, p, B, mid, B));
+    }
+  }
+  // ---- DiT ----
+  const int Fq = h->Fq, Wq = h->Wq, N = h->Ntok, NP = h->NP, hd = hid / c.heads;
+  const long M = (long)B * N;
+  {
+    GemmParams p = gp_base(c);
+    gp_geom(p, B, Fq, Wq);
+    gp_a(p, h->tokS, 2 * mid, 0, mid, mid);
+    gp_b(p, h->pe_w, mid, hid);
+    p.epi.bias = h->pe_b;
+    gp_out_f(p, h->xe, hid);
+    DEXB_TRY(plan_shared(&h->g_pe, p));
+  }
+  {
+    const int G = c.conv_pos_groups, cg = hid / G;
+    GemmParams p = gp_base(c);
+    gp_geom(p, B * G, Fq, Wq + 1);
+    p.nheads = G;
+    p.CH = Fq; p.CW = Wq; p.OH = Fq; p.OW = Wq;
+    gp_a(p, h->pairs, 4L * hid, 0, 2 * hid, 2 * cg);
+    p.a_head_stride = 2 * cg;
+    gp_b(p, h->posconv_w, 2 * cg, cg);
+    p.b_rows_per_tap = hid; p.b_head_rows = cg;
+    gp_taps(p, c.conv_pos, c.conv_pos / 2, -(c.conv_pos / 2), -(c.conv_pos / 2) + 1);
+    p.tap_sw = 2;
+    p.epi.bias = h->posconv_b; p.epi.bias_head_stride = cg;
+    p.epi.act = 1;
+    p.epi.colmean = h->pe; p.epi.colmean_ld = hid; p.epi.colmean_scale = 1.f / (float)Fq;
+    p.epi.o_head_stride = cg;
+    DEXB_TRY(plan_shared(&h->g_posconv, p));
+  }
+  for (int i = 0; i < c.depth; ++i) {
+    DitBlockW& k = h->blocks[i];
+    {
+      GemmParams p = gp_base(c);                      // qkv: q,k -> split rows, v -> transposed split
+      gp_geom(p, B, 1, N);
+      gp_a(p, h->hS, 2 * hid, 0, hid, hid);
+      gp_b(p, k.qkv_w, hid, 3 * hid);
+      p.epi.bias = k.qkv_b;
+      gp_out_s(p, h->qk, 4 * hid, 0, 2 * hid);
+      p.epi.out_s_ncols = 2 * hid;
+      p.epi.out_vt = h->vT; p.epi.out_vt_zstride = (long)hd * 2 * NP; p.epi.out_vt_rstride = 2L * NP;
+      p.epi.out_vt_lo = NP; p.epi.out_vt_hd = hd; p.epi.out_vt_heads = c.heads;
+      DEXB_TRY(plan_shared(&k.qkv, p));
+    }
+    {
+      GemmParams p = gp_base(c);                      // scores[z] = (q k^T) * hd^-0.5
+      gp_geom(p, B * c.heads, 1, N);
+      p.nheads = c.heads;
+      gp_a(p, h->qk, 4 * hid, 0, 2 * hid, hd);
+      p.a_head_stride = hd;
+      p.Bw = h->qk; p.b_row_stride = 4 * hid; p.b_hi = hid; p.b_lo = 3 * hid; p.b_head_stride = hd;
+      p.b_rows_per_tap = N; p.N = N; p.b_mode = 1; p.b_mat_stride = (long)N * 4 * hid;
+      p.epi.alpha = 1.f / sqrtf((float)hd);
+      gp_out_f(p, h->scores, NP);
+      p.epi.o_by_z = 1;
+      gp_tile(p);
+      DEXB_TRY(gemm_plan_init(&k.scores, p, B, N, B));
+    }
+    {
+      GemmParams p = gp_base(c);                      // out[z] = P[z] V[z]
+      gp_geom(p, B * c.heads, 1, N);
+      p.nheads = c.heads; p.a_by_z = 1;
+      gp_a(p, h->P, 2L * NP, 0, NP, NP);
+      p.Bw = h->vT; p.b_row_stride = 2L * NP; p.b_hi = 0; p.b_lo = NP;
+      p.b_rows_per_tap = hd; p.N = hd; p.b_mode = 2; p.b_mat_stride = (long)hd * 2 * NP;
+      gp_out_s(p, h->attnS, 2 * hid, 0, hid);
+      p.epi.out_s_ncols = hd;
+      p.epi.o_head_stride = hd;
+      gp_tile(p);
+      DEXB_TRY(gemm_plan_init(&k.pv, p, B * c.heads, hd, B * c.heads));
+    }
+    {
+      GemmParams p = gp_base(c);                      // x += gate_msa * proj(attn)
+      gp_geom(p, 1, 1, (int)M);
+      gp_a(p, h->attnS, 2 * hid, 0, hid, hid);
+      gp_b(p, k.proj_w, hid, hid);
+      p.epi.bias = k.proj_b;
+      p.epi.resid_f32 = h->xtok; p.epi.resid_f32_stride = hid;
+      gp_out_f(p, h->xtok, hid);
+      DEXB_TRY(plan_shared(&k.proj, p));
+    }
+    {
+      GemmParams p = gp_base(c);                      // gelu(fc1)
+      gp_geom(p, 1, 1, (int)M);
+      gp_a(p, h->hS, 2 * hid, 0, hid, hid);
+      gp_b(p, k.fc1_w, hid, c.mlp_hidden);
+      p.epi.bias = k.fc1_b; p.epi.act = 1;
+      gp_out_s(p, h->h2S, 2 * c.mlp_hidden, 0, c.mlp_hidden);
+      DEXB_TRY(plan_shared(&k.fc1, p));
+    }
+    {
+      GemmParams p = gp_base(c);                      // x += gate_mlp * fc2
+      gp_geom(p, 1, 1, (int)M);
+      gp_a(p, h->h2S, 2 * c.mlp_hidden, 0, c.mlp_hidden, c.mlp_hidden);
+      gp_b(p, k.fc2_w, c.mlp_hidden, hid);
+      p.epi.bias = k.fc2_b;
+      p.epi.resid_f32 = h->xtok; p.epi.resid_f32_stride = hid;
+      gp_out_f(p, h->xtok, hid);
+      DEXB_TRY(plan_shared(&k.fc2, p));
+    }
+  }
+  {
+    const int nout = c.stride * c.stride * mid;
+    GemmParams p = gp_base(c);
+    gp_geom(p, 1, 1, (int)M);
+    gp_a(p, h->hS, 2 * hid, 0, hid, hid);
+    gp_b(p, h->final_w, hid, nout);
+    p.epi.bias = h->final_b;
+    gp_out_f(p, h->ytok, nout);
+    DEXB_TRY(plan_shared(&h->g_final, p));
+  }
+  // ---- up ----
+  DEXB_TRY(plan_block_conv(h, h->u00.b1, h->cat, 4 * mid, 0, 2 * mid, H1, W1, h->raw1));
+  DEXB_TRY(plan_block_conv(h, h->u00.b2, h->A1, 2 * d, 0, d, H1, W1, h->raw1));
+  {
+    GemmParams p = gp_base(c);
+    gp_geom(p, B, H1, W1);
+    gp_a(p, h->cat, 4 * mid, 0, 2 * mid, 2 * mid);
+    gp_b(p, h->u00.res_w, 2 * mid, d);
+    p.epi.bias = h->u00.res_b;
+    gp_out_f(p, h->resid1, d);
+    DEXB_TRY(plan_shared(&h->u00.res, p));
+  }
+  DEXB_TRY(plan_block_conv(h, h->u01.b1, h->B1, 2 * d, 0, d, H1, W1, h->raw1));
+  DEXB_TRY(plan_block_conv(h, h->u01.b2, h->A1, 2 * d, 0, d, H1, W1, h->raw1));
+  DEXB_TRY(plan_la(h, h->la2, h->C1, 2 * d, 0, d, H1, W1, h->mask1, h->A1, 2 * d, 0, d));
+  for (int ph = 0; ph < 4; ++ph) {
+    const int ry = ph / 2, rx = ph % 2;
+    GemmParams p = gp_base(c);
+    gp_geom(p, B, H1, W1);
+    p.OH = H0; p.OW = W0; p.out_scale = 2; p.out_offh = ry; p.out_offw = rx;
+    gp_a(p, h->A1, 2 * d, 0, d, d);
+    gp_b(p, h->up_w + (long)ph * 4 * d * 2 * d, d, d);
+    gp_taps(p, 2, 2, ry - 1, rx - 1);
+    p.epi.bias = h->up_b;
+    gp_rowmask(p, h->mask0, W0);
+    gp_out_s(p, h->A0, 2 * d, 0, d);
+    DEXB_TRY(plan_shared(&h->g_up[ph], p));
+  }
+  DEXB_TRY(plan_block_conv(h, h->fin, h->A0, 2 * d, 0, d, H0, W0, h->raw0));
+  return 0;
+}
+
+static int build_tables(dexb_handle* h, cudaStream_t st) {
+  const dexb_config& c = h->cfg;
+  const int d = c.dim, mid = 2 * d, hid = c.hidden, steps = h->steps;
+  const bool dex = c.variant == 1;
+  auto W = [&](const char* n) { return find_w(h, n)->p; };
+  launch_time_embed(h->tab, steps, h->t_init, d, c.pe_scale, 0, st);
+  launch_small_linear(h->t_init, d, W("mlp.0.weight"), W("mlp.0.bias"), h->t_hid, 4 * d, steps, 4 * d, d, 0, 1, st);
+  launch_small_linear(h->t_hid, 4 * d, W("mlp.2.weight"), W("mlp.2.bias"), h->t_unet, d, steps, d, 4 * d, 0, 0, st);
+  ResnetW* rs[6] = {&h->d00, &h->d01, &h->d10, &h->d11, &h->u00, &h->u01};
+  for (ResnetW* r : rs)
+    launch_small_linear(h->t_unet, d, r->mlp_w, r->mlp_b, r->tbias, r->co, steps, r->co, d, 1, 0, st);
+  if (dex) {
+    launch_small_linear(h->t_init, d, W("mlp_adap.0.weight"), W("mlp_adap.0.bias"), h->t_hid2, d, steps, d, d, 0, 1, st);
+    launch_small_linear(h->t_hid2, d, W("mlp_adap.2.weight"), W("mlp_adap.2.bias"), h->t_adap, mid, steps, mid, d, 0, 0, st);
+    launch_small_linear(h->t_init, d, W("mlp_adap_sty.0.weight"), W("mlp_adap_sty.0.bias"), h->t_hid2, d, steps, d, d, 0, 1, st);
+    launch_small_linear(h->t_hid2, d, W("mlp_adap_sty.2.weight"), W("mlp_adap_sty.2.bias"), h->t_sty, mid, steps, mid, d, 0, 0, st);
+    // time token row of K and V (TVAdaptor: cat([time, sty]) -> w_k / w_v), folded with W_q / linear
+    launch_small_linear(h->t_sty, mid, h->tv_wk, nullptr, h->k0, mid, steps, mid, mid, 0, 0, st);
+    launch_small_linear(h->k0, mid, h->wqT_s, nullptr, h->kw0, mid, steps, mid, mid, 0, 0, st);
+    launch_small_linear(h->t_sty, mid, h->tv_wv, nullptr, h->v0, mid, steps, mid, mid, 0, 0, st);
+    launch_small_linear(h->v0, mid, h->tv_wl, nullptr, h->vl0, mid, steps, mid, mid, 0, 0, st);
+  }
+  launch_time_embed(h->tab, steps, h->temb, 256, 1.f, 1, st);
+  launch_small_linear(h->temb, 256, W("vit.t_embedder.mlp.0.weight"), W("vit.t_embedder.mlp.0.bias"), h->tc_hid, hid, steps,
+                      hid, 256, 0, 2, st);
+  launch_small_linear(h->tc_hid, hid, W("vit.t_embedder.mlp.2.weight"), W("vit.t_embedder.mlp.2.bias"), h->tc, hid, steps, hid,
+                      hid, 0, 0, st);
+  for (int i = 0; i < c.depth; ++i)
+    launch_small_linear(h->tc, hid, h->blocks[i].ada_w, h->blocks[i].ada_b, h->mod + (long)i * 6 * hid, (long)c.depth * 6 * hid,
+                        steps, 6 * hid, hid, 2, 0, st);
+  launch_small_linear(h->tc, hid, W("vit.final_layer.adaLN_modulation.1.weight"), W("vit.final_layer.adaLN_modulation.1.bias"),
+                      h->fmod, 2 * hid, steps, 2 * hid, hid, 2, 0, st);
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* ws_bytes) {
+  DEXB_CHECK(h->finalized, "dexb_plan: weights are not finalized");
+  const dexb_config& c = h->cfg;
+  DEXB_CHECK(B >= 1 && T >= 8 && T % 4 == 0, "dexb_plan: need B >= 1 and T a multiple of 4 (fix_len_compatibility), got B=%d T=%d", B, T);
+  DEXB_CHECK(n_steps >= 1 && sigmas_host != nullptr, "dexb_plan: need n_steps >= 1 and the sigma schedule");
+  DEXB_CHECK(c.variant == 0 || (Ts >= 2 && Ts + 1 <= 512), "dexb_plan: style length must be in [2, 511], got %d", Ts);
+  engine_release_plan(h);
+  DEXB_TRY(gemm_global_init());
+  DEXB_TRY(kernels_global_init());
+  h->B = B; h->T = T; h->Ts = (c.variant == 1) ? Ts : 0; h->steps = n_steps;
+  h->H0 = c.n_feats; h->W0 = T; h->H1 = c.n_feats / 2; h->W1 = T / 2;
+  const int p = c.patch, s = c.stride;
+  const int wp = (h->W1 % p == 0) ? h->W1 : h->W1 + (p - h->W1 % p);
+  h->Fq = (h->H1 + 2 * (p / 2) - p) / s + 1;
+  h->Wq = (wp + 2 * (p / 2) - p) / s + 1;
+  DEXB_CHECK(h->Fq == h->H1 / s && h->Wq * s >= h->W1, "dexb_plan: patch %d / stride %d does not tile a %d x %d bottleneck", p, s,
+             h->H1, h->W1);
+  h->Ntok = h->Fq * h->Wq;
+  h->NP = (h->Ntok + 63) / 64 * 64;
+  h->NK = h->Ts + 1;
+  h->KP = (h->NK + 63) / 64 * 64;
+  // GroupNorm statistic slots
+  int slot = 0;
+  ResnetW* rs[6] = {&h->d00, &h->d01, &h->d10, &h->d11, &h->u00, &h->u01};
+  for (ResnetW* r : rs) { r->b1.slot = slot++; r->b2.slot = slot++; }
+  h->fin.slot = slot++;
+  h->n_slots = slot;
+  h->tab_host.resize(n_steps);
+  for (int i = 0; i < n_steps; ++i) {
+    StepScalars& t = h->tab_host[i];
+    const float sg = sigmas_host[i], sd = 0.5f;
+    t.sigma = sg; t.sigma_next = sigmas_host[i + 1];
+    const float q = sg * sg + sd * sd;                       // EDMPrecond.forward, edm.py:90-94
+    t.c_skip = (sd * sd) / q;
+    t.c_out = sg * sd / sqrtf(q);
+    t.c_in = 1.f / sqrtf(q);
+    t.c_noise = logf(sg) / 4.f;
+  }
+  Arena m;
+  DEXB_TRY(layout_ws(h, m));
+  h->ws_bytes = m.off + 4096;
+  DEXB_CUDA_OK(cudaMalloc(&h->ws_base, h->ws_bytes));
+  DEXB_CUDA_OK(cudaMemset(h->ws_base, 0, h->ws_bytes));
+  Arena ar; ar.base = h->ws_base;
+  DEXB_TRY(layout_ws(h, ar));
+  DEXB_CUDA_OK(cudaMemcpy(h->tab, h->tab_host.data(), sizeof(StepScalars) * n_steps, cudaMemcpyHostToDevice));
+  DEXB_TRY(build_plans(h));
+  DEXB_TRY(build_tables(h, 0));
+  DEXB_CUDA_OK(cudaDeviceSynchronize());
+  if (ws_bytes != nullptr) *ws_bytes = h->ws_bytes;
+  const char* ng = getenv("DEXB_NO_GRAPH");
+  h->use_graph = !(ng != nullptr && ng[0] == '1');
+  h->planned = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one network call + Euler update
+// ------------------------------------------------------------------------------------------------
+static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, int P, int W, const float* mask, bf16* out,
+                           long out_stride, int out_hi, int out_lo) {
+  GnApplyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.raw = raw; a.C = b.co; a.G = 8;
+  a.stats = h->gn_stats + (long)b.slot * h->B * 16;
+  a.gamma = b.gamma; a.beta = b.beta;
+  a.B = h->B; a.P = P; a.W = W;
+  a.mask = mask; a.mask_stride = W;
+  a.out.p = out; a.out.stride = out_stride; a.out.hi = out_hi; a.out.lo = out_lo;
+  return a;
+}
+
+static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
+  GEMM(la.kv, la.kv.p);
+  LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
+  LAUNCH(launch_la_ctx(h->kv, la.kmax, la.ctx, la.ssum, h->B, P, st));
+  LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.weff, la.beff, h->B, la.C, st));
+  GEMM(la.apply, la.apply.p);
+  return 0;
+}
+
+// ResnetBlock on S tensors: in -> (tmp) -> out.  `in` must already be masked (diffusion.py:70-74).
+static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const float* mask, float* raw, bf16* tmp,
+                      long tmp_stride, bf16* out, long out_stride, const bf16* in, long in_stride, int in_hi, int in_lo,
+                      bool first, cudaStream_t st) {
+  const int P = H * W;
+  if (first) {
+    LAUNCH(launch_conv_in(h->x, h->mu, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
+                          h->gn_stats + (long)r.b1.slot * h->B * 16, h->B, H, W, r.co, st));
+  } else {
+    GEMM(r.b1.conv, r.b1.conv.p);
+  }
+  {
+    GnApplyArgs a = gn_args(h, r.b1, raw, P, W, mask, tmp, tmp_stride, 0, (int)(tmp_stride / 2));
+    a.tbias = r.tbias + (long)step * r.co;
+    LAUNCH(launch_gn_apply(a, st));
+  }
+  GEMM(r.b2.conv, r.b2.conv.p);
+  if (r.res_w != nullptr) GEMM(r.res, r.res.p);
+  {
+    GnApplyArgs a = gn_args(h, r.b2, raw, P, W, mask, out, out_stride, 0, (int)(out_stride / 2));
+    if (first) {
+      a.rin_w = r.rin_w; a.rin_b = r.res_b; a.x = h->x; a.mu = h->mu; a.tab = h->tab; a.step = step;
+    } else if (r.res_w != nullptr) {
+      a.resid_f = h->resid1; a.resid_f_stride = r.co;
+    } else {
+      a.resid_s.p = const_cast<bf16*>(in); a.resid_s.stride = in_stride; a.resid_s.hi = in_hi; a.resid_s.lo = in_lo;
+    }
+    LAUNCH(launch_gn_apply(a, st));
+  }
+  return 0;
+}
+
+static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
+  const dexb_config& c = h->cfg;
+  const int B = h->B, d = c.dim, mid = 2 * d, hid = c.hidden;
+  const int H0 = h->H0, W0 = h->W0, H1 = h->H1, W1 = h->W1, P0 = H0 * W0, P1 = H1 * W1;
+  const bool dex = c.variant == 1;
+  DEXB_CUDA_OK(cudaMemsetAsync(h->zero_base, 0, h->zero_bytes, st));
+  ++h->launches;
+  // ---- level 0 ----
+  DEXB_TRY(run_resnet(h, h->d00, step, H0, W0, h->mask0, h->raw0, h->A0, 2 * d, h->B0, 2 * d, nullptr, 0, 0, 0, true, st));
+  DEXB_TRY(run_resnet(h, h->d01, step, H0, W0, h->mask0, h->raw0, h->A0, 2 * d, h->C0, 2 * d, h->B0, 2 * d, 0, d, false, st));
+  DEXB_TRY(run_la(h, h->la0, P0, st));                                  // C0 -> A0 (masked)
+  GEMM(h->g_down, h->g_down.p);                                         // A0 -> D1 (masked)
+  // ---- level 1 ----
+  DEXB_TRY(run_resnet(h, h->d10, step, H1, W1, h->mask1, h->raw1, h->A1, 2 * mid, h->B1, 2 * mid, h->D1, 2 * d, 0, d, false, st));
+  DEXB_TRY(run_resnet(h, h->d11, step, H1, W1, h->mask1, h->raw1, h->A1, 2 * mid, h->C1, 2 * mid, h->B1, 2 * mid, 0, mid, false, st));
+  DEXB_TRY(run_la(h, h->la1, P1, st));                                  // C1 -> cat[:, mid:] (masked skip)
+  SView skip = {h->cat, 4L * mid, mid, 3 * mid};
+  SView tok = {h->tokS, 2L * mid, 0, mid};
+  if (dex) {
+    // TVAdaptor (ref_encoder.py:154-179)
+    LAUNCH(launch_chan_stats_s(skip, h->cstats, B, P1, mid, st));
+    LAUNCH(launch_tv_fold(h->kw, h->kw0 + (long)step * mid, h->cstats, P1, h->kq, h->sbias, B, h->NK, h->KP, mid, st));
+    LAUNCH(launch_tv_vl0(h->vl0 + (long)step * mid, h->vlt, B, mid, h->KP, st));
+    GEMM(h->g_tvs, h->g_tvs.p);
+    LAUNCH(launch_tv_softmax(h->tvscores, h->KP, h->sty_len, h->tvP, B, P1, h->NK, h->KP, st));
+    GEMM(h->g_tvo, h->g_tvo.p);
+    // TIVAdaptor (AdaIN, ref_encoder.py:264-273) folded into the patch-embed front
+    double* cs1 = h->cstats + (long)B * mid * 2;
+    LAUNCH(launch_chan_stats_f(h->tvout, mid, cs1, B, P1, mid, st));
+    LAUNCH(launch_dw_patch(h->tvout, cs1, h->tiv_scale + (long)step * B * mid, h->tiv_shift + (long)step * B * mid, 1, h->dw_w,
+                           h->dw_b, tok, B, H1, W1, mid, c.patch, c.stride, h->Fq, h->Wq, st));
+  } else {
+    LAUNCH(launch_dw_patch_s(skip, h->dw_w, h->dw_b, tok, B, H1, W1, mid, c.patch, c.stride, h->Fq, h->Wq, st));
+  }
+  // ---- DiT (dit.py:479-519) ----
+  const int N = h->Ntok;
+  const long M = (long)B * N;
+  GEMM(h->g_pe, h->g_pe.p);
+  LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, st));
+  GEMM(h->g_posconv, h->g_posconv.p);
+  const float* mod = h->mod + (long)step * c.depth * 6 * hid;
+  SView hs = {h->hS, 2L * hid, 0, hid};
+  LAUNCH(launch_tok_assemble(h->xe, h->pe, h->fpos, h->xtok, mod, mod + hid, hs, B, h->Fq, h->Wq, hid, st));
+  for (int i = 0; i < c.depth; ++i) {
+    DitBlockW& k = h->blocks[i];
+    const float* m = mod + (long)i * 6 * hid;
+    GEMM(k.qkv, k.qkv.p);
+    GEMM(k.scores, k.scores.p);
+    LAUNCH(launch_attn_softmax(h->scores, h->NP, h->P, h->NP, (long)B * c.heads * N, N, st));
+    GEMM(k.pv, k.pv.p);
+    {
+      GemmParams p = k.proj.p;
+      p.epi.gate = m + 2 * hid;
+      GEMM(k.proj, p);
+    }
+    LAUNCH(launch_ln_mod(h->xtok, m + 3 * hid, m + 4 * hid, hs, M, hid, st));
+    GEMM(k.fc1, k.fc1.p);
+    {
+      GemmParams p = k.fc2.p;
+      p.epi.gate = m + 5 * hid;
+      GEMM(k.fc2, p);
+    }
+    if (i + 1 < c.depth) {
+      const float* mn = mod + (long)(i + 1) * 6 * hid;
+      LAUNCH(launch_ln_mod(h->xtok, mn, mn + hid, hs, M, hid, st));
+    } else {
+      const float* fm = h->fmod + (long)step * 2 * hid;
+      LAUNCH(launch_ln_mod(h->xtok, fm, fm + hid, hs, M, hid, st));
+    }
+  }
+  GEMM(h->g_final, h->g_final.p);
+  SView dit_out = {h->cat, 4L * mid, 0, 2 * mid};
+  LAUNCH(launch_unpatchify(h->ytok, dit_out, h->mask1, B, h->Fq, h->Wq, c.stride, mid, H1, W1, st));
+  // ---- up ----
+  DEXB_TRY(run_resnet(h, h->u00, step, H1, W1, h->mask1, h->raw1, h->A1, 2 * d, h->B1, 2 * d, h->cat, 4 * mid, 0, 2 * mid, false, st));
+  DEXB_TRY(run_resnet(h, h->u01, step, H1, W1, h->mask1, h->raw1, h->A1, 2 * d, h->C1, 2 * d, h->B1, 2 * d, 0, d, false, st));
+  DEXB_TRY(run_la(h, h->la2, P1, st));                                  // C1 -> A1 (masked)
+  for (int ph = 0; ph < 4; ++ph) GEMM(h->g_up[ph], h->g_up[ph].p);      // A1 -> A0 (masked)
+  GEMM(h->fin.conv, h->fin.conv.p);
+  LAUNCH(launch_gn_final(h->raw0, d, 8, h->gn_stats + (long)h->fin.slot * B * 16, h->fin.gamma, h->fin.beta, h->fc_w, h->fc_b,
+                         h->mask0, h->x, den_out, h->tab, step, B, H0, W0, st));
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// conditioning-dependent, step-invariant work (DEX only)
+static int run_prepare(dexb_handle* h, cudaStream_t st) {
+  const dexb_config& c = h->cfg;
+  const int B = h->B, mid = 2 * c.dim, Ts = h->Ts;
+  LAUNCH(launch_mask_down(h->mask0, h->mask1, B, h->W0, h->W1, st));
+  if (c.variant != 1) return 0;
+  LAUNCH(launch_bct_to_btc(h->sty, h->styT, B, mid, Ts, st));
+  LAUNCH(launch_small_linear(h->styT, mid, h->tv_wk, nullptr, h->kmat, mid, B * Ts, mid, mid, 0, 0, st));
+  LAUNCH(launch_small_linear(h->kmat, mid, h->wqT_s, nullptr, h->kw, mid, B * Ts, mid, mid, 0, 0, st));
+  LAUNCH(launch_small_linear(h->styT, mid, h->tv_wv, nullptr, h->vmat, mid, B * Ts, mid, mid, 0, 0, st));
+  LAUNCH(launch_small_linear(h->vmat, mid, h->tv_wl, nullptr, h->vl, mid, B * Ts, mid, mid, 0, 0, st));
+  LAUNCH(launch_tv_vlt_pack(h->vl, h->vlt, B, Ts, mid, h->KP, st));
+  for (int l = 0; l < 6; ++l) LAUNCH(launch_ref_stats(h->refs[l], h->ref_mean, h->ref_std, B, mid, h->Tr, 6, l, st));
+  LAUNCH(launch_tiv_sap(h->t_adap, h->ref_mean, h->sap_m_w, h->sap_m_b, h->tiv_shift, h->steps, B, mid, 6, st));
+  LAUNCH(launch_tiv_sap(h->t_adap, h->ref_std, h->sap_s_w, h->sap_s_b, h->tiv_scale, h->steps, B, mid, 6, st));
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int enqueue_all(dexb_handle* h, int only_step, float* den_out, cudaStream_t st) {
+  DEXB_TRY(run_prepare(h, st));
+  if (only_step >= 0) return run_step(h, only_step, den_out, st);
+  LAUNCH(launch_scale(h->x, (long)h->B * h->H0 * h->W0, h->tab_host[0].sigma, st));     // x <- latents * sigma_0 (edm.py:184)
+  for (int s = 0; s < h->steps; ++s) DEXB_TRY(run_step(h, s, nullptr, st));
+  return 0;
+}
+
+int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mask, const dexb_cond* cond, int only_step,
+               float* den_out, cudaStream_t st) {
+  DEXB_CHECK(h->planned, "dexb_reverse_diffusion: call dexb_plan first");
+  const dexb_config& c = h->cfg;
+  const long n0 = (long)h->B * h->H0 * h->W0;
+  const int mid = 2 * c.dim;
+  DEXB_CHECK(only_step < h->steps, "step %d out of range", only_step);
+  if (x_inout != h->x) DEXB_CUDA_OK(cudaMemcpyAsync(h->x, x_inout, n0 * 4, cudaMemcpyDeviceToDevice, st));
+  if (mu != h->mu) DEXB_CUDA_OK(cudaMemcpyAsync(h->mu, mu, n0 * 4, cudaMemcpyDeviceToDevice, st));
+  if (mask != h->mask0) DEXB_CUDA_OK(cudaMemcpyAsync(h->mask0, mask, (long)h->B * h->W0 * 4, cudaMemcpyDeviceToDevice, st));
+  if (c.variant == 1) {
+    DEXB_CHECK(cond != nullptr && cond->sty_dev != nullptr && cond->sty_len_dev != nullptr, "DEX-TTS needs conditioning");
+    DEXB_CHECK(cond->Tr == h->Ts, "this build expects ref skips of the style length (Tr %d != Ts %d)", cond->Tr, h->Ts);
+    h->Tr = cond->Tr;
+    if (cond->sty_dev != h->sty)
+      DEXB_CUDA_OK(cudaMemcpyAsync(h->sty, cond->sty_dev, (long)h->B * mid * h->Ts * 4, cudaMemcpyDeviceToDevice, st));
+    if (cond->sty_len_dev != h->sty_len)
+      DEXB_CUDA_OK(cudaMemcpyAsync(h->sty_len, cond->sty_len_dev, (long)h->B * 4, cudaMemcpyDeviceToDevice, st));
+    for (int l = 0; l < 6; ++l) {
+      DEXB_CHECK(cond->ref_skips_dev[l] != nullptr, "ref skip %d is null", l);
+      if (cond->ref_skips_dev[l] != h->refs[l])
+        DEXB_CUDA_OK(cudaMemcpyAsync(h->refs[l], cond->ref_skips_dev[l], (long)h->B * mid * h->Tr * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  h->launches = 0;
+  if (only_step < 0 && h->use_graph) {
+    if (h->graph_exec == nullptr) {
+      DEXB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int r = enqueue_all(h, -1, nullptr, st);
+      cudaGraph_t g = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (r != 0) { if (g != nullptr) cudaGraphDestroy(g); return r; }
+      DEXB_CHECK(e == cudaSuccess && g != nullptr, "graph capture failed: %s", cudaGetErrorString(e));
+      h->graph = g;
+      DEXB_CUDA_OK(cudaGraphInstantiate(&h->graph_exec, g, 0));
+    } else {
+      size_t nn = 0;
+      cudaGraphGetNodes(h->graph, nullptr, &nn);
+      h->launches = (long)nn;
+    }
+    DEXB_CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
+  } else {
+    DEXB_TRY(enqueue_all(h, only_step, den_out, st));
+  }
+  if (only_step < 0 && x_inout != h->x) DEXB_CUDA_OK(cudaMemcpyAsync(x_inout, h->x, n0 * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+}  // namespace dexb

@@ -1,0 +1,120 @@
+// Host side of the implicit-GEMM engine: tensor-map construction (driver entry point resolved at run time, so the
+// library does not link libcuda), tile-shape selection and launch of either engine.
+#include "gemm.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdio.h>
+
+namespace dexb {
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int resolve_encode() {
+  if (g_encode != nullptr) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return 0;
+}
+
+static int encode_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
+                       const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+  DEXB_TRY(resolve_encode());
+  DEXB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map %s: base not 16 B aligned", what);
+  for (int i = 0; i + 1 < rank; ++i)
+    DEXB_CHECK(strides_b[i] % 16 == 0, "tensor map %s: stride %d (%llu B) not a multiple of 16", what, i,
+               (unsigned long long)strides_b[i]);
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DEXB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+static int pick_block_n(int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N % 256 == 0 || N > 512) return 256;
+  return 128;
+}
+
+int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, int n_bmat) {
+  gp->p = p;
+  GemmParams& q = gp->p;
+  DEXB_CHECK(q.BH * q.BW == 128, "gemm: tile %d x %d is not 128 pixels", q.BH, q.BW);
+  DEXB_CHECK(q.K % 16 == 0 && q.K > 0, "gemm: K = %d must be a positive multiple of 16", q.K);
+  DEXB_CHECK(q.nheads >= 1 && q.nz >= 1 && q.nz % q.nheads == 0, "gemm: nz %d / nheads %d", q.nz, q.nheads);
+  q.TH = cdiv(q.CH, q.BH);
+  q.TW = cdiv(q.CW, q.BW);
+  gp->block_n = pick_block_n(q.N);
+  gp->n_img_a = n_img_a;
+  gp->tc_ok = (q.K % kTcBlockK == 0) && (q.a_row_stride % 8 == 0) && (q.b_row_stride % 8 == 0) &&
+              (q.in_stride == 1 || q.in_stride == 2) && (q.BW * q.in_stride <= 256) && (q.BH * q.in_stride <= 256) &&
+              ((q.a_hi | q.a_lo | q.b_hi | q.b_lo | q.a_head_stride | q.b_head_stride) % 8 == 0);
+  if (!gp->tc_ok) return 0;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)q.a_row_stride, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)n_img_a};
+    const cuuint64_t str[3] = {(cuuint64_t)q.a_row_stride * 2, (cuuint64_t)q.a_row_stride * 2 * q.W,
+                               (cuuint64_t)q.a_row_stride * 2 * q.W * q.H};
+    const cuuint32_t box[4] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(q.BW * q.in_stride), (cuuint32_t)(q.BH * q.in_stride), 1};
+    const cuuint32_t es[4] = {1, (cuuint32_t)q.in_stride, (cuuint32_t)q.in_stride, 1};
+    DEXB_TRY(encode_bf16(&gp->tmA, q.A, 4, dims, str, box, es, "A"));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)q.b_row_stride, (cuuint64_t)b_rows, (cuuint64_t)n_bmat};
+    const cuuint64_t str[2] = {(cuuint64_t)q.b_row_stride * 2,
+                               (cuuint64_t)(n_bmat > 1 ? q.b_mat_stride : q.b_row_stride * b_rows) * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)gp->block_n, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    DEXB_TRY(encode_bf16(&gp->tmB, q.Bw, 3, dims, str, box, es, "B"));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch
+// ------------------------------------------------------------------------------------------------
+int gemm_global_init() {
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::kBytes));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::kBytes));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::kBytes));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::kBytes));
+  return resolve_encode();
+}
+
+template <int BN>
+static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
+  dim3 grid((unsigned)(p.nz * p.TH * p.TW), (unsigned)cdiv(p.N, BN));
+  gemm_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p);
+  return 0;
+}
+
+int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st) {
+  if (engine == 0 && gp.tc_ok) {
+    switch (gp.block_n) {
+      case 32: DEXB_TRY(launch_tc<32>(gp, p, st)); break;
+      case 64: DEXB_TRY(launch_tc<64>(gp, p, st)); break;
+      case 128: DEXB_TRY(launch_tc<128>(gp, p, st)); break;
+      default: DEXB_TRY(launch_tc<256>(gp, p, st)); break;
+    }
+  } else {
+    dim3 grid((unsigned)(p.nz * p.TH * p.TW), (unsigned)cdiv(p.N, 64));
+    gemm_simt_kernel<<<grid, kSimtThreads, 0, st>>>(p);
+  }
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dexb

@@ -1,0 +1,418 @@
+// U-Net side kernels: first conv, GroupNorm-apply/Mish fusions, EDM update, LinearAttention reductions.
+// Reference semantics: DEX-TTS/model/diffusion.py:44-105,190-236 and DEX-TTS/model/edm.py:88-98,185-203.
+#include "kernels.cuh"
+
+namespace dexb {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_zero(uint4* p, size_t n16) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
+}
+void launch_fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  const size_t n16 = bytes / 16;                       // callers keep scratch regions 16 B granular
+  int blocks = (int)((n16 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_fill_zero<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+}
+
+__global__ void k_scale(float* x, long n, float s) {
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= s;
+}
+void launch_scale(float* x, long n, float s, cudaStream_t st) { k_scale<<<cdiv(n, 256), 256, 0, st>>>(x, n, s); }
+
+__global__ void k_mask_down(const float* mask, float* mask1, int B, int T, int W1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * W1) { int b = i / W1, w = i % W1; mask1[i] = mask[(long)b * T + 2 * w]; }
+}
+void launch_mask_down(const float* mask, float* mask1, int B, int T, int W1, cudaStream_t st) {
+  k_mask_down<<<cdiv((long)B * W1, 256), 256, 0, st>>>(mask, mask1, B, T, W1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_in: one thread per pixel computes all C(=64) outputs of the 2->C 3x3 conv (K = 18: CUDA cores, the
+// contraction is too short for tensor cores).  Input = stack[mu, c_in * x] * mask  (diffusion.py:198,52; edm.py:96).
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) k_conv_in(const float* __restrict__ x, const float* __restrict__ mu,
+                                                 const float* __restrict__ mask, const StepScalars* __restrict__ tab,
+                                                 int step, const float* __restrict__ w, const float* __restrict__ bias,
+                                                 float* __restrict__ raw, double* __restrict__ stats, int B, int H,
+                                                 int W) {
+  __shared__ float ws[C * 18];
+  __shared__ float bs[C];
+  __shared__ float red[4][C / 8][2];
+  for (int i = threadIdx.x; i < C * 18; i += 128) ws[i] = w[i];
+  for (int i = threadIdx.x; i < C; i += 128) bs[i] = bias[i];
+  __syncthreads();
+  const int wt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int wcol = wt * 128 + threadIdx.x;
+  const bool valid = wcol < W;
+  const float c_in = tab[step].c_in;
+  float in[18];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int hh = h + dy - 1, ww = wcol + dx - 1;
+      float a = 0.f, c = 0.f;
+      if (valid && hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        const float m = mask[(long)b * W + ww];
+        const long idx = ((long)b * H + hh) * W + ww;
+        a = mu[idx] * m;
+        c = (c_in * x[idx]) * m;
+      }
+      in[dy * 3 + dx] = a;
+      in[9 + dy * 3 + dx] = c;
+    }
+  float* orow = raw + (((long)b * H + h) * W + wcol) * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int g = 0; g < C / 8; ++g) {
+    float o[8];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      float acc = bs[co];
+#pragma unroll
+      for (int k = 0; k < 18; ++k) acc = fmaf(ws[co * 18 + k], in[k], acc);
+      o[j] = acc;
+      if (valid) { s += acc; ss += acc * acc; }
+    }
+    if (valid) {
+      *reinterpret_cast<float4*>(orow + g * 8) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(orow + g * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if (lane == 0) { red[warp][g][0] = s; red[warp][g][1] = ss; }
+  }
+  __syncthreads();
+  if (threadIdx.x < C / 8) {
+    const int g = threadIdx.x;               // channels-per-group == 8 when C == 64 (GroupNorm(8, 64))
+    double s = 0., ss = 0.;
+    for (int wq = 0; wq < 4; ++wq) { s += red[wq][g][0]; ss += red[wq][g][1]; }
+    atomicAdd(&stats[((long)b * (C / 8) + g) * 2], s);
+    atomicAdd(&stats[((long)b * (C / 8) + g) * 2 + 1], ss);
+  }
+}
+
+void launch_conv_in(const float* x, const float* mu, const float* mask, const StepScalars* tab, int step,
+                    const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
+                    cudaStream_t st) {
+  dim3 grid(cdiv(W, 128), H, B);
+  // stats layout is [B][8 groups][2]; with C == 64 a group is 8 channels, with C == 128 it is 16 (two 8-chunks):
+  // the C==128 instantiation folds pairs of chunks on the host side by giving G = C/8 "half groups" -- not needed
+  // for the shipped configs (dim 64), so only C == 64 is instantiated.
+  if (C == 64) k_conv_in<64><<<grid, 128, 0, st>>>(x, mu, mask, tab, step, w, bias, raw, stats, B, H, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm-apply + Mish + mask (+ time bias | + residual) -> split-bf16.  8 channels per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gn_apply(const GnApplyArgs a) {
+  const int cpt = a.C / 8;                                   // threads per pixel
+  const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)a.B * a.P * cpt;
+  if (gid >= total) return;
+  const int c0 = (int)(gid % cpt) * 8;
+  const long pix = gid / cpt;                                // global pixel row
+  const int b = (int)(pix / a.P);
+  const int w = (int)((pix % a.P) % a.W);
+  const int gs = a.C / a.G;
+  const int g = c0 / gs;
+  const double n = (double)a.P * gs;
+  const double s = a.stats[((long)b * a.G + g) * 2], ss = a.stats[((long)b * a.G + g) * 2 + 1];
+  const double mean_d = s / n;
+  double var_d = ss / n - mean_d * mean_d;
+  if (var_d < 0.) var_d = 0.;
+  const float mean = (float)mean_d;
+  const float rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+  const float m = a.mask[(long)b * a.mask_stride + w];
+  const float* rp = a.raw + pix * a.C + c0;
+  const float4 r0 = *reinterpret_cast<const float4*>(rp);
+  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+  float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  float res[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) res[i] = 0.f;
+  if (a.resid_s.p != nullptr) {
+    const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
+    load_split8(q + a.resid_s.hi, q + a.resid_s.lo, res);
+  } else if (a.resid_f != nullptr) {
+    const float* q = a.resid_f + pix * a.resid_f_stride + c0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = q[i] * m;
+  } else if (a.rin_w != nullptr) {
+    // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
+    const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    float y = (v[i] - mean) * rstd * a.gamma[c] + a.beta[c];
+    y = mish_f(y) * m;
+    if (a.tbias != nullptr) y = (y + a.tbias[c]) * m;
+    v[i] = y + res[i];
+  }
+  bf16* op = a.out.p + pix * a.out.stride + c0;
+  store_split8(op + a.out.hi, op + a.out.lo, v);
+}
+void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
+  const long total = (long)a.B * a.P * (a.C / 8);
+  k_gn_apply<<<cdiv(total, 256), 256, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// final: GN + Mish + mask -> 1x1 conv (C -> 1) + bias -> mask = F_x;  D = c_skip*x + c_out*F_x;
+// d = x/sigma - D/sigma;  x <- x + (sigma_next - sigma) * d        (edm.py:97,197,203)
+// 8 lanes per pixel (C == 64).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gn_final(const float* __restrict__ raw, int C, int G,
+                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, const float* __restrict__ fc_w,
+                                                  const float* __restrict__ fc_b, const float* __restrict__ mask,
+                                                  float* __restrict__ x, float* __restrict__ den_out,
+                                                  const StepScalars* __restrict__ tab, int step, int B, int P, int W) {
+  const int cpt = C / 8;                                      // == 8
+  const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)B * P * cpt;
+  const bool active = gid < total;
+  const long pix = active ? gid / cpt : 0;
+  const int c0 = (int)(gid % cpt) * 8;
+  const int b = (int)(pix / P);
+  const int w = (int)((pix % P) % W);
+  float part = 0.f;
+  float m = 0.f;
+  if (active) {
+    const int gs = C / G;
+    const int g = c0 / gs;
+    const double n = (double)P * gs;
+    const double s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
+    const double mean_d = s / n;
+    double var_d = ss / n - mean_d * mean_d;
+    if (var_d < 0.) var_d = 0.;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    m = mask[(long)b * W + w];
+    const float* rp = raw + pix * C + c0;
+    const float4 r0 = *reinterpret_cast<const float4*>(rp);
+    const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
+    const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      const float y = mish_f((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
+      part = fmaf(fc_w[c], y * m, part);
+    }
+  }
+  // reduce over the 8 lanes of a pixel (cpt == 8, aligned groups of lanes)
+  part += __shfl_xor_sync(0xffffffffu, part, 1);
+  part += __shfl_xor_sync(0xffffffffu, part, 2);
+  part += __shfl_xor_sync(0xffffffffu, part, 4);
+  if (active && c0 == 0) {
+    const StepScalars sc = tab[step];
+    const float fx = (part + fc_b[0]) * m;
+    const float xv = x[pix];
+    const float den = sc.c_skip * xv + sc.c_out * fx;
+    const float inv = 1.f / sc.sigma;
+    const float d = inv * xv - inv * den;
+    if (den_out != nullptr) den_out[pix] = den;
+    else x[pix] = xv + (sc.sigma_next - sc.sigma) * d;
+  }
+}
+void launch_gn_final(const float* raw, int C, int G, const double* stats, const float* gamma, const float* beta,
+                     const float* fc_w, const float* fc_b, const float* mask, float* x, float* den_out,
+                     const StepScalars* tab, int step, int B, int H, int W, cudaStream_t st) {
+  const long total = (long)B * H * W * (C / 8);
+  k_gn_final<<<cdiv(total, 256), 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B,
+                                                H * W, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LinearAttention (diffusion.py:82-95): softmax of k over ALL pixels, context = softmax(k) v^T (32x32 per head).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned enc_ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ord(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// column max of k: kv rows are [k(128) | v(128)]; block = 128 threads (one per k column) over a chunk of pixels
+__global__ void __launch_bounds__(128) k_la_colmax(const float* __restrict__ kv, unsigned* __restrict__ kmax, int P,
+                                                   int chunk) {
+  const int b = blockIdx.y;
+  const long p0 = (long)blockIdx.x * chunk;
+  long p1 = p0 + chunk;
+  if (p1 > P) p1 = P;
+  float m = -INFINITY;
+  const float* base = kv + ((long)b * P) * 256 + threadIdx.x;
+  for (long p = p0; p < p1; ++p) m = fmaxf(m, base[p * 256]);
+  atomicMax(&kmax[b * 128 + threadIdx.x], enc_ord(m));
+}
+void launch_la_colmax(const float* kv, unsigned* kmax_enc, int B, int P, cudaStream_t st) {
+  const int chunk = 256;
+  dim3 grid(cdiv(P, chunk), B);
+  k_la_colmax<<<grid, 128, 0, st>>>(kv, kmax_enc, P, chunk);
+}
+
+// ctx[b][h][d][e] += sum_n exp(k[n][h*32+d] - max) * v[n][h*32+e];  ssum[b][h*32+d] += sum_n exp(..)
+// block (256 threads) = one (b, head, pixel chunk); thread = (d = tid/8, e0 = (tid%8)*4)
+__global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, const unsigned* __restrict__ kmax,
+                                                float* __restrict__ ctx, float* __restrict__ ssum, int P, int chunk) {
+  __shared__ float ps[64][33];
+  __shared__ float vs[64][32];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const long p0 = (long)blockIdx.x * chunk;
+  long p1 = p0 + chunk;
+  if (p1 > P) p1 = P;
+  const int tid = threadIdx.x;
+  const int d = tid >> 3, e0 = (tid & 7) * 4;
+  const int lc = tid & 31, lr = tid >> 5;                   // loader: column lc, rows lr, lr+8, ...
+  const float kmx = dec_ord(kmax[b * 128 + h * 32 + lc]);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float sacc = 0.f;
+  for (long t0 = p0; t0 < p1; t0 += 64) {
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = lr + rr * 8;
+      const long pp = t0 + r;
+      float pk = 0.f, pv = 0.f;
+      if (pp < p1) {
+        const float* row = kv + ((long)b * P + pp) * 256;
+        pk = expf(row[h * 32 + lc] - kmx);
+        pv = row[128 + h * 32 + lc];
+      }
+      ps[r][lc] = pk;
+      vs[r][lc] = pv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) {
+      const float pk = ps[r][d];
+      const float4 v4 = *reinterpret_cast<const float4*>(&vs[r][e0]);
+      acc[0] = fmaf(pk, v4.x, acc[0]);
+      acc[1] = fmaf(pk, v4.y, acc[1]);
+      acc[2] = fmaf(pk, v4.z, acc[2]);
+      acc[3] = fmaf(pk, v4.w, acc[3]);
+      sacc += pk;
+    }
+  }
+  float* cp = ctx + (((long)b * 4 + h) * 32 + d) * 32 + e0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) atomicAdd(cp + i, acc[i]);
+  if (e0 == 0) atomicAdd(&ssum[b * 128 + h * 32 + d], sacc);
+}
+void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx, float* ssum, int B, int P, cudaStream_t st) {
+  const int chunk = 512;
+  dim3 grid(cdiv(P, chunk), 4, B);
+  k_la_ctx<<<grid, 256, 0, st>>>(kv, kmax_enc, ctx, ssum, P, chunk);
+}
+
+// W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
+// (q is linear in x, so  x + g*to_out(ctx^T q) == W_eff x + g*b_out : the whole attention read-out is one
+//  per-sample CxC matrix.)   grid = B, block = 256, dynamic smem = 128*C floats.
+__global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, const float* __restrict__ ssum,
+                                                 const float* __restrict__ wq, const float* __restrict__ wout,
+                                                 const float* __restrict__ bout, const float* __restrict__ g,
+                                                 bf16* __restrict__ weff, float* __restrict__ beff, int C) {
+  extern __shared__ float m1[];                               // [128 (h*32+e)][C]
+  const int b = blockIdx.x;
+  const float gg = g[0];
+  for (int idx = threadIdx.x; idx < 128 * C; idx += blockDim.x) {
+    const int he = idx / C, ci = idx % C;
+    const int h = he >> 5, e = he & 31;
+    float acc = 0.f;
+    for (int d = 0; d < 32; ++d) {
+      const float cn = ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] / ssum[b * 128 + h * 32 + d];
+      acc = fmaf(cn, wq[(h * 32 + d) * C + ci], acc);
+    }
+    m1[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int co = idx / C, ci = idx % C;
+    float acc = 0.f;
+    for (int he = 0; he < 128; ++he) acc = fmaf(wout[co * 128 + he], m1[he * C + ci], acc);
+    const float v = gg * acc + (co == ci ? 1.f : 0.f);
+    bf16* row = weff + ((long)b * C + co) * (2 * C);
+    split2(v, row[ci], row[C + ci]);
+  }
+  for (int co = threadIdx.x; co < C; co += blockDim.x) beff[b * C + co] = gg * bout[co];
+}
+int kernels_global_init() {
+  DEXB_CUDA_OK(cudaFuncSetAttribute(k_la_weff, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(float)));
+  return 0;
+}
+void launch_la_weff(const float* ctx, const float* ssum, const float* wq, const float* wout, const float* bout,
+                    const float* g, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
+  k_la_weff<<<B, 256, 128 * C * sizeof(float), st>>>(ctx, ssum, wq, wout, bout, g, weff, beff, C);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-(image, channel) sum / sumsq (InstanceNorm2D statistics, base.py:95-103)
+// block = 256 threads = 32 pixel-lanes x (C/8 <= 16 ... ) ; simple: thread handles 8 channels of a pixel stream
+// ------------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) k_chan_stats(const bf16* __restrict__ xs, long s_stride, int hi, int lo,
+                                                    const float* __restrict__ xf, long f_stride,
+                                                    double* __restrict__ stats, int P, int C, int chunk) {
+  __shared__ float red[256][17];
+  const int cpt = C / 8;                                      // 16 for C == 128, 8 for C == 64
+  const int rows_per_iter = 256 / cpt;
+  const int cg = threadIdx.x % cpt, pr = threadIdx.x / cpt;
+  const int b = blockIdx.y;
+  const long p0 = (long)blockIdx.x * chunk;
+  long p1 = p0 + chunk;
+  if (p1 > P) p1 = P;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+  for (long p = p0 + pr; p < p1; p += rows_per_iter) {
+    float v[8];
+    const long row = (long)b * P + p;
+    if (SPLIT) {
+      const bf16* q = xs + row * s_stride + cg * 8;
+      load_split8(q + hi, q + lo, v);
+    } else {
+      const float* q = xf + row * f_stride + cg * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(q);
+      const float4 a1 = *reinterpret_cast<const float4*>(q + 4);
+      v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x][i] = s[i]; red[threadIdx.x][8 + i] = ss[i]; }
+  __syncthreads();
+  // thread t < C sums channel t over the pixel-rows of the block
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const int g = c / 8, i = c % 8;
+    double a = 0., q = 0.;
+    for (int r = 0; r < rows_per_iter; ++r) { a += red[r * cpt + g][i]; q += red[r * cpt + g][8 + i]; }
+    atomicAdd(&stats[((long)b * C + c) * 2], a);
+    atomicAdd(&stats[((long)b * C + c) * 2 + 1], q);
+  }
+}
+void launch_chan_stats_s(SView x, double* stats, int B, int P, int C, cudaStream_t st) {
+  const int chunk = 1024;
+  dim3 grid(cdiv(P, chunk), B);
+  k_chan_stats<true><<<grid, 256, 0, st>>>(x.p, x.stride, x.hi, x.lo, nullptr, 0, stats, P, C, chunk);
+}
+void launch_chan_stats_f(const float* x, long stride, double* stats, int B, int P, int C, cudaStream_t st) {
+  const int chunk = 1024;
+  dim3 grid(cdiv(P, chunk), B);
+  k_chan_stats<false><<<grid, 256, 0, st>>>(nullptr, 0, 0, 0, x, stride, stats, P, C, chunk);
+}
+
+}  // namespace dexb

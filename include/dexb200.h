@@ -1,0 +1,108 @@
+/* dexb200 -- C ABI of the B200-native reverse-diffusion path of DEX-TTS / GeDEX-TTS.
+ *
+ * The reference has no FFI: its boundary for this path is the Python call
+ *     model.decoder(z, mask, mu, [ref, ref_lengths, sty, sty_lengths,] n_timesteps=, infer=True, temperature=)
+ * (DEX-TTS/model/diffusion.py:250-259, GeDEX-TTS/model/diffusion.py:220-229).  The drop-in `model` package in
+ * dex-tts_b200/model binds the entry points below through ctypes.
+ *
+ * Conventions: every pointer named *_dev is a CUDA device pointer owned by the caller and only has to stay alive
+ * for the duration of the call; `stream` is a cudaStream_t passed as void*; hot calls never allocate, never
+ * create streams and never synchronise the host.  Return value 0 = success, negative = error
+ * (message from dexb_last_error()).  One handle per (device, model); a handle is not thread-safe, distinct handles are.
+ * sm_100a only: there is no CPU fallback.
+ */
+#ifndef DEXB200_H_
+#define DEXB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dexb_handle dexb_handle;
+
+/* Hyper-parameters of Diffusion / DiffusionDenoiser / DiTMask (DEX-TTS/config/VCTK/base.yaml:56-78). */
+typedef struct dexb_config {
+  int variant;         /* 1 = DEX-TTS (TV/TIV adaptors), 0 = GeDEX-TTS */
+  int dim;             /* decoder.dim (64) */
+  int hidden;          /* dit.hidden_size (256) */
+  int depth;           /* dit.depth (4) */
+  int heads;           /* dit.num_heads (2) */
+  int mlp_hidden;      /* hidden * mlp_ratio (512) */
+  int patch;           /* dit.patch_size (3 | 7) */
+  int stride;          /* dit.stride_size (2 | 4) */
+  int conv_pos;        /* 16 */
+  int conv_pos_groups; /* 8 */
+  int n_feats;         /* 80 */
+  float pe_scale;      /* 1000 */
+  int gemm_engine;     /* 0 = tcgen05 (product), 1 = CUDA-core cross-check engine */
+  int nsplit;          /* 3 = bf16x3 split precision (parity-safe default), 1 = plain bf16 operands */
+} dexb_config;
+
+/* DEX-TTS conditioning that reaches the loop (DEX-TTS/model/diffusion.py:190-196,220-221). */
+typedef struct dexb_cond {
+  const float* sty_dev;          /* (B, 2*dim, Ts) fp32: `sty` of DiffusionDenoiser.forward */
+  const int32_t* sty_len_dev;    /* (B) */
+  const float* ref_skips_dev[6]; /* 6 x (B, 2*dim, Tr) fp32: `ref` skip tensors of the TIV encoder */
+  int Tr;
+} dexb_cond;
+
+const char* dexb_last_error(void);
+int dexb_version(void);
+
+/* replaces: Diffusion.__init__ (DEX-TTS/model/diffusion.py:239-247) */
+int dexb_create(const dexb_config* cfg, dexb_handle** out);
+void dexb_destroy(dexb_handle* h);
+
+/* replaces: load_state_dict for the `decoder.denoise_fn.*` tensors (DEX-TTS/synthesize.py:68-72).
+ * `name` is the reference key relative to `denoise_fn.` (e.g. "downs.0.0.block1.block.0.weight"); the tensor is
+ * copied, so the caller may free it.  Call dexb_finalize_weights once after the last tensor. */
+int dexb_load_weight(dexb_handle* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_finalize_weights(dexb_handle* h, void* stream);
+
+/* Allocate the workspace (owned by the handle; its size is returned in *workspace_bytes), build the TMA descriptors,
+ * the per-step scalar / embedding tables and the launch plan for a (B, T, Ts, n_steps) problem.
+ * `sigmas_host` = the n_steps + 1 noise levels t_0 .. t_N (t_N = 0) of ablation_sampler's 'edm' discretisation
+ * (DEX-TTS/model/edm.py:152,179-180), computed by the caller in fp32 exactly as the reference does.
+ * T must be a multiple of 4 (model.utils.fix_len_compatibility).  Ts is ignored for GeDEX-TTS. */
+int dexb_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* workspace_bytes);
+
+/* replaces: Diffusion.forward(infer=True) after the Gaussian draw -- i.e. ablation_sampler(...)
+ * (DEX-TTS/model/edm.py:104-211) over EDMPrecond (edm.py:88-98) over DiffusionDenoiser.forward
+ * (DEX-TTS/model/diffusion.py:190-236).
+ *   x_inout_dev (B, 80, T): in = z / temperature + mu, out = the generated mel
+ *   mu_dev (B, 80, T), mask_dev (B, T) in {0,1}; cond = NULL for GeDEX-TTS. */
+int dexb_reverse_diffusion(dexb_handle* h, float* x_inout_dev, const float* mu_dev, const float* mask_dev,
+                           const dexb_cond* cond, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies in, runs, copies the mel back, synchronises `stream`. */
+int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float* mu_host, const float* mask_host,
+                                const float* sty_host, const int32_t* sty_len_host, const float* const* ref_skips_host,
+                                int Tr, void* stream);
+
+/* One preconditioned network call D(x; sigma_step) written to out_dev (x untouched) -- unit parity of EDMPrecond. */
+int dexb_denoise_once(dexb_handle* h, const float* x_dev, const float* mu_dev, const float* mask_dev,
+                      const dexb_cond* cond, int step, float* out_dev, void* stream);
+
+/* Unit parity of the implicit-GEMM engine: out[img][h][w][n] = sum_{tap,k} A[img][h+dy][w+dx][k] * Wt[tap][n][k] + bias[n]
+ * with zero padding; input pixel = output pixel * in_stride + (dy, dx), output is ceil(H/in_stride) x ceil(W/in_stride);
+ * engine 0 = tcgen05, 1 = CUDA cores.  All fp32 device buffers.  Allocates scratch and synchronises (test entry). */
+int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, int W, int K, const float* w_dev, int N,
+                   int KH, int KW, int offH, int offW, int in_stride, const float* bias_dev, float* out_dev, void* stream);
+
+/* replaces: TacotronSTFT.mel_spectrogram (DEX-TTS/audio/stft.py:159-178) for 22.05 kHz / n_fft 1024 / hop 256 / 80 mels.
+ * wav_dev (B, S) in [-1, 1]; mel_dev (B, 80, 1 + S/256) log-mel; mel_basis_dev (80, 513), window_dev (1024). */
+int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft,
+                  int hop, int n_mels, float* mel_dev, void* stream);
+
+/* Number of kernels (graph nodes) launched by the last dexb_reverse_diffusion on this handle (bench.py's gpu_launches). */
+long dexb_last_launch_count(const dexb_handle* h);
+/* Number of GEMMs per step that the tcgen05 engine could not take (shape ineligible) and ran on CUDA cores instead. */
+int dexb_simt_fallbacks(const dexb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEXB200_H_ */
