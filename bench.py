@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the reverse-diffusion hot path (BASELINE.json metric: mel-frames/sec through 50-step reverse diffusion).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C1|C3|C4|C5]
+
+A bench "step" is ONE complete reverse diffusion (all sampler steps) of one batch of synthetic utterances.
+Default workload = BASELINE.json configs[1] ("C2"): DEX-TTS, batch 8 per GPU, 50 sampler steps, 80x512 mel, style
+length 259, synthetic inputs and seeded random ("live") weights of the reference architecture.
+  value : mel-frames/s with inputs resident in HBM (CUDA events around K trajectories, max over ranks)
+  e2e   : the same metric through the host-buffer entry point (pinned host inputs -> device -> mel back on the host)
+  roofline     : the dominant kernel class (tcgen05 implicit-GEMM), timed live with CUDA events around its launches
+  cpu_baseline : the CPU oracle (port of the reference path, oracle/dex_oracle.py) timed on this box's host cores on a
+                 bounded sample (a few sampler steps of the same batch), extrapolated to the full step count
+`--impl reference` times that CPU path as the main line (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "dex-tts_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+from dexb200.manifest import DecoderCfg  # noqa: E402
+from dexb200.synth import synth_decoder_weights, synth_inputs  # noqa: E402
+
+WORKLOADS = {
+    # name: (variant, B per GPU, T, Ts, sampler steps)
+    "C1": ("gedex", 1, 200, 0, 10),
+    "C2": ("dex", 8, 512, 259, 50),
+    "C3": ("dex", 32, 512, 259, 100),
+    "C4": ("gedex", 32, 512, 0, 50),
+    "C5": ("dex", 8, 2000, 259, 50),
+}
+METRIC = "mel-frames/sec through 50-step reverse diffusion"
+
+
+def algorithmic_flops(variant, T, Ts):
+    """SURVEY.md 8(d) closed form (2*MAC) of one denoiser call for one utterance."""
+    import dex_oracle as O
+    return O.flops_per_sample_step(O.make_cfg(variant), T, Ts)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_run(variant, B, T, Ts, n_steps, sample_steps, repeats):
+    """Time the CPU oracle on `sample_steps` sampler steps of the workload's batch; returns (sec per sampler step, cores)."""
+    import dex_oracle as O
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    cfg = DecoderCfg.make(variant)
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=1234)
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]) if variant == "dex" else None
+    ocfg = O.make_cfg(variant)
+    ts = O.sigma_schedule(n_steps)
+    x = (inp["z"] / 1.5 + inp["mu"]) * ts[0]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            xx = x
+            for i in range(sample_steps):
+                den = O.edm_precond(w, ocfg, xx, ts[i], inp["mask"], inp["mu"], cond=cond)
+                xx = xx + (ts[i + 1] - ts[i]) * ((1 / ts[i]) * xx - 1 / ts[i] * den)
+            dt = (time.perf_counter() - t0) / sample_steps
+            best = dt if best is None else min(best, dt)
+    return best, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dexb200")
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print the per-launch breakdown of one network call to stderr")
+    ap.add_argument("--gemm-engine", type=int, default=0)
+    ap.add_argument("--nsplit", type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    variant, B, T, Ts, n_steps = WORKLOADS[args.workload]
+    wl = f"{args.workload}: {'DEX-TTS' if variant == 'dex' else 'GeDEX-TTS'} B={B}/GPU T={T} (80x{T} mel) Ts={Ts} {n_steps} sampler steps"
+    config = {"workload": wl, "batch_per_gpu": B, "mel_frames": T, "sampler_steps": n_steps, "style_len": Ts,
+              "parallelism": f"dp{world}", "l2": "per-step working set (hundreds of MB of activations) exceeds the 126 MB L2",
+              "weights": "seeded random init of the reference architecture, zero-initialised tensors re-drawn (live)"}
+
+    # -------------------------------------------------------------------------------- reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K = max(1, args.steps)
+        times = []
+        for i in range(args.warmup + K):
+            dt, cores = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
+            if i >= args.warmup:
+                times.append(dt)
+            if sum(times) * args.cpu_sample_steps > 120:        # keep the whole arm within a few minutes
+                break
+        sec_step = sum(times) / len(times)
+        sec_traj = sec_step * n_steps
+        val = B * T / sec_traj
+        sample = (f"{args.cpu_sample_steps} of {n_steps} sampler steps of the full batch (B={B}, T={T}) per bench step, "
+                  f"extrapolated x{n_steps}/{args.cpu_sample_steps}; torch CPU fp32, {cores} threads")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": len(times),
+                "warmup": args.warmup, "ms_per_step": sec_traj * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # -------------------------------------------------------------------------------- CUDA arm
+    from dexb200.engine import ReverseDiffusion
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = DecoderCfg.make(variant)
+    eng = ReverseDiffusion(cfg, gemm_engine=args.gemm_engine, nsplit=args.nsplit)
+    eng.load_state_dict(synth_decoder_weights(cfg, seed=100, live=True))
+    inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=1234 + rank)
+    x0 = inp["z"] / 1.5 + inp["mu"]
+    cond_h = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]) if variant == "dex" else None
+    dev = lambda t: t.cuda(non_blocking=True)
+    cond_d = dict(sty=dev(cond_h["sty"]), sty_lengths=dev(cond_h["sty_lengths"]), ref_skips=[dev(r) for r in cond_h["ref_skips"]]) \
+        if cond_h else None
+    x0_d, mask_d, mu_d = dev(x0), dev(inp["mask"]), dev(inp["mu"])
+    gathered = torch.empty(world * B, 80, T, device="cuda") if world > 1 else None
+
+    def one_pass():
+        y = eng.sample(x0_d, mask_d, mu_d, n_steps, cond=cond_d)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)        # the path's only collective: finished mels
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        y = one_pass()
+    barrier()
+    assert torch.isfinite(y).all(), "non-finite mel"
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per = ms / args.steps
+    value = world * B * T / (ms_per * 1e-3)
+    launches = eng.launches * args.steps
+
+    # ---- e2e: host buffers in, host mel out, through the host entry point (pinned memory)
+    pin = lambda t: t.contiguous().pin_memory()
+    x0_p, mask_p, mu_p = pin(x0), pin(inp["mask"]), pin(inp["mu"])
+    cond_p = dict(sty=pin(cond_h["sty"]), sty_lengths=cond_h["sty_lengths"].to(torch.int32), ref_skips=[pin(r) for r in cond_h["ref_skips"]]) \
+        if cond_h else None
+    h2d = sum(t.numel() * 4 for t in (x0_p, mask_p, mu_p))
+    if cond_p:
+        h2d += cond_p["sty"].numel() * 4 + B * 4 + sum(r.numel() * 4 for r in cond_p["ref_skips"])
+    d2h = x0_p.numel() * 4
+    eng.sample_host(x0_p, mask_p, mu_p, n_steps, cond=cond_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.sample_host(x0_p, mask_p, mu_p, n_steps, cond=cond_p)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * B * T / e2e_s
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- dominant kernel class, timed live: CUDA events around every launch of un-graphed network calls
+    pk = peaks()
+    roof = None
+    if rank == 0:
+        agg = {}
+        reps = 3
+        for r in range(reps):
+            for tag, ms_k, gf in eng.profile_step(step=n_steps // 2):
+                a = agg.setdefault(tag, [0, 0.0, 0.0])
+                a[0] += 1; a[1] += ms_k; a[2] += gf
+        tot = sum(a[1] for a in agg.values())
+        gem = [(t, a) for t, a in agg.items() if t.startswith("gemm:")]
+        g_ms, g_gf, g_n = sum(a[1] for _, a in gem), sum(a[2] for _, a in gem), sum(a[0] for _, a in gem)
+        if args.profile:
+            for t, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                print(f"  {t:46s} n={a[0] // reps:3d} {a[1] / reps:8.3f} ms/call-of-net {a[2] / reps:9.2f} GFLOP "
+                      f"{(a[2] / a[1]) if a[1] > 0 else 0:8.1f} TFLOP/s {100 * a[1] / tot:5.1f}%", file=sys.stderr)
+        ach = g_gf / g_ms if g_ms > 0 else 0.0                 # GFLOP / ms = TFLOP/s
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BLOCK_N> (tcgen05 implicit GEMM, all conv/linear/attention contractions)",
+                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+                "launches_per_net_call": g_n // reps, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / tot if tot else None,
+                "peak_source": f"{pk['src']} sustained dense bf16 (MEASURED_PEAKS.json)",
+                "note": f"algorithmic fp32 FLOPs; the kernel issues {args.nsplit} bf16 MMAs per product (split-bf16 for the 1e-3 parity "
+                        f"bound), so the attainable fraction is <= 1/{args.nsplit}"}
+    flops_traj = algorithmic_flops(variant, T, Ts) * B * n_steps
+    whole = {"algorithmic_tflop_per_step": flops_traj * 1e-12, "achieved_tflops": flops_traj * 1e-12 / (ms_per * 1e-3),
+             "frac_of_sustained_bf16_peak": flops_traj * 1e-12 / (ms_per * 1e-3) / pk["tf_sust"]}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        sec_step, cores = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
+        cpu = {"value": B * T / (sec_step * n_steps), "unit": "mel-frames/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_sample_steps} of {n_steps} sampler steps of one batch (B={B}, T={T}) on the host cores, extrapolated "
+                         f"x{n_steps}/{args.cpu_sample_steps}; oracle/dex_oracle.py (torch CPU fp32, {cores} threads)"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 x3 MMA)",
+                "data": "synthetic", "config": config, "rtf": (ms_per * 1e-3) / (world * B * T * 256 / 22050.0),
+                "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": launches, "simt_fallback_gemms_per_net_call": eng.simt_fallbacks, "clocks": clk, "roofline": roof,
+                "whole_step": whole, "cpu_baseline": cpu, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

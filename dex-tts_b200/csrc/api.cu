@@ -117,6 +117,11 @@ int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float
   return 0;
 }
 
+int dexb_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, void* stream) {
+  DEXB_CHECK(h != nullptr, "null handle");
+  return engine_profile_step(h, step, buf, buflen, (cudaStream_t)stream);
+}
+
 long dexb_last_launch_count(const dexb_handle* h) { return h != nullptr ? h->launches : 0; }
 
 int dexb_simt_fallbacks(const dexb_handle* h) {

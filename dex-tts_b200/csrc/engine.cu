@@ -3,20 +3,37 @@
 #include "engine.cuh"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 namespace dexb {
 
-#define LAUNCH(expr)      \
-  do {                    \
-    expr;                 \
-    ++h->launches;        \
+static void prof_begin(dexb_handle* h, const char* tag, double flop, cudaStream_t st) {
+  dexb_handle::ProfRec r;
+  r.tag = tag; r.flop = flop;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  h->prof_recs.push_back(r);
+}
+static void prof_end(dexb_handle* h, cudaStream_t st) { cudaEventRecord(h->prof_recs.back().b, st); }
+static double gemm_flop(const GemmParams& p) {
+  return 2.0 * p.nz * p.CH * p.CW * (double)p.N * p.K * p.KH * p.KW;
+}
+
+#define LAUNCH(expr)                              \
+  do {                                            \
+    if (h->prof) prof_begin(h, #expr, 0.0, st);   \
+    expr;                                         \
+    if (h->prof) prof_end(h, st);                 \
+    ++h->launches;                                \
   } while (0)
-#define GEMM(plan, params)                                          \
-  do {                                                              \
-    DEXB_TRY(gemm_launch((plan), (params), h->cfg.gemm_engine, st)); \
-    ++h->launches;                                                  \
+#define GEMM(plan, params)                                            \
+  do {                                                                \
+    if (h->prof) prof_begin(h, "gemm:" #plan, gemm_flop(params), st); \
+    DEXB_TRY(gemm_launch((plan), (params), h->cfg.gemm_engine, st));  \
+    if (h->prof) prof_end(h, st);                                     \
+    ++h->launches;                                                    \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
@@ -247,6 +264,7 @@ void engine_release_weights(dexb_handle* h) {
 void engine_release_plan(dexb_handle* h) {
   if (h->graph_exec != nullptr) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
   if (h->graph != nullptr) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  if (h->cap_stream != nullptr) { cudaStreamDestroy(h->cap_stream); h->cap_stream = nullptr; }
   if (h->ws_base != nullptr) { cudaFree(h->ws_base); h->ws_base = nullptr; }
   h->planned = false;
 }
@@ -908,24 +926,56 @@ int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mas
   h->launches = 0;
   if (only_step < 0 && h->use_graph) {
     if (h->graph_exec == nullptr) {
-      DEXB_CUDA_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int r = enqueue_all(h, -1, nullptr, st);
+      // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured);
+      // the instantiated graph is then launched into the caller's stream.
+      if (h->cap_stream == nullptr) DEXB_CUDA_OK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+      DEXB_CUDA_OK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int r = enqueue_all(h, -1, nullptr, h->cap_stream);
       cudaGraph_t g = nullptr;
-      const cudaError_t e = cudaStreamEndCapture(st, &g);
+      const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
       if (r != 0) { if (g != nullptr) cudaGraphDestroy(g); return r; }
       DEXB_CHECK(e == cudaSuccess && g != nullptr, "graph capture failed: %s", cudaGetErrorString(e));
       h->graph = g;
       DEXB_CUDA_OK(cudaGraphInstantiate(&h->graph_exec, g, 0));
-    } else {
-      size_t nn = 0;
-      cudaGraphGetNodes(h->graph, nullptr, &nn);
-      h->launches = (long)nn;
+      h->graph_launches = h->launches;
     }
+    h->launches = h->graph_launches;
     DEXB_CUDA_OK(cudaGraphLaunch(h->graph_exec, st));
   } else {
     DEXB_TRY(enqueue_all(h, only_step, den_out, st));
   }
   if (only_step < 0 && x_inout != h->x) DEXB_CUDA_OK(cudaMemcpyAsync(x_inout, h->x, n0 * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// One un-graphed network call with CUDA events around every launch; writes "tag\tms\tgflop" lines into buf.
+int engine_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, cudaStream_t st) {
+  DEXB_CHECK(h->planned, "dexb_profile_step: call dexb_plan (and one dexb_reverse_diffusion) first");
+  DEXB_CHECK(step >= 0 && step < h->steps && buf != nullptr && buflen > 0, "dexb_profile_step: bad argument");
+  h->prof = true;
+  h->prof_recs.clear();
+  const long saved = h->launches;
+  // den_out = a scratch buffer, so the sampler state x is left untouched (raw0 is dead after gn_final has read it)
+  const int r = run_step(h, step, reinterpret_cast<float*>(h->kv), st);
+  h->prof = false;
+  h->launches = saved;
+  cudaError_t e = cudaStreamSynchronize(st);
+  size_t off = 0;
+  buf[0] = 0;
+  for (auto& rec : h->prof_recs) {
+    float ms = 0.f;
+    if (r == 0 && e == cudaSuccess) cudaEventElapsedTime(&ms, rec.a, rec.b);
+    std::string tag = rec.tag;
+    const size_t par = tag.find('(');
+    if (par != std::string::npos) tag = tag.substr(0, par);
+    if (off + tag.size() + 64 < buflen)
+      off += snprintf(buf + off, buflen - off, "%s\t%.6f\t%.6f\n", tag.c_str(), ms, rec.flop * 1e-9);
+    cudaEventDestroy(rec.a);
+    cudaEventDestroy(rec.b);
+  }
+  h->prof_recs.clear();
+  if (r != 0) return r;
+  DEXB_CHECK(e == cudaSuccess, "dexb_profile_step: %s", cudaGetErrorString(e));
   return 0;
 }
 

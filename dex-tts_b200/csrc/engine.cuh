@@ -131,6 +131,12 @@ struct dexb_handle {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;
+  // per-launch profiling (dexb_profile_step): events around every launch of one un-graphed step
+  struct ProfRec { std::string tag; cudaEvent_t a, b; double flop; };
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+  long graph_launches = 0;
 };
 
 namespace dexb {
@@ -139,5 +145,6 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* 
 int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mask, const dexb_cond* cond,
                int only_step, float* den_out, cudaStream_t st);
 void engine_release_plan(dexb_handle* h);
+int engine_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, cudaStream_t st);
 void engine_release_weights(dexb_handle* h);
 }  // namespace dexb

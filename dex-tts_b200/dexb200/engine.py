@@ -165,6 +165,16 @@ class ReverseDiffusion:
         del keep
         return out
 
+    def profile_step(self, step=0):
+        """[(tag, ms, gflop)] for every launch of one network call (un-graphed, events around each launch)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(self.L.dexb_profile_step(self.h, int(step), buf, len(buf), _stream()), "dexb_profile_step")
+        out = []
+        for line in buf.value.decode().splitlines():
+            tag, ms, gf = line.split("\t")
+            out.append((tag, float(ms), float(gf)))
+        return out
+
     @property
     def launches(self):
         return int(self.L.dexb_last_launch_count(self.h))

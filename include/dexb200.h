@@ -97,6 +97,10 @@ int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, 
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft,
                   int hop, int n_mels, float* mel_dev, void* stream);
 
+/* Profiling aid: runs network call `step` once, un-graphed, with CUDA events around every launch, on the inputs staged
+ * by the last dexb_reverse_diffusion; writes one "tag<TAB>ms<TAB>gflop" line per launch into buf.  Synchronises. */
+int dexb_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, void* stream);
+
 /* Number of kernels (graph nodes) launched by the last dexb_reverse_diffusion on this handle (bench.py's gpu_launches). */
 long dexb_last_launch_count(const dexb_handle* h);
 /* Number of GEMMs per step that the tcgen05 engine could not take (shape ineligible) and ran on CUDA cores instead. */

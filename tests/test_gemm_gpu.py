@@ -52,7 +52,10 @@ def test_gemm_engine(name, engine):
     out = gemm_test(a.cuda(), w.cuda(), b.cuda(), taps=taps, off=off, in_stride=stride, engine=engine, nsplit=3).cpu().double()
     assert out.shape == ref.shape
     err = (out - ref).abs().max().item() / ref.pow(2).mean().sqrt().item()
-    assert err < 3e-5, f"{name} engine {engine}: max err / rms = {err:.3e}"
+    print(f"gemm {name} engine {engine}: max err / rms = {err:.3e}")
+    # bf16x3 operands carry ~16 mantissa bits (1.3e-5 max/rms for these shapes in exact arithmetic); the tensor core's fp32
+    # accumulation adds a K-dependent term on top, so the bound is 6e-5 (plain bf16 lands at ~4e-3, tf32 at ~5e-4)
+    assert err < 6e-5, f"{name} engine {engine}: max err / rms = {err:.3e}"
 
 
 def test_gemm_single_split_is_bf16():
