@@ -383,6 +383,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   for (LinAttW* la : las) {
     la->weff = ar.get<bf16>((long)B * la->C * 2 * la->C);
     la->beff = ar.get<float>((long)B * la->C);
+    la->m1 = ar.get<float>((long)B * 128 * la->C);
   }
   // tables
   h->t_init = ar.get<float>((long)steps * d); h->t_hid = ar.get<float>((long)steps * 4 * d);
@@ -421,7 +422,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
   h->xtok = ar.get<float>(M * hid);
   h->hS = ar.get<bf16>(M * 2 * hid);
-  h->qk = ar.get<bf16>(M * 4 * hid);
+  h->qk = ar.get<bf16>(M * 6 * hid);
   h->vT = ar.get<bf16>((long)B * hid * 2 * h->NP);
   h->scores = ar.get<float>((long)B * c.heads * h->Ntok * h->NP);
   h->P = ar.get<bf16>((long)B * c.heads * h->Ntok * 2 * h->NP);
@@ -528,25 +529,22 @@ static int build_plans(dexb_handle* h) {
   for (int i = 0; i < c.depth; ++i) {
     DitBlockW& k = h->blocks[i];
     {
-      GemmParams p = gp_base(c);                      // qkv: q,k -> split rows, v -> transposed split
-      gp_geom(p, B, 1, N);
+      GemmParams p = gp_base(c);                      // qkv -> split rows [hi(3*hid) | lo(3*hid)]
+      gp_geom(p, 1, 1, (int)M);
       gp_a(p, h->hS, 2 * hid, 0, hid, hid);
       gp_b(p, k.qkv_w, hid, 3 * hid);
       p.epi.bias = k.qkv_b;
-      gp_out_s(p, h->qk, 4 * hid, 0, 2 * hid);
-      p.epi.out_s_ncols = 2 * hid;
-      p.epi.out_vt = h->vT; p.epi.out_vt_zstride = (long)hd * 2 * NP; p.epi.out_vt_rstride = 2L * NP;
-      p.epi.out_vt_lo = NP; p.epi.out_vt_hd = hd; p.epi.out_vt_heads = c.heads;
+      gp_out_s(p, h->qk, 6 * hid, 0, 3 * hid);
       DEXB_TRY(plan_shared(&k.qkv, p));
     }
     {
       GemmParams p = gp_base(c);                      // scores[z] = (q k^T) * hd^-0.5
       gp_geom(p, B * c.heads, 1, N);
       p.nheads = c.heads;
-      gp_a(p, h->qk, 4 * hid, 0, 2 * hid, hd);
+      gp_a(p, h->qk, 6 * hid, 0, 3 * hid, hd);
       p.a_head_stride = hd;
-      p.Bw = h->qk; p.b_row_stride = 4 * hid; p.b_hi = hid; p.b_lo = 3 * hid; p.b_head_stride = hd;
-      p.b_rows_per_tap = N; p.N = N; p.b_mode = 1; p.b_mat_stride = (long)N * 4 * hid;
+      p.Bw = h->qk; p.b_row_stride = 6 * hid; p.b_hi = hid; p.b_lo = 4 * hid; p.b_head_stride = hd;
+      p.b_rows_per_tap = N; p.N = N; p.b_mode = 1; p.b_mat_stride = (long)N * 6 * hid;
       p.epi.alpha = 1.f / sqrtf((float)hd);
       gp_out_f(p, h->scores, NP);
       p.epi.o_by_z = 1;
@@ -750,7 +748,7 @@ static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
   GEMM(la.kv, la.kv.p);
   LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
   LAUNCH(launch_la_ctx(h->kv, la.kmax, la.ctx, la.ssum, h->B, P, st));
-  LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.weff, la.beff, h->B, la.C, st));
+  LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.m1, la.weff, la.beff, h->B, la.C, st));
   GEMM(la.apply, la.apply.p);
   return 0;
 }
@@ -834,6 +832,7 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     DitBlockW& k = h->blocks[i];
     const float* m = mod + (long)i * 6 * hid;
     GEMM(k.qkv, k.qkv.p);
+    LAUNCH(launch_transpose_v(h->qk, 6L * hid, 2 * hid, 5 * hid, h->vT, B, N, h->NP, hid, hid / c.heads, st));
     GEMM(k.scores, k.scores.p);
     LAUNCH(launch_attn_softmax(h->scores, h->NP, h->P, h->NP, (long)B * c.heads * N, N, st));
     GEMM(k.pv, k.pv.p);

@@ -60,7 +60,8 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx /*[B][4
                    int B, int P, cudaStream_t st);
 // W_eff[b] = I + g * W_out * ctxn^T * W_q  -> packed split weights [B][C][hi(C)|lo(C)], beff[b] = g * b_out
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq /*[128][C]*/, const float* wout /*[C][128]*/,
-                    const float* bout, const float* g, bf16* weff, float* beff, int B, int C, cudaStream_t st);
+                    const float* bout, const float* g, float* m1 /*[B][128][C] scratch*/, bf16* weff, float* beff, int B,
+                    int C, cudaStream_t st);
 
 // per-(image, channel) sum / sumsq over all pixels of an S tensor (InstanceNorm2D statistics)
 void launch_chan_stats_s(SView x, double* stats /*[B][C][2]*/, int B, int P, int C, cudaStream_t st);
@@ -89,6 +90,9 @@ void launch_tok_assemble(const float* xe, const float* pe, const float* fpos /*[
 void launch_ln_mod(const float* x, const float* shift, const float* scale, SView out, long M, int D, cudaStream_t st);
 // attention row softmax: scores F[z][N][NS] -> P S[z][N][hi(NP)|lo(NP)] (zero padded)
 void launch_attn_softmax(const float* scores, long NS, bf16* P_, long NP, long rows, int N, cudaStream_t st);
+// v columns of the qkv rows -> transposed split operand vT[b][D][hi(NP)|lo(NP)] (D = heads*hd, head-major)
+void launch_transpose_v(const bf16* qkv, long row_stride, int v_hi, int v_lo, bf16* vT, int B, int N, long NP, int D, int hd,
+                        cudaStream_t st);
 // unpatchify + crop + mask: y F[B][Fq*Wq][s*s*C] -> S[B][H][W][...]
 void launch_unpatchify(const float* y, SView out, const float* mask1, int B, int Fq, int Wq, int s, int C, int H,
                        int W, cudaStream_t st);

@@ -293,6 +293,34 @@ void launch_attn_softmax(const float* scores, long NS, bf16* P_, long NP, long r
 }
 
 // ------------------------------------------------------------------------------------------------
+// V of the attention: qkv rows hold v token-major; the P.V GEMM wants it as a K-major B operand, i.e. transposed
+// vT[b][head][d][hi(NP)|lo(NP)].  32x32 bf16 tiles through shared memory, coalesced on both sides.
+// grid = (ceil(N/32), D/32, B*2 [hi|lo]), block = (32, 8).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_transpose_v(const bf16* __restrict__ qkv, long row_stride, int v_hi, int v_lo,
+                                                     bf16* __restrict__ vT, int N, long NP, int D, int hd) {
+  __shared__ bf16 tile[32][34];
+  const int b = blockIdx.z >> 1, part = blockIdx.z & 1;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int src_col = (part ? v_lo : v_hi) + c0;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int t = t0 + r;
+    tile[r][threadIdx.x] = (t < N) ? qkv[((long)b * N + t) * row_stride + src_col + threadIdx.x] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c = c0 + r;                                   // channel = head * hd + d
+    const int t = t0 + threadIdx.x;
+    if (t < N) vT[((long)b * D + c) * (2 * NP) + (part ? NP : 0) + t] = tile[threadIdx.x][r];
+  }
+}
+void launch_transpose_v(const bf16* qkv, long row_stride, int v_hi, int v_lo, bf16* vT, int B, int N, long NP, int D, int hd,
+                        cudaStream_t st) {
+  dim3 grid(cdiv(N, 32), D / 32, B * 2), block(32, 8);
+  k_transpose_v<<<grid, block, 0, st>>>(qkv, row_stride, v_hi, v_lo, vT, N, NP, D, hd);
+}
+
+// ------------------------------------------------------------------------------------------------
 // unpatchify 'B (h w) (p1 p2 C) -> B C (h p1) (w p2)', crop to W, mask (dit.py:452-457,516-517) -> S (NHWC)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_unpatchify(const float* __restrict__ y, SView out,

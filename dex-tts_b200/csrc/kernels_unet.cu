@@ -319,42 +319,47 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx, float*
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
 // (q is linear in x, so  x + g*to_out(ctx^T q) == W_eff x + g*b_out : the whole attention read-out is one
-//  per-sample CxC matrix.)   grid = B, block = 256, dynamic smem = 128*C floats.
-__global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, const float* __restrict__ ssum,
-                                                 const float* __restrict__ wq, const float* __restrict__ wout,
+//  per-sample CxC matrix.)   Two small fully parallel kernels: m1 = ctxn^T Wq, then W_eff = I + g Wout m1.
+__global__ void __launch_bounds__(256) k_la_m1(const float* __restrict__ ctx, const float* __restrict__ ssum,
+                                               const float* __restrict__ wq, float* __restrict__ m1, int B, int C) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= (long)B * 128 * C) return;
+  const int ci = (int)(idx % C);
+  const int he = (int)((idx / C) % 128);
+  const int b = (int)(idx / ((long)C * 128));
+  const int h = he >> 5, e = he & 31;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int d = 0; d < 32; ++d) {
+    const float cn = ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] / ssum[b * 128 + h * 32 + d];
+    acc = fmaf(cn, wq[(h * 32 + d) * C + ci], acc);
+  }
+  m1[idx] = acc;
+}
+__global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ m1, const float* __restrict__ wout,
                                                  const float* __restrict__ bout, const float* __restrict__ g,
-                                                 bf16* __restrict__ weff, float* __restrict__ beff, int C) {
-  extern __shared__ float m1[];                               // [128 (h*32+e)][C]
-  const int b = blockIdx.x;
+                                                 bf16* __restrict__ weff, float* __restrict__ beff, int B, int C) {
+  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (idx >= (long)B * C * C) return;
+  const int ci = (int)(idx % C);
+  const int co = (int)((idx / C) % C);
+  const int b = (int)(idx / ((long)C * C));
   const float gg = g[0];
-  for (int idx = threadIdx.x; idx < 128 * C; idx += blockDim.x) {
-    const int he = idx / C, ci = idx % C;
-    const int h = he >> 5, e = he & 31;
-    float acc = 0.f;
-    for (int d = 0; d < 32; ++d) {
-      const float cn = ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] / ssum[b * 128 + h * 32 + d];
-      acc = fmaf(cn, wq[(h * 32 + d) * C + ci], acc);
-    }
-    m1[idx] = acc;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
-    const int co = idx / C, ci = idx % C;
-    float acc = 0.f;
-    for (int he = 0; he < 128; ++he) acc = fmaf(wout[co * 128 + he], m1[he * C + ci], acc);
-    const float v = gg * acc + (co == ci ? 1.f : 0.f);
-    bf16* row = weff + ((long)b * C + co) * (2 * C);
-    split2(v, row[ci], row[C + ci]);
-  }
-  for (int co = threadIdx.x; co < C; co += blockDim.x) beff[b * C + co] = gg * bout[co];
+  const float* mp = m1 + (long)b * 128 * C + ci;
+  const float* wp = wout + (long)co * 128;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int he = 0; he < 128; ++he) acc = fmaf(wp[he], mp[(long)he * C], acc);
+  const float v = gg * acc + (co == ci ? 1.f : 0.f);
+  bf16* row = weff + ((long)b * C + co) * (2 * C);
+  split2(v, row[ci], row[C + ci]);
+  if (ci == 0) beff[b * C + co] = gg * bout[co];
 }
-int kernels_global_init() {
-  DEXB_CUDA_OK(cudaFuncSetAttribute(k_la_weff, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * (int)sizeof(float)));
-  return 0;
-}
+int kernels_global_init() { return 0; }
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq, const float* wout, const float* bout,
-                    const float* g, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
-  k_la_weff<<<B, 256, 128 * C * sizeof(float), st>>>(ctx, ssum, wq, wout, bout, g, weff, beff, C);
+                    const float* g, float* m1, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
+  k_la_m1<<<cdiv((long)B * 128 * C, 256), 256, 0, st>>>(ctx, ssum, wq, m1, B, C);
+  k_la_weff<<<cdiv((long)B * C * C, 256), 256, 0, st>>>(m1, wout, bout, g, weff, beff, B, C);
 }
 
 // ------------------------------------------------------------------------------------------------
