@@ -185,6 +185,31 @@ int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, 
   return 0;
 }
 
+int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float* out_dev, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_CHECK(qkv_dev != nullptr && out_dev != nullptr && B >= 1 && N >= 1, "attn_test: bad argument");
+  DEXB_CHECK(attn_supported(hid / heads), "attn_test: head dim %d not supported", hid / heads);
+  DEXB_TRY(attn_global_init());
+  const long M = (long)B * N;
+  const int NP = (N + 63) / 64 * 64;
+  bf16 *qs = nullptr, *vT = nullptr, *os = nullptr;
+  DEXB_CUDA_OK(cudaMalloc(&qs, M * 6 * hid * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&vT, (long)B * hid * 2 * NP * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&os, M * 2 * hid * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMemsetAsync(vT, 0, (long)B * hid * 2 * NP * sizeof(bf16), st));
+  launch_pack_rows(qkv_dev, qs, M, 3 * hid, st);
+  launch_transpose_v(qs, 6L * hid, 2 * hid, 5 * hid, vT, B, N, NP, hid, hid / heads, st);
+  AttnPlan ap;
+  int r = attn_plan_init(&ap, qs, vT, os, B, N, NP, heads, hid);
+  if (r == 0) r = attn_launch(ap, st);
+  if (r == 0) launch_unpack_rows(os, out_dev, M, hid, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(qs); cudaFree(vT); cudaFree(os);
+  if (r != 0) return r;
+  DEXB_CHECK(e == cudaSuccess, "attn_test: kernel failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft, int hop,
                   int n_mels, float* mel_dev, void* stream) {
   DEXB_CHECK(wav_dev != nullptr && window_dev != nullptr && mel_basis_dev != nullptr && mel_dev != nullptr, "null argument");

@@ -1,0 +1,292 @@
+// Fused DiT self-attention (timm Attention inside DiTBlock, DEX-TTS/model/dit.py:270,282): softmax(q k^T / sqrt(hd)) v
+// for one (sample, head) and 128 queries per CTA, no key mask (the reference has none), split-bf16 x3 precision.
+//
+// Exact two-pass softmax without accumulator rescaling:
+//   pass 1: S = Qhi Khi^T (bf16 only -- the row maximum only has to be approximately right) -> running row max m
+//   pass 2: S = Q K^T (3 MMAs per product) -> P = exp2((S - m) * scale * log2e) -> split P to shared memory
+//           -> O += P V (3 MMAs per product), row sums l in registers;  out = O / l.
+// S (2 x 64 columns) and O (128 columns) live in TMEM; K / V^T tiles of 64 keys stream through a 2-stage TMA ring;
+// warp 0 = TMA, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax (one query row per thread) + epilogue.
+// S(j+1) is issued before P(j) V(j) so the tensor pipe works while the softmax warps exponentiate.
+#include "attn.cuh"
+
+#include <cudaTypedefs.h>
+
+#include "ptx.cuh"
+
+namespace dexb {
+
+constexpr int kAtBM = 128;          // queries per CTA
+constexpr int kAtBN = 64;           // keys per iteration
+constexpr int kAtHD = 128;          // head dim
+constexpr int kAtThreads = 192;
+constexpr int kQBytes = 4 * 16384;                        // [hi kc0][hi kc1][lo kc0][lo kc1], 128 rows x 128 B each
+constexpr int kKBytes = 4 * 8192;                         // same order, 64 rows x 128 B each
+constexpr int kVBytes = 2 * 16384;                        // [hi][lo], 128 d-rows x 128 B (64 keys) each
+constexpr int kStage = kKBytes + kVBytes;                 // 64 KiB
+constexpr int kPOff = kQBytes + 2 * kStage;               // 192 KiB
+constexpr int kPBytes = 2 * 16384;                        // [hi][lo], 128 rows x 128 B (64 keys)
+constexpr int kBarOff = kPOff + kPBytes;                  // 224 KiB
+constexpr int kAtSmem = kBarOff + 256 + 1024;
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* s_empty = bars + 7;       // 2
+  uint64_t* p_full = bars + 9;        // 1
+  uint64_t* p_empty = bars + 10;      // 1
+  uint64_t* o_full = bars + 11;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kAtBM;
+  const int z = blockIdx.y;
+  const int b = z / p.nheads, head = z % p.nheads;
+  const int nt = p.nt;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 128);
+    }
+    ptx::mbar_init(p_full, 128); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tm_o = tmem + 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      const int qcol = head * kAtHD, kcol = p.hid + head * kAtHD, lo = 3 * p.hid;
+      ptx::mbar_expect_tx(q_full, kQBytes);
+      for (int part = 0; part < 2; ++part)
+        for (int kc = 0; kc < 2; ++kc)
+          ptx::tma_load_3d(smem + (part * 2 + kc) * 16384, &tmQ, q_full, part * lo + qcol + kc * 64, m0, b);
+      for (int it = 0; it < 2 * nt; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        uint8_t* st = smem + kQBytes + s * kStage;
+        if (it < nt) {
+          ptx::mbar_expect_tx(&k_full[s], 2 * 8192);
+          for (int kc = 0; kc < 2; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, it * kAtBN, b);
+        } else {
+          const int j = it - nt;
+          ptx::mbar_expect_tx(&k_full[s], kStage);
+          for (int part = 0; part < 2; ++part)
+            for (int kc = 0; kc < 2; ++kc)
+              ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
+          for (int part = 0; part < 2; ++part)
+            ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.NP + j * kAtBN, head * kAtHD, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kAtBN);
+    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kAtHD);
+    const uint32_t q_base = ptx::smem_u32(smem);
+    const uint32_t p_base = ptx::smem_u32(smem + kPOff);
+    ptx::mbar_wait(q_full, 0);
+    // S[it & 1] = Q K^T for iteration `it` (nsplit terms); frees the stage itself only in pass 1
+    auto issue_s = [&](int it, bool full) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      ptx::mbar_wait(&k_full[s], ph);
+      ptx::mbar_wait(&s_empty[s], ph ^ 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t k_base = ptx::smem_u32(smem + kQBytes + s * kStage);
+        const uint32_t d = tmem + (uint32_t)(s * kAtBN);
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t qh = ptx::make_desc_k128(q_base + kc * 16384 + kk * 32);
+            const uint64_t kh = ptx::make_desc_k128(k_base + kc * 8192 + kk * 32);
+            ptx::mma_bf16_ss(d, qh, kh, idesc_s, (kc | kk) ? 1u : 0u);
+            if (full) {
+              const uint64_t ql = ptx::make_desc_k128(q_base + (2 + kc) * 16384 + kk * 32);
+              const uint64_t kl = ptx::make_desc_k128(k_base + (2 + kc) * 8192 + kk * 32);
+              ptx::mma_bf16_ss(d, qh, kl, idesc_s, 1u);
+              ptx::mma_bf16_ss(d, ql, kh, idesc_s, 1u);
+            }
+          }
+        if (!full) ptx::mma_commit(&k_empty[s]);
+        ptx::mma_commit(&s_full[s]);
+      }
+      __syncwarp();
+    };
+    for (int it = 0; it < nt; ++it) issue_s(it, false);
+    issue_s(nt, true);
+    for (int j = 0; j < nt; ++j) {
+      const int it = nt + j;
+      if (j + 1 < nt) issue_s(it + 1, true);
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t v_base = ptx::smem_u32(smem + kQBytes + (it & 1) * kStage + kKBytes);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t ph_ = ptx::make_desc_k128(p_base + kk * 32);
+          const uint64_t pl_ = ptx::make_desc_k128(p_base + 16384 + kk * 32);
+          const uint64_t vh = ptx::make_desc_k128(v_base + kk * 32);
+          const uint64_t vl = ptx::make_desc_k128(v_base + 16384 + kk * 32);
+          ptx::mma_bf16_ss(tm_o, ph_, vh, idesc_o, (j | kk) ? 1u : 0u);
+          ptx::mma_bf16_ss(tm_o, ph_, vl, idesc_o, 1u);
+          ptx::mma_bf16_ss(tm_o, pl_, vh, idesc_o, 1u);
+        }
+        ptx::mma_commit(p_empty);
+        ptx::mma_commit(&k_empty[it & 1]);
+        if (j == nt - 1) ptx::mma_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + epilogue, one query row per thread
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    const uint32_t tl = tmem + ((uint32_t)(lg * 32) << 16);
+    float v[64];
+    float m = -INFINITY;
+    for (int it = 0; it < nt; ++it) {
+      const int s = it & 1;
+      ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      ptx::tmem_ld32(tl + s * kAtBN, *reinterpret_cast<float(*)[32]>(&v[0]));
+      ptx::tmem_ld32(tl + s * kAtBN + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_empty[s]);
+      const int nvalid = p.N - it * kAtBN;
+#pragma unroll
+      for (int c = 0; c < 64; ++c)
+        if (c < nvalid) m = fmaxf(m, v[c]);
+    }
+    const float sl2 = p.scale_log2e;
+    const float msl = m * sl2;
+    float l = 0.f;
+    uint8_t* prow_hi = smem + kPOff + (r >> 3) * 1024 + (r & 7) * 128;
+    uint8_t* prow_lo = prow_hi + 16384;
+    for (int j = 0; j < nt; ++j) {
+      const int it = nt + j, s = it & 1;
+      ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      ptx::tmem_ld32(tl + s * kAtBN, *reinterpret_cast<float(*)[32]>(&v[0]));
+      ptx::tmem_ld32(tl + s * kAtBN + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&s_empty[s]);
+      const int nvalid = p.N - j * kAtBN;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float e = (c < nvalid) ? exp2f(fmaf(v[c], sl2, -msl)) : 0.f;
+        v[c] = e;
+        l += e;
+      }
+      ptx::mbar_wait(p_empty, (j & 1) ^ 1);
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        __align__(16) bf16 hh[8];
+        __align__(16) bf16 ll[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split2(v[c8 * 8 + i], hh[i], ll[i]);
+        const int off = ((c8 ^ (r & 7)) * 16);
+        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(hh);
+        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(ll);
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = 1.f / l;
+    const int row = m0 + r;
+#pragma unroll 1
+    for (int c = 0; c < kAtHD / 32; ++c) {
+      float o[32];
+      ptx::tmem_ld32(tl + 128 + c * 32, o);
+      if (row < p.N) {
+        bf16* op = p.out + ((long)b * p.N + row) * p.out_stride + head * kAtHD + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= inv;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) store_split8(op + p.out_hi + i, op + p.out_lo + i, &o[i]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_enc = nullptr;
+
+static int enc3(CUtensorMap* tm, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t s1_bytes,
+                cuuint64_t s2_bytes, cuuint32_t b0, cuuint32_t b1, const char* what) {
+  if (g_enc == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DEXB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    DEXB_CHECK(q == cudaDriverEntryPointSuccess && fn != nullptr, "cuTensorMapEncodeTiled not available");
+    g_enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t str[2] = {s1_bytes, s2_bytes};
+  const cuuint32_t box[3] = {b0, b1, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = g_enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, str, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DEXB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(attention %s) failed with CUresult %d", what, (int)r);
+  return 0;
+}
+
+int attn_global_init() {
+  DEXB_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+  return 0;
+}
+
+bool attn_supported(int hd) { return hd == kAtHD; }
+
+int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int B, int N, int NP, int heads, int hid) {
+  DEXB_CHECK(hid / heads == kAtHD, "fused attention is instantiated for head dim %d", kAtHD);
+  ap->B = B;
+  AttnParams& p = ap->p;
+  p.N = N; p.NP = NP; p.nheads = heads; p.hid = hid;
+  p.nt = (N + kAtBN - 1) / kAtBN;
+  p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
+  p.out = out; p.out_stride = 2L * hid; p.out_hi = 0; p.out_lo = hid;
+  const cuuint64_t qrow = 6ull * hid * 2;
+  DEXB_TRY(enc3(&ap->tmQ, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBM, "Q"));
+  DEXB_TRY(enc3(&ap->tmK, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBN, "K"));
+  const cuuint64_t vrow = 2ull * NP * 2;
+  DEXB_TRY(enc3(&ap->tmV, vT, 2ull * NP, (cuuint64_t)hid, (cuuint64_t)B, vrow, vrow * hid, 64, kAtHD, "V"));
+  return 0;
+}
+
+int attn_launch(const AttnPlan& ap, cudaStream_t st) {
+  dim3 grid((unsigned)((ap.p.N + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
+  attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmQ, ap.tmK, ap.tmV, ap.p);
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+double attn_flop(const AttnPlan& ap) { return 4.0 * ap.B * ap.p.nheads * (double)ap.p.N * ap.p.N * kAtHD; }
+
+}  // namespace dexb

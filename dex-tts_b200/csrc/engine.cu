@@ -424,8 +424,10 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->hS = ar.get<bf16>(M * 2 * hid);
   h->qk = ar.get<bf16>(M * 6 * hid);
   h->vT = ar.get<bf16>((long)B * hid * 2 * h->NP);
-  h->scores = ar.get<float>((long)B * c.heads * h->Ntok * h->NP);
-  h->P = ar.get<bf16>((long)B * c.heads * h->Ntok * 2 * h->NP);
+  const char* ea = getenv("DEXB_ATTN");
+  const bool fused = attn_supported(hid / c.heads) && !(ea != nullptr && ea[0] == '0');
+  h->scores = ar.get<float>(fused ? 16 : (long)B * c.heads * h->Ntok * h->NP);
+  h->P = ar.get<bf16>(fused ? 16 : (long)B * c.heads * h->Ntok * 2 * h->NP);
   h->attnS = ar.get<bf16>(M * 2 * hid);
   h->h2S = ar.get<bf16>(M * 2 * c.mlp_hidden);
   h->ytok = ar.get<float>(M * c.stride * c.stride * mid);
@@ -525,6 +527,11 @@ static int build_plans(dexb_handle* h) {
     p.epi.colmean = h->pe; p.epi.colmean_ld = hid; p.epi.colmean_scale = 1.f / (float)Fq;
     p.epi.o_head_stride = cg;
     DEXB_TRY(plan_shared(&h->g_posconv, p));
+  }
+  {
+    const char* ea = getenv("DEXB_ATTN");
+    h->fused_attn = attn_supported(hd) && !(ea != nullptr && ea[0] == '0');
+    if (h->fused_attn) DEXB_TRY(attn_plan_init(&h->attn, h->qk, h->vT, h->attnS, B, N, NP, c.heads, hid));
   }
   for (int i = 0; i < c.depth; ++i) {
     DitBlockW& k = h->blocks[i];
@@ -681,6 +688,7 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* 
   engine_release_plan(h);
   DEXB_TRY(gemm_global_init());
   DEXB_TRY(kernels_global_init());
+  DEXB_TRY(attn_global_init());
   h->B = B; h->T = T; h->Ts = (c.variant == 1) ? Ts : 0; h->steps = n_steps;
   h->H0 = c.n_feats; h->W0 = T; h->H1 = c.n_feats / 2; h->W1 = T / 2;
   const int p = c.patch, s = c.stride;
@@ -833,9 +841,16 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     const float* m = mod + (long)i * 6 * hid;
     GEMM(k.qkv, k.qkv.p);
     LAUNCH(launch_transpose_v(h->qk, 6L * hid, 2 * hid, 5 * hid, h->vT, B, N, h->NP, hid, hid / c.heads, st));
-    GEMM(k.scores, k.scores.p);
-    LAUNCH(launch_attn_softmax(h->scores, h->NP, h->P, h->NP, (long)B * c.heads * N, N, st));
-    GEMM(k.pv, k.pv.p);
+    if (h->fused_attn) {
+      if (h->prof) prof_begin(h, "attn_fwd_kernel", attn_flop(h->attn), st);
+      DEXB_TRY(attn_launch(h->attn, st));
+      if (h->prof) prof_end(h, st);
+      ++h->launches;
+    } else {
+      GEMM(k.scores, k.scores.p);
+      LAUNCH(launch_attn_softmax(h->scores, h->NP, h->P, h->NP, (long)B * c.heads * N, N, st));
+      GEMM(k.pv, k.pv.p);
+    }
     {
       GemmParams p = k.proj.p;
       p.epi.gate = m + 2 * hid;

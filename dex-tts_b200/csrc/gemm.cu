@@ -86,7 +86,12 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
 // ------------------------------------------------------------------------------------------------
 // launch
 // ------------------------------------------------------------------------------------------------
+static int g_num_sms = 148;
+
 int gemm_global_init() {
+  int dev = 0;
+  DEXB_CUDA_OK(cudaGetDevice(&dev));
+  DEXB_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::kBytes));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::kBytes));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::kBytes));
@@ -96,8 +101,10 @@ int gemm_global_init() {
 
 template <int BN>
 static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
-  dim3 grid((unsigned)(p.nz * p.TH * p.TW), (unsigned)cdiv(p.N, BN));
-  gemm_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p);
+  const int ntn = cdiv(p.N, BN);
+  const long total = (long)p.nz * p.TH * p.TW * ntn;
+  const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+  gemm_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p, (int)total, ntn);
   return 0;
 }
 

@@ -28,36 +28,84 @@ namespace dexb {
 template <int NV>
 __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int nheads, int oh, int ow, int OH, int OW,
                                           bool valid, int n0, float (&v)[NV]) {
+  // Every branch below is warp-uniform and taken once per NV-column chunk; the per-element loops are branch-free
+  // (a first version tested the optional features per element and was instruction-issue bound: ~45 SASS instructions
+  // per output element, 20 % of the stalls on instruction fetch -- profiles/r01_ncu_gemm_v1.md).
   const int head = z % nheads;
   const int img = e.o_by_z ? z : z / nheads;
   const long row = ((long)img * OH + oh) * OW + ow;
   const int nc0 = n0 + head * e.o_head_stride;     // output column of v[0]
-  float rm = 1.f;
-  if (e.rowmask != nullptr && valid) rm = e.rowmask[(long)img * e.rowmask_stride + ow];
+  const bool full = (n0 + NV <= N);
+  if (e.alpha != 1.f) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int n = n0 + i;
-    float x = v[i] * e.alpha;
-    if (n < N) {
-      if (e.bias != nullptr) x += e.bias[(long)z * e.bias_zstride + head * e.bias_head_stride + n];
-      if (e.act == 1) x = gelu_f(x);
-      if (valid) {
-        float r = 0.f;
-        bool has_r = false;
-        if (e.resid_f32 != nullptr) { r = e.resid_f32[row * e.resid_f32_stride + nc0 + i]; has_r = true; }
-        if (e.resid_s != nullptr) {
-          const bf16* rp = e.resid_s + row * e.resid_s_stride + nc0 + i;
-          r += join2(rp[e.resid_s_hi], rp[e.resid_s_lo]);
-          has_r = true;
-        }
-        if (e.gate != nullptr) x = r + e.gate[n] * x;
-        else if (has_r) x = r + x;
+    for (int i = 0; i < NV; ++i) v[i] *= e.alpha;
+  }
+  if (e.bias != nullptr) {
+    const float* bp = e.bias + (long)z * e.bias_zstride + head * e.bias_head_stride + n0;
+    if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
       }
-      x *= rm;
     } else {
-      x = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) if (n0 + i < N) v[i] += bp[i];
     }
-    v[i] = x;
+  }
+  if (!full) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (n0 + i >= N) v[i] = 0.f;
+  }
+  if (e.act == 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);          // gelu(0) == 0 keeps the out-of-range columns at zero
+  }
+  if (valid && (e.resid_f32 != nullptr || e.resid_s != nullptr || e.gate != nullptr)) {
+    float r[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r[i] = 0.f;
+    if (e.resid_f32 != nullptr) {
+      const float* rp = e.resid_f32 + row * e.resid_f32_stride + nc0;
+      if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+          r[i] = r4.x; r[i + 1] = r4.y; r[i + 2] = r4.z; r[i + 3] = r4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) if (n0 + i < N) r[i] = rp[i];
+      }
+    }
+    if (e.resid_s != nullptr) {
+      const bf16* rp = e.resid_s + row * e.resid_s_stride + nc0;
+      if (full && (((reinterpret_cast<uintptr_t>(rp + e.resid_s_hi) | reinterpret_cast<uintptr_t>(rp + e.resid_s_lo)) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 8) {
+          float t[8];
+          load_split8(rp + e.resid_s_hi + i, rp + e.resid_s_lo + i, t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) r[i + j] += t[j];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) if (n0 + i < N) r[i] += join2(rp[e.resid_s_hi + i], rp[e.resid_s_lo + i]);
+      }
+    }
+    if (e.gate != nullptr) {
+      const float* gp = e.gate + n0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = r[i] + ((n0 + i < N) ? __ldg(gp + i) : 0.f) * v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] += r[i];
+    }
+  }
+  if (e.rowmask != nullptr && valid) {
+    const float rm = e.rowmask[(long)img * e.rowmask_stride + ow];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= rm;
   }
   if (e.gn_stats != nullptr) {
     // per-(image, group) sum / sum-of-squares: thread-local over its channels, warp-shuffle over the 32 rows
@@ -141,43 +189,52 @@ struct TcSmem {
   static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
 };
 
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs
+// that run concurrently share the A tile in L2).  The smem ring and both TMEM accumulator buffers stay live across
+// tiles, so the MMA warp starts tile i+1 while the epilogue warps drain tile i (acc_full / acc_empty barriers).
+struct TcTile {
+  int z, head, img_a, ch0, cw0, n0;
+};
+__device__ __forceinline__ TcTile tc_decode_tile(const GemmParams& p, int t, int ntn, int block_n) {
+  TcTile r;
+  r.n0 = (t % ntn) * block_n; t /= ntn;
+  const int tw = t % p.TW; t /= p.TW;
+  const int th = t % p.TH; t /= p.TH;
+  r.z = t;
+  r.head = r.z % p.nheads;
+  r.img_a = p.a_by_z ? r.z : r.z / p.nheads;
+  r.ch0 = th * p.BH; r.cw0 = tw * p.BW;
+  return r;
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const GemmParams p, const int total_tiles, const int ntn) {
   using SM = TcSmem<BLOCK_N>;
   constexpr int STAGES = SM::kStages;
+  constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;        // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile decode: blockIdx.x = (z, th, tw), blockIdx.y = n tile
-  int t = blockIdx.x;
-  const int tw = t % p.TW; t /= p.TW;
-  const int th = t % p.TH; t /= p.TH;
-  const int z = t;
-  const int head = z % p.nheads;
-  const int img_a = p.a_by_z ? z : z / p.nheads;
-  const int ch0 = th * p.BH, cw0 = tw * p.BW;            // first computed pixel of the tile
-  const int n0 = blockIdx.y * BLOCK_N;
   const int kchunks = p.K / kTcBlockK;
-  const int ntaps = p.KH * p.KW;
-  const int nk = ntaps * kchunks;
+  const int nk = p.KH * p.KW * kchunks;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    ptx::mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 128); }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<BLOCK_N>(tmem_slot);
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -186,79 +243,104 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (ptx::elect_one()) {
-      const int bz = (p.b_mode == 0) ? 0 : (p.b_mode == 1 ? z / p.nheads : z);
       const uint32_t tx_bytes = (p.nsplit == 3) ? (uint32_t)SM::kStageBytes : (uint32_t)(SM::kABytes + SM::kBBytes);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = it / kchunks, kc = it % kchunks;
-        const int dy = tap / p.KW + p.offH, dx = (tap % p.KW) * p.tap_sw + p.offW;
-        uint8_t* st = smem + s * SM::kStageBytes;
-        ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
-        const int acol = kc * kTcBlockK + head * p.a_head_stride;
-        const int bcol = kc * kTcBlockK + head * p.b_head_stride;
-        const int brow = tap * p.b_rows_per_tap + n0 + head * p.b_head_rows;
-        ptx::tma_load_4d(st, &tmA, &full_bar[s], p.a_hi + acol, cw0 * p.in_stride + dx, ch0 * p.in_stride + dy, img_a);
-        ptx::tma_load_3d(st + 2 * SM::kABytes, &tmB, &full_bar[s], p.b_hi + bcol, brow, bz);
-        if (p.nsplit == 3) {
-          ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, cw0 * p.in_stride + dx,
-                           ch0 * p.in_stride + dy, img_a);
-          ptx::tma_load_3d(st + 2 * SM::kABytes + SM::kBBytes, &tmB, &full_bar[s], p.b_lo + bcol, brow, bz);
+      uint32_t g = 0;                                        // ring position, continues across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
+        const int bz = (p.b_mode == 0) ? 0 : (p.b_mode == 1 ? tl.z / p.nheads : tl.z);
+        for (int it = 0; it < nk; ++it, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          const int tap = it / kchunks, kc = it % kchunks;
+          const int dy = tap / p.KW + p.offH, dx = (tap % p.KW) * p.tap_sw + p.offW;
+          uint8_t* st = smem + s * SM::kStageBytes;
+          ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
+          const int acol = kc * kTcBlockK + tl.head * p.a_head_stride;
+          const int bcol = kc * kTcBlockK + tl.head * p.b_head_stride;
+          const int brow = tap * p.b_rows_per_tap + tl.n0 + tl.head * p.b_head_rows;
+          const int ax = tl.cw0 * p.in_stride + dx, ay = tl.ch0 * p.in_stride + dy;
+          ptx::tma_load_4d(st, &tmA, &full_bar[s], p.a_hi + acol, ax, ay, tl.img_a);
+          ptx::tma_load_3d(st + 2 * SM::kABytes, &tmB, &full_bar[s], p.b_hi + bcol, brow, bz);
+          if (p.nsplit == 3) {
+            ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, ax, ay, tl.img_a);
+            ptx::tma_load_3d(st + 2 * SM::kABytes + SM::kBBytes, &tmB, &full_bar[s], p.b_lo + bcol, brow, bz);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kTcBlockM, BLOCK_N);
-    for (int it = 0; it < nk; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      ptx::mbar_wait(&full_bar[s], ph);
+    uint32_t g = 0;
+    int li = 0;                                              // local tile counter -> accumulator buffer li & 1
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+      const int buf = li & 1;
+      ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_hi = ptx::smem_u32(smem + s * SM::kStageBytes);
-        const uint32_t a_lo = a_hi + SM::kABytes;
-        const uint32_t b_hi = a_hi + 2 * SM::kABytes;
-        const uint32_t b_lo = b_hi + SM::kBBytes;
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BLOCK_N);
+      for (int it = 0; it < nk; ++it, ++g) {
+        const int s = g % STAGES;
+        const uint32_t ph = (g / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_hi = ptx::smem_u32(smem + s * SM::kStageBytes);
+          const uint32_t a_lo = a_hi + SM::kABytes;
+          const uint32_t b_hi = a_hi + 2 * SM::kABytes;
+          const uint32_t b_lo = b_hi + SM::kBBytes;
 #pragma unroll
-        for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
-          const uint32_t ko = kk * 32;                       // 16 bf16 = 32 B inside the 128 B swizzle span
-          const uint64_t dah = ptx::make_desc_k128(a_hi + ko);
-          const uint64_t dbh = ptx::make_desc_k128(b_hi + ko);
-          ptx::mma_bf16_ss(tmem_base, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          if (p.nsplit == 3) {
-            const uint64_t dal = ptx::make_desc_k128(a_lo + ko);
-            const uint64_t dbl = ptx::make_desc_k128(b_lo + ko);
-            ptx::mma_bf16_ss(tmem_base, dah, dbl, idesc, 1u);
-            ptx::mma_bf16_ss(tmem_base, dal, dbh, idesc, 1u);
+          for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+            const uint32_t ko = kk * 32;                     // 16 bf16 = 32 B inside the 128 B swizzle span
+            const uint64_t dah = ptx::make_desc_k128(a_hi + ko);
+            const uint64_t dbh = ptx::make_desc_k128(b_hi + ko);
+            ptx::mma_bf16_ss(tacc, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+            if (p.nsplit == 3) {
+              const uint64_t dal = ptx::make_desc_k128(a_lo + ko);
+              const uint64_t dbl = ptx::make_desc_k128(b_lo + ko);
+              ptx::mma_bf16_ss(tacc, dah, dbl, idesc, 1u);
+              ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
+            }
           }
+          ptx::mma_commit(&empty_bar[s]);                    // frees the smem stage when these MMAs retire
+          if (it == nk - 1) ptx::mma_commit(&acc_full[buf]); // accumulator complete
         }
-        ptx::mma_commit(&empty_bar[s]);                      // frees the smem stage when these MMAs retire
-        if (it == nk - 1) ptx::mma_commit(acc_bar);          // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    ptx::mbar_wait(acc_bar, 0);
-    ptx::tc_fence_after();
     const int lg = warp & 3;                                 // TMEM lane group this warp may read
     const int r = lg * 32 + lane;                            // row of the tile
-    const int ch = ch0 + r / p.BW, cw = cw0 + r % p.BW;
-    const bool valid = (ch < p.CH) && (cw < p.CW);
-    const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
+    int li = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+      const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
+      const int buf = li & 1;
+      ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
+      ptx::tc_fence_after();
+      const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
+      const bool valid = (ch < p.CH) && (cw < p.CW);
+      const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
+      const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+      constexpr int NCH = BLOCK_N / 32;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      if (n0 + c * 32 >= p.N) break;
-      float v[32];
-      ptx::tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
-      epi_apply<32>(p.epi, p.N, z, p.nheads, oh, ow, p.OH, p.OW, valid, n0 + c * 32, v);
+      for (int c = 0; c < NCH; ++c) {
+        const bool live = tl.n0 + c * 32 < p.N;
+        float v[32];
+        if (live) ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+        if (c == NCH - 1 || tl.n0 + (c + 1) * 32 >= p.N) {   // last chunk read: hand the buffer back to the MMA warp
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[buf]);
+        }
+        if (!live) break;
+        epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, tl.n0 + c * 32, v);
+        if (tl.n0 + (c + 1) * 32 >= p.N) break;
+      }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<BLOCK_N>(tmem_base);
+  if (warp == 1) ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------

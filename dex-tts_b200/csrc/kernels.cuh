@@ -122,6 +122,7 @@ void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, cuda
 void launch_pack_convT(const float* w, bf16* out, int Ci, int Co, cudaStream_t st);
 int launch_stft_mel(const float* wav, int B, int S, const float* window, const float* mel_basis, int n_fft, int hop,
                     int n_mels, float* mel, cudaStream_t st);
+void launch_unpack_rows(const bf16* in, float* out, long rows, int K, cudaStream_t st);
 void launch_pack_rows(const float* in, bf16* out, long rows, int K, cudaStream_t st);
 
 }  // namespace dexb

@@ -198,4 +198,16 @@ void launch_pack_rows(const float* in, bf16* out, long rows, int K, cudaStream_t
   launch_pack_split(in, K, out, 2L * K, K, (int)rows, K, st);
 }
 
+// split rows [hi(K) | lo(K)] -> fp32 [rows][K] (unit-test helper)
+__global__ void k_unpack_rows(const bf16* __restrict__ in, float* __restrict__ out, long rows, int K) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= rows * K) return;
+  const long r = i / K;
+  const int k = (int)(i % K);
+  out[i] = join2(in[r * 2 * K + k], in[r * 2 * K + K + k]);
+}
+void launch_unpack_rows(const bf16* in, float* out, long rows, int K, cudaStream_t st) {
+  k_unpack_rows<<<cdiv(rows * K, 256), 256, 0, st>>>(in, out, rows, K);
+}
+
 }  // namespace dexb

@@ -200,6 +200,18 @@ def gemm_test(a, w, bias=None, taps=(1, 1), off=(0, 0), in_stride=1, engine=0, n
     return out
 
 
+def attn_test(qkv, heads):
+    """Unit entry of the fused attention kernel: qkv (B, N, 3*hid) -> (B, N, hid)."""
+    L = _lib.load()
+    qkv = qkv.float().contiguous()
+    B, N, C3 = qkv.shape
+    hid = C3 // 3
+    out = torch.zeros(B, N, hid, device=qkv.device, dtype=torch.float32)
+    torch.cuda.synchronize()
+    _lib.check(L.dexb_attn_test(_ptr(qkv), B, N, heads, hid, _ptr(out), _stream()), "dexb_attn_test")
+    return out
+
+
 def stft_mel(wav, window, mel_basis, n_fft=1024, hop=256):
     """wav (B,S) in [-1,1] on CUDA -> log-mel (B, n_mels, 1 + S // hop).  Mirrors TacotronSTFT.mel_spectrogram."""
     L = _lib.load()

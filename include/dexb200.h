@@ -92,6 +92,11 @@ int dexb_denoise_once(dexb_handle* h, const float* x_dev, const float* mu_dev, c
 int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, int W, int K, const float* w_dev, int N,
                    int KH, int KW, int offH, int offW, int in_stride, const float* bias_dev, float* out_dev, void* stream);
 
+/* Unit parity of the fused attention kernel (timm Attention inside DiTBlock, DEX-TTS/model/dit.py:270,282):
+ * qkv_dev (B, N, 3*hid) fp32 = output of the qkv Linear -> out_dev (B, N, hid) = softmax(q k^T / sqrt(hd)) v, heads
+ * concatenated (before the proj Linear).  Allocates scratch and synchronises (test entry). */
+int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float* out_dev, void* stream);
+
 /* replaces: TacotronSTFT.mel_spectrogram (DEX-TTS/audio/stft.py:159-178) for 22.05 kHz / n_fft 1024 / hop 256 / 80 mels.
  * wav_dev (B, S) in [-1, 1]; mel_dev (B, 80, 1 + S/256) log-mel; mel_basis_dev (80, 513), window_dev (1024). */
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft,
