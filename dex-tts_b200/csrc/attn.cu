@@ -19,15 +19,22 @@ namespace dexb {
 constexpr int kAtBM = 128;          // queries per CTA
 constexpr int kAtBN = 64;           // keys per iteration
 constexpr int kAtHD = 128;          // head dim
-constexpr int kAtThreads = 192;
-constexpr int kQBytes = 4 * 16384;                        // [hi kc0][hi kc1][lo kc0][lo kc1], 128 rows x 128 B each
-constexpr int kKBytes = 4 * 8192;                         // same order, 64 rows x 128 B each
+constexpr int kAtThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two column halves x four lane groups)
+constexpr int kAtStages = 3;
+constexpr int kKBytes = 4 * 8192;                         // [hi kc0][hi kc1][lo kc0][lo kc1], 64 rows x 128 B each
 constexpr int kVBytes = 2 * 16384;                        // [hi][lo], 128 d-rows x 128 B (64 keys) each
 constexpr int kStage = kKBytes + kVBytes;                 // 64 KiB
-constexpr int kPOff = kQBytes + 2 * kStage;               // 192 KiB
-constexpr int kPBytes = 2 * 16384;                        // [hi][lo], 128 rows x 128 B (64 keys)
-constexpr int kBarOff = kPOff + kPBytes;                  // 224 KiB
-constexpr int kAtSmem = kBarOff + 256 + 1024;
+constexpr int kBarOff = kAtStages * kStage;               // 192 KiB
+constexpr int kAtSmem = kBarOff + 128 + 1024 + 1024;      // barriers (128 B) + max/sum exchange (1 KiB) + alignment slack
+// tensor-memory columns (512 allocated): both MMA A operands (Q and P) live here, so shared memory only carries the
+// streamed K / V^T tiles -- with split-bf16 every A tile would otherwise be re-read from shared memory three times per
+// k-step and the kernel is shared-memory-bandwidth bound (profiles/r01_ncu_v4.md)
+constexpr uint32_t kTmS = 0;        // 2 x 64  fp32 score tiles
+constexpr uint32_t kTmO = 128;      // 128     fp32 output accumulator
+constexpr uint32_t kTmQh = 256;     // 64      Q hi: 128 bf16 per row, two per column
+constexpr uint32_t kTmQl = 320;     // 64      Q lo
+constexpr uint32_t kTmPh = 384;     // 32      P hi: 64 bf16 per row
+constexpr uint32_t kTmPl = 416;     // 32      P lo
 
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -36,14 +43,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* q_full = bars;            // 1
-  uint64_t* k_full = bars + 1;        // 2
-  uint64_t* k_empty = bars + 3;       // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* s_empty = bars + 7;       // 2
-  uint64_t* p_full = bars + 9;        // 1
-  uint64_t* p_empty = bars + 10;      // 1
-  uint64_t* o_full = bars + 11;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* k_full = bars + 1;        // 3
+  uint64_t* k_empty = bars + 4;       // 3
+  uint64_t* s_full = bars + 7;        // 2
+  uint64_t* s_empty = bars + 9;       // 2
+  uint64_t* p_full = bars + 11;       // 1
+  uint64_t* p_empty = bars + 12;      // 1
+  uint64_t* o_full = bars + 13;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kAtBM;
@@ -53,34 +60,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    ptx::mbar_init(q_full, 1);
+    ptx::mbar_init(q_full, 256);
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
-      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 128);
+      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 256);
     }
-    ptx::mbar_init(p_full, 128); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
+    for (int s = 0; s < kAtStages; ++s) { ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1); }
+    ptx::mbar_init(p_full, 256); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tm_o = tmem + 128;
+  const uint32_t tm_o = tmem + kTmO;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      const int qcol = head * kAtHD, kcol = p.hid + head * kAtHD, lo = 3 * p.hid;
-      ptx::mbar_expect_tx(q_full, kQBytes);
-      for (int part = 0; part < 2; ++part)
-        for (int kc = 0; kc < 2; ++kc)
-          ptx::tma_load_3d(smem + (part * 2 + kc) * 16384, &tmQ, q_full, part * lo + qcol + kc * 64, m0, b);
+      const int kcol = p.hid + head * kAtHD, lo = 3 * p.hid;
       for (int it = 0; it < 2 * nt; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+        const int s = it % kAtStages;
+        const uint32_t ph = (it / kAtStages) & 1;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
-        uint8_t* st = smem + kQBytes + s * kStage;
+        uint8_t* st = smem + s * kStage;
         if (it < nt) {
           ptx::mbar_expect_tx(&k_full[s], 2 * 8192);
           for (int kc = 0; kc < 2; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, it * kAtBN, b);
@@ -99,35 +102,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kAtBN);
     constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kAtHD);
-    const uint32_t q_base = ptx::smem_u32(smem);
-    const uint32_t p_base = ptx::smem_u32(smem + kPOff);
     ptx::mbar_wait(q_full, 0);
-    // S[it & 1] = Q K^T for iteration `it` (nsplit terms); frees the stage itself only in pass 1
+    ptx::tc_fence_after();
+    // S[it & 1] = Q K^T for iteration `it` (Q from tensor memory); frees the stage itself only in pass 1
     auto issue_s = [&](int it, bool full) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      ptx::mbar_wait(&k_full[s], ph);
-      ptx::mbar_wait(&s_empty[s], ph ^ 1);
+      const int st = it % kAtStages, sb = it & 1;
+      ptx::mbar_wait(&k_full[st], (it / kAtStages) & 1);
+      ptx::mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t k_base = ptx::smem_u32(smem + kQBytes + s * kStage);
-        const uint32_t d = tmem + (uint32_t)(s * kAtBN);
+        const uint32_t k_base = ptx::smem_u32(smem + st * kStage);
+        const uint32_t d = tmem + kTmS + (uint32_t)(sb * kAtBN);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t qh = ptx::make_desc_k128(q_base + kc * 16384 + kk * 32);
+            const uint32_t qh = tmem + kTmQh + (uint32_t)(kc * 32 + kk * 8);
+            const uint32_t ql = tmem + kTmQl + (uint32_t)(kc * 32 + kk * 8);
             const uint64_t kh = ptx::make_desc_k128(k_base + kc * 8192 + kk * 32);
-            ptx::mma_bf16_ss(d, qh, kh, idesc_s, (kc | kk) ? 1u : 0u);
+            ptx::mma_bf16_ts(d, qh, kh, idesc_s, (kc | kk) ? 1u : 0u);
             if (full) {
-              const uint64_t ql = ptx::make_desc_k128(q_base + (2 + kc) * 16384 + kk * 32);
               const uint64_t kl = ptx::make_desc_k128(k_base + (2 + kc) * 8192 + kk * 32);
-              ptx::mma_bf16_ss(d, qh, kl, idesc_s, 1u);
-              ptx::mma_bf16_ss(d, ql, kh, idesc_s, 1u);
+              ptx::mma_bf16_ts(d, qh, kl, idesc_s, 1u);
+              ptx::mma_bf16_ts(d, ql, kh, idesc_s, 1u);
             }
           }
-        if (!full) ptx::mma_commit(&k_empty[s]);
-        ptx::mma_commit(&s_full[s]);
+        if (!full) ptx::mma_commit(&k_empty[st]);
+        ptx::mma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
@@ -139,87 +140,121 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::mbar_wait(p_full, j & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t v_base = ptx::smem_u32(smem + kQBytes + (it & 1) * kStage + kKBytes);
+        const uint32_t v_base = ptx::smem_u32(smem + (it % kAtStages) * kStage + kKBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t ph_ = ptx::make_desc_k128(p_base + kk * 32);
-          const uint64_t pl_ = ptx::make_desc_k128(p_base + 16384 + kk * 32);
+          const uint32_t ph_ = tmem + kTmPh + (uint32_t)(kk * 8);
+          const uint32_t pl_ = tmem + kTmPl + (uint32_t)(kk * 8);
           const uint64_t vh = ptx::make_desc_k128(v_base + kk * 32);
           const uint64_t vl = ptx::make_desc_k128(v_base + 16384 + kk * 32);
-          ptx::mma_bf16_ss(tm_o, ph_, vh, idesc_o, (j | kk) ? 1u : 0u);
-          ptx::mma_bf16_ss(tm_o, ph_, vl, idesc_o, 1u);
-          ptx::mma_bf16_ss(tm_o, pl_, vh, idesc_o, 1u);
+          ptx::mma_bf16_ts(tm_o, ph_, vh, idesc_o, (j | kk) ? 1u : 0u);
+          ptx::mma_bf16_ts(tm_o, ph_, vl, idesc_o, 1u);
+          ptx::mma_bf16_ts(tm_o, pl_, vh, idesc_o, 1u);
         }
         ptx::mma_commit(p_empty);
-        ptx::mma_commit(&k_empty[it & 1]);
+        ptx::mma_commit(&k_empty[it % kAtStages]);
         if (j == nt - 1) ptx::mma_commit(o_full);
       }
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ softmax + epilogue, one query row per thread
+    // ------------------------------------------------------------ softmax + epilogue
+    // 8 warps: lane group lg = warp & 3 (the TMEM lanes a warp may touch), column half hf = (warp - 2) >> 2.
+    // Thread (r, hf) owns row r and 32 of the 64 key columns of every S tile / 64 of the 128 output columns.
     const int lg = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = lg * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(lg * 32) << 16);
-    float v[64];
+    float* xch = reinterpret_cast<float*>(smem + kBarOff + 128);        // [2][128] exchange of row max / row sum halves
+    {
+      // stage this thread's half of the query row (64 of the 128 head dims, hi and lo) into tensor memory
+      uint32_t qh[32], ql[32];
+      const int row = m0 + r;
+      if (row < p.N) {
+        const bf16* qp = p.qkv + ((long)b * p.N + row) * (6L * p.hid) + head * kAtHD + hf * 64;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 a = *reinterpret_cast<const uint4*>(qp + i * 8);
+          const uint4 c = *reinterpret_cast<const uint4*>(qp + 3 * p.hid + i * 8);
+          qh[i * 4] = a.x; qh[i * 4 + 1] = a.y; qh[i * 4 + 2] = a.z; qh[i * 4 + 3] = a.w;
+          ql[i * 4] = c.x; ql[i * 4 + 1] = c.y; ql[i * 4 + 2] = c.z; ql[i * 4 + 3] = c.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { qh[i] = 0u; ql[i] = 0u; }
+      }
+      ptx::tmem_st32(tl + kTmQh + hf * 32, qh);
+      ptx::tmem_st32(tl + kTmQl + hf * 32, ql);
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(q_full);
+    }
+    float v[32];
     float m = -INFINITY;
     for (int it = 0; it < nt; ++it) {
       const int s = it & 1;
       ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
       ptx::tc_fence_after();
-      ptx::tmem_ld32(tl + s * kAtBN, *reinterpret_cast<float(*)[32]>(&v[0]));
-      ptx::tmem_ld32(tl + s * kAtBN + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = p.N - it * kAtBN;
+      const int nvalid = p.N - it * kAtBN - hf * 32;
 #pragma unroll
-      for (int c = 0; c < 64; ++c)
+      for (int c = 0; c < 32; ++c)
         if (c < nvalid) m = fmaxf(m, v[c]);
     }
+    // combine the two column halves of every row (named barrier over the 256 softmax threads only)
+    xch[hf * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(m, xch[(hf ^ 1) * 128 + r]);
     const float sl2 = p.scale_log2e;
     const float msl = m * sl2;
     float l = 0.f;
-    uint8_t* prow_hi = smem + kPOff + (r >> 3) * 1024 + (r & 7) * 128;
-    uint8_t* prow_lo = prow_hi + 16384;
     for (int j = 0; j < nt; ++j) {
       const int it = nt + j, s = it & 1;
       ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
       ptx::tc_fence_after();
-      ptx::tmem_ld32(tl + s * kAtBN, *reinterpret_cast<float(*)[32]>(&v[0]));
-      ptx::tmem_ld32(tl + s * kAtBN + 32, *reinterpret_cast<float(*)[32]>(&v[32]));
+      ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = p.N - j * kAtBN;
+      const int nvalid = p.N - j * kAtBN - hf * 32;
+      uint32_t hi2[16], lo2[16];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float e = (c < nvalid) ? exp2f(fmaf(v[c], sl2, -msl)) : 0.f;
-        v[c] = e;
-        l += e;
+      for (int c = 0; c < 32; c += 2) {
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(v[c], sl2, -msl)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(v[c + 1], sl2, -msl)));
+        if (c >= nvalid) e0 = 0.f;
+        if (c + 1 >= nvalid) e1 = 0.f;
+        l += e0 + e1;
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(e0 - __uint_as_float(hb << 16), e1 - __uint_as_float(hb & 0xffff0000u));
+        hi2[c >> 1] = hb;
+        lo2[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      ptx::mbar_wait(p_empty, (j & 1) ^ 1);
-#pragma unroll
-      for (int c8 = 0; c8 < 8; ++c8) {
-        __align__(16) bf16 hh[8];
-        __align__(16) bf16 ll[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split2(v[c8 * 8 + i], hh[i], ll[i]);
-        const int off = ((c8 ^ (r & 7)) * 16);
-        *reinterpret_cast<uint4*>(prow_hi + off) = *reinterpret_cast<const uint4*>(hh);
-        *reinterpret_cast<uint4*>(prow_lo + off) = *reinterpret_cast<const uint4*>(ll);
-      }
-      ptx::fence_proxy_async_smem();
+      ptx::mbar_wait(p_empty, (j & 1) ^ 1);               // P(j-1) V(j-1) has consumed the previous P
+      ptx::tc_fence_after();
+      ptx::tmem_st16(tl + kTmPh + hf * 16, hi2);
+      ptx::tmem_st16(tl + kTmPl + hf * 16, lo2);
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
       ptx::mbar_arrive(p_full);
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the max exchange
+    xch[hf * 128 + r] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += xch[(hf ^ 1) * 128 + r];
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
     const int row = m0 + r;
 #pragma unroll 1
-    for (int c = 0; c < kAtHD / 32; ++c) {
+    for (int c = 0; c < 2; ++c) {
       float o[32];
-      ptx::tmem_ld32(tl + 128 + c * 32, o);
+      ptx::tmem_ld32(tl + kTmO + hf * 64 + c * 32, o);
       if (row < p.N) {
-        bf16* op = p.out + ((long)b * p.N + row) * p.out_stride + head * kAtHD + c * 32;
+        bf16* op = p.out + ((long)b * p.N + row) * p.out_stride + head * kAtHD + hf * 64 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
 #pragma unroll
@@ -229,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,6 +306,7 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   p.N = N; p.NP = NP; p.nheads = heads; p.hid = hid;
   p.nt = (N + kAtBN - 1) / kAtBN;
   p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
+  p.qkv = qkv;
   p.out = out; p.out_stride = 2L * hid; p.out_hi = 0; p.out_lo = hid;
   const cuuint64_t qrow = 6ull * hid * 2;
   DEXB_TRY(enc3(&ap->tmQ, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBM, "Q"));

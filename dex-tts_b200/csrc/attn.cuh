@@ -10,6 +10,7 @@ struct AttnParams {
   int N, NP;                 // tokens per sample, padded token count of the V^T rows
   int nheads, hid;           // heads, hidden size (qkv rows are [hi(3*hid) | lo(3*hid)], q | k | v, head-major inside)
   int nt;                    // key tiles of 64
+  const bf16* qkv;           // the qkv rows themselves (Q is staged to tensor memory by the softmax warps)
   float scale_log2e;         // hd^-0.5 * log2(e)
   bf16* out;                 // split rows [hi(hid) | lo(hid)], head h at column h*hd
   long out_stride;

@@ -264,56 +264,75 @@ void launch_la_colmax(const float* kv, unsigned* kmax_enc, int B, int P, cudaStr
 }
 
 // ctx[b][h][d][e] += sum_n exp(k[n][h*32+d] - max) * v[n][h*32+e];  ssum[b][h*32+d] += sum_n exp(..)
-// block (256 threads) = one (b, head, pixel chunk); thread = (d = tid/8, e0 = (tid%8)*4)
+// One block (256 threads) = one (b, pixel chunk), all 4 heads: the full 1 KiB kv row of every pixel is read once,
+// coalesced; thread (h, dq, eq) keeps a 4x4 register block of the 32x32 context of head h (16 FMA per 2 LDS.128).
+constexpr int kLaTile = 32;
 __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, const unsigned* __restrict__ kmax,
                                                 float* __restrict__ ctx, float* __restrict__ ssum, int P, int chunk) {
-  __shared__ float ps[64][33];
-  __shared__ float vs[64][32];
-  const int h = blockIdx.y, b = blockIdx.z;
+  __shared__ __align__(16) float ps[kLaTile][128];
+  __shared__ __align__(16) float vs[kLaTile][128];
+  const int b = blockIdx.y;
   const long p0 = (long)blockIdx.x * chunk;
   long p1 = p0 + chunk;
   if (p1 > P) p1 = P;
   const int tid = threadIdx.x;
-  const int d = tid >> 3, e0 = (tid & 7) * 4;
-  const int lc = tid & 31, lr = tid >> 5;                   // loader: column lc, rows lr, lr+8, ...
-  const float kmx = dec_ord(kmax[b * 128 + h * 32 + lc]);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float sacc = 0.f;
-  for (long t0 = p0; t0 < p1; t0 += 64) {
+  const int h = tid >> 6, dq = (tid & 63) >> 3, eq = tid & 7;
+  const int d0 = h * 32 + dq * 4, e0 = h * 32 + eq * 4;
+  // loader: thread handles float4 column group lc4 (0..63: 0..31 = k, 32..63 = v) of rows lr, lr+4, ...
+  const int lc4 = tid & 63, lr = tid >> 6;
+  float4 kmx = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lc4 < 32) {
+    const unsigned* km = kmax + b * 128 + lc4 * 4;
+    kmx = make_float4(dec_ord(km[0]), dec_ord(km[1]), dec_ord(km[2]), dec_ord(km[3]));
+  }
+  float acc[4][4];
+  float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long t0 = p0; t0 < p1; t0 += kLaTile) {
     __syncthreads();
 #pragma unroll
-    for (int rr = 0; rr < 8; ++rr) {
-      const int r = lr + rr * 8;
+    for (int rr = 0; rr < kLaTile / 4; ++rr) {
+      const int r = lr + rr * 4;
       const long pp = t0 + r;
-      float pk = 0.f, pv = 0.f;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pp < p1) {
-        const float* row = kv + ((long)b * P + pp) * 256;
-        pk = expf(row[h * 32 + lc] - kmx);
-        pv = row[128 + h * 32 + lc];
+        x = *reinterpret_cast<const float4*>(kv + ((long)b * P + pp) * 256 + lc4 * 4);
+        if (lc4 < 32) x = make_float4(expf(x.x - kmx.x), expf(x.y - kmx.y), expf(x.z - kmx.z), expf(x.w - kmx.w));
       }
-      ps[r][lc] = pk;
-      vs[r][lc] = pv;
+      if (lc4 < 32) *reinterpret_cast<float4*>(&ps[r][lc4 * 4]) = x;
+      else *reinterpret_cast<float4*>(&vs[r][(lc4 - 32) * 4]) = x;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int r = 0; r < 64; ++r) {
-      const float pk = ps[r][d];
+    for (int r = 0; r < kLaTile; ++r) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&ps[r][d0]);
       const float4 v4 = *reinterpret_cast<const float4*>(&vs[r][e0]);
-      acc[0] = fmaf(pk, v4.x, acc[0]);
-      acc[1] = fmaf(pk, v4.y, acc[1]);
-      acc[2] = fmaf(pk, v4.z, acc[2]);
-      acc[3] = fmaf(pk, v4.w, acc[3]);
-      sacc += pk;
+      const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pp[i], vv[j], acc[i][j]);
+        sacc[i] += pp[i];
+      }
     }
   }
-  float* cp = ctx + (((long)b * 4 + h) * 32 + d) * 32 + e0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) atomicAdd(cp + i, acc[i]);
-  if (e0 == 0) atomicAdd(&ssum[b * 128 + h * 32 + d], sacc);
+  for (int i = 0; i < 4; ++i) {
+    float* cp = ctx + (((long)b * 4 + h) * 32 + dq * 4 + i) * 32 + eq * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(cp + j, acc[i][j]);
+    if (eq == 0) atomicAdd(&ssum[b * 128 + d0 + i], sacc[i]);
+  }
 }
 void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx, float* ssum, int B, int P, cudaStream_t st) {
-  const int chunk = 512;
-  dim3 grid(cdiv(P, chunk), 4, B);
+  // enough blocks to fill the machine a few times over, each long enough to amortise its 1040 atomics
+  int chunk = 512;
+  while (chunk > 128 && (long)cdiv(P, chunk) * B < 2 * 148) chunk >>= 1;
+  dim3 grid(cdiv(P, chunk), B);
   k_la_ctx<<<grid, 256, 0, st>>>(kv, kmax_enc, ctx, ssum, P, chunk);
 }
 
