@@ -4,6 +4,7 @@
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace dexb {
 
@@ -43,9 +44,14 @@ static int encode_bf16(CUtensorMap* tm, const void* base, int rank, const cuuint
 // plan
 // ------------------------------------------------------------------------------------------------
 static int pick_block_n(int N) {
+  static int bn_max = -1;
+  if (bn_max < 0) {
+    const char* e = getenv("DEXB_BN_MAX");
+    bn_max = (e != nullptr) ? atoi(e) : 128;   // 128: three 64 KiB stages hide the TMA latency; 256 only has room for two
+  }
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
+  if (N <= 128 || bn_max <= 128) return 128;
   if (N % 256 == 0 || N > 512) return 256;
   return 128;
 }

@@ -104,3 +104,23 @@ def test_tcgen05_takes_every_gemm():
             cond = to_cuda(dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]))
         eng.sample(inp["z"].cuda(), inp["mask"].cuda(), inp["mu"].cuda(), 2, cond=cond)
         assert eng.simt_fallbacks == 0
+
+
+@pytest.mark.parametrize("variant,T", [("gedex", 200), ("dex", 120)])
+def test_fifty_step_trajectory_matches_oracle(variant, T):
+    """The headline setting (50 Euler steps, temperature 1.5): errors compound over the trajectory, so this is the case
+    that decides whether split-bf16 x3 is precise enough.  CPU oracle on the same seeded inputs."""
+    cfg = DecoderCfg.make(variant)
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    inp = synth_inputs(cfg, 1, T, Ts=40, seed=77)
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]) if variant == "dex" else None
+    steps = 50
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    with torch.no_grad():
+        y_ref = O.reverse_diffusion(w, O.make_cfg(variant), inp["z"], inp["mask"], inp["mu"], steps, temperature=1.5, cond=cond)
+    eng = get_engine(variant, True, 0)
+    x0 = inp["z"] / 1.5 + inp["mu"]
+    y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
+    v = per_bin_violation(y, y_ref)
+    print(f"50-step {variant} T={T}: per-bin violation {v:.3e} (tol {REL_TOL:g})")
+    assert v < REL_TOL
