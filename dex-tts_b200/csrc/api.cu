@@ -185,6 +185,63 @@ int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, 
   return 0;
 }
 
+int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, int KW, int offH, int offW, int in_stride,
+                    int out_mode, int dbg, int iters, float* ms_out) {
+  DEXB_CHECK(ms_out != nullptr && iters >= 1, "gemm_bench: bad argument");
+  DEXB_TRY(gemm_global_init());
+  const long rows = (long)nimg * H * W;
+  const int taps = KH * KW;
+  const int CH = (H + in_stride - 1) / in_stride, CW = (W + in_stride - 1) / in_stride;
+  const long orows = (long)nimg * CH * CW;
+  bf16 *as = nullptr, *ws = nullptr;
+  float* bias = nullptr;
+  void* out = nullptr;
+  DEXB_CUDA_OK(cudaMalloc(&as, rows * 2 * K * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&ws, (long)taps * N * 2 * K * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&bias, N * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&out, orows * N * 4));
+  DEXB_CUDA_OK(cudaMemset(as, 0x3c, rows * 2 * K * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMemset(ws, 0x3c, (long)taps * N * 2 * K * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMemset(bias, 0, N * sizeof(float)));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nz = nimg; p.nheads = 1; p.H = H; p.W = W; p.in_stride = in_stride;
+  p.CH = CH; p.CW = CW; p.OH = CH; p.OW = CW; p.out_scale = 1; p.tap_sw = 1;
+  p.KH = KH; p.KW = KW; p.offH = offH; p.offW = offW; p.K = K; p.N = N;
+  p.A = as; p.a_row_stride = 2L * K; p.a_hi = 0; p.a_lo = K;
+  p.Bw = ws; p.b_row_stride = 2L * K; p.b_hi = 0; p.b_lo = K; p.b_rows_per_tap = N;
+  p.nsplit = nsplit; p.dbg = dbg;
+  p.epi.alpha = 1.f; p.epi.bias = bias; p.epi.out_s_ncols = 1 << 30;
+  if (out_mode == 0) { p.epi.out_f32 = (float*)out; p.epi.out_f32_stride = N; }
+  else { p.epi.out_s = (bf16*)out; p.epi.out_s_stride = 2L * N; p.epi.out_s_hi = 0; p.epi.out_s_lo = N; }
+  int best_bw = 128; long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    const long tiles = (long)cdiv(CH, 128 / bw) * cdiv(CW, bw);
+    if (bw * in_stride > 256) continue;
+    if (best < 0 || tiles < best) { best = tiles; best_bw = bw; }
+  }
+  p.BW = best_bw; p.BH = 128 / best_bw;
+  GemmPlan gp;
+  int r = gemm_plan_init(&gp, p, nimg, (long)taps * N, 1);
+  if (r == 0 && !gp.tc_ok) { set_last_error("gemm_bench: shape not eligible for the tcgen05 engine"); r = -1; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  if (r == 0) r = gemm_launch(gp, gp.p, 0, 0);
+  if (r == 0) r = gemm_launch(gp, gp.p, 0, 0);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < iters && r == 0; ++i) r = gemm_launch(gp, gp.p, 0, 0);
+  cudaEventRecord(e1, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(as); cudaFree(ws); cudaFree(bias); cudaFree(out);
+  if (r != 0) return r;
+  DEXB_CHECK(e == cudaSuccess, "gemm_bench: kernel failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float* out_dev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DEXB_CHECK(qkv_dev != nullptr && out_dev != nullptr && B >= 1 && N >= 1, "attn_test: bad argument");

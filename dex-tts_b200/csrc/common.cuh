@@ -61,6 +61,38 @@ __device__ __forceinline__ void load_split8(const bf16* hi_ptr, const bf16* lo_p
   for (int i = 0; i < 8; ++i) v[i] = join2(h[i], l[i]);
 }
 
+// ---- 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): the GEMM epilogue is bound by the number of
+// store instructions a warp has in flight, so 32 B per lane halves its cost.  Pointers must be 32 B aligned.
+__device__ __forceinline__ void st256_f32(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld256_f32(const float* p, float* v) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p)
+               : "memory");
+}
+// 16 consecutive values -> 16 hi (32 B) + 16 lo (32 B)
+__device__ __forceinline__ void store_split16(bf16* hi_ptr, bf16* lo_ptr, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - __uint_as_float(hb << 16), v[2 * i + 1] - __uint_as_float(hb & 0xffff0000u));
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(hi_ptr), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]),
+               "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7])
+               : "memory");
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(lo_ptr), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]),
+               "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7])
+               : "memory");
+}
+
 // ---- activations (accurate; never compile this project with --use_fast_math) --------------------
 // Mish(x) = x * tanh(softplus(x)); with w = e^x, tanh(log(1+w)) = w(w+2) / (w(w+2) + 2): one exp, one divide,
 // no cancellation.  torch's softplus switches to identity above 20, where tanh(x) == 1 in fp32 anyway.

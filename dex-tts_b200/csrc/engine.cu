@@ -536,12 +536,15 @@ static int build_plans(dexb_handle* h) {
   for (int i = 0; i < c.depth; ++i) {
     DitBlockW& k = h->blocks[i];
     {
-      GemmParams p = gp_base(c);                      // qkv -> split rows [hi(3*hid) | lo(3*hid)]
-      gp_geom(p, 1, 1, (int)M);
+      GemmParams p = gp_base(c);                      // qkv: q,k -> split rows [hi(3*hid) | lo(3*hid)], v -> transposed
+      gp_geom(p, B, 1, N);                            // per-image geometry: the V^T store needs (image, token)
       gp_a(p, h->hS, 2 * hid, 0, hid, hid);
       gp_b(p, k.qkv_w, hid, 3 * hid);
       p.epi.bias = k.qkv_b;
       gp_out_s(p, h->qk, 6 * hid, 0, 3 * hid);
+      p.epi.out_s_ncols = 2 * hid;
+      p.epi.out_vt = h->vT; p.epi.out_vt_zstride = (long)hd * 2 * NP; p.epi.out_vt_rstride = 2L * NP;
+      p.epi.out_vt_lo = NP; p.epi.out_vt_hd = hd; p.epi.out_vt_heads = c.heads;
       DEXB_TRY(plan_shared(&k.qkv, p));
     }
     {
@@ -840,7 +843,6 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     DitBlockW& k = h->blocks[i];
     const float* m = mod + (long)i * 6 * hid;
     GEMM(k.qkv, k.qkv.p);
-    LAUNCH(launch_transpose_v(h->qk, 6L * hid, 2 * hid, 5 * hid, h->vT, B, N, h->NP, hid, hid / c.heads, st));
     if (h->fused_attn) {
       if (h->prof) prof_begin(h, "attn_fwd_kernel", attn_flop(h->attn), st);
       DEXB_TRY(attn_launch(h->attn, st));

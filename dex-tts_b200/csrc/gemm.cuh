@@ -67,7 +67,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
     for (int i = 0; i < NV; ++i) r[i] = 0.f;
     if (e.resid_f32 != nullptr) {
       const float* rp = e.resid_f32 + row * e.resid_f32_stride + nc0;
-      if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      if (NV % 8 == 0 && full && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0)) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 8) ld256_f32(rp + i, &r[i]);
+      } else if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
         for (int i = 0; i < NV; i += 4) {
           const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
@@ -130,7 +133,10 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
   if (!valid) return;
   if (e.out_f32 != nullptr) {
     float* op = e.out_f32 + row * e.out_f32_stride + e.out_f32_col + nc0;
-    if (n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+    if (NV % 8 == 0 && n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 31) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 8) st256_f32(op + i, &v[i]);
+    } else if (n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
@@ -141,8 +147,12 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
   if (e.out_s != nullptr && n0 < e.out_s_ncols) {
     bf16* hp = e.out_s + row * e.out_s_stride + e.out_s_hi + nc0;
     bf16* lp = e.out_s + row * e.out_s_stride + e.out_s_lo + nc0;
-    if (n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) &&
-        ((reinterpret_cast<uintptr_t>(lp) & 15) == 0)) {
+    if (NV % 16 == 0 && n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) &&
+        ((reinterpret_cast<uintptr_t>(lp) & 31) == 0)) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 16) store_split16(hp + i, lp + i, &v[i]);
+    } else if (n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) &&
+               ((reinterpret_cast<uintptr_t>(lp) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) store_split8(hp + i, lp + i, &v[i]);
     } else {
@@ -174,10 +184,38 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Note on store coalescing (measured, profiles/r01_epilogue_experiments.md): tcgen05.ld hands every thread one ROW of
+// the tile, so a warp-level float4 store touches 32 different cache lines.  Transposing each 32x32 chunk through shared
+// memory so that lane = column (128 contiguous bytes per warp store) was 4-5x SLOWER: it needs 4x as many store
+// instructions, and the epilogue is bound by the number of store instructions a warp can have in flight, not by
+// sectors.  The engine therefore keeps the row-per-thread 16 B stores and doubles the number of epilogue warps instead.
+// ------------------------------------------------------------------------------------------------
+// V of the attention, stored transposed (vT[img][head][d][token]) from the row-per-thread registers: consecutive lanes
+// hold consecutive tokens, so every store of the warp is one contiguous 64 B run.  A 32-column chunk never straddles heads.
+__device__ __forceinline__ void epi_store_vt(const EpiParams& e, int N, int z, int nheads, long token, bool valid, int n0,
+                                             const float (&v)[32]) {
+  if (!valid) return;
+  const int img = z / nheads;
+  const int c0 = n0 - e.out_s_ncols;
+  const int hd_i = c0 / e.out_vt_hd, d0 = c0 % e.out_vt_hd;
+  bf16* base = e.out_vt + ((long)img * e.out_vt_heads + hd_i) * e.out_vt_zstride + (long)d0 * e.out_vt_rstride + token;
+  const float* bp = (e.bias != nullptr) ? e.bias + n0 : nullptr;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (n0 + i < N) {
+      const float x = v[i] * e.alpha + (bp != nullptr ? __ldg(bp + i) : 0.f);
+      bf16* q = base + (long)i * e.out_vt_rstride;
+      split2(x, q[0], q[e.out_vt_lo]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 engine
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcBlockM = 128;
-constexpr int kTcThreads = 192;                // warp 0: TMA, warp 1: MMA (+TMEM alloc), warps 2..5: epilogue
+constexpr int kTcThreads = 320;                // warp 0: TMA, warp 1: MMA (+TMEM alloc), warps 2..9: epilogue
+constexpr int kTcEpiThreads = 256;             // two warps per TMEM lane group, alternating 32-column chunks
 
 template <int BLOCK_N>
 struct TcSmem {
@@ -231,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kTcEpiThreads); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -285,6 +323,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
+          if (!(p.dbg & 2)) {
           const uint32_t a_hi = ptx::smem_u32(smem + s * SM::kStageBytes);
           const uint32_t a_lo = a_hi + SM::kABytes;
           const uint32_t b_hi = a_hi + 2 * SM::kABytes;
@@ -302,6 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
             }
           }
+          }
           ptx::mma_commit(&empty_bar[s]);                    // frees the smem stage when these MMAs retire
           if (it == nk - 1) ptx::mma_commit(&acc_full[buf]); // accumulator complete
         }
@@ -310,31 +350,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    const int lg = warp & 3;                                 // TMEM lane group this warp may read
+    // 8 warps: lane group lg = warp & 3 (the TMEM lanes a warp may touch); the two warps of a lane group take the
+    // even / odd 32-column chunks, which doubles the number of global stores in flight per tile.
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;                            // row of the tile
     int li = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
       const int buf = li & 1;
-      ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
-      ptx::tc_fence_after();
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
       const bool valid = (ch < p.CH) && (cw < p.CW);
       const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
+      ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
+      ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BLOCK_N);
       constexpr int NCH = BLOCK_N / 32;
+      // chunks this warp owns: c = half, half + 2, ... while n0 + 32 c < N
+      int nmine = 0;
+      for (int c = half; c < NCH && tl.n0 + c * 32 < p.N; c += 2) ++nmine;
+      if (nmine == 0) {
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acc_empty[buf]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const bool live = tl.n0 + c * 32 < p.N;
+      for (int k = 0; k < nmine; ++k) {
+        const int c = half + 2 * k;
         float v[32];
-        if (live) ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
-        if (c == NCH - 1 || tl.n0 + (c + 1) * 32 >= p.N) {   // last chunk read: hand the buffer back to the MMA warp
+        ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+        if (k == nmine - 1) {                                // last chunk read: hand the buffer back to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[buf]);
         }
-        if (!live) break;
-        epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, tl.n0 + c * 32, v);
-        if (tl.n0 + (c + 1) * 32 >= p.N) break;
+        if (!(p.dbg & 1)) {
+          const int n0c = tl.n0 + c * 32;
+          if (p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols)
+            epi_store_vt(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
+          else
+            epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v);
+        }
       }
     }
   }

@@ -67,6 +67,7 @@ struct GemmParams {
   int b_head_rows;             // extra B row offset per head
   int b_mode;                  // 0: shared weights, 1: per image (z / nheads), 2: per z
   int nsplit;                  // 3 = bf16x3 (default), 1 = hi*hi only
+  int dbg;                     // tuning aid (dexb_gemm_bench): bit 0 = skip the epilogue, bit 1 = skip the MMAs, bit 2 = skip TMA of A
   EpiParams epi;
   // raw views for the SIMT engine
   const bf16* A;

@@ -114,24 +114,46 @@ void launch_conv_in(const float* x, const float* mu, const float* mask, const St
 // ------------------------------------------------------------------------------------------------
 // GroupNorm-apply + Mish + mask (+ time bias | + residual) -> split-bf16.  8 channels per thread.
 // ------------------------------------------------------------------------------------------------
+// mean / rstd of the (at most two) images a 256-thread block touches, computed once per block from the double sums
+__device__ __forceinline__ void gn_block_stats(const double* __restrict__ stats, int B, int G, double n, int b0,
+                                               float (*s_mean)[8], float (*s_rstd)[8]) {
+  if (threadIdx.x < 2 * G) {
+    const int bi = threadIdx.x / G, g = threadIdx.x % G;
+    const int b = b0 + bi;
+    if (b < B) {
+      const double s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
+      const double mean_d = s / n;
+      double var_d = ss / n - mean_d * mean_d;
+      if (var_d < 0.) var_d = 0.;
+      s_mean[bi][g] = (float)mean_d;
+      s_rstd[bi][g] = (float)(1.0 / sqrt(var_d + 1e-5));
+    }
+  }
+  __syncthreads();
+}
+// Mish with fast intrinsics (ex2.approx / approximate divide: ~1e-6 relative, far inside the split-bf16 noise floor)
+__device__ __forceinline__ float mish_fast(float x) {
+  if (x > 20.f) return x;
+  const float w = __expf(x);
+  const float n = w * (w + 2.f);
+  return x * __fdividef(n, n + 2.f);
+}
+
 __global__ void __launch_bounds__(256) k_gn_apply(const GnApplyArgs a) {
+  __shared__ float s_mean[2][8], s_rstd[2][8];
   const int cpt = a.C / 8;                                   // threads per pixel
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)a.B * a.P * cpt;
+  const int gs = a.C / a.G;
+  const int b0 = (int)((blockIdx.x * (long)blockDim.x / cpt) / a.P);
+  gn_block_stats(a.stats, a.B, a.G, (double)a.P * gs, b0, s_mean, s_rstd);
   if (gid >= total) return;
   const int c0 = (int)(gid % cpt) * 8;
   const long pix = gid / cpt;                                // global pixel row
   const int b = (int)(pix / a.P);
   const int w = (int)((pix % a.P) % a.W);
-  const int gs = a.C / a.G;
   const int g = c0 / gs;
-  const double n = (double)a.P * gs;
-  const double s = a.stats[((long)b * a.G + g) * 2], ss = a.stats[((long)b * a.G + g) * 2 + 1];
-  const double mean_d = s / n;
-  double var_d = ss / n - mean_d * mean_d;
-  if (var_d < 0.) var_d = 0.;
-  const float mean = (float)mean_d;
-  const float rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+  const float mean = s_mean[b - b0][g], rstd = s_rstd[b - b0][g];
   const float m = a.mask[(long)b * a.mask_stride + w];
   const float* rp = a.raw + pix * a.C + c0;
   const float4 r0 = *reinterpret_cast<const float4*>(rp);
@@ -145,20 +167,34 @@ __global__ void __launch_bounds__(256) k_gn_apply(const GnApplyArgs a) {
     load_split8(q + a.resid_s.hi, q + a.resid_s.lo, res);
   } else if (a.resid_f != nullptr) {
     const float* q = a.resid_f + pix * a.resid_f_stride + c0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) res[i] = q[i] * m;
+    const float4 q0 = *reinterpret_cast<const float4*>(q);
+    const float4 q1 = *reinterpret_cast<const float4*>(q + 4);
+    res[0] = q0.x * m; res[1] = q0.y * m; res[2] = q0.z * m; res[3] = q0.w * m;
+    res[4] = q1.x * m; res[5] = q1.y * m; res[6] = q1.z * m; res[7] = q1.w * m;
   } else if (a.rin_w != nullptr) {
     // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
     const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
 #pragma unroll
     for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
   }
+  float ga[8], be[8], tb[8];
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
+    const float4 b0v = __ldg(reinterpret_cast<const float4*>(a.beta + c0)), b1v = __ldg(reinterpret_cast<const float4*>(a.beta + c0 + 4));
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0v.x; be[1] = b0v.y; be[2] = b0v.z; be[3] = b0v.w; be[4] = b1v.x; be[5] = b1v.y; be[6] = b1v.z; be[7] = b1v.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tb[i] = 0.f;
+    if (a.tbias != nullptr) {
+      const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0)), t1 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0 + 4));
+      tb[0] = t0.x; tb[1] = t0.y; tb[2] = t0.z; tb[3] = t0.w; tb[4] = t1.x; tb[5] = t1.y; tb[6] = t1.z; tb[7] = t1.w;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    float y = (v[i] - mean) * rstd * a.gamma[c] + a.beta[c];
-    y = mish_f(y) * m;
-    if (a.tbias != nullptr) y = (y + a.tbias[c]) * m;
+    float y = (v[i] - mean) * rstd * ga[i] + be[i];
+    y = mish_fast(y) * m;
+    y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
     v[i] = y + res[i];
   }
   bf16* op = a.out.p + pix * a.out.stride + c0;
@@ -188,17 +224,15 @@ __global__ void __launch_bounds__(256) k_gn_final(const float* __restrict__ raw,
   const int c0 = (int)(gid % cpt) * 8;
   const int b = (int)(pix / P);
   const int w = (int)((pix % P) % W);
+  __shared__ float s_mean[2][8], s_rstd[2][8];
+  const int b0 = (int)((blockIdx.x * (long)blockDim.x / cpt) / P);
+  gn_block_stats(stats, B, G, (double)P * (C / G), b0, s_mean, s_rstd);
   float part = 0.f;
   float m = 0.f;
   if (active) {
     const int gs = C / G;
     const int g = c0 / gs;
-    const double n = (double)P * gs;
-    const double s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
-    const double mean_d = s / n;
-    double var_d = ss / n - mean_d * mean_d;
-    if (var_d < 0.) var_d = 0.;
-    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    const float mean = s_mean[b - b0][g], rstd = s_rstd[b - b0][g];
     m = mask[(long)b * W + w];
     const float* rp = raw + pix * C + c0;
     const float4 r0 = *reinterpret_cast<const float4*>(rp);
@@ -207,7 +241,7 @@ __global__ void __launch_bounds__(256) k_gn_final(const float* __restrict__ raw,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = c0 + i;
-      const float y = mish_f((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
+      const float y = mish_fast((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
       part = fmaf(fc_w[c], y * m, part);
     }
   }

@@ -24,6 +24,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- explicit shared-memory accesses
+// (a generic pointer into shared memory makes the compiler emit generic LD/ST, which it must order against every
+//  global store -- inside an epilogue loop that serialises each iteration on the previous iteration's STG)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v)); }
+__device__ __forceinline__ void sts_b32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v)); }
+__device__ __forceinline__ void sts_b64(uint32_t addr, uint64_t v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v)); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint32_t lds_b32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint64_t lds_b64(uint32_t addr) { uint64_t v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr)); return v; }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

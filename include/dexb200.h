@@ -92,6 +92,11 @@ int dexb_denoise_once(dexb_handle* h, const float* x_dev, const float* mu_dev, c
 int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, int W, int K, const float* w_dev, int N,
                    int KH, int KW, int offH, int offW, int in_stride, const float* bias_dev, float* out_dev, void* stream);
 
+/* Tuning aid: time `iters` launches of the tcgen05 implicit-GEMM engine on a synthetic problem of the given shape
+ * (out_mode 0 = fp32 rows, 1 = split-bf16 rows; dbg bit 0 skips the epilogue, bit 1 the MMAs).  Allocates, synchronises. */
+int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, int KW, int offH, int offW, int in_stride,
+                    int out_mode, int dbg, int iters, float* ms_out);
+
 /* Unit parity of the fused attention kernel (timm Attention inside DiTBlock, DEX-TTS/model/dit.py:270,282):
  * qkv_dev (B, N, 3*hid) fp32 = output of the qkv Linear -> out_dev (B, N, hid) = softmax(q k^T / sqrt(hd)) v, heads
  * concatenated (before the proj Linear).  Allocates scratch and synchronises (test entry). */
