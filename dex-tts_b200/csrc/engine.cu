@@ -377,13 +377,13 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
     la->ctx = ar.get<float>((long)B * 4 * 32 * 32);
     la->ssum = ar.get<float>((long)B * 128);
   }
-  h->pe = ar.get<float>((long)B * h->Wq * hid);
   h->zero_base = ar.base + z0;
   h->zero_bytes = ((ar.off - z0) + 15) & ~(size_t)15;
   for (LinAttW* la : las) {
     la->weff = ar.get<bf16>((long)B * la->C * 2 * la->C);
     la->beff = ar.get<float>((long)B * la->C);
     la->m1 = ar.get<float>((long)B * 128 * la->C);
+    la->part = ar.get<float>((long)B * la_ctx_blocks(B, la == &h->la0 ? h->H0 * h->W0 : h->H1 * h->W1) * 4224);
   }
   // tables
   h->t_init = ar.get<float>((long)steps * d); h->t_hid = ar.get<float>((long)steps * 4 * d);
@@ -419,6 +419,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->cat = ar.get<bf16>(P1 * 4 * mid);
   h->tokS = ar.get<bf16>(M * 2 * mid);
   h->xe = ar.get<float>(M * hid);
+  h->pe = ar.get<float>(M * hid);                       // GELU(pos_conv) per grid position; averaged over freq downstream
   h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
   h->xtok = ar.get<float>(M * hid);
   h->hS = ar.get<bf16>(M * 2 * hid);
@@ -524,7 +525,7 @@ static int build_plans(dexb_handle* h) {
     p.tap_sw = 2;
     p.epi.bias = h->posconv_b; p.epi.bias_head_stride = cg;
     p.epi.act = 1;
-    p.epi.colmean = h->pe; p.epi.colmean_ld = hid; p.epi.colmean_scale = 1.f / (float)Fq;
+    gp_out_f(p, h->pe, hid);                       // mean over the frequency axis is taken in tok_assemble (fixed order)
     p.epi.o_head_stride = cg;
     DEXB_TRY(plan_shared(&h->g_posconv, p));
   }
@@ -758,7 +759,7 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
 static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
   GEMM(la.kv, la.kv.p);
   LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
-  LAUNCH(launch_la_ctx(h->kv, la.kmax, la.ctx, la.ssum, h->B, P, st));
+  LAUNCH(launch_la_ctx(h->kv, la.kmax, la.part, la.ctx, la.ssum, h->B, P, st));
   LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.m1, la.weff, la.beff, h->B, la.C, st));
   GEMM(la.apply, la.apply.p);
   return 0;

@@ -55,7 +55,7 @@ struct LinAttW {
   int C = 0;
   GemmPlan kv, apply;
   unsigned* kmax = nullptr;           // [B][128]
-  float *ctx = nullptr, *ssum = nullptr, *beff = nullptr, *m1 = nullptr;
+  float *ctx = nullptr, *ssum = nullptr, *beff = nullptr, *m1 = nullptr, *part = nullptr;
   bf16* weff = nullptr;               // [B][C][hi(C)|lo(C)]
 };
 

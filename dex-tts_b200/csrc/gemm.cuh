@@ -25,9 +25,11 @@ namespace dexb {
 // Epilogue shared by both engines: one output row, NV consecutive columns starting at n0.
 // Must be called by all 32 lanes of a warp with the same n0 (it shuffles); `valid` masks stores.
 // ------------------------------------------------------------------------------------------------
+// `gacc` (optional): per-thread GroupNorm partial sums [NV/8][2] that the caller keeps across tiles of one image and
+// flushes with epi_flush_gn -- 17x fewer double atomics (and no shuffles per tile) than accumulating per tile.
 template <int NV>
 __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int nheads, int oh, int ow, int OH, int OW,
-                                          bool valid, int n0, float (&v)[NV]) {
+                                          bool valid, int n0, float (&v)[NV], float* gacc = nullptr) {
   // Every branch below is warp-uniform and taken once per NV-column chunk; the per-element loops are branch-free
   // (a first version tested the optional features per element and was instruction-issue bound: ~45 SASS instructions
   // per output element, 20 % of the stalls on instruction fetch -- profiles/r01_ncu_gemm_v1.md).
@@ -110,7 +112,18 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] *= rm;
   }
-  if (e.gn_stats != nullptr) {
+  if (e.gn_stats != nullptr && gacc != nullptr) {
+    if (valid) {
+#pragma unroll
+      for (int g0 = 0; g0 < NV; g0 += 8) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s += v[g0 + i]; ss = fmaf(v[g0 + i], v[g0 + i], ss); }
+        gacc[(g0 >> 3) * 2] += s;
+        gacc[(g0 >> 3) * 2 + 1] += ss;
+      }
+    }
+  } else if (e.gn_stats != nullptr) {
     // per-(image, group) sum / sum-of-squares: thread-local over its channels, warp-shuffle over the 32 rows
     // of this warp (all rows of a tile belong to one image), one double atomic per (warp, group).
     const int gs = e.gn_gs;
@@ -206,6 +219,29 @@ __device__ __forceinline__ void epi_store_vt(const EpiParams& e, int N, int z, i
       const float x = v[i] * e.alpha + (bp != nullptr ? __ldg(bp + i) : 0.f);
       bf16* q = base + (long)i * e.out_vt_rstride;
       split2(x, q[0], q[e.out_vt_lo]);
+    }
+  }
+}
+
+// Flush the deferred GroupNorm partial sums of one warp: gacc[k][g][2] for the warp's k-th chunk (columns n0 = 64 k +
+// 32 half when there is a single n-tile) -> warp reduction -> one double atomic per (warp, 8-column group).
+template <int MAXCH>
+__device__ __forceinline__ void epi_flush_gn(const EpiParams& e, int N, int img, int half, float (&gacc)[MAXCH][8]) {
+  const int gs = e.gn_gs;
+#pragma unroll
+  for (int k = 0; k < MAXCH; ++k) {
+    const int n0 = (half + 2 * k) * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float s = warp_sum(gacc[k][g * 2]);
+      const float ss = warp_sum(gacc[k][g * 2 + 1]);
+      gacc[k][g * 2] = 0.f;
+      gacc[k][g * 2 + 1] = 0.f;
+      if ((threadIdx.x & 31) == 0 && n0 + g * 8 < N) {
+        double* dst = e.gn_stats + ((long)img * (N / gs) + (n0 + g * 8) / gs) * 2;
+        atomicAdd(dst, (double)s);
+        atomicAdd(dst + 1, (double)ss);
+      }
     }
   }
 }
@@ -355,10 +391,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;                            // row of the tile
+    constexpr int MAXCH = (BLOCK_N / 32 + 1) / 2;            // chunks one warp owns per tile
+    const bool defer_gn = p.epi.gn_stats != nullptr && ntn == 1 && p.nheads == 1;
+    float gacc[MAXCH][8];
+#pragma unroll
+    for (int k = 0; k < MAXCH; ++k)
+#pragma unroll
+      for (int g = 0; g < 8; ++g) gacc[k][g] = 0.f;
+    int gn_img = -1;                                         // image the deferred sums belong to
     int li = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
       const int buf = li & 1;
+      if (defer_gn && tl.z != gn_img) {
+        if (gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, gacc);
+        gn_img = tl.z;
+      }
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
       const bool valid = (ch < p.CH) && (cw < p.CW);
       const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
@@ -387,10 +435,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols)
             epi_store_vt(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
           else
-            epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v);
+            epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, defer_gn ? &gacc[k][0] : nullptr);
         }
       }
     }
+    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, gacc);
   }
   ptx::tc_fence_before();
   __syncthreads();

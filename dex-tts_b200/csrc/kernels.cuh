@@ -56,8 +56,9 @@ void launch_gn_final(const float* raw, int C, int G, const double* stats, const 
 
 // LinearAttention pieces (kv = F[M][256] = [k(128) | v(128)])
 void launch_la_colmax(const float* kv, unsigned* kmax_enc /*[B][128]*/, int B, int P, cudaStream_t st);
-void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx /*[B][4][32][32]*/, float* ssum /*[B][128]*/,
-                   int B, int P, cudaStream_t st);
+int la_ctx_blocks(int B, int P);                      // pixel blocks per image of launch_la_ctx (sizes `part`)
+void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part /*[B][blocks][4224] scratch*/,
+                   float* ctx /*[B][4][32][32]*/, float* ssum /*[B][128]*/, int B, int P, cudaStream_t st);
 // W_eff[b] = I + g * W_out * ctxn^T * W_q  -> packed split weights [B][C][hi(C)|lo(C)], beff[b] = g * b_out
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq /*[128][C]*/, const float* wout /*[C][128]*/,
                     const float* bout, const float* g, float* m1 /*[B][128][C] scratch*/, bf16* weff, float* beff, int B,
@@ -84,7 +85,7 @@ void launch_dw_patch(const float* tv, const double* stats, const float* tiv_scal
 void launch_dw_patch_s(SView in, const float* dw_w, const float* dw_b, SView out, int B, int H, int W, int C, int p,
                        int s, int Fq, int Wq, cudaStream_t st);
 
-// tokens: x = xe + pe[b][w] + fpos[h]  (F), and LN+modulate -> S
+// tokens: x = xe + mean_h'(pg[b][h'][w]) + fpos[h]  (F), and LN+modulate -> S   (pg = GELU(pos_conv) per grid row)
 void launch_tok_assemble(const float* xe, const float* pe, const float* fpos /*[Fq][D]*/, float* x, const float* shift,
                          const float* scale, SView out, int B, int Fq, int Wq, int D, cudaStream_t st);
 void launch_ln_mod(const float* x, const float* shift, const float* scale, SView out, long M, int D, cudaStream_t st);

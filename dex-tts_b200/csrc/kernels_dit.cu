@@ -240,7 +240,13 @@ __global__ void __launch_bounds__(256) k_tok_assemble(const float* __restrict__ 
   for (int g = 0; g < PER_LANE; g += 4) {
     const int c = (g / 4) * 128 + lane * 4;
     const float4 a = *reinterpret_cast<const float4*>(xe + row * D + c);
-    const float4 p = *reinterpret_cast<const float4*>(pe + ((long)b * Wq + wq) * D + c);
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int hh = 0; hh < Fq; ++hh) {                      // mean over the frequency axis (dit.py:445), fixed order
+      const float4 q = *reinterpret_cast<const float4*>(pe + (((long)b * Fq + hh) * Wq + wq) * D + c);
+      p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+    }
+    const float inv_fq = 1.f / (float)Fq;
+    p.x *= inv_fq; p.y *= inv_fq; p.z *= inv_fq; p.w *= inv_fq;
     const float4 f = *reinterpret_cast<const float4*>(fpos + (long)hq * D + c);
     v[g] = (a.x + p.x) + f.x; v[g + 1] = (a.y + p.y) + f.y; v[g + 2] = (a.z + p.z) + f.z; v[g + 3] = (a.w + p.w) + f.w;
     *reinterpret_cast<float4*>(x + row * D + c) = make_float4(v[g], v[g + 1], v[g + 2], v[g + 3]);

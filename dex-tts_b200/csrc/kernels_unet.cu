@@ -301,8 +301,9 @@ void launch_la_colmax(const float* kv, unsigned* kmax_enc, int B, int P, cudaStr
 // One block (256 threads) = one (b, pixel chunk), all 4 heads: the full 1 KiB kv row of every pixel is read once,
 // coalesced; thread (h, dq, eq) keeps a 4x4 register block of the 32x32 context of head h (16 FMA per 2 LDS.128).
 constexpr int kLaTile = 32;
+constexpr int kLaPartial = 4096 + 128;       // one block's partial: ctx[4][32][32] | ssum[128]
 __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, const unsigned* __restrict__ kmax,
-                                                float* __restrict__ ctx, float* __restrict__ ssum, int P, int chunk) {
+                                                float* __restrict__ part, int P, int chunk) {
   __shared__ __align__(16) float ps[kLaTile][128];
   __shared__ __align__(16) float vs[kLaTile][128];
   const int b = blockIdx.y;
@@ -354,20 +355,39 @@ __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, co
       }
     }
   }
+  // per-block partial sums, reduced in a fixed order by k_la_reduce: deterministic (fp32 atomics made the whole
+  // trajectory vary by ~5e-5 from run to run) and no contention on the 4224 addresses of an image
+  float* pb = part + ((long)b * gridDim.x + blockIdx.x) * kLaPartial;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float* cp = ctx + (((long)b * 4 + h) * 32 + dq * 4 + i) * 32 + eq * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(cp + j, acc[i][j]);
-    if (eq == 0) atomicAdd(&ssum[b * 128 + d0 + i], sacc[i]);
+    *reinterpret_cast<float4*>(pb + ((h * 32 + dq * 4 + i) * 32 + eq * 4)) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (eq == 0) pb[4096 + d0 + i] = sacc[i];
   }
 }
-void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* ctx, float* ssum, int B, int P, cudaStream_t st) {
-  // enough blocks to fill the machine a few times over, each long enough to amortise its 1040 atomics
+// ctx[b][4096] | ssum[b][128]  =  sum over the blocks of an image, in block order
+__global__ void __launch_bounds__(256) k_la_reduce(const float* __restrict__ part, float* __restrict__ ctx,
+                                                   float* __restrict__ ssum, int B, int nblk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * kLaPartial) return;
+  const int b = i / kLaPartial, k = i % kLaPartial;
+  const float* p = part + (long)b * nblk * kLaPartial + k;
+  float a = 0.f;
+  for (int j = 0; j < nblk; ++j) a += p[(long)j * kLaPartial];
+  if (k < 4096) ctx[(long)b * 4096 + k] = a;
+  else ssum[b * 128 + (k - 4096)] = a;
+}
+int la_ctx_blocks(int B, int P) {
   int chunk = 512;
   while (chunk > 128 && (long)cdiv(P, chunk) * B < 2 * 148) chunk >>= 1;
-  dim3 grid(cdiv(P, chunk), B);
-  k_la_ctx<<<grid, 256, 0, st>>>(kv, kmax_enc, ctx, ssum, P, chunk);
+  return cdiv(P, chunk);
+}
+void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float* ctx, float* ssum, int B, int P,
+                   cudaStream_t st) {
+  const int nblk = la_ctx_blocks(B, P);
+  const int chunk = cdiv(cdiv(P, nblk), kLaTile) * kLaTile;
+  dim3 grid(nblk, B);
+  k_la_ctx<<<grid, 256, 0, st>>>(kv, kmax_enc, part, P, chunk);
+  k_la_reduce<<<cdiv((long)B * kLaPartial, 256), 256, 0, st>>>(part, ctx, ssum, B, nblk);
 }
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]

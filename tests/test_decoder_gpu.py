@@ -89,8 +89,11 @@ def test_host_entry_point_equals_device_entry_point(path):
     x0 = inp["z"] / float(g["temperature"]) + inp["mu"]
     y_dev = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
     y_host = eng.sample_host(x0, inp["mask"], inp["mu"], steps, cond=cond)
-    # atomics make GroupNorm sums order-dependent: equal up to fp32 reassociation noise
-    assert per_bin_violation(y_host, y_dev) < 1e-4
+    # the pipeline is deterministic (fixed-order reductions; the only atomics left add fp32 partials in double precision):
+    # both entry points run the same graph and must agree bit for bit
+    assert torch.equal(y_host, y_dev)
+    y_dev2 = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
+    assert torch.equal(y_dev2, y_dev)
 
 
 def test_tcgen05_takes_every_gemm():
