@@ -138,7 +138,7 @@ int dexb_simt_fallbacks(const dexb_handle* h) {
   for (int i = 0; i < 3; ++i) { chk(las[i]->kv); chk(las[i]->apply); }
   chk(h->g_down);
   for (int i = 0; i < 4; ++i) chk(h->g_up[i]);
-  if (h->cfg.variant == 1) { chk(h->g_tvs); chk(h->g_tvo); }
+  if (h->cfg.variant == 1 && !h->fused_tv) { chk(h->g_tvs); chk(h->g_tvo); }
   chk(h->g_pe); chk(h->g_posconv); chk(h->g_final); chk(h->fin.conv);
   for (const auto& k : h->blocks) { chk(k.qkv); chk(k.scores); chk(k.pv); chk(k.proj); chk(k.fc1); chk(k.fc2); }
   return n;

@@ -11,6 +11,7 @@
 #include "attn.cuh"
 
 #include <cudaTypedefs.h>
+#include <string.h>
 
 #include "ptx.cuh"
 
@@ -37,8 +38,7 @@ constexpr uint32_t kTmPh = 384;     // 32      P hi: 64 bf16 per row
 constexpr uint32_t kTmPl = 416;     // 32      P lo
 
 __global__ void __launch_bounds__(kAtThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -59,7 +59,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nt = p.nt;
 
   if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(q_full, 256);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 256);
@@ -78,7 +78,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      const int kcol = p.hid + head * kAtHD, lo = 3 * p.hid;
+      const int kcol = p.k_hi + head * kAtHD, lo = p.k_lo - p.k_hi;
       for (int it = 0; it < 2 * nt; ++it) {
         const int s = it % kAtStages;
         const uint32_t ph = (it / kAtStages) & 1;
@@ -94,7 +94,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int kc = 0; kc < 2; ++kc)
               ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
           for (int part = 0; part < 2; ++part)
-            ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.NP + j * kAtBN, head * kAtHD, b);
+            ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
         }
       }
     }
@@ -170,12 +170,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // stage this thread's half of the query row (64 of the 128 head dims, hi and lo) into tensor memory
       uint32_t qh[32], ql[32];
       const int row = m0 + r;
-      if (row < p.N) {
-        const bf16* qp = p.qkv + ((long)b * p.N + row) * (6L * p.hid) + head * kAtHD + hf * 64;
+      if (row < p.NQ) {
+        const bf16* qp = p.q + ((long)b * p.NQ + row) * p.q_stride + head * kAtHD + hf * 64;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const uint4 a = *reinterpret_cast<const uint4*>(qp + i * 8);
-          const uint4 c = *reinterpret_cast<const uint4*>(qp + 3 * p.hid + i * 8);
+          const uint4 a = *reinterpret_cast<const uint4*>(qp + p.q_hi + i * 8);
+          const uint4 c = *reinterpret_cast<const uint4*>(qp + p.q_lo + i * 8);
           qh[i * 4] = a.x; qh[i * 4 + 1] = a.y; qh[i * 4 + 2] = a.z; qh[i * 4 + 3] = a.w;
           ql[i * 4] = c.x; ql[i * 4 + 1] = c.y; ql[i * 4 + 2] = c.z; ql[i * 4 + 3] = c.w;
         }
@@ -189,6 +189,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_before();
       ptx::mbar_arrive(q_full);
     }
+    // keys that take part: all NK, or only the visible ones of this image (TV adaptor)
+    const int nkv = (p.vis_len != nullptr) ? min(p.NK, p.vis_len[b] + 1) : p.NK;
+    const float* kb = (p.kbias != nullptr) ? p.kbias + (long)b * p.kbias_stride : nullptr;
     float v[32];
     float m = -INFINITY;
     for (int it = 0; it < nt; ++it) {
@@ -198,10 +201,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = p.N - it * kAtBN - hf * 32;
+      const int nvalid = nkv - it * kAtBN - hf * 32;
+      if (kb != nullptr) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < nvalid) m = fmaxf(m, v[c]);
+        for (int c = 0; c < 32; ++c)
+          if (c < nvalid) m = fmaxf(m, v[c] + __ldg(kb + it * kAtBN + hf * 32 + c));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < nvalid) m = fmaxf(m, v[c]);
+      }
     }
     // combine the two column halves of every row (named barrier over the 256 softmax threads only)
     xch[hf * 128 + r] = m;
@@ -217,7 +226,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = p.N - j * kAtBN - hf * 32;
+      const int nvalid = nkv - j * kAtBN - hf * 32;
+      if (kb != nullptr) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + j * kAtBN + hf * 32 + c);
+      }
       uint32_t hi2[16], lo2[16];
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
@@ -253,12 +266,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int c = 0; c < 2; ++c) {
       float o[32];
       ptx::tmem_ld32(tl + kTmO + hf * 64 + c * 32, o);
-      if (row < p.N) {
-        bf16* op = p.out + ((long)b * p.N + row) * p.out_stride + head * kAtHD + hf * 64 + c * 32;
+      if (row < p.NQ) {
+        const long grow = (long)b * p.NQ + row;
+        const int col = head * kAtHD + hf * 64 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
+        if (p.out_mode == 0) {
+          bf16* op = p.out + grow * p.out_stride + col;
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) store_split8(op + p.out_hi + i, op + p.out_lo + i, &o[i]);
+          for (int i = 0; i < 32; i += 16) store_split16(op + p.out_hi + i, op + p.out_lo + i, &o[i]);
+        } else {
+          const bf16* qp = p.q + grow * p.q_stride + col;          // residual = the query row itself
+          const float rm = (p.rowmask != nullptr) ? p.rowmask[(long)b * p.rowmask_w + row % p.rowmask_w] : 1.f;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float x[8];
+            load_split8(qp + p.q_hi + i, qp + p.q_lo + i, x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[i + k] = (x[k] + o[i + k]) * rm;
+          }
+          float* of = p.out_f + grow * p.out_f_stride + col;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) st256_f32(of + i, &o[i]);
+        }
       }
     }
   }
@@ -303,26 +333,51 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   DEXB_CHECK(hid / heads == kAtHD, "fused attention is instantiated for head dim %d", kAtHD);
   ap->B = B;
   AttnParams& p = ap->p;
-  p.N = N; p.NP = NP; p.nheads = heads; p.hid = hid;
+  memset(&p, 0, sizeof(p));
+  p.NQ = N; p.NK = N; p.KP = NP; p.nheads = heads;
   p.nt = (N + kAtBN - 1) / kAtBN;
+  p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid;
+  p.k_hi = hid; p.k_lo = 4 * hid;
   p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
-  p.qkv = qkv;
+  p.out_mode = 0;
   p.out = out; p.out_stride = 2L * hid; p.out_hi = 0; p.out_lo = hid;
   const cuuint64_t qrow = 6ull * hid * 2;
-  DEXB_TRY(enc3(&ap->tmQ, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBM, "Q"));
   DEXB_TRY(enc3(&ap->tmK, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBN, "K"));
   const cuuint64_t vrow = 2ull * NP * 2;
   DEXB_TRY(enc3(&ap->tmV, vT, 2ull * NP, (cuuint64_t)hid, (cuuint64_t)B, vrow, vrow * hid, 64, kAtHD, "V"));
   return 0;
 }
 
+int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* kq, const float* sbias,
+                      const bf16* vlt, const int* sty_len, float* out, const float* mask, int mask_w, int B, int P, int NK, int KP,
+                      int C) {
+  DEXB_CHECK(C == kAtHD, "fused TV attention is instantiated for %d channels", kAtHD);
+  DEXB_CHECK(KP % kAtBN == 0 && NK <= KP, "TV attention: key padding %d / %d", NK, KP);
+  ap->B = B;
+  AttnParams& p = ap->p;
+  memset(&p, 0, sizeof(p));
+  p.NQ = P; p.NK = NK; p.KP = KP; p.nheads = 1;
+  p.nt = (NK + kAtBN - 1) / kAtBN;
+  p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo;
+  p.k_hi = 0; p.k_lo = C;
+  p.scale_log2e = 1.4426950408889634f;              // 1/sqrt(C) is folded into the key matrix (k_tv_fold)
+  p.kbias = sbias; p.kbias_stride = KP; p.vis_len = sty_len;
+  p.out_mode = 1;
+  p.out_f = out; p.out_f_stride = C; p.rowmask = mask; p.rowmask_w = mask_w;
+  const cuuint64_t krow = 2ull * C * 2;
+  DEXB_TRY(enc3(&ap->tmK, kq, 2ull * C, (cuuint64_t)KP, (cuuint64_t)B, krow, krow * KP, 64, kAtBN, "TV K"));
+  const cuuint64_t vrow = 2ull * KP * 2;
+  DEXB_TRY(enc3(&ap->tmV, vlt, 2ull * KP, (cuuint64_t)C, (cuuint64_t)B, vrow, vrow * C, 64, kAtHD, "TV V"));
+  return 0;
+}
+
 int attn_launch(const AttnPlan& ap, cudaStream_t st) {
-  dim3 grid((unsigned)((ap.p.N + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
-  attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmQ, ap.tmK, ap.tmV, ap.p);
+  dim3 grid((unsigned)((ap.p.NQ + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
+  attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, ap.p);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-double attn_flop(const AttnPlan& ap) { return 4.0 * ap.B * ap.p.nheads * (double)ap.p.N * ap.p.N * kAtHD; }
+double attn_flop(const AttnPlan& ap) { return 4.0 * ap.B * ap.p.nheads * (double)ap.p.NQ * ap.p.NK * kAtHD; }
 
 }  // namespace dexb

@@ -7,25 +7,48 @@
 namespace dexb {
 
 struct AttnParams {
-  int N, NP;                 // tokens per sample, padded token count of the V^T rows
-  int nheads, hid;           // heads, hidden size (qkv rows are [hi(3*hid) | lo(3*hid)], q | k | v, head-major inside)
+  int NQ;                    // query rows per image
+  int NK;                    // keys per image
+  int KP;                    // padded key count: lo half of a V^T row starts at column KP
+  int nheads;
   int nt;                    // key tiles of 64
-  const bf16* qkv;           // the qkv rows themselves (Q is staged to tensor memory by the softmax warps)
-  float scale_log2e;         // hd^-0.5 * log2(e)
-  bf16* out;                 // split rows [hi(hid) | lo(hid)], head h at column h*hd
+  // Q rows (staged to tensor memory by the softmax warps): q + (b*NQ + row)*q_stride + head*128, hi at q_hi, lo at q_lo
+  const bf16* q;
+  long q_stride;
+  int q_hi, q_lo;
+  int k_hi, k_lo;            // columns of the K rows inside the tmK tensor (hi / lo), head h at + h*128
+  float scale_log2e;         // score scale * log2(e)
+  // optional (TV adaptor): additive per-key score bias [b][kbias_stride] and visible key count vis_len[b] + 1
+  // (keys beyond it carry -1e4 in the reference, ref_encoder.py:171 -- exactly zero weight after the softmax)
+  const float* kbias;
+  long kbias_stride;
+  const int* vis_len;
+  // epilogue: mode 0 = split rows (head h at column h*128); mode 1 = fp32 rows (O/l + the Q row as residual) * rowmask
+  int out_mode;
+  bf16* out;
   long out_stride;
   int out_hi, out_lo;
+  float* out_f;
+  long out_f_stride;
+  const float* rowmask;      // [b][rowmask_w], column = row % rowmask_w
+  int rowmask_w;
 };
 
 struct AttnPlan {
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmK, tmV;
   AttnParams p;
   int B;
 };
 
 int attn_global_init();
 bool attn_supported(int hd);
+// DiT self-attention over qkv rows [hi(3*hid) | lo(3*hid)] and V^T [b][hid][hi(NP)|lo(NP)] -> split rows `out`
 int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int B, int N, int NP, int heads, int hid);
+// TV adaptor cross-attention (single head, C = 128): queries = the split rows x (also the residual), keys kq [b][KP][hi(C)|lo(C)]
+// with score bias sbias [b][KP], values vlt [b][C][hi(KP)|lo(KP)], output fp32 rows (x + attn) * mask
+int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* kq, const float* sbias,
+                      const bf16* vlt, const int* sty_len, float* out, const float* mask, int mask_w, int B, int P, int NK, int KP,
+                      int C);
 int attn_launch(const AttnPlan& ap, cudaStream_t st);
 double attn_flop(const AttnPlan& ap);
 

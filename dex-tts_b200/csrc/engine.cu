@@ -476,6 +476,13 @@ static int build_plans(dexb_handle* h) {
   DEXB_TRY(plan_la(h, h->la1, h->C1, 2 * mid, 0, mid, H1, W1, h->mask1, h->cat, 4 * mid, mid, 3 * mid));
   if (dex) {
     {
+      const char* ea = getenv("DEXB_ATTN");
+      h->fused_tv = attn_supported(mid) && !(ea != nullptr && ea[0] == '0');
+      if (h->fused_tv)
+        DEXB_TRY(attn_plan_init_tv(&h->attn_tv, h->cat, 4L * mid, mid, 3 * mid, h->kq, h->sbias, h->vlt, h->sty_len, h->tvout,
+                                   h->mask1, W1, B, H1 * W1, h->NK, h->KP, mid));
+    }
+    {
       GemmParams p = gp_base(c);                      // S = x . KQ^T + sb      (ref_encoder.py:170)
       gp_geom(p, B, H1, W1);
       gp_a(p, h->cat, 4 * mid, mid, 3 * mid, mid);
@@ -820,9 +827,16 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     LAUNCH(launch_chan_stats_s(skip, h->cstats, B, P1, mid, st));
     LAUNCH(launch_tv_fold(h->kw, h->kw0 + (long)step * mid, h->cstats, P1, h->kq, h->sbias, B, h->NK, h->KP, mid, st));
     LAUNCH(launch_tv_vl0(h->vl0 + (long)step * mid, h->vlt, B, mid, h->KP, st));
-    GEMM(h->g_tvs, h->g_tvs.p);
-    LAUNCH(launch_tv_softmax(h->tvscores, h->KP, h->sty_len, h->tvP, B, P1, h->NK, h->KP, st));
-    GEMM(h->g_tvo, h->g_tvo.p);
+    if (h->fused_tv) {
+      if (h->prof) prof_begin(h, "attn_fwd_kernel(tv)", attn_flop(h->attn_tv), st);
+      DEXB_TRY(attn_launch(h->attn_tv, st));
+      if (h->prof) prof_end(h, st);
+      ++h->launches;
+    } else {
+      GEMM(h->g_tvs, h->g_tvs.p);
+      LAUNCH(launch_tv_softmax(h->tvscores, h->KP, h->sty_len, h->tvP, B, P1, h->NK, h->KP, st));
+      GEMM(h->g_tvo, h->g_tvo.p);
+    }
     // TIVAdaptor (AdaIN, ref_encoder.py:264-273) folded into the patch-embed front
     double* cs1 = h->cstats + (long)B * mid * 2;
     LAUNCH(launch_chan_stats_f(h->tvout, mid, cs1, B, P1, mid, st));

@@ -128,8 +128,8 @@ struct dexb_handle {
   int n_slots = 0;
   // plans of the non-block GEMMs
   dexb::GemmPlan g_down, g_up[4], g_tvs, g_tvo, g_pe, g_posconv, g_final;
-  dexb::AttnPlan attn;
-  bool fused_attn = false;
+  dexb::AttnPlan attn, attn_tv;
+  bool fused_attn = false, fused_tv = false;
   // CUDA graph of one whole trajectory
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
