@@ -287,7 +287,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const GemmParams p, const int total_tiles, const int ntn) {
   using SM = TcSmem<BLOCK_N>;
   constexpr int STAGES = SM::kStages;
-  constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;
+  // Stacked-N split product (BLOCK_N <= 128): B_hi and B_lo tiles are adjacent in shared memory, so ONE MMA with
+  // N = 2*BLOCK_N computes A_hi*B_hi (columns [0, BN)) and A_hi*B_lo (columns [BN, 2BN)); a second MMA adds A_lo*B_hi to
+  // the first half; the epilogue sums the halves.  An SS-mode MMA costs ~64-70 cycles for the 4 KiB A read regardless of
+  // N <= 128 (measured: tools/gemm_bench.py `mma-only`), so two MMAs instead of three is ~25-30 % less tensor time.
+  constexpr bool STACKED = BLOCK_N <= 128;
+  constexpr int ACC_COLS = STACKED ? 2 * BLOCK_N : BLOCK_N;          // TMEM columns of one accumulator buffer
+  constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::kStageBytes);
@@ -329,6 +335,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = it / kchunks, kc = it % kchunks;
           const int dy = tap / p.KW + p.offH, dx = (tap % p.KW) * p.tap_sw + p.offW;
           uint8_t* st = smem + s * SM::kStageBytes;
+          if (p.dbg & 4) { ptx::mbar_arrive(&full_bar[s]); continue; }   // tuning aid: no operand traffic at all
           ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
           const int acol = kc * kTcBlockK + tl.head * p.a_head_stride;
           const int bcol = kc * kTcBlockK + tl.head * p.b_head_stride;
@@ -346,13 +353,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kTcBlockM, BLOCK_N);
+    constexpr uint32_t idesc2 = ptx::make_idesc_bf16(kTcBlockM, STACKED ? 2 * BLOCK_N : BLOCK_N);
     uint32_t g = 0;
     int li = 0;                                              // local tile counter -> accumulator buffer li & 1
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const int buf = li & 1;
       ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * BLOCK_N);
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
       for (int it = 0; it < nk; ++it, ++g) {
         const int s = g % STAGES;
         const uint32_t ph = (g / STAGES) & 1;
@@ -369,12 +377,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t ko = kk * 32;                     // 16 bf16 = 32 B inside the 128 B swizzle span
             const uint64_t dah = ptx::make_desc_k128(a_hi + ko);
             const uint64_t dbh = ptx::make_desc_k128(b_hi + ko);
-            ptx::mma_bf16_ss(tacc, dah, dbh, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
             if (p.nsplit == 3) {
               const uint64_t dal = ptx::make_desc_k128(a_lo + ko);
-              const uint64_t dbl = ptx::make_desc_k128(b_lo + ko);
-              ptx::mma_bf16_ss(tacc, dah, dbl, idesc, 1u);
-              ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
+              if constexpr (STACKED) {
+                ptx::mma_bf16_ss(tacc, dah, dbh, idesc2, acc);            // [A_hi B_hi | A_hi B_lo]
+                ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);              //  + A_lo B_hi
+              } else {
+                const uint64_t dbl = ptx::make_desc_k128(b_lo + ko);
+                ptx::mma_bf16_ss(tacc, dah, dbh, idesc, acc);
+                ptx::mma_bf16_ss(tacc, dah, dbl, idesc, 1u);
+                ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
+              }
+            } else {
+              ptx::mma_bf16_ss(tacc, dah, dbh, idesc, acc);
             }
           }
           }
@@ -412,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
       ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * BLOCK_N);
+      const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ACC_COLS);
       constexpr int NCH = BLOCK_N / 32;
       // chunks this warp owns: c = half, half + 2, ... while n0 + 32 c < N
       int nmine = 0;
@@ -426,6 +442,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c = half + 2 * k;
         float v[32];
         ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+        if (STACKED && p.nsplit == 3) {                      // add the A_hi * B_lo half
+          float v2[32];
+          ptx::tmem_ld32(tacc + (uint32_t)(BLOCK_N + c * 32), v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        }
         if (k == nmine - 1) {                                // last chunk read: hand the buffer back to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[buf]);
