@@ -315,13 +315,14 @@ __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, co
   const int d0 = h * 32 + dq * 4, e0 = h * 32 + eq * 4;
   // loader: thread handles float4 column group lc4 (0..63: 0..31 = k, 32..63 = v) of rows lr, lr+4, ...
   const int lc4 = tid & 63, lr = tid >> 6;
-  float4 kmx = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float kLog2e = 1.4426950408889634f;
+  float4 kmx = make_float4(0.f, 0.f, 0.f, 0.f);           // column maxima, pre-multiplied by log2(e)
   if (lc4 < 32) {
     const unsigned* km = kmax + b * 128 + lc4 * 4;
-    kmx = make_float4(dec_ord(km[0]), dec_ord(km[1]), dec_ord(km[2]), dec_ord(km[3]));
+    kmx = make_float4(dec_ord(km[0]) * kLog2e, dec_ord(km[1]) * kLog2e, dec_ord(km[2]) * kLog2e, dec_ord(km[3]) * kLog2e);
   }
   float acc[4][4];
-  float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);          // loader threads: running sum of exp(k - max) of their 4 columns
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -335,7 +336,13 @@ __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, co
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
       if (pp < p1) {
         x = *reinterpret_cast<const float4*>(kv + ((long)b * P + pp) * 256 + lc4 * 4);
-        if (lc4 < 32) x = make_float4(expf(x.x - kmx.x), expf(x.y - kmx.y), expf(x.z - kmx.z), expf(x.w - kmx.w));
+        if (lc4 < 32) {                                   // exp(k - max) = exp2(k log2e - max log2e): one FFMA + one MUFU
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x.x) : "f"(fmaf(x.x, kLog2e, -kmx.x)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x.y) : "f"(fmaf(x.y, kLog2e, -kmx.y)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x.z) : "f"(fmaf(x.z, kLog2e, -kmx.z)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(x.w) : "f"(fmaf(x.w, kLog2e, -kmx.w)));
+          psum.x += x.x; psum.y += x.y; psum.z += x.z; psum.w += x.w;
+        }
       }
       if (lc4 < 32) *reinterpret_cast<float4*>(&ps[r][lc4 * 4]) = x;
       else *reinterpret_cast<float4*>(&vs[r][(lc4 - 32) * 4]) = x;
@@ -348,21 +355,22 @@ __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, co
       const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
       const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pp[i], vv[j], acc[i][j]);
-        sacc[i] += pp[i];
-      }
     }
   }
   // per-block partial sums, reduced in a fixed order by k_la_reduce: deterministic (fp32 atomics made the whole
   // trajectory vary by ~5e-5 from run to run) and no contention on the 4224 addresses of an image
   float* pb = part + ((long)b * gridDim.x + blockIdx.x) * kLaPartial;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(pb + ((h * 32 + dq * 4 + i) * 32 + eq * 4)) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if (eq == 0) pb[4096 + d0 + i] = sacc[i];
-  }
+  // column sums: the 4 loader rows (lr = 0..3) of a column group combine through shared memory in a fixed order
+  __syncthreads();
+  if (lc4 < 32) *reinterpret_cast<float4*>(&ps[lr][lc4 * 4]) = psum;
+  __syncthreads();
+  if (tid < 128) pb[4096 + tid] = ((ps[0][tid] + ps[1][tid]) + ps[2][tid]) + ps[3][tid];
 }
 // ctx[b][4096] | ssum[b][128]  =  sum over the blocks of an image, in block order
 __global__ void __launch_bounds__(256) k_la_reduce(const float* __restrict__ part, float* __restrict__ ctx,
