@@ -206,8 +206,8 @@ def main():
             stft_mel(audio_d, win_d, fb_d)
         y = eng.sample(x0_d, mask_d, mu_d, n_steps, cond=cond_d)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, y)        # the path's only collective: finished mels
-        return y
+            dist.all_gather_into_tensor(gathered, y)        # the path's only collective: finished mels (SURVEY.md 8e,
+        return y                                            # dexb200.parallel.gather_mels does the same for ragged shards)
 
     def barrier():
         if world > 1:

@@ -68,9 +68,9 @@ int dexb_finalize_weights(dexb_handle* h, void* stream) {
   return engine_finalize(h, (cudaStream_t)stream);
 }
 
-int dexb_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* workspace_bytes) {
+int dexb_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const float* sigmas_host, size_t* workspace_bytes) {
   DEXB_CHECK(h != nullptr, "null handle");
-  return engine_plan(h, B, T, Ts, n_steps, sigmas_host, workspace_bytes);
+  return engine_plan(h, B, T, Ts, Tr, n_steps, sigmas_host, workspace_bytes);
 }
 
 int dexb_reverse_diffusion(dexb_handle* h, float* x_inout_dev, const float* mu_dev, const float* mask_dev,
@@ -102,7 +102,7 @@ int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float
   memset(&cond, 0, sizeof(cond));
   if (h->cfg.variant == 1) {
     DEXB_CHECK(sty_host != nullptr && sty_len_host != nullptr && ref_skips_host != nullptr, "DEX-TTS needs conditioning");
-    DEXB_CHECK(Tr == h->Ts, "Tr %d != planned style length %d", Tr, h->Ts);
+    DEXB_CHECK(Tr == h->Tr, "Tr %d != planned reference length %d", Tr, h->Tr);
     DEXB_CUDA_OK(cudaMemcpyAsync(h->sty, sty_host, (long)h->B * mid * h->Ts * 4, cudaMemcpyHostToDevice, st));
     DEXB_CUDA_OK(cudaMemcpyAsync(h->sty_len, sty_len_host, (long)h->B * 4, cudaMemcpyHostToDevice, st));
     for (int l = 0; l < 6; ++l)

@@ -398,7 +398,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
     h->k0 = ar.get<float>((long)steps * mid); h->kw0 = ar.get<float>((long)steps * mid);
     h->v0 = ar.get<float>((long)steps * mid); h->vl0 = ar.get<float>((long)steps * mid);
     h->sty = ar.get<float>((long)B * mid * h->Ts); h->sty_len = ar.get<int>(B);
-    for (int i = 0; i < 6; ++i) h->refs[i] = ar.get<float>((long)B * mid * h->Ts);
+    for (int i = 0; i < 6; ++i) h->refs[i] = ar.get<float>((long)B * mid * h->Tr);
     h->ref_mean = ar.get<float>((long)B * 6 * mid); h->ref_std = ar.get<float>((long)B * 6 * mid);
     h->tiv_shift = ar.get<float>((long)steps * B * mid); h->tiv_scale = ar.get<float>((long)steps * B * mid);
     h->styT = ar.get<float>((long)B * h->Ts * mid);
@@ -690,7 +690,7 @@ static int build_tables(dexb_handle* h, cudaStream_t st) {
   return 0;
 }
 
-int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* ws_bytes) {
+int engine_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const float* sigmas_host, size_t* ws_bytes) {
   DEXB_CHECK(h->finalized, "dexb_plan: weights are not finalized");
   const dexb_config& c = h->cfg;
   DEXB_CHECK(B >= 1 && T >= 8 && T % 4 == 0, "dexb_plan: need B >= 1 and T a multiple of 4 (fix_len_compatibility), got B=%d T=%d", B, T);
@@ -700,7 +700,8 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* 
   DEXB_TRY(gemm_global_init());
   DEXB_TRY(kernels_global_init());
   DEXB_TRY(attn_global_init());
-  h->B = B; h->T = T; h->Ts = (c.variant == 1) ? Ts : 0; h->steps = n_steps;
+  DEXB_CHECK(c.variant == 0 || Tr >= 2, "dexb_plan: reference length must be >= 2, got %d", Tr);
+  h->B = B; h->T = T; h->Ts = (c.variant == 1) ? Ts : 0; h->Tr = (c.variant == 1) ? Tr : 0; h->steps = n_steps;
   h->H0 = c.n_feats; h->W0 = T; h->H1 = c.n_feats / 2; h->W1 = T / 2;
   const int p = c.patch, s = c.stride;
   const int wp = (h->W1 % p == 0) ? h->W1 : h->W1 + (p - h->W1 % p);
@@ -942,8 +943,7 @@ int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mas
   if (mask != h->mask0) DEXB_CUDA_OK(cudaMemcpyAsync(h->mask0, mask, (long)h->B * h->W0 * 4, cudaMemcpyDeviceToDevice, st));
   if (c.variant == 1) {
     DEXB_CHECK(cond != nullptr && cond->sty_dev != nullptr && cond->sty_len_dev != nullptr, "DEX-TTS needs conditioning");
-    DEXB_CHECK(cond->Tr == h->Ts, "this build expects ref skips of the style length (Tr %d != Ts %d)", cond->Tr, h->Ts);
-    h->Tr = cond->Tr;
+    DEXB_CHECK(cond->Tr == h->Tr, "ref skips have length %d but the plan was made for %d: call dexb_plan again", cond->Tr, h->Tr);
     if (cond->sty_dev != h->sty)
       DEXB_CUDA_OK(cudaMemcpyAsync(h->sty, cond->sty_dev, (long)h->B * mid * h->Ts * 4, cudaMemcpyDeviceToDevice, st));
     if (cond->sty_len_dev != h->sty_len)

@@ -144,7 +144,7 @@ struct dexb_handle {
 
 namespace dexb {
 int engine_finalize(dexb_handle* h, cudaStream_t st);
-int engine_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* ws_bytes);
+int engine_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const float* sigmas_host, size_t* ws_bytes);
 int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mask, const dexb_cond* cond,
                int only_step, float* den_out, cudaStream_t st);
 void engine_release_plan(dexb_handle* h);

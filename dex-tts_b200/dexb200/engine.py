@@ -79,14 +79,15 @@ class ReverseDiffusion:
         self.plan_key = None
 
     # ---- plan --------------------------------------------------------------------------------------
-    def plan(self, B, T, Ts, n_steps):
-        key = (int(B), int(T), int(Ts), int(n_steps))
+    def plan(self, B, T, Ts, n_steps, Tr=None):
+        Tr = Ts if Tr is None else Tr
+        key = (int(B), int(T), int(Ts), int(Tr), int(n_steps))
         if key == self.plan_key:
             return
         sig = edm_sigmas(n_steps).contiguous()
         self.sigmas = sig
         ws = ctypes.c_size_t(0)
-        _lib.check(self.L.dexb_plan(self.h, key[0], key[1], key[2], key[3],
+        _lib.check(self.L.dexb_plan(self.h, key[0], key[1], key[2], key[3], key[4],
                                     sig.numpy().ctypes.data_as(_lib.c_float_p), ctypes.byref(ws)), "dexb_plan")
         self.workspace_bytes = ws.value
         self.plan_key = key
@@ -112,7 +113,8 @@ class ReverseDiffusion:
         """x0 = z / temperature + mu (B,80,T) -> generated mel (B,80,T).  mask (B,1,T) or (B,T).  All CUDA fp32."""
         B, F, T = x0.shape
         Ts = cond["sty"].shape[-1] if self.cfg.variant == "dex" else 0
-        self.plan(B, T, Ts, n_steps)
+        Tr = cond["ref_skips"][0].shape[-1] if self.cfg.variant == "dex" else 0
+        self.plan(B, T, Ts, n_steps, Tr)
         x = x0.detach().float().contiguous().clone()
         mu = mu.detach().float().contiguous()
         m = mask.detach().float().reshape(B, T).contiguous()
@@ -127,7 +129,8 @@ class ReverseDiffusion:
         (host<->device copies happen inside the C call, which synchronises the stream)."""
         B, F, T = x0.shape
         Ts = cond["sty"].shape[-1] if self.cfg.variant == "dex" else 0
-        self.plan(B, T, Ts, n_steps)
+        Tr = cond["ref_skips"][0].shape[-1] if self.cfg.variant == "dex" else 0
+        self.plan(B, T, Ts, n_steps, Tr)
         x = x0.float().contiguous().clone()
         if x0.is_pinned():
             x = x.pin_memory()
@@ -153,7 +156,8 @@ class ReverseDiffusion:
         """D(x; sigma_step) of EDMPrecond (edm.py:88-98) for unit parity; x is the sampler state at that step."""
         B, F, T = x.shape
         Ts = cond["sty"].shape[-1] if self.cfg.variant == "dex" else 0
-        self.plan(B, T, Ts, n_steps)
+        Tr = cond["ref_skips"][0].shape[-1] if self.cfg.variant == "dex" else 0
+        self.plan(B, T, Ts, n_steps, Tr)
         x = x.detach().float().contiguous()
         mu = mu.detach().float().contiguous()
         m = mask.detach().float().reshape(B, T).contiguous()

@@ -34,7 +34,7 @@ SYMBOLS = {
     "dexb_destroy": (None, [ctypes.c_void_p]),
     "dexb_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, c_int64_p, ctypes.c_int]),
     "dexb_finalize_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
-    "dexb_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p,
+    "dexb_plan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p,
                                  ctypes.POINTER(ctypes.c_size_t)]),
     "dexb_reverse_diffusion": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.POINTER(DexbCond), ctypes.c_void_p]),

@@ -63,11 +63,12 @@ int dexb_load_weight(dexb_handle* h, const char* name, const float* data_dev, co
 int dexb_finalize_weights(dexb_handle* h, void* stream);
 
 /* Allocate the workspace (owned by the handle; its size is returned in *workspace_bytes), build the TMA descriptors,
- * the per-step scalar / embedding tables and the launch plan for a (B, T, Ts, n_steps) problem.
+ * the per-step scalar / embedding tables and the launch plan for a (B, T, Ts, Tr, n_steps) problem.
  * `sigmas_host` = the n_steps + 1 noise levels t_0 .. t_N (t_N = 0) of ablation_sampler's 'edm' discretisation
  * (DEX-TTS/model/edm.py:152,179-180), computed by the caller in fp32 exactly as the reference does.
- * T must be a multiple of 4 (model.utils.fix_len_compatibility).  Ts is ignored for GeDEX-TTS. */
-int dexb_plan(dexb_handle* h, int B, int T, int Ts, int n_steps, const float* sigmas_host, size_t* workspace_bytes);
+ * T must be a multiple of 4 (model.utils.fix_len_compatibility).  Ts = length of `sty`, Tr = length of the 6 `ref` skip
+ * tensors (both = the reference mel length in synthesize.py); ignored for GeDEX-TTS. */
+int dexb_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const float* sigmas_host, size_t* workspace_bytes);
 
 /* replaces: Diffusion.forward(infer=True) after the Gaussian draw -- i.e. ablation_sampler(...)
  * (DEX-TTS/model/edm.py:104-211) over EDMPrecond (edm.py:88-98) over DiffusionDenoiser.forward
