@@ -419,7 +419,9 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->cat = ar.get<bf16>(P1 * 4 * mid);
   h->tokS = ar.get<bf16>(M * 2 * mid);
   h->xe = ar.get<float>(M * hid);
-  h->pe = ar.get<float>(M * hid);                       // GELU(pos_conv) per grid position; averaged over freq downstream
+  h->pg = ar.get<float>(M * hid);                       // GELU(pos_conv) per grid position
+  h->pe = ar.get<float>((long)B * h->Wq * hid);         // its mean over the frequency axis
+  h->tiv_a = ar.get<float>((long)B * mid); h->tiv_d = ar.get<float>((long)B * mid);
   h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
   h->xtok = ar.get<float>(M * hid);
   h->hS = ar.get<bf16>(M * 2 * hid);
@@ -532,7 +534,7 @@ static int build_plans(dexb_handle* h) {
     p.tap_sw = 2;
     p.epi.bias = h->posconv_b; p.epi.bias_head_stride = cg;
     p.epi.act = 1;
-    gp_out_f(p, h->pe, hid);                       // mean over the frequency axis is taken in tok_assemble (fixed order)
+    gp_out_f(p, h->pg, hid);                       // the mean over the frequency axis is taken by k_freq_mean (fixed order)
     p.epi.o_head_stride = cg;
     DEXB_TRY(plan_shared(&h->g_posconv, p));
   }
@@ -841,8 +843,10 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     // TIVAdaptor (AdaIN, ref_encoder.py:264-273) folded into the patch-embed front
     double* cs1 = h->cstats + (long)B * mid * 2;
     LAUNCH(launch_chan_stats_f(h->tvout, mid, cs1, B, P1, mid, st));
-    LAUNCH(launch_dw_patch(h->tvout, cs1, h->tiv_scale + (long)step * B * mid, h->tiv_shift + (long)step * B * mid, 1, h->dw_w,
-                           h->dw_b, tok, B, H1, W1, mid, c.patch, c.stride, h->Fq, h->Wq, st));
+    LAUNCH(launch_tiv_affine(cs1, h->tiv_scale + (long)step * B * mid, h->tiv_shift + (long)step * B * mid, h->tiv_a, h->tiv_d, B,
+                             mid, P1, st));
+    LAUNCH(launch_dw_patch(h->tvout, cs1, h->tiv_a, h->tiv_d, 1, h->dw_w, h->dw_b, tok, B, H1, W1, mid, c.patch, c.stride, h->Fq,
+                           h->Wq, st));
   } else {
     LAUNCH(launch_dw_patch_s(skip, h->dw_w, h->dw_b, tok, B, H1, W1, mid, c.patch, c.stride, h->Fq, h->Wq, st));
   }
@@ -852,6 +856,7 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
   GEMM(h->g_pe, h->g_pe.p);
   LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, st));
   GEMM(h->g_posconv, h->g_posconv.p);
+  LAUNCH(launch_freq_mean(h->pg, h->pe, B, h->Fq, h->Wq, hid, st));
   const float* mod = h->mod + (long)step * c.depth * 6 * hid;
   SView hs = {h->hS, 2L * hid, 0, hid};
   LAUNCH(launch_tok_assemble(h->xe, h->pe, h->fpos, h->xtok, mod, mod + hid, hs, B, h->Fq, h->Wq, hid, st));

@@ -77,7 +77,11 @@ void launch_tv_vl0(const float* vl0 /*[C]*/, bf16* vlt /*[B][C][hi(KP)|lo(KP)]*/
 void launch_tv_softmax(const float* scores, long sstride, const int* sty_len, bf16* P_, int B, int Ppix, int NK, int KP,
                        cudaStream_t st);
 
-// TIV AdaIN + DiT patch embed front: affine(InstanceNorm) -> zero pad -> depthwise conv pxp stride s -> SiLU -> S
+void launch_freq_mean(const float* pg /*[B][Fq][Wq][D]*/, float* pe /*[B][Wq][D]*/, int B, int Fq, int Wq, int D, cudaStream_t st);
+// AdaIN affine coefficients a, d [B][C] from the InstanceNorm sums and the pooled TIV scale / shift
+void launch_tiv_affine(const double* stats, const float* sc, const float* sh, float* a_out, float* d_out, int B, int C, int P,
+                       cudaStream_t st);
+// TIV AdaIN (tiv_scale = a, tiv_shift = d from launch_tiv_affine) + DiT patch embed front: affine(InstanceNorm) -> zero pad -> depthwise conv pxp stride s -> SiLU -> S
 void launch_dw_patch(const float* tv, const double* stats, const float* tiv_scale, const float* tiv_shift,
                      int use_tiv, const float* dw_w /*[C][p][p]*/, const float* dw_b, SView out, int B, int H, int W,
                      int C, int p, int s, int Fq, int Wq, cudaStream_t st);
@@ -85,7 +89,7 @@ void launch_dw_patch(const float* tv, const double* stats, const float* tiv_scal
 void launch_dw_patch_s(SView in, const float* dw_w, const float* dw_b, SView out, int B, int H, int W, int C, int p,
                        int s, int Fq, int Wq, cudaStream_t st);
 
-// tokens: x = xe + mean_h'(pg[b][h'][w]) + fpos[h]  (F), and LN+modulate -> S   (pg = GELU(pos_conv) per grid row)
+// tokens: x = xe + pe[b][w] + fpos[h]  (F), and LN+modulate -> S   (pe = launch_freq_mean of GELU(pos_conv))
 void launch_tok_assemble(const float* xe, const float* pe, const float* fpos /*[Fq][D]*/, float* x, const float* shift,
                          const float* scale, SView out, int B, int Fq, int Wq, int D, cudaStream_t st);
 void launch_ln_mod(const float* x, const float* shift, const float* scale, SView out, long M, int D, cudaStream_t st);

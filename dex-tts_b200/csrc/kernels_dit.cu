@@ -99,6 +99,26 @@ void launch_tv_softmax(const float* scores, long sstride, const int* sty_len, bf
 // DiT front: (TIV AdaIN affine) -> F.pad to a multiple of PATCH size with zeros -> depthwise conv p x p, stride s,
 // padding p//2 -> SiLU -> S tokens.  dit.py:434-441,50-52.   One thread = 8 channels of one token.
 // ------------------------------------------------------------------------------------------------
+// AdaIN of the TIV adaptor as a per-(b, c) affine map  y = a x + d:  a = sc / std,  d = sh - mean * a
+// (InstanceNorm2D: unbiased variance over all pixels, eps 1e-5; base.py:95-109, ref_encoder.py:264-273)
+__global__ void k_tiv_affine(const double* __restrict__ stats, const float* __restrict__ sc, const float* __restrict__ sh,
+                             float* __restrict__ a_out, float* __restrict__ d_out, int n, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sm = stats[(long)i * 2], ss = stats[(long)i * 2 + 1];
+  const double mean = sm / P;
+  double var = (ss - sm * mean) / (double)(P - 1);
+  if (var < 0.) var = 0.;
+  const float istd = (float)(1.0 / sqrt(var + 1e-5));
+  const float a = istd * sc[i];
+  a_out[i] = a;
+  d_out[i] = sh[i] - (float)mean * a;
+}
+void launch_tiv_affine(const double* stats, const float* sc, const float* sh, float* a_out, float* d_out, int B, int C, int P,
+                       cudaStream_t st) {
+  k_tiv_affine<<<cdiv((long)B * C, 128), 128, 0, st>>>(stats, sc, sh, a_out, d_out, B * C, P);
+}
+
 template <bool SPLIT_IN>
 __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin, SView sin,
                                                   const double* __restrict__ stats, const float* __restrict__ tiv_scale,
@@ -112,26 +132,17 @@ __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin,
   const int c0 = (int)(gid % cpt) * 8;
   const long tok = gid / cpt;
   const int wq = (int)(tok % Wq), hq = (int)((tok / Wq) % Fq), b = (int)(tok / ((long)Wq * Fq));
-  const int P = H * W;
   float a[8], d[8], acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     a[i] = 1.f; d[i] = 0.f;
     acc[i] = dw_b[c0 + i];
   }
-  if (use_tiv) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const double sm = stats[((long)b * C + c) * 2], ss = stats[((long)b * C + c) * 2 + 1];
-      const double mean = sm / P;
-      double var = (ss - sm * mean) / (double)(P - 1);
-      if (var < 0.) var = 0.;
-      const float istd = (float)(1.0 / sqrt(var + 1e-5));
-      const float sc = tiv_scale[b * C + c], sh = tiv_shift[b * C + c];
-      a[i] = istd * sc;                                        // (x - mean)/std * sc + sh
-      d[i] = sh - (float)mean * istd * sc;
-    }
+  if (use_tiv) {                                               // a, d precomputed per (b, c) by k_tiv_affine
+    const float4 a0 = *reinterpret_cast<const float4*>(tiv_scale + (long)b * C + c0), a1 = *reinterpret_cast<const float4*>(tiv_scale + (long)b * C + c0 + 4);
+    const float4 d0 = *reinterpret_cast<const float4*>(tiv_shift + (long)b * C + c0), d1 = *reinterpret_cast<const float4*>(tiv_shift + (long)b * C + c0 + 4);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
   }
   const int pad = p / 2;
   for (int ky = 0; ky < p; ++ky) {
@@ -224,6 +235,27 @@ void launch_ln_mod(const float* x, const float* shift, const float* scale, SView
   else if (D == 384) k_ln_mod<12><<<cdiv(M * 32, 256), 256, 0, st>>>(x, shift, scale, out, M, D);
 }
 
+// pe[b][w][c] = mean over the frequency rows of pg[b][h][w][c] (dit.py:445), summed in a fixed order.  One thread = 4 channels.
+__global__ void __launch_bounds__(256) k_freq_mean(const float* __restrict__ pg, float* __restrict__ pe, int B, int Fq, int Wq,
+                                                   int D) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)B * Wq * (D / 4);
+  if (i >= total) return;
+  const int c = (int)(i % (D / 4)) * 4;
+  const int w = (int)((i / (D / 4)) % Wq);
+  const int b = (int)(i / ((long)(D / 4) * Wq));
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int h = 0; h < Fq; ++h) {
+    const float4 q = *reinterpret_cast<const float4*>(pg + (((long)b * Fq + h) * Wq + w) * D + c);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  const float inv = 1.f / (float)Fq;
+  *reinterpret_cast<float4*>(pe + ((long)b * Wq + w) * D + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+}
+void launch_freq_mean(const float* pg, float* pe, int B, int Fq, int Wq, int D, cudaStream_t st) {
+  k_freq_mean<<<cdiv((long)B * Wq * (D / 4), 256), 256, 0, st>>>(pg, pe, B, Fq, Wq, D);
+}
+
 // x = xe + pe[b][w] + fpos[h]  (dit.py:444-447), stored fp32 (residual stream) and LN+modulated for block 0
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) k_tok_assemble(const float* __restrict__ xe, const float* __restrict__ pe,
@@ -240,13 +272,7 @@ __global__ void __launch_bounds__(256) k_tok_assemble(const float* __restrict__ 
   for (int g = 0; g < PER_LANE; g += 4) {
     const int c = (g / 4) * 128 + lane * 4;
     const float4 a = *reinterpret_cast<const float4*>(xe + row * D + c);
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int hh = 0; hh < Fq; ++hh) {                      // mean over the frequency axis (dit.py:445), fixed order
-      const float4 q = *reinterpret_cast<const float4*>(pe + (((long)b * Fq + hh) * Wq + wq) * D + c);
-      p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
-    }
-    const float inv_fq = 1.f / (float)Fq;
-    p.x *= inv_fq; p.y *= inv_fq; p.z *= inv_fq; p.w *= inv_fq;
+    const float4 p = *reinterpret_cast<const float4*>(pe + ((long)b * Wq + wq) * D + c);
     const float4 f = *reinterpret_cast<const float4*>(fpos + (long)hq * D + c);
     v[g] = (a.x + p.x) + f.x; v[g + 1] = (a.y + p.y) + f.y; v[g + 2] = (a.z + p.z) + f.z; v[g + 3] = (a.w + p.w) + f.w;
     *reinterpret_cast<float4*>(x + row * D + c) = make_float4(v[g], v[g + 1], v[g + 2], v[g + 3]);

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) k_la_reduce(const float* __restrict__ par
 }
 int la_ctx_blocks(int B, int P) {
   int chunk = 512;
-  while (chunk > 128 && (long)cdiv(P, chunk) * B < 2 * 148) chunk >>= 1;
+  while (chunk > 128 && (long)cdiv(P, chunk) * B < 4 * 148) chunk >>= 1;
   return cdiv(P, chunk);
 }
 void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float* ctx, float* ssum, int B, int P,
@@ -491,12 +491,12 @@ __global__ void __launch_bounds__(256) k_chan_stats(const bf16* __restrict__ xs,
   }
 }
 void launch_chan_stats_s(SView x, double* stats, int B, int P, int C, cudaStream_t st) {
-  const int chunk = 1024;
+  const int chunk = 128;                                 // 80 -> 640 blocks at C2: the kernel was latency-bound
   dim3 grid(cdiv(P, chunk), B);
   k_chan_stats<true><<<grid, 256, 0, st>>>(x.p, x.stride, x.hi, x.lo, nullptr, 0, stats, P, C, chunk);
 }
 void launch_chan_stats_f(const float* x, long stride, double* stats, int B, int P, int C, cudaStream_t st) {
-  const int chunk = 1024;
+  const int chunk = 128;                                 // 80 -> 640 blocks at C2: the kernel was latency-bound
   dim3 grid(cdiv(P, chunk), B);
   k_chan_stats<false><<<grid, 256, 0, st>>>(nullptr, 0, 0, 0, x, stride, stats, P, C, chunk);
 }
