@@ -53,10 +53,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kAtBM;
+  // DiT / TV: blockIdx.x = query tile, all key tiles.  Split-KV mode (linear-attention context, one 128-row query tile):
+  // blockIdx.x = key split, the CTA covers key tiles [t0, t0 + nt) and writes un-normalised partials.
+  const int split = (p.kv_splits > 1) ? (int)blockIdx.x : 0;
+  const int m0 = (p.kv_splits > 1) ? 0 : (int)blockIdx.x * kAtBM;
   const int z = blockIdx.y;
   const int b = z / p.nheads, head = z % p.nheads;
-  const int nt = p.nt;
+  const int t0 = split * p.tiles_per_split;
+  const int nt = max(0, min(p.nt, t0 + p.tiles_per_split) - t0);
+  const int kch = p.kchunks;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
@@ -85,13 +90,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
         uint8_t* st = smem + s * kStage;
         if (it < nt) {
-          ptx::mbar_expect_tx(&k_full[s], 2 * 8192);
-          for (int kc = 0; kc < 2; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, it * kAtBN, b);
+          ptx::mbar_expect_tx(&k_full[s], kch * 8192);
+          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, (t0 + it) * kAtBN, b);
         } else {
-          const int j = it - nt;
-          ptx::mbar_expect_tx(&k_full[s], kStage);
+          const int j = t0 + it - nt;
+          ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192 + kVBytes);
           for (int part = 0; part < 2; ++part)
-            for (int kc = 0; kc < 2; ++kc)
+            for (int kc = 0; kc < kch; ++kc)
               ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
           for (int part = 0; part < 2; ++part)
             ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
@@ -117,6 +122,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (kc >= kch) continue;
             const uint32_t qh = tmem + kTmQh + (uint32_t)(kc * 32 + kk * 8);
             const uint32_t ql = tmem + kTmQl + (uint32_t)(kc * 32 + kk * 8);
             const uint64_t kh = ptx::make_desc_k128(k_base + kc * 8192 + kk * 32);
@@ -133,7 +139,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       __syncwarp();
     };
     for (int it = 0; it < nt; ++it) issue_s(it, false);
-    issue_s(nt, true);
+    if (nt > 0) issue_s(nt, true);
     for (int j = 0; j < nt; ++j) {
       const int it = nt + j;
       if (j + 1 < nt) issue_s(it + 1, true);
@@ -170,8 +176,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       // stage this thread's half of the query row (64 of the 128 head dims, hi and lo) into tensor memory
       uint32_t qh[32], ql[32];
       const int row = m0 + r;
-      if (row < p.NQ) {
-        const bf16* qp = p.q + ((long)b * p.NQ + row) * p.q_stride + head * kAtHD + hf * 64;
+      if (row < p.NQ && hf < kch) {
+        const bf16* qp = p.q + ((long)b * p.q_img_rows + row) * p.q_stride + head * kAtHD + hf * 64;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const uint4 a = *reinterpret_cast<const uint4*>(qp + p.q_hi + i * 8);
@@ -201,11 +207,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = nkv - it * kAtBN - hf * 32;
+      const int nvalid = nkv - (t0 + it) * kAtBN - hf * 32;
       if (kb != nullptr) {
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (c < nvalid) m = fmaxf(m, v[c] + __ldg(kb + it * kAtBN + hf * 32 + c));
+          if (c < nvalid) m = fmaxf(m, v[c] + __ldg(kb + (t0 + it) * kAtBN + hf * 32 + c));
       } else {
 #pragma unroll
         for (int c = 0; c < 32; ++c)
@@ -226,10 +232,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&s_empty[s]);
-      const int nvalid = nkv - j * kAtBN - hf * 32;
+      const int nvalid = nkv - (t0 + j) * kAtBN - hf * 32;
       if (kb != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + j * kAtBN + hf * 32 + c);
+        for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + (t0 + j) * kAtBN + hf * 32 + c);
       }
       uint32_t hi2[16], lo2[16];
 #pragma unroll
@@ -258,10 +264,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     xch[hf * 128 + r] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += xch[(hf ^ 1) * 128 + r];
+    const int row = m0 + r;
+    if (p.out_mode == 2) {
+      // split-KV partials: O (un-normalised, fp32), row sum l and row max m of this key range
+      float* po = p.part_o + (((long)b * p.kv_splits + split) * kAtBM + r) * kAtHD;
+      if (hf == 0) {
+        p.part_l[((long)b * p.kv_splits + split) * kAtBM + r] = l;
+        p.part_m[((long)b * p.kv_splits + split) * kAtBM + r] = m;
+      }
+      if (nt > 0) {
+        ptx::mbar_wait(o_full, 0);
+        ptx::tc_fence_after();
+      }
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        float o[32];
+        if (nt > 0) ptx::tmem_ld32(tl + kTmO + hf * 64 + c * 32, o);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) st256_f32(po + hf * 64 + c * 32 + i, &o[i]);
+      }
+    } else {
     ptx::mbar_wait(o_full, 0);
     ptx::tc_fence_after();
     const float inv = 1.f / l;
-    const int row = m0 + r;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       float o[32];
@@ -290,6 +319,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
           for (int i = 0; i < 32; i += 8) st256_f32(of + i, &o[i]);
         }
       }
+    }
     }
   }
   ptx::tc_fence_before();
@@ -336,7 +366,8 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   memset(&p, 0, sizeof(p));
   p.NQ = N; p.NK = N; p.KP = NP; p.nheads = heads;
   p.nt = (N + kAtBN - 1) / kAtBN;
-  p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid;
+  p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid; p.q_img_rows = N;
+  p.kchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
   p.k_hi = hid; p.k_lo = 4 * hid;
   p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
   p.out_mode = 0;
@@ -358,7 +389,8 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   memset(&p, 0, sizeof(p));
   p.NQ = P; p.NK = NK; p.KP = KP; p.nheads = 1;
   p.nt = (NK + kAtBN - 1) / kAtBN;
-  p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo;
+  p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo; p.q_img_rows = P;
+  p.kchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
   p.k_hi = 0; p.k_lo = C;
   p.scale_log2e = 1.4426950408889634f;              // 1/sqrt(C) is folded into the key matrix (k_tv_fold)
   p.kbias = sbias; p.kbias_stride = KP; p.vis_len = sty_len;
@@ -371,8 +403,32 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   return 0;
 }
 
+int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
+                      float* part_l, float* part_m, int B, int P, int PP, int C, int splits) {
+  DEXB_CHECK(C == 64 || C == 128, "linear-attention context: C must be 64 or 128 (got %d)", C);
+  DEXB_CHECK(PP % kAtBN == 0 && PP >= P && splits >= 1, "linear-attention context: bad padding / split");
+  ap->B = B;
+  AttnParams& p = ap->p;
+  memset(&p, 0, sizeof(p));
+  p.NQ = 128; p.NK = P; p.KP = PP; p.nheads = 1;
+  p.nt = (P + kAtBN - 1) / kAtBN;
+  p.kv_splits = splits;
+  p.tiles_per_split = (p.nt + splits - 1) / splits;
+  p.kchunks = C / 64;
+  p.q = wk; p.q_stride = 2L * C; p.q_hi = 0; p.q_lo = C; p.q_img_rows = 0;      // the k rows of to_qkv, shared by all images
+  p.k_hi = x_hi; p.k_lo = x_lo;
+  p.scale_log2e = 1.4426950408889634f;
+  p.out_mode = 2;
+  p.part_o = part_o; p.part_l = part_l; p.part_m = part_m;
+  const cuuint64_t xrow = (cuuint64_t)x_stride * 2;
+  DEXB_TRY(enc3(&ap->tmK, x, (cuuint64_t)x_stride, (cuuint64_t)P, (cuuint64_t)B, xrow, xrow * P, 64, kAtBN, "LA x"));
+  const cuuint64_t vrow = 2ull * PP * 2;
+  DEXB_TRY(enc3(&ap->tmV, vT, 2ull * PP, (cuuint64_t)kAtHD, (cuuint64_t)B, vrow, vrow * kAtHD, 64, kAtHD, "LA V"));
+  return 0;
+}
+
 int attn_launch(const AttnPlan& ap, cudaStream_t st) {
-  dim3 grid((unsigned)((ap.p.NQ + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
+  dim3 grid((unsigned)(ap.p.kv_splits > 1 ? ap.p.kv_splits : (ap.p.NQ + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
   attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, ap.p);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;

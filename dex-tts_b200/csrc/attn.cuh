@@ -12,6 +12,10 @@ struct AttnParams {
   int KP;                    // padded key count: lo half of a V^T row starts at column KP
   int nheads;
   int nt;                    // key tiles of 64
+  int kchunks;               // 64-wide chunks of the Q / K rows (head dim / 64): 2, or 1 for the C = 64 linear attention
+  int kv_splits;             // > 1: split-KV mode -- blockIdx.x = key split, one 128-row query tile, partial outputs
+  int tiles_per_split;
+  int q_img_rows;            // Q rows per image (0: the same Q rows for every image)
   // Q rows (staged to tensor memory by the softmax warps): q + (b*NQ + row)*q_stride + head*128, hi at q_hi, lo at q_lo
   const bf16* q;
   long q_stride;
@@ -23,7 +27,8 @@ struct AttnParams {
   const float* kbias;
   long kbias_stride;
   const int* vis_len;
-  // epilogue: mode 0 = split rows (head h at column h*128); mode 1 = fp32 rows (O/l + the Q row as residual) * rowmask
+  // epilogue: mode 0 = split rows (head h at column h*128); mode 1 = fp32 rows (O/l + the Q row as residual) * rowmask;
+  // mode 2 = split-KV partials: part_o [b][split][128][128] un-normalised, part_l / part_m [b][split][128]
   int out_mode;
   bf16* out;
   long out_stride;
@@ -32,6 +37,7 @@ struct AttnParams {
   long out_f_stride;
   const float* rowmask;      // [b][rowmask_w], column = row % rowmask_w
   int rowmask_w;
+  float *part_o, *part_l, *part_m;
 };
 
 struct AttnPlan {
@@ -49,6 +55,11 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
 int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* kq, const float* sbias,
                       const bf16* vlt, const int* sty_len, float* out, const float* mask, int mask_w, int B, int P, int NK, int KP,
                       int C);
+// LinearAttention context (diffusion.py:82-95) as attention with the roles swapped: "queries" = the 128 k-channels (rows of the
+// k part of to_qkv, split weights wk [128][hi(C)|lo(C)]), "keys" = the pixels x, softmax over ALL pixels of an image, "values" = v
+// (V^T [b][128][hi(PP)|lo(PP)] from the GEMM engine).  Split over the pixels; partials are merged by launch_la_combine.
+int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
+                      float* part_l, float* part_m, int B, int P, int PP, int C, int splits);
 int attn_launch(const AttnPlan& ap, cudaStream_t st);
 double attn_flop(const AttnPlan& ap);
 

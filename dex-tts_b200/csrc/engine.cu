@@ -341,6 +341,18 @@ static int plan_la(dexb_handle* h, LinAttW& la, const bf16* in, long in_stride, 
     gp_out_f(p, h->kv, 256);
     DEXB_TRY(plan_shared(&la.kv, p));
   }
+  if (h->fused_la) {
+    GemmParams p = gp_base(h->cfg);                   // v^T = (W_v x)^T, split, for the tensor-core context kernel
+    gp_geom(p, h->B, H, W);
+    gp_a(p, in, in_stride, in_hi, in_lo, la.C);
+    gp_b(p, la.kv_w + 128L * 2 * la.C, la.C, 128);
+    p.epi.out_s_ncols = 0;
+    p.epi.out_vt = h->la_vT; p.epi.out_vt_zstride = 128L * 2 * la.PP; p.epi.out_vt_rstride = 2L * la.PP;
+    p.epi.out_vt_lo = la.PP; p.epi.out_vt_hd = 128; p.epi.out_vt_heads = 1;
+    DEXB_TRY(plan_shared(&la.vt, p));
+    DEXB_TRY(attn_plan_init_la(&la.ctx_plan, la.kv_w, in, in_stride, in_hi, in_lo, h->la_vT, la.part_o, la.part_l, la.part_m, h->B,
+                               H * W, la.PP, la.C, la.splits));
+  }
   {
     GemmParams p = gp_base(h->cfg);
     gp_geom(p, h->B, H, W);
@@ -413,6 +425,24 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->raw0 = ar.get<float>(P0 * d);
   h->A0 = ar.get<bf16>(P0 * 2 * d); h->B0 = ar.get<bf16>(P0 * 2 * d); h->C0 = ar.get<bf16>(P0 * 2 * d);
   h->kv = ar.get<float>(P0 * 256);
+  {
+    const long pp0 = (long)(h->H0 * h->W0 + 63) / 64 * 64;
+    h->la_vT = ar.get<bf16>((long)B * 128 * 2 * pp0);
+    LinAttW* las2[3] = {&h->la0, &h->la1, &h->la2};
+    for (LinAttW* la : las2) {
+      const int Pl = (la == &h->la0) ? h->H0 * h->W0 : h->H1 * h->W1;
+      const int ntl = (Pl + 63) / 64;
+      la->PP = ntl * 64;
+      int sp = (2 * 148 + B - 1) / B;
+      if (sp > ntl) sp = ntl;
+      if (sp < 1) sp = 1;
+      const int tps = (ntl + sp - 1) / sp;
+      la->splits = (ntl + tps - 1) / tps;              // no empty splits
+      la->part_o = ar.get<float>((long)B * la->splits * 128 * 128);
+      la->part_l = ar.get<float>((long)B * la->splits * 128);
+      la->part_m = ar.get<float>((long)B * la->splits * 128);
+    }
+  }
   h->raw1 = ar.get<float>(P1 * mid); h->resid1 = ar.get<float>(P1 * mid);
   h->D1 = ar.get<bf16>(P1 * 2 * d);
   h->A1 = ar.get<bf16>(P1 * 2 * mid); h->B1 = ar.get<bf16>(P1 * 2 * mid); h->C1 = ar.get<bf16>(P1 * 2 * mid);
@@ -442,6 +472,10 @@ static int build_plans(dexb_handle* h) {
   const int B = h->B, d = c.dim, mid = 2 * d, hid = c.hidden;
   const int H0 = h->H0, W0 = h->W0, H1 = h->H1, W1 = h->W1;
   const bool dex = c.variant == 1;
+  {
+    const char* ea = getenv("DEXB_ATTN");
+    h->fused_la = !(ea != nullptr && ea[0] == '0');
+  }
   // ---- level 0 ----
   DEXB_TRY(plan_block_conv(h, h->d00.b2, h->A0, 2 * d, 0, d, H0, W0, h->raw0));
   DEXB_TRY(plan_block_conv(h, h->d01.b1, h->B0, 2 * d, 0, d, H0, W0, h->raw0));
@@ -767,9 +801,18 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
 }
 
 static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
-  GEMM(la.kv, la.kv.p);
-  LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
-  LAUNCH(launch_la_ctx(h->kv, la.kmax, la.part, la.ctx, la.ssum, h->B, P, st));
+  if (h->fused_la) {
+    GEMM(la.vt, la.vt.p);
+    if (h->prof) prof_begin(h, "attn_fwd_kernel(la ctx)", attn_flop(la.ctx_plan), st);
+    DEXB_TRY(attn_launch(la.ctx_plan, st));
+    if (h->prof) prof_end(h, st);
+    ++h->launches;
+    LAUNCH(launch_la_combine(la.part_o, la.part_l, la.part_m, la.ctx, la.ssum, h->B, la.splits, st));
+  } else {
+    GEMM(la.kv, la.kv.p);
+    LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
+    LAUNCH(launch_la_ctx(h->kv, la.kmax, la.part, la.ctx, la.ssum, h->B, P, st));
+  }
   LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.m1, la.weff, la.beff, h->B, la.C, st));
   GEMM(la.apply, la.apply.p);
   return 0;

@@ -54,6 +54,10 @@ struct LinAttW {
   const float *wq = nullptr, *wout = nullptr, *bout = nullptr, *g = nullptr;
   int C = 0;
   GemmPlan kv, apply;
+  GemmPlan vt;                        // fused path: v only, stored transposed for the tensor-core context kernel
+  AttnPlan ctx_plan;
+  int splits = 1, PP = 0;
+  float *part_o = nullptr, *part_l = nullptr, *part_m = nullptr;
   unsigned* kmax = nullptr;           // [B][128]
   float *ctx = nullptr, *ssum = nullptr, *beff = nullptr, *m1 = nullptr, *part = nullptr;
   bf16* weff = nullptr;               // [B][C][hi(C)|lo(C)]
@@ -130,7 +134,8 @@ struct dexb_handle {
   // plans of the non-block GEMMs
   dexb::GemmPlan g_down, g_up[4], g_tvs, g_tvo, g_pe, g_posconv, g_final;
   dexb::AttnPlan attn, attn_tv;
-  bool fused_attn = false, fused_tv = false;
+  bool fused_attn = false, fused_tv = false, fused_la = false;
+  dexb::bf16* la_vT = nullptr;                       // [B][128][hi(PP)|lo(PP)], shared by the three linear attentions
   // CUDA graph of one whole trajectory
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;

@@ -398,6 +398,36 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float
   k_la_reduce<<<cdiv((long)B * kLaPartial, 256), 256, 0, st>>>(part, ctx, ssum, B, nblk);
 }
 
+// Merge the split-KV partials of the tensor-core context kernel (attn.cu, out_mode 2), in split order:
+//   M[d] = max_s m_s[d];  ctx[b][h][d][e] = sum_s O_s[d][h*32+e] exp(m_s[d] - M[d]);  ssum[b][d] = sum_s l_s[d] exp(m_s[d] - M[d])
+// (only the 4 diagonal 32x32 head blocks of the 128x128 product are context).  One thread per output.
+__global__ void __launch_bounds__(256) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
+                                                    const float* __restrict__ part_m, float* __restrict__ ctx,
+                                                    float* __restrict__ ssum, int B, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 4096 + 128;
+  if (i >= B * per) return;
+  const int b = i / per, k = i % per;
+  int d, col;
+  if (k < 4096) { const int h = k >> 10, dl = (k >> 5) & 31, el = k & 31; d = h * 32 + dl; col = h * 32 + el; }
+  else { d = k - 4096; col = -1; }
+  float M = -INFINITY;
+  for (int s = 0; s < S; ++s) M = fmaxf(M, part_m[((long)b * S + s) * 128 + d]);
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const long ps = (long)b * S + s;
+    const float w = expf(part_m[ps * 128 + d] - M);          // exp(-inf) = 0 for an empty split
+    const float v = (col >= 0) ? part_o[(ps * 128 + d) * 128 + col] : part_l[ps * 128 + d];
+    acc = fmaf(v, w, acc);
+  }
+  if (col >= 0) ctx[(long)b * 4096 + k] = acc;
+  else ssum[b * 128 + d] = acc;
+}
+void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, float* ctx, float* ssum, int B, int S,
+                       cudaStream_t st) {
+  k_la_combine<<<cdiv((long)B * (4096 + 128), 256), 256, 0, st>>>(part_o, part_l, part_m, ctx, ssum, B, S);
+}
+
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
 // (q is linear in x, so  x + g*to_out(ctx^T q) == W_eff x + g*b_out : the whole attention read-out is one
 //  per-sample CxC matrix.)   Two small fully parallel kernels: m1 = ctxn^T Wq, then W_eff = I + g Wout m1.
