@@ -1,6 +1,7 @@
 // C ABI of the library (include/dexb200.h).  No torch types cross this boundary.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.cuh"
@@ -257,7 +258,8 @@ int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float
   launch_pack_rows(qkv_dev, qs, M, 3 * hid, st);
   launch_transpose_v(qs, 6L * hid, 2 * hid, 5 * hid, vT, B, N, NP, hid, hid / heads, st);
   AttnPlan ap;
-  int r = attn_plan_init(&ap, qs, vT, os, B, N, NP, heads, hid);
+  const char* vmn = getenv("DEXB_VMN");
+  int r = attn_plan_init(&ap, qs, (vmn != nullptr && vmn[0] == '1') ? nullptr : vT, os, B, N, NP, heads, hid);
   if (r == 0) r = attn_launch(ap, st);
   if (r == 0) launch_unpack_rows(os, out_dev, M, hid, st);
   cudaError_t e = cudaStreamSynchronize(st);

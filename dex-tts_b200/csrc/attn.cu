@@ -98,15 +98,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
           for (int part = 0; part < 2; ++part)
             for (int kc = 0; kc < kch; ++kc)
               ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
-          for (int part = 0; part < 2; ++part)
-            ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
+          if (p.v_mn) {                                    // row-major V: [part][d chunk of 64] boxes of 64 keys x 128 B
+            for (int part = 0; part < 2; ++part)
+              for (int c = 0; c < 2; ++c)
+                ptx::tma_load_3d(st + kKBytes + part * 16384 + c * 8192, &tmV, &k_full[s],
+                                 (part ? p.v_lo : p.v_hi) + head * kAtHD + c * 64, j * kAtBN, b);
+          } else {
+            for (int part = 0; part < 2; ++part)
+              ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kAtBN);
-    constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, kAtHD);
+    const uint32_t idesc_o = ptx::make_idesc_bf16(128, kAtHD, p.v_mn);
     ptx::mbar_wait(q_full, 0);
     ptx::tc_fence_after();
     // S[it & 1] = Q K^T for iteration `it` (Q from tensor memory); frees the stage itself only in pass 1
@@ -151,8 +158,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t ph_ = tmem + kTmPh + (uint32_t)(kk * 8);
           const uint32_t pl_ = tmem + kTmPl + (uint32_t)(kk * 8);
-          const uint64_t vh = ptx::make_desc_k128(v_base + kk * 32);
-          const uint64_t vl = ptx::make_desc_k128(v_base + 16384 + kk * 32);
+          // K-major V^T tile: 16 keys = 32 B inside the swizzle span; MN-major V tile: 16 keys = 16 rows = 2048 B
+          const uint64_t vh = p.v_mn ? ptx::make_desc_mn128(v_base + kk * 2048, 8192, 1024) : ptx::make_desc_k128(v_base + kk * 32);
+          const uint64_t vl = p.v_mn ? ptx::make_desc_mn128(v_base + 16384 + kk * 2048, 8192, 1024)
+                                     : ptx::make_desc_k128(v_base + 16384 + kk * 32);
           ptx::mma_bf16_ts(tm_o, ph_, vh, idesc_o, (j | kk) ? 1u : 0u);
           ptx::mma_bf16_ts(tm_o, ph_, vl, idesc_o, 1u);
           ptx::mma_bf16_ts(tm_o, pl_, vh, idesc_o, 1u);
@@ -374,6 +383,11 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   p.out = out; p.out_stride = 2L * hid; p.out_hi = 0; p.out_lo = hid;
   const cuuint64_t qrow = 6ull * hid * 2;
   DEXB_TRY(enc3(&ap->tmK, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBN, "K"));
+  if (vT == nullptr) {                                  // V read row-major straight from the qkv rows (MN-major B operand)
+    p.v_mn = 1; p.v_hi = 2 * hid; p.v_lo = 5 * hid;
+    DEXB_TRY(enc3(&ap->tmV, qkv, 6ull * hid, (cuuint64_t)N, (cuuint64_t)B, qrow, qrow * N, 64, kAtBN, "V rows"));
+    return 0;
+  }
   const cuuint64_t vrow = 2ull * NP * 2;
   DEXB_TRY(enc3(&ap->tmV, vT, 2ull * NP, (cuuint64_t)hid, (cuuint64_t)B, vrow, vrow * hid, 64, kAtHD, "V"));
   return 0;
@@ -422,8 +436,10 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   p.part_o = part_o; p.part_l = part_l; p.part_m = part_m;
   const cuuint64_t xrow = (cuuint64_t)x_stride * 2;
   DEXB_TRY(enc3(&ap->tmK, x, (cuuint64_t)x_stride, (cuuint64_t)P, (cuuint64_t)B, xrow, xrow * P, 64, kAtBN, "LA x"));
-  const cuuint64_t vrow = 2ull * PP * 2;
-  DEXB_TRY(enc3(&ap->tmV, vT, 2ull * PP, (cuuint64_t)kAtHD, (cuuint64_t)B, vrow, vrow * kAtHD, 64, kAtHD, "LA V"));
+  // v as split rows [pixel][hi(128) | lo(128)] straight from the GEMM engine (MN-major B operand: no transposed stores)
+  p.v_mn = 1; p.v_hi = 0; p.v_lo = kAtHD;
+  const cuuint64_t vrow = 2ull * kAtHD * 2;
+  DEXB_TRY(enc3(&ap->tmV, vT, 2ull * kAtHD, (cuuint64_t)P, (cuuint64_t)B, vrow, vrow * P, 64, kAtBN, "LA V rows"));
   return 0;
 }
 

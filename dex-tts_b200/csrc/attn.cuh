@@ -16,6 +16,8 @@ struct AttnParams {
   int kv_splits;             // > 1: split-KV mode -- blockIdx.x = key split, one 128-row query tile, partial outputs
   int tiles_per_split;
   int q_img_rows;            // Q rows per image (0: the same Q rows for every image)
+  int v_mn;                  // 1: V tiles come row-major [key][d] (MN-major B operand) from tmV at columns v_hi / v_lo (+ head*128)
+  int v_hi, v_lo;
   // Q rows (staged to tensor memory by the softmax warps): q + (b*NQ + row)*q_stride + head*128, hi at q_hi, lo at q_lo
   const bf16* q;
   long q_stride;
@@ -48,7 +50,8 @@ struct AttnPlan {
 
 int attn_global_init();
 bool attn_supported(int hd);
-// DiT self-attention over qkv rows [hi(3*hid) | lo(3*hid)] and V^T [b][hid][hi(NP)|lo(NP)] -> split rows `out`
+// DiT self-attention over qkv rows [hi(3*hid) | lo(3*hid)] -> split rows `out`.  vT == nullptr: V is read row-major from the
+// qkv rows (MN-major B operand); otherwise from the transposed copy V^T [b][hid][hi(NP)|lo(NP)].
 int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int B, int N, int NP, int heads, int hid);
 // TV adaptor cross-attention (single head, C = 128): queries = the split rows x (also the residual), keys kq [b][KP][hi(C)|lo(C)]
 // with score bias sbias [b][KP], values vlt [b][C][hi(KP)|lo(KP)], output fp32 rows (x + attn) * mask
@@ -57,7 +60,7 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
                       int C);
 // LinearAttention context (diffusion.py:82-95) as attention with the roles swapped: "queries" = the 128 k-channels (rows of the
 // k part of to_qkv, split weights wk [128][hi(C)|lo(C)]), "keys" = the pixels x, softmax over ALL pixels of an image, "values" = v
-// (V^T [b][128][hi(PP)|lo(PP)] from the GEMM engine).  Split over the pixels; partials are merged by launch_la_combine.
+// (split rows [b][P][hi(128)|lo(128)] from the GEMM engine, used as an MN-major B operand).  Split over the pixels; partials are merged by launch_la_combine.
 int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
                       float* part_l, float* part_m, int B, int P, int PP, int C, int splits);
 int attn_launch(const AttnPlan& ap, cudaStream_t st);

@@ -342,13 +342,11 @@ static int plan_la(dexb_handle* h, LinAttW& la, const bf16* in, long in_stride, 
     DEXB_TRY(plan_shared(&la.kv, p));
   }
   if (h->fused_la) {
-    GemmParams p = gp_base(h->cfg);                   // v^T = (W_v x)^T, split, for the tensor-core context kernel
+    GemmParams p = gp_base(h->cfg);                   // v = W_v x as split rows for the tensor-core context kernel
     gp_geom(p, h->B, H, W);
     gp_a(p, in, in_stride, in_hi, in_lo, la.C);
     gp_b(p, la.kv_w + 128L * 2 * la.C, la.C, 128);
-    p.epi.out_s_ncols = 0;
-    p.epi.out_vt = h->la_vT; p.epi.out_vt_zstride = 128L * 2 * la.PP; p.epi.out_vt_rstride = 2L * la.PP;
-    p.epi.out_vt_lo = la.PP; p.epi.out_vt_hd = 128; p.epi.out_vt_heads = 1;
+    gp_out_s(p, h->la_vT, 256, 0, 128);                // split rows [pixel][hi(128) | lo(128)]
     DEXB_TRY(plan_shared(&la.vt, p));
     DEXB_TRY(attn_plan_init_la(&la.ctx_plan, la.kv_w, in, in_stride, in_hi, in_lo, h->la_vT, la.part_o, la.part_l, la.part_m, h->B,
                                H * W, la.PP, la.C, la.splits));
@@ -427,7 +425,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->kv = ar.get<float>(P0 * 256);
   {
     const long pp0 = (long)(h->H0 * h->W0 + 63) / 64 * 64;
-    h->la_vT = ar.get<bf16>((long)B * 128 * 2 * pp0);
+    h->la_vT = ar.get<bf16>((long)B * pp0 * 256);         // v rows [b][pixel][hi(128)|lo(128)]
     LinAttW* las2[3] = {&h->la0, &h->la1, &h->la2};
     for (LinAttW* la : las2) {
       const int Pl = (la == &h->la0) ? h->H0 * h->W0 : h->H1 * h->W1;
@@ -575,7 +573,7 @@ static int build_plans(dexb_handle* h) {
   {
     const char* ea = getenv("DEXB_ATTN");
     h->fused_attn = attn_supported(hd) && !(ea != nullptr && ea[0] == '0');
-    if (h->fused_attn) DEXB_TRY(attn_plan_init(&h->attn, h->qk, h->vT, h->attnS, B, N, NP, c.heads, hid));
+    if (h->fused_attn) DEXB_TRY(attn_plan_init(&h->attn, h->qk, nullptr, h->attnS, B, N, NP, c.heads, hid));
   }
   for (int i = 0; i < c.depth; ++i) {
     DitBlockW& k = h->blocks[i];
@@ -586,9 +584,11 @@ static int build_plans(dexb_handle* h) {
       gp_b(p, k.qkv_w, hid, 3 * hid);
       p.epi.bias = k.qkv_b;
       gp_out_s(p, h->qk, 6 * hid, 0, 3 * hid);
-      p.epi.out_s_ncols = 2 * hid;
-      p.epi.out_vt = h->vT; p.epi.out_vt_zstride = (long)hd * 2 * NP; p.epi.out_vt_rstride = 2L * NP;
-      p.epi.out_vt_lo = NP; p.epi.out_vt_hd = hd; p.epi.out_vt_heads = c.heads;
+      if (!h->fused_attn) {                           // the unfused fallback wants V^T as a K-major operand of the P.V GEMM
+        p.epi.out_s_ncols = 2 * hid;
+        p.epi.out_vt = h->vT; p.epi.out_vt_zstride = (long)hd * 2 * NP; p.epi.out_vt_rstride = 2L * NP;
+        p.epi.out_vt_lo = NP; p.epi.out_vt_hd = hd; p.epi.out_vt_heads = c.heads;
+      }
       DEXB_TRY(plan_shared(&k.qkv, p));
     }
     {

@@ -54,7 +54,7 @@ struct LinAttW {
   const float *wq = nullptr, *wout = nullptr, *bout = nullptr, *g = nullptr;
   int C = 0;
   GemmPlan kv, apply;
-  GemmPlan vt;                        // fused path: v only, stored transposed for the tensor-core context kernel
+  GemmPlan vt;                        // fused path: v only, split rows for the tensor-core context kernel
   AttnPlan ctx_plan;
   int splits = 1, PP = 0;
   float *part_o = nullptr, *part_l = nullptr, *part_m = nullptr;
@@ -135,7 +135,7 @@ struct dexb_handle {
   dexb::GemmPlan g_down, g_up[4], g_tvs, g_tvo, g_pe, g_posconv, g_final;
   dexb::AttnPlan attn, attn_tv;
   bool fused_attn = false, fused_tv = false, fused_la = false;
-  dexb::bf16* la_vT = nullptr;                       // [B][128][hi(PP)|lo(PP)], shared by the three linear attentions
+  dexb::bf16* la_vT = nullptr;                       // v rows [B][P][hi(128)|lo(128)], shared by the three linear attentions
   // CUDA graph of one whole trajectory
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;

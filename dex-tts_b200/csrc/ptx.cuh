@@ -125,11 +125,25 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, SWIZZLE_128B descriptor (B operand stored [k rows][64 n-elements = 128 B], e.g. V rows [key][d]):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16 B units -- LBO = byte offset between 64-element groups along N,
+// SBO = byte offset between groups of 8 k-rows (1024 B when the rows are packed).
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, dense, M x N.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_major = 0) {
   return (1u << 4)                 // c_format = F32
          | (1u << 7)               // a_format = BF16
          | (1u << 10)              // b_format = BF16
+         | ((uint32_t)(b_mn_major & 1) << 16)   // b_major: 0 = K-major, 1 = MN-major
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
