@@ -152,6 +152,7 @@ static int layout_weights(dexb_handle* h, Arena& ar) {
     NEED_W(cb, "vit.pos_conv.0.bias", hid);
     (void)cw; h->posconv_b = cb->p;
     h->posconv_w = ar.get<bf16>((long)c.conv_pos * (c.conv_pos / 2) * hid * 4 * cg);
+    if (posconv_supported(hid, c.conv_pos_groups, c.conv_pos)) h->pc_w = ar.get<bf16>((long)hid * cg * c.conv_pos * c.conv_pos * 2);
     NEED_W(t0, "vit.t_embedder.mlp.0.weight", hid, 256);
     NEED_W(t2, "vit.t_embedder.mlp.2.weight", hid, hid);
     (void)t0; (void)t2;
@@ -236,6 +237,7 @@ int engine_finalize(dexb_handle* h, cudaStream_t st) {
   launch_transpose_scale(find_w(h, "vit.freq_new_pos_embed")->p, h->fpos, hid, fq, 1.f, st);
   launch_pack_split(find_w(h, "vit.x_embedder.proj.2.weight")->p, mid, h->pe_w, 2L * mid, mid, hid, mid, st);
   launch_pack_posconv(find_w(h, "vit.pos_conv.0.weight")->p, h->posconv_w, hid, hid / c.conv_pos_groups, c.conv_pos, st);
+  if (h->pc_w != nullptr) launch_posconv_pack_w(find_w(h, "vit.pos_conv.0.weight")->p, h->pc_w, c.conv_pos_groups, c.conv_pos, st);
   for (int i = 0; i < c.depth; ++i) {
     const std::string b = "vit.blocks." + std::to_string(i);
     DitBlockW& k = h->blocks[i];
@@ -451,6 +453,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->pe = ar.get<float>((long)B * h->Wq * hid);         // its mean over the frequency axis
   h->tiv_a = ar.get<float>((long)B * mid); h->tiv_d = ar.get<float>((long)B * mid);
   h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
+  h->pc_in = ar.get<bf16>(M * 2 * hid);
   h->xtok = ar.get<float>(M * hid);
   h->hS = ar.get<bf16>(M * 2 * hid);
   h->qk = ar.get<bf16>(M * 6 * hid);
@@ -569,6 +572,10 @@ static int build_plans(dexb_handle* h) {
     gp_out_f(p, h->pg, hid);                       // the mean over the frequency axis is taken by k_freq_mean (fixed order)
     p.epi.o_head_stride = cg;
     DEXB_TRY(plan_shared(&h->g_posconv, p));
+    const char* ep = getenv("DEXB_POSCONV");
+    h->ws_posconv = h->pc_w != nullptr && !(ep != nullptr && ep[0] == '0');
+    if (h->ws_posconv)
+      DEXB_TRY(posconv_plan_init(&h->pc_plan, h->pc_in, h->pc_w, h->posconv_b, h->pg, B, Fq, Wq, hid, G, c.conv_pos));
   }
   {
     const char* ea = getenv("DEXB_ATTN");
@@ -736,6 +743,7 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const
   DEXB_TRY(gemm_global_init());
   DEXB_TRY(kernels_global_init());
   DEXB_TRY(attn_global_init());
+  DEXB_TRY(posconv_global_init());
   DEXB_CHECK(c.variant == 0 || Tr >= 2, "dexb_plan: reference length must be >= 2, got %d", Tr);
   h->B = B; h->T = T; h->Ts = (c.variant == 1) ? Ts : 0; h->Tr = (c.variant == 1) ? Tr : 0; h->steps = n_steps;
   h->H0 = c.n_feats; h->W0 = T; h->H1 = c.n_feats / 2; h->W1 = T / 2;
@@ -897,8 +905,16 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
   const int N = h->Ntok;
   const long M = (long)B * N;
   GEMM(h->g_pe, h->g_pe.p);
-  LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, st));
-  GEMM(h->g_posconv, h->g_posconv.p);
+  if (h->ws_posconv) {
+    LAUNCH(launch_posconv_pack_in(h->xe, h->pc_in, B, h->Fq, h->Wq, hid, c.conv_pos_groups, st));
+    if (h->prof) prof_begin(h, "posconv_kernel", posconv_flop(h->pc_plan), st);
+    DEXB_TRY(posconv_launch(h->pc_plan, st));
+    if (h->prof) prof_end(h, st);
+    ++h->launches;
+  } else {
+    LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, st));
+    GEMM(h->g_posconv, h->g_posconv.p);
+  }
   LAUNCH(launch_freq_mean(h->pg, h->pe, B, h->Fq, h->Wq, hid, st));
   const float* mod = h->mod + (long)step * c.depth * 6 * hid;
   SView hs = {h->hS, 2L * hid, 0, hid};

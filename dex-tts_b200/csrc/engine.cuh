@@ -9,6 +9,7 @@
 #include "attn.cuh"
 #include "gemm_host.cuh"
 #include "kernels.cuh"
+#include "posconv.cuh"
 
 namespace dexb {
 
@@ -134,7 +135,9 @@ struct dexb_handle {
   // plans of the non-block GEMMs
   dexb::GemmPlan g_down, g_up[4], g_tvs, g_tvo, g_pe, g_posconv, g_final;
   dexb::AttnPlan attn, attn_tv;
-  bool fused_attn = false, fused_tv = false, fused_la = false;
+  dexb::PosConvPlan pc_plan;
+  bool fused_attn = false, fused_tv = false, fused_la = false, ws_posconv = false;
+  dexb::bf16 *pc_w = nullptr, *pc_in = nullptr;      // weight-stationary pos-conv: packed weights / packed input rows
   dexb::bf16* la_vT = nullptr;                       // v rows [B][P][hi(128)|lo(128)], shared by the three linear attentions
   // CUDA graph of one whole trajectory
   cudaGraph_t graph = nullptr;
