@@ -36,68 +36,89 @@ void launch_mask_down(const float* mask, float* mask1, int B, int T, int W1, cud
 // conv_in: one thread per pixel computes all C(=64) outputs of the 2->C 3x3 conv (K = 18: CUDA cores, the
 // contraction is too short for tensor cores).  Input = stack[mu, c_in * x] * mask  (diffusion.py:198,52; edm.py:96).
 // ------------------------------------------------------------------------------------------------
+// Thread = 8 output channels (one GroupNorm group at C == 64) x 4 x-adjacent pixels: the 144 weights of its channel octet
+// come from shared memory as 36 LDS.128 for 576 FMAs (the one-pixel-per-thread version issued one LDS per FMA and was
+// shared-memory bound: 57 us for 0.75 GFLOP).  8 consecutive lanes write the 256 B row of a pixel.
 template <int C>
-__global__ void __launch_bounds__(128) k_conv_in(const float* __restrict__ x, const float* __restrict__ mu,
+__global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, const float* __restrict__ mu,
                                                  const float* __restrict__ mask, const StepScalars* __restrict__ tab,
                                                  int step, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ raw, double* __restrict__ stats, int B, int H,
                                                  int W) {
-  __shared__ float ws[C * 18];
-  __shared__ float bs[C];
-  __shared__ float red[4][C / 8][2];
-  for (int i = threadIdx.x; i < C * 18; i += 128) ws[i] = w[i];
-  for (int i = threadIdx.x; i < C; i += 128) bs[i] = bias[i];
+  static_assert(C == 64, "one GroupNorm group per channel octet");
+  __shared__ __align__(16) float wsT[18][C];                 // [k][co]
+  __shared__ float red[8][C / 8][2];
+  for (int i = threadIdx.x; i < C * 18; i += 256) wsT[i % 18][i / 18] = w[i];
   __syncthreads();
-  const int wt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int wcol = wt * 128 + threadIdx.x;
-  const bool valid = wcol < W;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int oct = threadIdx.x & 7, quad = threadIdx.x >> 3;
+  const int c0 = oct * 8;
+  const int x0 = blockIdx.x * 128 + quad * 4;
   const float c_in = tab[step].c_in;
-  float in[18];
+  float va[3][6], vc[3][6];                                  // mu*mask and c_in*x*mask at rows h-1..h+1, columns x0-1..x0+4
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
+  for (int col = 0; col < 6; ++col) {
+    const int ww = x0 + col - 1;
+    const bool cok = ww >= 0 && ww < W;
+    const float m = cok ? mask[(long)b * W + ww] : 0.f;
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int hh = h + dy - 1, ww = wcol + dx - 1;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hh = h + dy - 1;
       float a = 0.f, c = 0.f;
-      if (valid && hh >= 0 && hh < H && ww >= 0 && ww < W) {
-        const float m = mask[(long)b * W + ww];
+      if (cok && hh >= 0 && hh < H) {
         const long idx = ((long)b * H + hh) * W + ww;
         a = mu[idx] * m;
         c = (c_in * x[idx]) * m;
       }
-      in[dy * 3 + dx] = a;
-      in[9 + dy * 3 + dx] = c;
+      va[dy][col] = a;
+      vc[dy][col] = c;
     }
-  float* orow = raw + (((long)b * H + h) * W + wcol) * C;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int g = 0; g < C / 8; ++g) {
-    float o[8];
-    float s = 0.f, ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int co = g * 8 + j;
-      float acc = bs[co];
-#pragma unroll
-      for (int k = 0; k < 18; ++k) acc = fmaf(ws[co * 18 + k], in[k], acc);
-      o[j] = acc;
-      if (valid) { s += acc; ss += acc * acc; }
-    }
-    if (valid) {
-      *reinterpret_cast<float4*>(orow + g * 8) = make_float4(o[0], o[1], o[2], o[3]);
-      *reinterpret_cast<float4*>(orow + g * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-    }
-    s = warp_sum(s);
-    ss = warp_sum(ss);
-    if (lane == 0) { red[warp][g][0] = s; red[warp][g][1] = ss; }
   }
+  float acc[4][8];
+  {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w;
+      acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 18; ++k) {                             // same accumulation order as the reference-ordered oracle: mu taps, then x taps
+    const float4 w0 = *reinterpret_cast<const float4*>(&wsT[k][c0]);
+    const float4 w1 = *reinterpret_cast<const float4*>(&wsT[k][c0 + 4]);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const int dy = (k % 9) / 3, dx = k % 3;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float iv = (k < 9) ? va[dy][p + dx] : vc[dy][p + dx];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(wv[i], iv, acc[p][i]);
+    }
+  }
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int wcol = x0 + p;
+    if (wcol < W) {
+      float* orow = raw + (((long)b * H + h) * W + wcol) * C + c0;
+      *reinterpret_cast<float4*>(orow) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+      *reinterpret_cast<float4*>(orow + 4) = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s += acc[p][i]; ss += acc[p][i] * acc[p][i]; }
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane < 8) { red[warp][lane][0] = s; red[warp][lane][1] = ss; }
   __syncthreads();
   if (threadIdx.x < C / 8) {
     const int g = threadIdx.x;               // channels-per-group == 8 when C == 64 (GroupNorm(8, 64))
-    double s = 0., ss = 0.;
-    for (int wq = 0; wq < 4; ++wq) { s += red[wq][g][0]; ss += red[wq][g][1]; }
-    atomicAdd(&stats[((long)b * (C / 8) + g) * 2], s);
-    atomicAdd(&stats[((long)b * (C / 8) + g) * 2 + 1], ss);
+    double ds = 0., dss = 0.;
+    for (int wq = 0; wq < 8; ++wq) { ds += red[wq][g][0]; dss += red[wq][g][1]; }
+    atomicAdd(&stats[((long)b * (C / 8) + g) * 2], ds);
+    atomicAdd(&stats[((long)b * (C / 8) + g) * 2 + 1], dss);
   }
 }
 
@@ -105,31 +126,25 @@ void launch_conv_in(const float* x, const float* mu, const float* mask, const St
                     const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
                     cudaStream_t st) {
   dim3 grid(cdiv(W, 128), H, B);
-  // stats layout is [B][8 groups][2]; with C == 64 a group is 8 channels, with C == 128 it is 16 (two 8-chunks):
-  // the C==128 instantiation folds pairs of chunks on the host side by giving G = C/8 "half groups" -- not needed
-  // for the shipped configs (dim 64), so only C == 64 is instantiated.
-  if (C == 64) k_conv_in<64><<<grid, 128, 0, st>>>(x, mu, mask, tab, step, w, bias, raw, stats, B, H, W);
+  // stats layout is [B][8 groups][2]; only C == 64 (decoder.dim 64, GroupNorm(8, 64): one group per channel octet) is
+  // instantiated -- engine_finalize rejects other widths.
+  if (C == 64) k_conv_in<64><<<grid, 256, 0, st>>>(x, mu, mask, tab, step, w, bias, raw, stats, B, H, W);
 }
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm-apply + Mish + mask (+ time bias | + residual) -> split-bf16.  8 channels per thread.
 // ------------------------------------------------------------------------------------------------
-// mean / rstd of the (at most two) images a 256-thread block touches, computed once per block from the double sums
-__device__ __forceinline__ void gn_block_stats(const double* __restrict__ stats, int B, int G, double n, int b0,
-                                               float (*s_mean)[8], float (*s_rstd)[8]) {
-  if (threadIdx.x < 2 * G) {
-    const int bi = threadIdx.x / G, g = threadIdx.x % G;
-    const int b = b0 + bi;
-    if (b < B) {
-      const double s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
-      const double mean_d = s / n;
-      double var_d = ss / n - mean_d * mean_d;
-      if (var_d < 0.) var_d = 0.;
-      s_mean[bi][g] = (float)mean_d;
-      s_rstd[bi][g] = (float)(1.0 / sqrt(var_d + 1e-5));
-    }
-  }
-  __syncthreads();
+// mean / rstd of one (image, group) straight from the double sums, per thread: two broadcast loads and a handful of DP
+// instructions -- no shared memory, no block barrier (a per-block prologue with __syncthreads was the top stall reason of the
+// GroupNorm-apply kernels: 2-2.8 stalled warps per issue slot, profiles/r01_ncu_small_kernels.md).
+__device__ __forceinline__ void gn_thread_stats(const double* __restrict__ stats, int G, double inv_n, int b, int g, float& mean,
+                                                float& rstd) {
+  const double2 s = *reinterpret_cast<const double2*>(stats + ((long)b * G + g) * 2);
+  const double mean_d = s.x * inv_n;
+  double var_d = s.y * inv_n - mean_d * mean_d;
+  if (var_d < 0.) var_d = 0.;
+  mean = (float)mean_d;
+  rstd = 1.f / sqrtf((float)(var_d + 1e-5));                // sums and the variance in double, only the root in fp32
 }
 // Mish with fast intrinsics (ex2.approx / approximate divide: ~1e-6 relative, far inside the split-bf16 noise floor)
 __device__ __forceinline__ float mish_fast(float x) {
@@ -139,44 +154,21 @@ __device__ __forceinline__ float mish_fast(float x) {
   return x * __fdividef(n, n + 2.f);
 }
 
-__global__ void __launch_bounds__(256) k_gn_apply(const GnApplyArgs a) {
-  __shared__ float s_mean[2][8], s_rstd[2][8];
-  const int cpt = a.C / 8;                                   // threads per pixel
-  const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long total = (long)a.B * a.P * cpt;
+// grid = (chunks of ITEMS * 256 eight-channel groups, image): all index math is 32-bit with shifts (C/8 is a power of two) --
+// the first version derived (image, pixel, column) from a flat 64-bit index with four 64-bit divisions per item and was bound
+// by that integer code (2.7 TB/s), not by memory.  The double-precision statistics prologue is paid once per block and every
+// thread has ITEMS independent 32 B loads (+ residual) in flight; 256 % (C/8) == 0, so a thread keeps the same channel group
+// c0 for all its items (gamma / beta / time bias live in registers).
+template <int ITEMS>
+__global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
+  const int b = blockIdx.y;
+  const int cpt = a.C >> 3;                                  // threads per pixel: 8 or 16
+  const int cshift = 31 - __clz(cpt);
+  const unsigned ngroups = (unsigned)a.P << cshift;          // eight-channel groups per image
+  const unsigned base = blockIdx.x * (unsigned)(256 * ITEMS);
   const int gs = a.C / a.G;
-  const int b0 = (int)((blockIdx.x * (long)blockDim.x / cpt) / a.P);
-  gn_block_stats(a.stats, a.B, a.G, (double)a.P * gs, b0, s_mean, s_rstd);
-  if (gid >= total) return;
-  const int c0 = (int)(gid % cpt) * 8;
-  const long pix = gid / cpt;                                // global pixel row
-  const int b = (int)(pix / a.P);
-  const int w = (int)((pix % a.P) % a.W);
+  const int c0 = (int)(threadIdx.x & (cpt - 1)) * 8;
   const int g = c0 / gs;
-  const float mean = s_mean[b - b0][g], rstd = s_rstd[b - b0][g];
-  const float m = a.mask[(long)b * a.mask_stride + w];
-  const float* rp = a.raw + pix * a.C + c0;
-  const float4 r0 = *reinterpret_cast<const float4*>(rp);
-  const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-  float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-  float res[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) res[i] = 0.f;
-  if (a.resid_s.p != nullptr) {
-    const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
-    load_split8(q + a.resid_s.hi, q + a.resid_s.lo, res);
-  } else if (a.resid_f != nullptr) {
-    const float* q = a.resid_f + pix * a.resid_f_stride + c0;
-    const float4 q0 = *reinterpret_cast<const float4*>(q);
-    const float4 q1 = *reinterpret_cast<const float4*>(q + 4);
-    res[0] = q0.x * m; res[1] = q0.y * m; res[2] = q0.z * m; res[3] = q0.w * m;
-    res[4] = q1.x * m; res[5] = q1.y * m; res[6] = q1.z * m; res[7] = q1.w * m;
-  } else if (a.rin_w != nullptr) {
-    // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
-    const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
-  }
   float ga[8], be[8], tb[8];
   {
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
@@ -190,19 +182,80 @@ __global__ void __launch_bounds__(256) k_gn_apply(const GnApplyArgs a) {
       tb[0] = t0.x; tb[1] = t0.y; tb[2] = t0.z; tb[3] = t0.w; tb[4] = t1.x; tb[5] = t1.y; tb[6] = t1.z; tb[7] = t1.w;
     }
   }
+  const long img_row0 = (long)b * a.P;                       // first pixel row of this image
+  // ---- phase 1: all loads
+  float4 r0[ITEMS], r1[ITEMS];
+  uint4 q0[ITEMS], q1[ITEMS];                                // residual: (hi, lo) of an S row or two float4 of an F row
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float y = (v[i] - mean) * rstd * ga[i] + be[i];
-    y = mish_fast(y) * m;
-    y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
-    v[i] = y + res[i];
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned gi = base + j * 256 + threadIdx.x;
+    const long pix = img_row0 + ((gi < ngroups) ? (gi >> cshift) : 0u);
+    const float* rp = a.raw + pix * a.C + c0;
+    r0[j] = *reinterpret_cast<const float4*>(rp);
+    r1[j] = *reinterpret_cast<const float4*>(rp + 4);
+    q0[j] = make_uint4(0, 0, 0, 0); q1[j] = make_uint4(0, 0, 0, 0);
+    if (a.resid_s.p != nullptr) {
+      const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
+      q0[j] = *reinterpret_cast<const uint4*>(q + a.resid_s.hi);
+      q1[j] = *reinterpret_cast<const uint4*>(q + a.resid_s.lo);
+    } else if (a.resid_f != nullptr) {
+      const float* q = a.resid_f + pix * a.resid_f_stride + c0;
+      q0[j] = *reinterpret_cast<const uint4*>(q);
+      q1[j] = *reinterpret_cast<const uint4*>(q + 4);
+    }
   }
-  bf16* op = a.out.p + pix * a.out.stride + c0;
-  store_split8(op + a.out.hi, op + a.out.lo, v);
+  float mean, rstd;
+  gn_thread_stats(a.stats, a.G, 1.0 / ((double)a.P * gs), b, g, mean, rstd);
+  // ---- phase 2: normalise, Mish, mask, (+ time bias), + residual, split store
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned gi = base + j * 256 + threadIdx.x;
+    if (gi >= ngroups) continue;
+    const unsigned p = gi >> cshift;                          // pixel inside the image
+    const long pix = img_row0 + p;
+    const int w = (int)(p % (unsigned)a.W);
+    const float m = a.mask[(long)b * a.mask_stride + w];
+    float v[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+    float res[8];
+    if (a.resid_s.p != nullptr) {
+      const bf16* hh = reinterpret_cast<const bf16*>(&q0[j]);
+      const bf16* ll = reinterpret_cast<const bf16*>(&q1[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = join2(hh[i], ll[i]);
+    } else if (a.resid_f != nullptr) {
+      const float* f0 = reinterpret_cast<const float*>(&q0[j]);
+      const float* f1 = reinterpret_cast<const float*>(&q1[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { res[i] = f0[i] * m; res[4 + i] = f1[i] * m; }
+    } else if (a.rin_w != nullptr) {
+      // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
+      const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = (v[i] - mean) * rstd * ga[i] + be[i];
+      y = mish_fast(y) * m;
+      y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
+      v[i] = y + res[i];
+    }
+    bf16* op = a.out.p + pix * a.out.stride + c0;
+    store_split8(op + a.out.hi, op + a.out.lo, v);
+  }
 }
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
-  const long total = (long)a.B * a.P * (a.C / 8);
-  k_gn_apply<<<cdiv(total, 256), 256, 0, st>>>(a);
+  const long ngroups = (long)a.P * (a.C / 8);
+  if (ngroups >= 8 * 256) {
+    dim3 grid(cdiv(ngroups, 2 * 256), a.B);
+    k_gn_apply<2><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid(cdiv(ngroups, 256), a.B);
+    k_gn_apply<1><<<grid, 256, 0, st>>>(a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -210,62 +263,80 @@ void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
 // d = x/sigma - D/sigma;  x <- x + (sigma_next - sigma) * d        (edm.py:97,197,203)
 // 8 lanes per pixel (C == 64).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gn_final(const float* __restrict__ raw, int C, int G,
+template <int ITEMS>
+__global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ raw, int C, int G,
                                                   const double* __restrict__ stats, const float* __restrict__ gamma,
                                                   const float* __restrict__ beta, const float* __restrict__ fc_w,
                                                   const float* __restrict__ fc_b, const float* __restrict__ mask,
                                                   float* __restrict__ x, float* __restrict__ den_out,
                                                   const StepScalars* __restrict__ tab, int step, int B, int P, int W) {
-  const int cpt = C / 8;                                      // == 8
-  const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long total = (long)B * P * cpt;
-  const bool active = gid < total;
-  const long pix = active ? gid / cpt : 0;
-  const int c0 = (int)(gid % cpt) * 8;
-  const int b = (int)(pix / P);
-  const int w = (int)((pix % P) % W);
-  __shared__ float s_mean[2][8], s_rstd[2][8];
-  const int b0 = (int)((blockIdx.x * (long)blockDim.x / cpt) / P);
-  gn_block_stats(stats, B, G, (double)P * (C / G), b0, s_mean, s_rstd);
-  float part = 0.f;
-  float m = 0.f;
-  if (active) {
-    const int gs = C / G;
-    const int g = c0 / gs;
-    const float mean = s_mean[b - b0][g], rstd = s_rstd[b - b0][g];
-    m = mask[(long)b * W + w];
-    const float* rp = raw + pix * C + c0;
-    const float4 r0 = *reinterpret_cast<const float4*>(rp);
-    const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-    const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+  // grid = (chunks of ITEMS * 256 eight-channel groups, image); C == 64: 8 lanes per pixel (32-bit index math, see k_gn_apply)
+  const int b = blockIdx.y;
+  const unsigned ngroups = (unsigned)P << 3;
+  const unsigned base = blockIdx.x * (unsigned)(256 * ITEMS);
+  const int c0 = (int)(threadIdx.x & 7) * 8;
+  const int g = c0 / (C / G);
+  float ga[8], be[8], fw[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const float y = mish_fast((v[i] - mean) * rstd * gamma[c] + beta[c]) * m;
-      part = fmaf(fc_w[c], y * m, part);
-    }
+  for (int i = 0; i < 8; ++i) { ga[i] = gamma[c0 + i]; be[i] = beta[c0 + i]; fw[i] = fc_w[c0 + i]; }
+  const long img_row0 = (long)b * P;
+  float4 r0[ITEMS], r1[ITEMS];
+  float xin[ITEMS];
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned gi = base + j * 256 + threadIdx.x;
+    const float* rp = raw + (img_row0 + ((gi < ngroups) ? (gi >> 3) : 0u)) * C + c0;
+    r0[j] = *reinterpret_cast<const float4*>(rp);
+    r1[j] = *reinterpret_cast<const float4*>(rp + 4);
+    xin[j] = (gi < ngroups && c0 == 0) ? x[img_row0 + (gi >> 3)] : 0.f;
   }
-  // reduce over the 8 lanes of a pixel (cpt == 8, aligned groups of lanes)
-  part += __shfl_xor_sync(0xffffffffu, part, 1);
-  part += __shfl_xor_sync(0xffffffffu, part, 2);
-  part += __shfl_xor_sync(0xffffffffu, part, 4);
-  if (active && c0 == 0) {
-    const StepScalars sc = tab[step];
-    const float fx = (part + fc_b[0]) * m;
-    const float xv = x[pix];
-    const float den = sc.c_skip * xv + sc.c_out * fx;
-    const float inv = 1.f / sc.sigma;
-    const float d = inv * xv - inv * den;
-    if (den_out != nullptr) den_out[pix] = den;
-    else x[pix] = xv + (sc.sigma_next - sc.sigma) * d;
+  const StepScalars sc = tab[step];
+  const float fcb = fc_b[0];
+  float mean, rstd;
+  gn_thread_stats(stats, G, 1.0 / ((double)P * (C / G)), b, g, mean, rstd);
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const unsigned gi = base + j * 256 + threadIdx.x;
+    const bool active = gi < ngroups;
+    const unsigned p = active ? (gi >> 3) : 0u;
+    const long pix = img_row0 + p;
+    float part = 0.f;
+    float m = 0.f;
+    if (active) {
+      m = mask[(long)b * W + (int)(p % (unsigned)W)];
+      const float v[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = mish_fast((v[i] - mean) * rstd * ga[i] + be[i]) * m;
+        part = fmaf(fw[i], y * m, part);
+      }
+    }
+    // reduce over the 8 lanes of a pixel (aligned groups of lanes)
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (active && c0 == 0) {
+      const float fx = (part + fcb) * m;
+      const float xv = xin[j];
+      const float den = sc.c_skip * xv + sc.c_out * fx;
+      const float inv = 1.f / sc.sigma;
+      const float d = inv * xv - inv * den;
+      if (den_out != nullptr) den_out[pix] = den;
+      else x[pix] = xv + (sc.sigma_next - sc.sigma) * d;
+    }
   }
 }
 void launch_gn_final(const float* raw, int C, int G, const double* stats, const float* gamma, const float* beta,
                      const float* fc_w, const float* fc_b, const float* mask, float* x, float* den_out,
                      const StepScalars* tab, int step, int B, int H, int W, cudaStream_t st) {
-  const long total = (long)B * H * W * (C / 8);
-  k_gn_final<<<cdiv(total, 256), 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B,
-                                                H * W, W);
+  const long ngroups = (long)H * W * 8;                     // C == 64 (engine_finalize)
+  if (ngroups >= 8 * 256) {
+    dim3 grid(cdiv(ngroups, 2 * 256), B);
+    k_gn_final<2><<<grid, 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
+  } else {
+    dim3 grid(cdiv(ngroups, 256), B);
+    k_gn_final<1><<<grid, 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,47 +501,65 @@ void launch_la_combine(const float* part_o, const float* part_l, const float* pa
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
 // (q is linear in x, so  x + g*to_out(ctx^T q) == W_eff x + g*b_out : the whole attention read-out is one
-//  per-sample CxC matrix.)   Two small fully parallel kernels: m1 = ctxn^T Wq, then W_eff = I + g Wout m1.
-__global__ void __launch_bounds__(256) k_la_m1(const float* __restrict__ ctx, const float* __restrict__ ssum,
-                                               const float* __restrict__ wq, float* __restrict__ m1, int B, int C) {
-  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (idx >= (long)B * 128 * C) return;
-  const int ci = (int)(idx % C);
-  const int he = (int)((idx / C) % 128);
-  const int b = (int)(idx / ((long)C * 128));
-  const int h = he >> 5, e = he & 31;
-  float acc = 0.f;
-#pragma unroll 8
-  for (int d = 0; d < 32; ++d) {
-    const float cn = ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] / ssum[b * 128 + h * 32 + d];
-    acc = fmaf(cn, wq[(h * 32 + d) * C + ci], acc);
-  }
-  m1[idx] = acc;
-}
-__global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ m1, const float* __restrict__ wout,
+//  per-sample CxC matrix.)
+// One block = (sample b, 8 output channels): T[r][h,d] = sum_e W_out[co][h,e] ctxn[b][h][d][e] through shared memory, then
+// W_eff[co][ci] = delta + g * sum_{h,d} T[r][h,d] W_q[h,d][ci].  (The first version materialised ctxn^T W_q with two dependent
+// launches of 128-step serial loops: 31 us per LinearAttention for 6 MFLOP.)
+__global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, const float* __restrict__ ssum,
+                                                 const float* __restrict__ wq, const float* __restrict__ wout,
                                                  const float* __restrict__ bout, const float* __restrict__ g,
-                                                 bf16* __restrict__ weff, float* __restrict__ beff, int B, int C) {
-  const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (idx >= (long)B * C * C) return;
-  const int ci = (int)(idx % C);
-  const int co = (int)((idx / C) % C);
-  const int b = (int)(idx / ((long)C * C));
+                                                 bf16* __restrict__ weff, float* __restrict__ beff, int C) {
+  __shared__ float cn[4][32][33];
+  __shared__ float Ts[8][128];
+  const int b = blockIdx.y, co0 = blockIdx.x * 8, tid = threadIdx.x;
+  for (int i = tid; i < 4096; i += 256) {
+    const int h = i >> 10, d = (i >> 5) & 31, e = i & 31;
+    cn[h][d][e] = ctx[(long)b * 4096 + i] / ssum[b * 128 + h * 32 + d];
+  }
+  __syncthreads();
+  for (int o = tid; o < 1024; o += 256) {
+    const int r = o >> 7, hd = o & 127, h = hd >> 5, d = hd & 31;
+    const float* wp = wout + (long)(co0 + r) * 128 + h * 32;
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc = fmaf(__ldg(wp + e), cn[h][d][e], acc);
+    Ts[r][hd] = acc;
+  }
+  __syncthreads();
+  // thread = input channel ci and rows r0, r0 + 256/C, ...: one W_q column serves all its outputs; 32 independent loads in flight
   const float gg = g[0];
-  const float* mp = m1 + (long)b * 128 * C + ci;
-  const float* wp = wout + (long)co * 128;
-  float acc = 0.f;
-#pragma unroll 8
-  for (int he = 0; he < 128; ++he) acc = fmaf(wp[he], mp[(long)he * C], acc);
-  const float v = gg * acc + (co == ci ? 1.f : 0.f);
-  bf16* row = weff + ((long)b * C + co) * (2 * C);
-  split2(v, row[ci], row[C + ci]);
-  if (ci == 0) beff[b * C + co] = gg * bout[co];
+  const int ci = tid % C, r0 = tid / C, rstep = 256 / C;     // C == 64: rows r0, r0+4;  C == 128: rows r0, r0+2, r0+4, r0+6
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int nr = 8 / rstep;                                  // 2 or 4
+#pragma unroll 4
+  for (int h0 = 0; h0 < 128; h0 += 32) {
+    float wv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wv[k] = __ldg(wq + (long)(h0 + k) * C + ci);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i < nr) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[i] = fmaf(Ts[r0 + i * rstep][h0 + k], wv[k], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= nr) break;
+    const int co = co0 + r0 + i * rstep;
+    const float v = gg * acc[i] + (co == ci ? 1.f : 0.f);
+    bf16* row = weff + ((long)b * C + co) * (2 * C);
+    split2(v, row[ci], row[C + ci]);
+    if (ci == 0) beff[b * C + co] = gg * bout[co];
+  }
 }
 int kernels_global_init() { return 0; }
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq, const float* wout, const float* bout,
                     const float* g, float* m1, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
-  k_la_m1<<<cdiv((long)B * 128 * C, 256), 256, 0, st>>>(ctx, ssum, wq, m1, B, C);
-  k_la_weff<<<cdiv((long)B * C * C, 256), 256, 0, st>>>(m1, wout, bout, g, weff, beff, B, C);
+  (void)m1;
+  dim3 grid(C / 8, B);
+  k_la_weff<<<grid, 256, 0, st>>>(ctx, ssum, wq, wout, bout, g, weff, beff, C);
 }
 
 // ------------------------------------------------------------------------------------------------

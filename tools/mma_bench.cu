@@ -1,0 +1,140 @@
+// Micro-benchmark of tcgen05.mma on B200 (tuning aid, not part of the library):
+//   1. cycles per MMA for M = 128, K = 16 bf16, N in {16..256}, A from shared memory (SS) or tensor memory (TS);
+//   2. correctness of a K-major SWIZZLE_128B A descriptor whose start address is shifted by whole 128 B rows
+//      (not 1024 B aligned) -- the "halo" trick a 3x3 convolution needs to reuse one staged row slab for its dx taps.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I dex-tts_b200/csrc tools/mma_bench.cu -o gpurun_out/mma_bench
+#include <cuda_bf16.h>
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+using namespace dexb;
+
+__global__ void __launch_bounds__(128, 1) k_time(int n, int ts_mode, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 64 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+  if (threadIdx.x < 32) ptx::tmem_alloc<512>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, n);
+    const uint32_t a = ptx::smem_u32(smem), b = a + 16384;
+    long long best = 1ll << 60;
+    for (int r = 0; r < 5; ++r) {
+      __syncwarp();
+      long long t0 = 0, t1 = 0;
+      if (ptx::elect_one()) {
+        t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+          const uint32_t ko = (i & 3) * 32;
+          if (ts_mode) ptx::mma_bf16_ts(tmem, tmem + 256 + (i & 3) * 8, ptx::make_desc_k128(b + ko), idesc, i ? 1u : 0u);
+          else ptx::mma_bf16_ss(tmem, ptx::make_desc_k128(a + ko), ptx::make_desc_k128(b + ko), idesc, i ? 1u : 0u);
+        }
+        ptx::mma_commit(&bar);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&bar, r & 1);
+      t1 = clock64();
+      long long mx = t0;
+      for (int o = 16; o > 0; o >>= 1) { long long v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+      if (t1 - mx < best) best = t1 - mx;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = best;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
+}
+
+// A[r][k] = (k == 0) ? r + 1 : 0 for r in [0, 144), written with the TMA 128B swizzle; B[n][k] = (n == 0 && k == 0).
+// D = A_shift B^T  -> D[m][0] must be m + shift + 1.
+__global__ void __launch_bounds__(128, 1) k_shift(int shift, int use_base_offset, float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  __syncthreads();
+  __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* Bm = reinterpret_cast<__nv_bfloat16*>(smem + 32768);
+  for (int r = threadIdx.x; r < 144; r += 128) {
+    // element (r, k = 0): 16-byte chunk 0 of row r lands at chunk (0 ^ (r & 7))
+    A[(r * 128 + ((0 ^ (r & 7)) << 4)) / 2] = __float2bfloat16((float)(r + 1));
+  }
+  if (threadIdx.x == 0) Bm[0] = __float2bfloat16(1.f);
+  if (threadIdx.x == 0) { ptx::mbar_init(&bar, 1); ptx::fence_barrier_init(); }
+  if (threadIdx.x < 32) ptx::tmem_alloc<32>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x < 32) {
+    if (ptx::elect_one()) {
+      const uint32_t a = ptx::smem_u32(smem) + shift * 128;
+      uint64_t da = ptx::make_desc_k128(a);
+      if (use_base_offset) da |= (uint64_t)((a >> 7) & 7) << 49;
+      ptx::mma_bf16_ss(tmem, da, ptx::make_desc_k128(ptx::smem_u32(smem + 32768)), ptx::make_idesc_bf16(128, 16), 0u);
+      ptx::mma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  ptx::mbar_wait(&bar, 0);
+  ptx::tc_fence_after();
+  float v[32];
+  {
+    uint32_t* q = reinterpret_cast<uint32_t*>(v);
+    const uint32_t ta = tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                 : "r"(ta)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  }
+  out[threadIdx.x] = v[0];
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<32>(tmem);
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 8);
+  cudaFuncSetAttribute(k_time, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024);
+  cudaFuncSetAttribute(k_shift, cudaFuncAttributeMaxDynamicSharedMemorySize, 50 * 1024);
+  const int reps = 512;
+  const int ns[] = {16, 32, 64, 96, 128, 160, 192, 256};
+  for (int grid : {1, 148}) {
+    for (int mode = 0; mode < 2; ++mode) {
+      for (int n : ns) {
+        k_time<<<grid, 128, 66 * 1024>>>(n, mode, reps, d);
+        long long c = 0;
+        cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        printf("grid %3d  %s  M=128 N=%3d K=16: %7.1f cycles/MMA  (ideal %5.1f)\n", grid, mode ? "TS" : "SS", n, (double)c / reps,
+               128.0 * n / 256.0);
+      }
+    }
+  }
+  float* o;
+  cudaMalloc(&o, 128 * 4);
+  for (int bo = 0; bo < 2; ++bo)
+    for (int shift = 0; shift < 10; ++shift) {
+      k_shift<<<1, 128, 50 * 1024>>>(shift, bo, o);
+      float h[128];
+      cudaError_t e = cudaMemcpy(h, o, sizeof(h), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { printf("shift %d: error %s\n", shift, cudaGetErrorString(e)); return 1; }
+      int bad = 0;
+      for (int m = 0; m < 128; ++m) bad += (h[m] != (float)(m + shift + 1));
+      printf("row-shifted A descriptor: shift %d rows, base_offset field %s: %s (D[0..3][0] = %g %g %g %g, D[127][0] = %g)\n", shift,
+             bo ? "set" : "0", bad ? "MISMATCH" : "ok", h[0], h[1], h[2], h[3], h[127]);
+    }
+  return 0;
+}
