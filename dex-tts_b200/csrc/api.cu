@@ -260,10 +260,16 @@ int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float
   AttnPlan ap;
   const char* vmn = getenv("DEXB_VMN");
   int r = attn_plan_init(&ap, qs, (vmn != nullptr && vmn[0] == '1') ? nullptr : vT, os, B, N, NP, heads, hid);
+  float* tail = nullptr;                                 // tail-split partials (tile counts that leave a partial last wave)
+  const long tail_floats = attn_tail_scratch_floats(B, N, heads);
+  if (r == 0 && tail_floats > 0) {
+    if (cudaMalloc(&tail, tail_floats * sizeof(float)) == cudaSuccess) attn_plan_set_tail(&ap, tail);
+  }
   if (r == 0) r = attn_launch(ap, st);
   if (r == 0) launch_unpack_rows(os, out_dev, M, hid, st);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(qs); cudaFree(vT); cudaFree(os);
+  if (tail != nullptr) cudaFree(tail);
   if (r != 0) return r;
   DEXB_CHECK(e == cudaSuccess, "attn_test: kernel failed: %s", cudaGetErrorString(e));
   return 0;

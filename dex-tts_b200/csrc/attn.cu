@@ -11,6 +11,7 @@
 #include "attn.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ptx.cuh"
@@ -54,13 +55,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // DiT / TV: blockIdx.x = query tile, all key tiles.  Split-KV mode (linear-attention context, one 128-row query tile):
-  // blockIdx.x = key split, the CTA covers key tiles [t0, t0 + nt) and writes un-normalised partials.
-  const int split = (p.kv_splits > 1) ? (int)blockIdx.x : 0;
-  const int m0 = (p.kv_splits > 1) ? 0 : (int)blockIdx.x * kAtBM;
-  const int z = blockIdx.y;
+  // blockIdx.x = key split, the CTA covers key tiles [t0, t0 + nt) and writes un-normalised partials.  Tail-split mode (DiT):
+  // 1-D grid of work items, the last ones cover a key range of their tile only.
+  int split = 0, m0, z, t0 = 0, nt = p.nt, omode = p.out_mode;
+  long part_idx = 0;
+  if (p.tail_splits > 1) {
+    const int item = (int)blockIdx.x;
+    int tile = item;
+    if (item >= p.tail_first) {
+      const int k = item - p.tail_first;
+      tile = p.tail_first + k / p.tail_splits;
+      split = k % p.tail_splits;
+      t0 = split * p.tail_tps;
+      nt = max(0, min(p.nt, t0 + p.tail_tps) - t0);
+      omode = 2;
+      part_idx = k;
+    }
+    z = tile / p.q_tiles;
+    m0 = (tile % p.q_tiles) * kAtBM;
+  } else if (p.kv_splits > 1) {
+    split = (int)blockIdx.x;
+    m0 = 0;
+    z = blockIdx.y;
+    t0 = split * p.tiles_per_split;
+    nt = max(0, min(p.nt, t0 + p.tiles_per_split) - t0);
+    part_idx = (long)(z / p.nheads) * p.kv_splits + split;
+  } else {
+    m0 = (int)blockIdx.x * kAtBM;
+    z = blockIdx.y;
+  }
   const int b = z / p.nheads, head = z % p.nheads;
-  const int t0 = split * p.tiles_per_split;
-  const int nt = max(0, min(p.nt, t0 + p.tiles_per_split) - t0);
   const int kch = p.kchunks;
 
   if (threadIdx.x == 0) {
@@ -274,12 +298,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += xch[(hf ^ 1) * 128 + r];
     const int row = m0 + r;
-    if (p.out_mode == 2) {
+    if (omode == 2) {
       // split-KV partials: O (un-normalised, fp32), row sum l and row max m of this key range
-      float* po = p.part_o + (((long)b * p.kv_splits + split) * kAtBM + r) * kAtHD;
+      float* po = p.part_o + (part_idx * kAtBM + r) * kAtHD;
       if (hf == 0) {
-        p.part_l[((long)b * p.kv_splits + split) * kAtBM + r] = l;
-        p.part_m[((long)b * p.kv_splits + split) * kAtBM + r] = m;
+        p.part_l[part_idx * kAtBM + r] = l;
+        p.part_m[part_idx * kAtBM + r] = m;
       }
       if (nt > 0) {
         ptx::mbar_wait(o_full, 0);
@@ -309,7 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         const int col = head * kAtHD + hf * 64 + c * 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] *= inv;
-        if (p.out_mode == 0) {
+        if (omode == 0) {
           bf16* op = p.out + grow * p.out_stride + col;
 #pragma unroll
           for (int i = 0; i < 32; i += 16) store_split16(op + p.out_hi + i, op + p.out_lo + i, &o[i]);
@@ -377,6 +401,7 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   p.nt = (N + kAtBN - 1) / kAtBN;
   p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid; p.q_img_rows = N;
   p.kchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
+  p.q_tiles = (N + kAtBM - 1) / kAtBM; p.tail_first = B * heads * p.q_tiles; p.tail_splits = 1; p.tail_tps = p.nt;
   p.k_hi = hid; p.k_lo = 4 * hid;
   p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
   p.out_mode = 0;
@@ -443,12 +468,96 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   return 0;
 }
 
+// Merge of the tail-split partials: out = sum_s f_s O_s / sum_s f_s l_s,  f_s = exp2((m_s - max_s m_s) * scale*log2e)  -> split rows.
+// One block per split tile, thread = (row, half of the 128 output columns).
+__global__ void __launch_bounds__(256) k_attn_tail_merge(const AttnParams p) {
+  const int k = blockIdx.x, tile = p.tail_first + k;
+  const int z = tile / p.q_tiles, m0 = (tile % p.q_tiles) * kAtBM;
+  const int b = z / p.nheads, head = z % p.nheads;
+  const int r = threadIdx.x >> 1, hf = threadIdx.x & 1;
+  const int row = m0 + r;
+  if (row >= p.NQ) return;
+  const int S = p.tail_splits;
+  float M = -INFINITY;
+  for (int s = 0; s < S; ++s) M = fmaxf(M, p.part_m[((long)k * S + s) * kAtBM + r]);
+  float o[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  float l = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const long pi = ((long)k * S + s) * kAtBM + r;
+    const float f = exp2f((p.part_m[pi] - M) * p.scale_log2e);      // exp2(-inf) = 0 for an empty split
+    l = fmaf(f, p.part_l[pi], l);
+    const float* po = p.part_o + pi * kAtHD + hf * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+      float v[8];
+      ld256_f32(po + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[i + j] = fmaf(f, v[j], o[i + j]);
+    }
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o[i] *= inv;
+  bf16* op = p.out + ((long)b * p.NQ + row) * p.out_stride + head * kAtHD + hf * 64;
+#pragma unroll
+  for (int i = 0; i < 64; i += 16) store_split16(op + p.out_hi + i, op + p.out_lo + i, &o[i]);
+}
+
+static int attn_sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+// tiles beyond the last full wave, and how many key ranges each is cut into so that they all run at once
+static void attn_tail_shape(int total_tiles, int nt, int* first, int* splits, int* tps) {
+  const int sms = attn_sm_count();
+  const int rem = total_tiles % sms;
+  *first = total_tiles; *splits = 1; *tps = nt;
+  if (rem == 0 || total_tiles < sms) return;
+  int S = sms / rem;
+  if (S > 8) S = 8;
+  if (S > nt) S = nt;
+  if (S < 2) return;
+  const int t = (nt + S - 1) / S;
+  *first = total_tiles - rem; *splits = (nt + t - 1) / t; *tps = t;     // no empty ranges
+  if (*splits < 2) { *first = total_tiles; *splits = 1; *tps = nt; }
+}
+long attn_tail_scratch_floats(int B, int N, int heads) {
+  const int qt = (N + kAtBM - 1) / kAtBM, nt = (N + kAtBN - 1) / kAtBN;
+  int first, S, tps;
+  attn_tail_shape(B * heads * qt, nt, &first, &S, &tps);
+  if (S < 2) return 0;
+  return (long)(B * heads * qt - first) * S * (kAtBM * kAtHD + 2 * kAtBM);
+}
+void attn_plan_set_tail(AttnPlan* ap, float* scratch) {
+  AttnParams& p = ap->p;
+  const int total = ap->B * p.nheads * p.q_tiles;
+  int first, S, tps;
+  attn_tail_shape(total, p.nt, &first, &S, &tps);
+  const char* e = getenv("DEXB_ATTN_TAIL");
+  if (S < 2 || scratch == nullptr || (e != nullptr && e[0] == '0')) return;
+  p.tail_first = first; p.tail_splits = S; p.tail_tps = tps;
+  const long n = (long)(total - first) * S;
+  p.part_o = scratch; p.part_l = scratch + n * kAtBM * kAtHD; p.part_m = p.part_l + n * kAtBM;
+}
+
 int attn_launch(const AttnPlan& ap, cudaStream_t st) {
+  const AttnParams& p = ap.p;
+  if (p.tail_splits > 1) {
+    const int total = ap.B * p.nheads * p.q_tiles, rem = total - p.tail_first;
+    attn_fwd_kernel<<<p.tail_first + rem * p.tail_splits, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, p);
+    k_attn_tail_merge<<<rem, 256, 0, st>>>(p);
+    DEXB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((unsigned)(ap.p.kv_splits > 1 ? ap.p.kv_splits : (ap.p.NQ + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
   attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, ap.p);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
 }
+int attn_launch_count(const AttnPlan& ap) { return ap.p.tail_splits > 1 ? 2 : 1; }
 
 double attn_flop(const AttnPlan& ap) { return 4.0 * ap.B * ap.p.nheads * (double)ap.p.NQ * ap.p.NK * kAtHD; }
 

@@ -40,6 +40,11 @@ struct AttnParams {
   const float* rowmask;      // [b][rowmask_w], column = row % rowmask_w
   int rowmask_w;
   float *part_o, *part_l, *part_m;
+  // Tail split (DiT self-attention): the grid is 1-D over (image, head, query tile) work items.  Items [0, tail_first) run all key
+  // tiles; each of the remaining tiles -- the ones that would form a partial last wave on the SMs -- is cut into tail_splits
+  // key ranges of tail_tps tiles that run concurrently and write mode-2 partials, merged by k_attn_tail_merge.
+  int q_tiles;               // query tiles per (image, head)
+  int tail_first, tail_splits, tail_tps;
 };
 
 struct AttnPlan {
@@ -63,7 +68,12 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
 // (split rows [b][P][hi(128)|lo(128)] from the GEMM engine, used as an MN-major B operand).  Split over the pixels; partials are merged by launch_la_combine.
 int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
                       float* part_l, float* part_m, int B, int P, int PP, int C, int splits);
+// Balance the last partial wave of the DiT attention (see AttnParams::tail_first).  Returns the number of floats of scratch the
+// partials need (0: the tile count already fills the SMs evenly, nothing to do); call attn_plan_set_tail with that scratch.
+long attn_tail_scratch_floats(int B, int N, int heads);
+void attn_plan_set_tail(AttnPlan* ap, float* scratch);
 int attn_launch(const AttnPlan& ap, cudaStream_t st);
+int attn_launch_count(const AttnPlan& ap);      // kernels one attn_launch enqueues
 double attn_flop(const AttnPlan& ap);
 
 }  // namespace dexb

@@ -463,6 +463,11 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->scores = ar.get<float>(fused ? 16 : (long)B * c.heads * h->Ntok * h->NP);
   h->P = ar.get<bf16>(fused ? 16 : (long)B * c.heads * h->Ntok * 2 * h->NP);
   h->attnS = ar.get<bf16>(M * 2 * hid);
+  h->attn_tail = nullptr;
+  if (fused) {
+    const long nf = attn_tail_scratch_floats(B, h->Ntok, c.heads);
+    if (nf > 0) h->attn_tail = ar.get<float>(nf);
+  }
   h->h2S = ar.get<bf16>(M * 2 * c.mlp_hidden);
   h->ytok = ar.get<float>(M * c.stride * c.stride * mid);
   return 0;
@@ -580,7 +585,10 @@ static int build_plans(dexb_handle* h) {
   {
     const char* ea = getenv("DEXB_ATTN");
     h->fused_attn = attn_supported(hd) && !(ea != nullptr && ea[0] == '0');
-    if (h->fused_attn) DEXB_TRY(attn_plan_init(&h->attn, h->qk, nullptr, h->attnS, B, N, NP, c.heads, hid));
+    if (h->fused_attn) {
+      DEXB_TRY(attn_plan_init(&h->attn, h->qk, nullptr, h->attnS, B, N, NP, c.heads, hid));
+      attn_plan_set_tail(&h->attn, h->attn_tail);
+    }
   }
   for (int i = 0; i < c.depth; ++i) {
     DitBlockW& k = h->blocks[i];
@@ -927,7 +935,7 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
       if (h->prof) prof_begin(h, "attn_fwd_kernel", attn_flop(h->attn), st);
       DEXB_TRY(attn_launch(h->attn, st));
       if (h->prof) prof_end(h, st);
-      ++h->launches;
+      h->launches += attn_launch_count(h->attn);
     } else {
       GEMM(k.scores, k.scores.p);
       LAUNCH(launch_attn_softmax(h->scores, h->NP, h->P, h->NP, (long)B * c.heads * N, N, st));

@@ -124,6 +124,7 @@ struct dexb_handle {
   float* sbias = nullptr;
   dexb::bf16 *tokS = nullptr, *pairs = nullptr, *hS = nullptr, *qk = nullptr, *vT = nullptr, *P = nullptr,
              *attnS = nullptr, *h2S = nullptr;
+  float* attn_tail = nullptr;               // partials of the tail-split DiT attention tiles (attn.cuh)
   float *pg = nullptr, *tiv_a = nullptr, *tiv_d = nullptr;
   float *xe = nullptr, *pe = nullptr, *xtok = nullptr, *scores = nullptr, *ytok = nullptr;
   // per-step zeroed region
