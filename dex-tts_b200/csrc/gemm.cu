@@ -93,34 +93,101 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
 // launch
 // ------------------------------------------------------------------------------------------------
 static int g_num_sms = 148;
+static long g_generic_epilogues = 0;          // launches that could not take the FAST epilogue (diagnostic)
+long gemm_generic_epilogue_launches() { return g_generic_epilogues; }
 
 int gemm_global_init() {
   int dev = 0;
   DEXB_CUDA_OK(cudaGetDevice(&dev));
   DEXB_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::kBytes));
-  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::kBytes));
-  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::kBytes));
-  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::kBytes));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   return resolve_encode();
 }
 
-template <int BN>
+// Resident-B eligibility: shared weights, full split product, stacked-N tile widths, the whole weight tile (all taps and
+// k-chunks, hi + lo) plus at least `min_stages` A stages fit in shared memory, and every CTA gets at least two tiles.
+static int rb_stages_for(const GemmParams& p, int BN, long m_tiles, int ntn) {
+  static int mode = -1, min_stages = 3;
+  if (mode < 0) {
+    const char* e = getenv("DEXB_RB");
+    mode = (e != nullptr) ? atoi(e) : 1;
+    const char* m = getenv("DEXB_RB_MIN_STAGES");
+    if (m != nullptr) min_stages = atoi(m);
+  }
+  if (mode == 0 || p.b_mode != 0 || p.nheads != 1 || p.nsplit != 3 || BN > 128 || p.dbg != 0) return 0;
+  const int nk = p.KH * p.KW * (p.K / kTcBlockK);
+  int rb = (kTcSmemMax - tc_rb_bytes(BN, nk, 0)) / (2 * kTcBlockM * kTcBlockK * 2);
+  if (rb > kTcMaxStages) rb = kTcMaxStages;
+  if (rb < min_stages) return 0;
+  const int ctas_per_n = g_num_sms / ntn;
+  if (ctas_per_n < 1 || m_tiles < 2L * ctas_per_n) return 0;
+  return rb;
+}
+
+// The FAST epilogue instantiation (gemm.cuh: epi_apply) assumes the widest vector access everywhere.
+static bool epi_fast_ok(const GemmParams& p) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("DEXB_EPI_FAST");
+    mode = (e != nullptr) ? atoi(e) : 1;
+  }
+  if (mode == 0) return false;
+  const EpiParams& e = p.epi;
+  auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+  if (p.N % 32 != 0 || e.out_vt != nullptr || e.colmean != nullptr || e.o_head_stride % 16 != 0) return false;
+  if (e.bias != nullptr && !(al(e.bias, 16) && e.bias_zstride % 4 == 0 && e.bias_head_stride % 4 == 0)) return false;
+  if (e.gate != nullptr && !al(e.gate, 16)) return false;
+  if (e.resid_f32 != nullptr && !(al(e.resid_f32, 32) && e.resid_f32_stride % 8 == 0)) return false;
+  if (e.resid_s != nullptr && !(al(e.resid_s, 16) && e.resid_s_stride % 8 == 0 && e.resid_s_hi % 8 == 0 && e.resid_s_lo % 8 == 0))
+    return false;
+  if (e.out_f32 != nullptr && !(al(e.out_f32, 32) && e.out_f32_stride % 8 == 0 && e.out_f32_col % 8 == 0)) return false;
+  if (e.out_s != nullptr && !(al(e.out_s, 32) && e.out_s_stride % 16 == 0 && e.out_s_hi % 16 == 0 && e.out_s_lo % 16 == 0 &&
+                              e.out_s_ncols >= p.N))
+    return false;
+  return true;
+}
+
+template <int BN, bool FAST>
 static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
   const int ntn = cdiv(p.N, BN);
-  const long total = (long)p.nz * p.TH * p.TW * ntn;
+  const long m_tiles = (long)p.nz * p.TH * p.TW;
+  const long total = m_tiles * ntn;
+  const int rb = rb_stages_for(p, BN, m_tiles, ntn);
+  if (rb > 0) {
+    const int nk = p.KH * p.KW * (p.K / kTcBlockK);
+    const int grid = (g_num_sms / ntn) * ntn;            // multiple of ntn: a CTA never changes its n-tile
+    gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, tc_rb_bytes(BN, nk, rb), st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, rb);
+    return 0;
+  }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  gemm_tc_kernel<BN><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p, (int)total, ntn);
+  gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, 0);
   return 0;
 }
 
 int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st) {
   if (engine == 0 && gp.tc_ok) {
-    switch (gp.block_n) {
-      case 32: DEXB_TRY(launch_tc<32>(gp, p, st)); break;
-      case 64: DEXB_TRY(launch_tc<64>(gp, p, st)); break;
-      case 128: DEXB_TRY(launch_tc<128>(gp, p, st)); break;
-      default: DEXB_TRY(launch_tc<256>(gp, p, st)); break;
+    if (epi_fast_ok(p)) {
+      switch (gp.block_n) {
+        case 32: DEXB_TRY((launch_tc<32, true>(gp, p, st))); break;
+        case 64: DEXB_TRY((launch_tc<64, true>(gp, p, st))); break;
+        case 128: DEXB_TRY((launch_tc<128, true>(gp, p, st))); break;
+        default: DEXB_TRY((launch_tc<256, true>(gp, p, st))); break;
+      }
+    } else {
+      ++g_generic_epilogues;
+      switch (gp.block_n) {
+        case 32: DEXB_TRY((launch_tc<32, false>(gp, p, st))); break;
+        case 64: DEXB_TRY((launch_tc<64, false>(gp, p, st))); break;
+        case 128: DEXB_TRY((launch_tc<128, false>(gp, p, st))); break;
+        default: DEXB_TRY((launch_tc<256, false>(gp, p, st))); break;
+      }
     }
   } else {
     dim3 grid((unsigned)(p.nz * p.TH * p.TW), (unsigned)cdiv(p.N, 64));

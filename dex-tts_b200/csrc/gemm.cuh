@@ -27,52 +27,32 @@ namespace dexb {
 // ------------------------------------------------------------------------------------------------
 // `gacc` (optional): per-thread GroupNorm partial sums [NV/8][2] that the caller keeps across tiles of one image and
 // flushes with epi_flush_gn -- 17x fewer double atomics (and no shuffles per tile) than accumulating per tile.
-template <int NV>
-__device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int nheads, int oh, int ow, int OH, int OW,
-                                          bool valid, int n0, float (&v)[NV], float* gacc = nullptr) {
-  // Every branch below is warp-uniform and taken once per NV-column chunk; the per-element loops are branch-free
-  // (a first version tested the optional features per element and was instruction-issue bound: ~45 SASS instructions
-  // per output element, 20 % of the stalls on instruction fetch -- profiles/r01_ncu_gemm_v1.md).
+//
+// FAST = true is the instantiation every shipped shape runs: the host has verified (epi_fast_ok) that N is a multiple of 32 and
+// that every pointer / stride / column offset allows the widest vector access, so the scalar fallbacks, the transposed store and
+// the column-mean atomics are compiled out.  With them the kernel was 10 800 SASS instructions (170 KB, far beyond the
+// instruction caches; 17 % of the warp stall samples were instruction fetches -- profiles/r01_ncu_gemm_epilogue.md).
+//
+// The residual rows are the only operand that needs a full L2 round trip and does not depend on the accumulator:
+// epi_load_resid issues those loads BEFORE the caller waits for the tile / the tensor-memory load, so the latencies overlap.
+template <int NV, bool FAST>
+__device__ __forceinline__ void epi_load_resid(const EpiParams& e, int N, int z, int nheads, int oh, int ow, int OH, int OW,
+                                               bool valid, int n0, float (&r)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) r[i] = 0.f;
+  if (!valid || (e.resid_f32 == nullptr && e.resid_s == nullptr)) return;
   const int head = z % nheads;
   const int img = e.o_by_z ? z : z / nheads;
   const long row = ((long)img * OH + oh) * OW + ow;
-  const int nc0 = n0 + head * e.o_head_stride;     // output column of v[0]
-  const bool full = (n0 + NV <= N);
-  if (e.alpha != 1.f) {
+  const int nc0 = n0 + head * e.o_head_stride;
+  const bool full = FAST || (n0 + NV <= N);
+  if (e.resid_f32 != nullptr) {
+    const float* rp = e.resid_f32 + row * e.resid_f32_stride + nc0;
+    if (FAST || (NV % 8 == 0 && full && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0))) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] *= e.alpha;
-  }
-  if (e.bias != nullptr) {
-    const float* bp = e.bias + (long)z * e.bias_zstride + head * e.bias_head_stride + n0;
-    if (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
-#pragma unroll
-      for (int i = 0; i < NV; i += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
-        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) if (n0 + i < N) v[i] += bp[i];
-    }
-  }
-  if (!full) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) if (n0 + i >= N) v[i] = 0.f;
-  }
-  if (e.act == 1) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = gelu_f(v[i]);          // gelu(0) == 0 keeps the out-of-range columns at zero
-  }
-  if (valid && (e.resid_f32 != nullptr || e.resid_s != nullptr || e.gate != nullptr)) {
-    float r[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) r[i] = 0.f;
-    if (e.resid_f32 != nullptr) {
-      const float* rp = e.resid_f32 + row * e.resid_f32_stride + nc0;
-      if (NV % 8 == 0 && full && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0)) {
-#pragma unroll
-        for (int i = 0; i < NV; i += 8) ld256_f32(rp + i, &r[i]);
-      } else if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      for (int i = 0; i < NV; i += 8) ld256_f32(rp + i, &r[i]);
+    } else if constexpr (!FAST) {
+      if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
         for (int i = 0; i < NV; i += 4) {
           const float4 r4 = *reinterpret_cast<const float4*>(rp + i);
@@ -83,25 +63,76 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
         for (int i = 0; i < NV; ++i) if (n0 + i < N) r[i] = rp[i];
       }
     }
-    if (e.resid_s != nullptr) {
-      const bf16* rp = e.resid_s + row * e.resid_s_stride + nc0;
-      if (full && (((reinterpret_cast<uintptr_t>(rp + e.resid_s_hi) | reinterpret_cast<uintptr_t>(rp + e.resid_s_lo)) & 15) == 0)) {
+  }
+  if (e.resid_s != nullptr) {
+    const bf16* rp = e.resid_s + row * e.resid_s_stride + nc0;
+    if (FAST || (full && (((reinterpret_cast<uintptr_t>(rp + e.resid_s_hi) | reinterpret_cast<uintptr_t>(rp + e.resid_s_lo)) & 15) == 0))) {
 #pragma unroll
-        for (int i = 0; i < NV; i += 8) {
-          float t[8];
-          load_split8(rp + e.resid_s_hi + i, rp + e.resid_s_lo + i, t);
+      for (int i = 0; i < NV; i += 8) {
+        float t[8];
+        load_split8(rp + e.resid_s_hi + i, rp + e.resid_s_lo + i, t);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) r[i + j] += t[j];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) if (n0 + i < N) r[i] += join2(rp[e.resid_s_hi + i], rp[e.resid_s_lo + i]);
+        for (int j = 0; j < 8; ++j) r[i + j] += t[j];
       }
+    } else if constexpr (!FAST) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) if (n0 + i < N) r[i] += join2(rp[e.resid_s_hi + i], rp[e.resid_s_lo + i]);
     }
+  }
+}
+
+template <int NV, bool FAST = false>
+__device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int nheads, int oh, int ow, int OH, int OW,
+                                          bool valid, int n0, float (&v)[NV], const float (&r)[NV], float* gacc = nullptr) {
+  // Every branch below is warp-uniform and taken once per NV-column chunk; the per-element loops are branch-free
+  // (a first version tested the optional features per element and was instruction-issue bound: ~45 SASS instructions
+  // per output element, 20 % of the stalls on instruction fetch -- profiles/r01_ncu_gemm_v1.md).
+  const int head = z % nheads;
+  const int img = e.o_by_z ? z : z / nheads;
+  const long row = ((long)img * OH + oh) * OW + ow;
+  const int nc0 = n0 + head * e.o_head_stride;     // output column of v[0]
+  const bool full = FAST || (n0 + NV <= N);
+  if (e.alpha != 1.f) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= e.alpha;
+  }
+  if (e.bias != nullptr) {
+    const float* bp = e.bias + (long)z * e.bias_zstride + head * e.bias_head_stride + n0;
+    if (FAST || (full && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0))) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + i));
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+      }
+    } else if constexpr (!FAST) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) if (n0 + i < N) v[i] += bp[i];
+    }
+  }
+  if constexpr (!FAST) {
+    if (!full) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) if (n0 + i >= N) v[i] = 0.f;
+    }
+  }
+  if (e.act == 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = gelu_fast(v[i]);       // gelu(0) == 0 keeps the out-of-range columns at zero
+  }
+  if (valid && (e.resid_f32 != nullptr || e.resid_s != nullptr || e.gate != nullptr)) {
     if (e.gate != nullptr) {
       const float* gp = e.gate + n0;
+      if (FAST || (full && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0))) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) v[i] = r[i] + ((n0 + i < N) ? __ldg(gp + i) : 0.f) * v[i];
+        for (int i = 0; i < NV; i += 4) {
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gp + i));
+          v[i] = fmaf(g4.x, v[i], r[i]); v[i + 1] = fmaf(g4.y, v[i + 1], r[i + 1]);
+          v[i + 2] = fmaf(g4.z, v[i + 2], r[i + 2]); v[i + 3] = fmaf(g4.w, v[i + 3], r[i + 3]);
+        }
+      } else if constexpr (!FAST) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = fmaf((n0 + i < N) ? __ldg(gp + i) : 0.f, v[i], r[i]);
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] += r[i];
@@ -146,53 +177,59 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
   if (!valid) return;
   if (e.out_f32 != nullptr) {
     float* op = e.out_f32 + row * e.out_f32_stride + e.out_f32_col + nc0;
-    if (NV % 8 == 0 && n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 31) == 0)) {
+    if (FAST || (NV % 8 == 0 && n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 31) == 0))) {
 #pragma unroll
       for (int i = 0; i < NV; i += 8) st256_f32(op + i, &v[i]);
-    } else if (n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+    } else if constexpr (!FAST) {
+      if (n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-      for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    } else {
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) if (n0 + i < N) op[i] = v[i];
+        for (int i = 0; i < NV; ++i) if (n0 + i < N) op[i] = v[i];
+      }
     }
   }
   if (e.out_s != nullptr && n0 < e.out_s_ncols) {
     bf16* hp = e.out_s + row * e.out_s_stride + e.out_s_hi + nc0;
     bf16* lp = e.out_s + row * e.out_s_stride + e.out_s_lo + nc0;
-    if (NV % 16 == 0 && n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) &&
-        ((reinterpret_cast<uintptr_t>(lp) & 31) == 0)) {
+    if (FAST || (NV % 16 == 0 && n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(lp) & 31) == 0))) {
 #pragma unroll
       for (int i = 0; i < NV; i += 16) store_split16(hp + i, lp + i, &v[i]);
-    } else if (n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) &&
-               ((reinterpret_cast<uintptr_t>(lp) & 15) == 0)) {
+    } else if constexpr (!FAST) {
+      if (n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 15) == 0) &&
+          ((reinterpret_cast<uintptr_t>(lp) & 15) == 0)) {
 #pragma unroll
-      for (int i = 0; i < NV; i += 8) store_split8(hp + i, lp + i, &v[i]);
-    } else {
+        for (int i = 0; i < NV; i += 8) store_split8(hp + i, lp + i, &v[i]);
+      } else {
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        if (n0 + i < N && n0 + i < e.out_s_ncols) split2(v[i], hp[i], lp[i]);
-    }
-  }
-  if (e.out_vt != nullptr && n0 + NV > e.out_s_ncols) {
-    // transposed store (V of the attention): consecutive lanes hold consecutive tokens -> coalesced per d
-    const long token = (long)oh * OW + ow;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int n = n0 + i;
-      if (n >= e.out_s_ncols && n < N) {
-        const int c = n - e.out_s_ncols;
-        const int hd_i = c / e.out_vt_hd, d = c % e.out_vt_hd;
-        bf16* base = e.out_vt + ((long)img * e.out_vt_heads + hd_i) * e.out_vt_zstride + (long)d * e.out_vt_rstride + token;
-        split2(v[i], base[0], base[e.out_vt_lo]);
+        for (int i = 0; i < NV; ++i)
+          if (n0 + i < N && n0 + i < e.out_s_ncols) split2(v[i], hp[i], lp[i]);
       }
     }
   }
-  if (e.colmean != nullptr) {
-    float* cp = e.colmean + ((long)img * OW + ow) * e.colmean_ld + nc0;
+  if constexpr (!FAST) {
+    if (e.out_vt != nullptr && n0 + NV > e.out_s_ncols) {
+      // transposed store (V of the attention): consecutive lanes hold consecutive tokens -> coalesced per d
+      const long token = (long)oh * OW + ow;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      if (n0 + i < N) atomicAdd(cp + i, v[i] * e.colmean_scale);
+      for (int i = 0; i < NV; ++i) {
+        const int n = n0 + i;
+        if (n >= e.out_s_ncols && n < N) {
+          const int c = n - e.out_s_ncols;
+          const int hd_i = c / e.out_vt_hd, d = c % e.out_vt_hd;
+          bf16* base = e.out_vt + ((long)img * e.out_vt_heads + hd_i) * e.out_vt_zstride + (long)d * e.out_vt_rstride + token;
+          split2(v[i], base[0], base[e.out_vt_lo]);
+        }
+      }
+    }
+    if (e.colmean != nullptr) {
+      float* cp = e.colmean + ((long)img * OW + ow) * e.colmean_ld + nc0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (n0 + i < N) atomicAdd(cp + i, v[i] * e.colmean_scale);
+    }
   }
 }
 
@@ -262,6 +299,15 @@ struct TcSmem {
   // +1024 for manual 1024 B alignment (SWIZZLE_128B atoms), +256 for barriers / tmem pointer
   static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
 };
+// Resident-B mode ("rb" > 0 = number of A stages): all taps x k-chunks of the CTA's weight tile are loaded ONCE into shared memory
+// and the ring only carries A (32 KiB per stage instead of 48-64).  The grid is a multiple of the n-tile count, so t += gridDim.x
+// keeps a CTA on one n-tile for its whole life.  Small-K GEMMs (DiT linears: K = 256) are bound by the SM's L2->SMEM ingest
+// (~64 B/clk: `neither` column of profiles/r01_epilogue_experiments.md), and half of their ingest was the re-streamed weight tile.
+constexpr int kTcMaxStages = 6;
+constexpr int kTcSmemMax = 232448;             // 227 KiB: the most a CTA can opt in to
+__host__ __device__ constexpr int tc_rb_bytes(int block_n, int nk, int rb) {
+  return nk * 2 * block_n * kTcBlockK * 2 + rb * 2 * kTcBlockM * kTcBlockK * 2 + 1024 + 256;
+}
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ... (n-tile fastest, so CTAs
 // that run concurrently share the A tile in L2).  The smem ring and both TMEM accumulator buffers stay live across
@@ -281,12 +327,13 @@ __device__ __forceinline__ TcTile tc_decode_tile(const GemmParams& p, int t, int
   return r;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool FAST>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p, const int total_tiles, const int ntn) {
+               const GemmParams p, const int total_tiles, const int ntn, const int rb) {
   using SM = TcSmem<BLOCK_N>;
-  constexpr int STAGES = SM::kStages;
+  const int STAGES = rb > 0 ? rb : SM::kStages;
+  constexpr int BB2 = 2 * SM::kBBytes;                               // one resident weight chunk: [B_hi | B_lo]
   // Stacked-N split product (BLOCK_N <= 128): B_hi and B_lo tiles are adjacent in shared memory, so ONE MMA with
   // N = 2*BLOCK_N computes A_hi*B_hi (columns [0, BN)) and A_hi*B_lo (columns [BN, 2BN)); a second MMA adds A_lo*B_hi to
   // the first half; the epilogue sums the halves.  An SS-mode MMA costs ~64-70 cycles for the 4 KiB A read regardless of
@@ -296,22 +343,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * SM::kStageBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* acc_full = empty_bar + STAGES;        // [2]
-  uint64_t* acc_empty = acc_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int kchunks = p.K / kTcBlockK;
   const int nk = p.KH * p.KW * kchunks;
+  // ring stage: [A_hi | A_lo | B_hi | B_lo], or [A_hi | A_lo] behind the resident weights
+  const int stage_bytes = rb > 0 ? 2 * SM::kABytes : SM::kStageBytes;
+  uint8_t* ring = smem + (rb > 0 ? nk * BB2 : 0);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * stage_bytes);
+  uint64_t* empty_bar = full_bar + kTcMaxStages;
+  uint64_t* acc_full = empty_bar + kTcMaxStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint64_t* b_full = acc_empty + 2;               // resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kTcEpiThreads); }
+    ptx::mbar_init(b_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -323,7 +374,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
     if (ptx::elect_one()) {
-      const uint32_t tx_bytes = (p.nsplit == 3) ? (uint32_t)SM::kStageBytes : (uint32_t)(SM::kABytes + SM::kBBytes);
+      const uint32_t tx_bytes = (rb > 0) ? (uint32_t)(2 * SM::kABytes)
+                                         : ((p.nsplit == 3) ? (uint32_t)SM::kStageBytes : (uint32_t)(SM::kABytes + SM::kBBytes));
+      if (rb > 0 && blockIdx.x < total_tiles) {
+        // resident weights of this CTA's n-tile: every (tap, k-chunk), hi and lo, once
+        const int n0 = ((int)blockIdx.x % ntn) * BLOCK_N;
+        ptx::mbar_expect_tx(b_full, (uint32_t)(nk * BB2));
+        for (int it = 0; it < nk; ++it) {
+          const int tap = it / kchunks, kc = it % kchunks;
+          const int brow = tap * p.b_rows_per_tap + n0;
+          ptx::tma_load_3d(smem + it * BB2, &tmB, b_full, p.b_hi + kc * kTcBlockK, brow, 0);
+          ptx::tma_load_3d(smem + it * BB2 + SM::kBBytes, &tmB, b_full, p.b_lo + kc * kTcBlockK, brow, 0);
+        }
+      }
       uint32_t g = 0;                                        // ring position, continues across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
@@ -334,14 +397,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           const int tap = it / kchunks, kc = it % kchunks;
           const int dy = tap / p.KW + p.offH, dx = (tap % p.KW) * p.tap_sw + p.offW;
-          uint8_t* st = smem + s * SM::kStageBytes;
+          uint8_t* st = ring + s * stage_bytes;
           if (p.dbg & 4) { ptx::mbar_arrive(&full_bar[s]); continue; }   // tuning aid: no operand traffic at all
           ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
           const int acol = kc * kTcBlockK + tl.head * p.a_head_stride;
-          const int bcol = kc * kTcBlockK + tl.head * p.b_head_stride;
-          const int brow = tap * p.b_rows_per_tap + tl.n0 + tl.head * p.b_head_rows;
           const int ax = tl.cw0 * p.in_stride + dx, ay = tl.ch0 * p.in_stride + dy;
           ptx::tma_load_4d(st, &tmA, &full_bar[s], p.a_hi + acol, ax, ay, tl.img_a);
+          if (rb > 0) {
+            ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, ax, ay, tl.img_a);
+            continue;
+          }
+          const int bcol = kc * kTcBlockK + tl.head * p.b_head_stride;
+          const int brow = tap * p.b_rows_per_tap + tl.n0 + tl.head * p.b_head_rows;
           ptx::tma_load_3d(st + 2 * SM::kABytes, &tmB, &full_bar[s], p.b_hi + bcol, brow, bz);
           if (p.nsplit == 3) {
             ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, ax, ay, tl.img_a);
@@ -356,6 +423,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16(kTcBlockM, STACKED ? 2 * BLOCK_N : BLOCK_N);
     uint32_t g = 0;
     int li = 0;                                              // local tile counter -> accumulator buffer li & 1
+    if (rb > 0 && blockIdx.x < total_tiles) ptx::mbar_wait(b_full, 0);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const int buf = li & 1;
       ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
@@ -368,9 +436,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           if (!(p.dbg & 2)) {
-          const uint32_t a_hi = ptx::smem_u32(smem + s * SM::kStageBytes);
+          const uint32_t a_hi = ptx::smem_u32(ring + s * stage_bytes);
           const uint32_t a_lo = a_hi + SM::kABytes;
-          const uint32_t b_hi = a_hi + 2 * SM::kABytes;
+          const uint32_t b_hi = (rb > 0) ? ptx::smem_u32(smem + it * BB2) : a_hi + 2 * SM::kABytes;
           const uint32_t b_lo = b_hi + SM::kBBytes;
 #pragma unroll
           for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
@@ -426,38 +494,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
       const bool valid = (ch < p.CH) && (cw < p.CW);
       const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
-      ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
-      ptx::tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ACC_COLS);
       constexpr int NCH = BLOCK_N / 32;
       // chunks this warp owns: c = half, half + 2, ... while n0 + 32 c < N
       int nmine = 0;
       for (int c = half; c < NCH && tl.n0 + c * 32 < p.N; c += 2) ++nmine;
       if (nmine == 0) {
+        ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);       // never hand a buffer back before its MMAs have completed
         ptx::tc_fence_before();
         ptx::mbar_arrive(&acc_empty[buf]);
       }
 #pragma unroll 1
       for (int k = 0; k < nmine; ++k) {
         const int c = half + 2 * k;
+        const int n0c = tl.n0 + c * 32;
+        const bool use_vt = !FAST && p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols;
+        // residual rows first: their L2 round trip overlaps the wait for the accumulator and the tensor-memory load
+        float rpre[32];
+        if (!(p.dbg & 1) && !use_vt) epi_load_resid<32, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, rpre);
+        if (k == 0) {
+          ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
+          ptx::tc_fence_after();
+        }
         float v[32];
-        ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
         if (STACKED && p.nsplit == 3) {                      // add the A_hi * B_lo half
           float v2[32];
-          ptx::tmem_ld32(tacc + (uint32_t)(BLOCK_N + c * 32), v2);
+          ptx::tmem_ld32_nowait(tacc + (uint32_t)(c * 32), v);
+          ptx::tmem_ld32_nowait(tacc + (uint32_t)(BLOCK_N + c * 32), v2);
+          ptx::tmem_wait_ld();
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += v2[i];
+        } else {
+          ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
         }
         if (k == nmine - 1) {                                // last chunk read: hand the buffer back to the MMA warp
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[buf]);
         }
         if (!(p.dbg & 1)) {
-          const int n0c = tl.n0 + c * 32;
-          if (p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols)
-            epi_store_vt(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
-          else
-            epi_apply<32>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, defer_gn ? &gacc[k][0] : nullptr);
+          if constexpr (!FAST) {
+            if (use_vt) {
+              epi_store_vt(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
+              continue;
+            }
+          }
+          epi_apply<32, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, rpre, defer_gn ? &gacc[k][0] : nullptr);
         }
       }
     }
@@ -557,7 +638,9 @@ gemm_simt_kernel(const GemmParams p) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = acc[i][j];
-    epi_apply<8>(p.epi, p.N, z, p.nheads, oh, ow, p.OH, p.OW, valid, n0 + ty * 8, v);
+    float rr[8];
+    epi_load_resid<8, false>(p.epi, p.N, z, p.nheads, oh, ow, p.OH, p.OW, valid, n0 + ty * 8, rr);
+    epi_apply<8, false>(p.epi, p.N, z, p.nheads, oh, ow, p.OH, p.OW, valid, n0 + ty * 8, v, rr);
   }
 }
 

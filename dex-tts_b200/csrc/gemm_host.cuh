@@ -95,5 +95,7 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
 // Enqueue on `st`.  `p` is normally gp.p, possibly with per-step pointers (bias / gate / stats) patched.
 // engine 0 = tcgen05 (falls back to the CUDA-core kernel only for shapes the plan marked ineligible), 1 = CUDA cores.
 int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st);
+// number of tcgen05 launches so far that had to take the generic (scalar-fallback) epilogue instantiation
+long gemm_generic_epilogue_launches();
 
 }  // namespace dexb

@@ -224,7 +224,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         if (x >= p.Wq) break;
         float v = ((red[(0 * kPcXT + xr) * 33 + lane] + red[(1 * kPcXT + xr) * 33 + lane]) +
                    (red[(2 * kPcXT + xr) * 33 + lane] + red[(3 * kPcXT + xr) * 33 + lane])) + bias;
-        v = gelu_f(v);
+        v = gelu_fast(v);
         p.out[(((long)tl.b * p.Fq + tl.y) * p.Wq + x) * p.D + tl.g * 32 + lane] = v;
       }
       t = tn; have = have_n; tl = tln;

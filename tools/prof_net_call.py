@@ -23,8 +23,11 @@ inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=1234)
 cond = None
 if variant == "dex":
     cond = dict(sty=inp["sty"].cuda(), sty_lengths=inp["sty_lengths"].cuda(), ref_skips=[r.cuda() for r in inp["ref_skips"]])
-x = ((inp["z"] / 1.5 + inp["mu"]) * 80.0).cuda()
+from dexb200.engine import edm_sigmas  # noqa: E402
+step = n_steps // 2
+sig = float(edm_sigmas(n_steps)[step])
+x = (inp["mu"] + inp["z"] * sig).cuda()                  # a plausible sampler state at that step: signal + sigma * noise
 for i in range(n_calls):
-    out = eng.denoise_once(x, inp["mask"].cuda(), inp["mu"].cuda(), n_steps, n_steps // 2, cond=cond)
+    out = eng.denoise_once(x, inp["mask"].cuda(), inp["mu"].cuda(), n_steps, step, cond=cond)
 torch.cuda.synchronize()
 print("ok", float(out.abs().mean()))
