@@ -211,7 +211,10 @@ int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, in
   p.KH = KH; p.KW = KW; p.offH = offH; p.offW = offW; p.K = K; p.N = N;
   p.A = as; p.a_row_stride = 2L * K; p.a_hi = 0; p.a_lo = K;
   p.Bw = ws; p.b_row_stride = 2L * K; p.b_hi = 0; p.b_lo = K; p.b_rows_per_tap = N;
-  p.nsplit = nsplit; p.dbg = dbg;
+  p.nsplit = nsplit; p.dbg = dbg & 7;
+  p.epi.dbg_nostore = (dbg >> 3) & 1;
+  if (out_mode & 2) p.epi.act = 1;
+  out_mode &= 1;
   p.epi.alpha = 1.f; p.epi.bias = bias; p.epi.out_s_ncols = 1 << 30;
   if (out_mode == 0) { p.epi.out_f32 = (float*)out; p.epi.out_f32_stride = N; }
   else { p.epi.out_s = (bf16*)out; p.epi.out_s_stride = 2L * N; p.epi.out_s_hi = 0; p.epi.out_s_lo = N; }

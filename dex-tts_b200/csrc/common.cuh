@@ -109,7 +109,8 @@ __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff
 // erff costs ~3x the instructions and the fc1 epilogue is instruction-bound.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
   float p = 1.061405429f;
   p = fmaf(p, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);

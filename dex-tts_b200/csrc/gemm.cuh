@@ -174,7 +174,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
       }
     }
   }
-  if (!valid) return;
+  if (!valid || e.dbg_nostore) return;
   if (e.out_f32 != nullptr) {
     float* op = e.out_f32 + row * e.out_f32_stride + e.out_f32_col + nc0;
     if (FAST || (NV % 8 == 0 && n0 + NV <= N && ((reinterpret_cast<uintptr_t>(op) & 31) == 0))) {
@@ -242,8 +242,9 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
 // ------------------------------------------------------------------------------------------------
 // V of the attention, stored transposed (vT[img][head][d][token]) from the row-per-thread registers: consecutive lanes
 // hold consecutive tokens, so every store of the warp is one contiguous 64 B run.  A 32-column chunk never straddles heads.
+template <int NV>
 __device__ __forceinline__ void epi_store_vt(const EpiParams& e, int N, int z, int nheads, long token, bool valid, int n0,
-                                             const float (&v)[32]) {
+                                             const float (&v)[NV]) {
   if (!valid) return;
   const int img = z / nheads;
   const int c0 = n0 - e.out_s_ncols;
@@ -251,7 +252,7 @@ __device__ __forceinline__ void epi_store_vt(const EpiParams& e, int N, int z, i
   bf16* base = e.out_vt + ((long)img * e.out_vt_heads + hd_i) * e.out_vt_zstride + (long)d0 * e.out_vt_rstride + token;
   const float* bp = (e.bias != nullptr) ? e.bias + n0 : nullptr;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (n0 + i < N) {
       const float x = v[i] * e.alpha + (bp != nullptr ? __ldg(bp + i) : 0.f);
       bf16* q = base + (long)i * e.out_vt_rstride;
@@ -260,16 +261,25 @@ __device__ __forceinline__ void epi_store_vt(const EpiParams& e, int N, int z, i
   }
 }
 
+// warp 0: TMA, warp 1: MMA (+TMEM alloc), warps 2..: epilogue.  kTcEpiPerLG warps share each TMEM lane group and take every
+// kTcEpiPerLG-th 32-column chunk.  The epilogue is latency-bound (each warp issues one instruction per ~9 cycles: dependent
+// chains of the activation / split conversion, tensor-memory and store latencies), and for the K = 256 GEMMs it -- not the MMA
+// stream -- sets the tile time, so four warps per lane group (16 epilogue warps, <= 112 registers) beat two.
+constexpr int kTcEpiPerLG = 4;
+constexpr int kTcEpiCW = (kTcEpiPerLG == 4) ? 16 : 32;      // columns per epilogue chunk: 16 keeps 16 warps inside 96 registers
+constexpr int kTcEpiThreads = 128 * kTcEpiPerLG;
+constexpr int kTcThreads = 64 + kTcEpiThreads;
+
 // Flush the deferred GroupNorm partial sums of one warp: gacc[k][g][2] for the warp's k-th chunk (columns n0 = 64 k +
 // 32 half when there is a single n-tile) -> warp reduction -> one double atomic per (warp, 8-column group).
 template <int MAXCH>
-__device__ __forceinline__ void epi_flush_gn(const EpiParams& e, int N, int img, int half, float (&gacc)[MAXCH][8]) {
+__device__ __forceinline__ void epi_flush_gn(const EpiParams& e, int N, int img, int half, int nper, float (&gacc)[MAXCH][8]) {
   const int gs = e.gn_gs;
 #pragma unroll
   for (int k = 0; k < MAXCH; ++k) {
-    const int n0 = (half + 2 * k) * 32;
+    const int n0 = (half + nper * k) * kTcEpiCW;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < kTcEpiCW / 8; ++g) {
       const float s = warp_sum(gacc[k][g * 2]);
       const float ss = warp_sum(gacc[k][g * 2 + 1]);
       gacc[k][g * 2] = 0.f;
@@ -287,8 +297,6 @@ __device__ __forceinline__ void epi_flush_gn(const EpiParams& e, int N, int img,
 // tcgen05 engine
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcBlockM = 128;
-constexpr int kTcThreads = 320;                // warp 0: TMA, warp 1: MMA (+TMEM alloc), warps 2..9: epilogue
-constexpr int kTcEpiThreads = 256;             // two warps per TMEM lane group, alternating 32-column chunks
 
 template <int BLOCK_N>
 struct TcSmem {
@@ -327,6 +335,8 @@ __device__ __forceinline__ TcTile tc_decode_tile(const GemmParams& p, int t, int
   return r;
 }
 
+// 576 threads: registers are allocated per 4-warp group, so the block counts as 20 warps and gets 96 registers per thread
+// (112 fails to launch); the epilogue spills ~150 B per thread, which the extra warps more than pay for
 template <int BLOCK_N, bool FAST>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -475,7 +485,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;                            // row of the tile
-    constexpr int MAXCH = (BLOCK_N / 32 + 1) / 2;            // chunks one warp owns per tile
+    constexpr int CW = (BLOCK_N > 0) ? kTcEpiCW : 0;          // value-dependent, so `if constexpr (CW == 16)` discards the other branch
+    constexpr int MAXCH = (BLOCK_N / CW + kTcEpiPerLG - 1) / kTcEpiPerLG;   // chunks one warp owns per tile
     const bool defer_gn = p.epi.gn_stats != nullptr && ntn == 1 && p.nheads == 1;
     float gacc[MAXCH][8];
 #pragma unroll
@@ -488,17 +499,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
       const int buf = li & 1;
       if (defer_gn && tl.z != gn_img) {
-        if (gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, gacc);
+        if (gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, kTcEpiPerLG, gacc);
         gn_img = tl.z;
       }
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
       const bool valid = (ch < p.CH) && (cw < p.CW);
       const int oh = ch * p.out_scale + p.out_offh, ow = cw * p.out_scale + p.out_offw;
       const uint32_t tacc = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-      constexpr int NCH = BLOCK_N / 32;
-      // chunks this warp owns: c = half, half + 2, ... while n0 + 32 c < N
+      constexpr int NCH = BLOCK_N / CW;
+      // chunks this warp owns: c = half, half + kTcEpiPerLG, ... while n0 + 32 c < N
       int nmine = 0;
-      for (int c = half; c < NCH && tl.n0 + c * 32 < p.N; c += 2) ++nmine;
+      for (int c = half; c < NCH && tl.n0 + c * CW < p.N; c += kTcEpiPerLG) ++nmine;
       if (nmine == 0) {
         ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);       // never hand a buffer back before its MMAs have completed
         ptx::tc_fence_before();
@@ -506,26 +517,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll 1
       for (int k = 0; k < nmine; ++k) {
-        const int c = half + 2 * k;
-        const int n0c = tl.n0 + c * 32;
+        const int c = half + kTcEpiPerLG * k;
+        const int n0c = tl.n0 + c * CW;
         const bool use_vt = !FAST && p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols;
         // residual rows first: their L2 round trip overlaps the wait for the accumulator and the tensor-memory load
-        float rpre[32];
-        if (!(p.dbg & 1) && !use_vt) epi_load_resid<32, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, rpre);
+        float rpre[CW];
+        if (!(p.dbg & 1) && !use_vt) epi_load_resid<CW, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, rpre);
         if (k == 0) {
           ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
           ptx::tc_fence_after();
         }
-        float v[32];
-        if (STACKED && p.nsplit == 3) {                      // add the A_hi * B_lo half
-          float v2[32];
-          ptx::tmem_ld32_nowait(tacc + (uint32_t)(c * 32), v);
-          ptx::tmem_ld32_nowait(tacc + (uint32_t)(BLOCK_N + c * 32), v2);
-          ptx::tmem_wait_ld();
+        float v[CW];
+        if constexpr (CW == 16) {
+          if (STACKED && p.nsplit == 3) {                    // add the A_hi * B_lo half
+            float v2[16];
+            ptx::tmem_ld16_nowait(tacc + (uint32_t)(c * 16), v);
+            ptx::tmem_ld16_nowait(tacc + (uint32_t)(BLOCK_N + c * 16), v2);
+            ptx::tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
+          } else {
+            ptx::tmem_ld16_nowait(tacc + (uint32_t)(c * 16), v);
+            ptx::tmem_wait_ld();
+          }
         } else {
-          ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+          if (STACKED && p.nsplit == 3) {                    // add the A_hi * B_lo half
+            float v2[16];                                    // in two halves: 16 fewer live registers
+            ptx::tmem_ld32_nowait(tacc + (uint32_t)(c * 32), v);
+            ptx::tmem_ld16_nowait(tacc + (uint32_t)(BLOCK_N + c * 32), v2);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
+            ptx::tmem_ld16_nowait(tacc + (uint32_t)(BLOCK_N + c * 32 + 16), v2);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[16 + i] += v2[i];
+          } else {
+            ptx::tmem_ld32(tacc + (uint32_t)(c * 32), v);
+          }
         }
         if (k == nmine - 1) {                                // last chunk read: hand the buffer back to the MMA warp
           ptx::tc_fence_before();
@@ -534,15 +563,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (!(p.dbg & 1)) {
           if constexpr (!FAST) {
             if (use_vt) {
-              epi_store_vt(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
+              epi_store_vt<CW>(p.epi, p.N, tl.z, p.nheads, (long)oh * p.OW + ow, valid, n0c, v);
               continue;
             }
           }
-          epi_apply<32, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, rpre, defer_gn ? &gacc[k][0] : nullptr);
+          epi_apply<CW, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, rpre, defer_gn ? &gacc[k][0] : nullptr);
         }
       }
     }
-    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, gacc);
+    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, kTcEpiPerLG, gacc);
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -40,6 +40,7 @@ struct EpiParams {
   int colmean_ld;
   int o_head_stride;           // output column offset per head (z % nheads)
   int o_by_z;                  // 1: output image index = z, 0: = z / nheads
+  int dbg_nostore;             // tuning aid (dexb_gemm_bench bit 3): run the whole epilogue but skip the global stores
 };
 
 struct GemmParams {
