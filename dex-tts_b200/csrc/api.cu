@@ -136,7 +136,7 @@ int dexb_simt_fallbacks(const dexb_handle* h) {
     if (rs[i]->res_w != nullptr) chk(rs[i]->res);
   }
   const dexb::LinAttW* las[3] = {&h->la0, &h->la1, &h->la2};
-  for (int i = 0; i < 3; ++i) { chk(h->fused_la ? las[i]->vt : las[i]->kv); chk(las[i]->apply); }
+  for (int i = 0; i < 3; ++i) { if (!h->fused_la) chk(las[i]->kv); chk(las[i]->apply); }
   chk(h->g_down);
   for (int i = 0; i < 4; ++i) chk(h->g_up[i]);
   if (h->cfg.variant == 1 && !h->fused_tv) { chk(h->g_tvs); chk(h->g_tvo); }

@@ -118,13 +118,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
           for (int kc = 0; kc < kch; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, (t0 + it) * kAtBN, b);
         } else {
           const int j = t0 + it - nt;
-          ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192 + kVBytes);
+          ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192 + 2 * p.vchunks * 8192);
           for (int part = 0; part < 2; ++part)
             for (int kc = 0; kc < kch; ++kc)
               ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
           if (p.v_mn) {                                    // row-major V: [part][d chunk of 64] boxes of 64 keys x 128 B
             for (int part = 0; part < 2; ++part)
-              for (int c = 0; c < 2; ++c)
+              for (int c = 0; c < p.vchunks; ++c)
                 ptx::tma_load_3d(st + kKBytes + part * 16384 + c * 8192, &tmV, &k_full[s],
                                  (part ? p.v_lo : p.v_hi) + head * kAtHD + c * 64, j * kAtBN, b);
           } else {
@@ -137,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, kAtBN);
-    const uint32_t idesc_o = ptx::make_idesc_bf16(128, kAtHD, p.v_mn);
+    const uint32_t idesc_o = ptx::make_idesc_bf16(128, 64 * p.vchunks, p.v_mn);
     ptx::mbar_wait(q_full, 0);
     ptx::tc_fence_after();
     // S[it & 1] = Q K^T for iteration `it` (Q from tensor memory); frees the stage itself only in pass 1
@@ -311,6 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       }
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
+        if (hf >= p.vchunks) break;                           // output narrower than 128 columns (linear attention, C = 64)
         float o[32];
         if (nt > 0) ptx::tmem_ld32(tl + kTmO + hf * 64 + c * 32, o);
         else {
@@ -400,7 +401,7 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   p.NQ = N; p.NK = N; p.KP = NP; p.nheads = heads;
   p.nt = (N + kAtBN - 1) / kAtBN;
   p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid; p.q_img_rows = N;
-  p.kchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
+  p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
   p.q_tiles = (N + kAtBM - 1) / kAtBM; p.tail_first = B * heads * p.q_tiles; p.tail_splits = 1; p.tail_tps = p.nt;
   p.k_hi = hid; p.k_lo = 4 * hid;
   p.scale_log2e = (1.f / sqrtf((float)kAtHD)) * 1.4426950408889634f;
@@ -429,7 +430,7 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   p.NQ = P; p.NK = NK; p.KP = KP; p.nheads = 1;
   p.nt = (NK + kAtBN - 1) / kAtBN;
   p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo; p.q_img_rows = P;
-  p.kchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
+  p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
   p.k_hi = 0; p.k_lo = C;
   p.scale_log2e = 1.4426950408889634f;              // 1/sqrt(C) is folded into the key matrix (k_tv_fold)
   p.kbias = sbias; p.kbias_stride = KP; p.vis_len = sty_len;
@@ -442,7 +443,7 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   return 0;
 }
 
-int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
+int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, float* part_o,
                       float* part_l, float* part_m, int B, int P, int PP, int C, int splits) {
   DEXB_CHECK(C == 64 || C == 128, "linear-attention context: C must be 64 or 128 (got %d)", C);
   DEXB_CHECK(PP % kAtBN == 0 && PP >= P && splits >= 1, "linear-attention context: bad padding / split");
@@ -454,6 +455,7 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   p.kv_splits = splits;
   p.tiles_per_split = (p.nt + splits - 1) / splits;
   p.kchunks = C / 64;
+  p.vchunks = C / 64;
   p.q = wk; p.q_stride = 2L * C; p.q_hi = 0; p.q_lo = C; p.q_img_rows = 0;      // the k rows of to_qkv, shared by all images
   p.k_hi = x_hi; p.k_lo = x_lo;
   p.scale_log2e = 1.4426950408889634f;
@@ -461,10 +463,9 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   p.part_o = part_o; p.part_l = part_l; p.part_m = part_m;
   const cuuint64_t xrow = (cuuint64_t)x_stride * 2;
   DEXB_TRY(enc3(&ap->tmK, x, (cuuint64_t)x_stride, (cuuint64_t)P, (cuuint64_t)B, xrow, xrow * P, 64, kAtBN, "LA x"));
-  // v as split rows [pixel][hi(128) | lo(128)] straight from the GEMM engine (MN-major B operand: no transposed stores)
-  p.v_mn = 1; p.v_hi = 0; p.v_lo = kAtHD;
-  const cuuint64_t vrow = 2ull * kAtHD * 2;
-  DEXB_TRY(enc3(&ap->tmV, vT, 2ull * kAtHD, (cuuint64_t)P, (cuuint64_t)B, vrow, vrow * P, 64, kAtBN, "LA V rows"));
+  // "values" = the same activation rows (MN-major B operand, 64 pixels x 64 channels per box)
+  p.v_mn = 1; p.v_hi = x_hi; p.v_lo = x_lo;
+  DEXB_TRY(enc3(&ap->tmV, x, (cuuint64_t)x_stride, (cuuint64_t)P, (cuuint64_t)B, xrow, xrow * P, 64, kAtBN, "LA x as V"));
   return 0;
 }
 
@@ -559,6 +560,8 @@ int attn_launch(const AttnPlan& ap, cudaStream_t st) {
 }
 int attn_launch_count(const AttnPlan& ap) { return ap.p.tail_splits > 1 ? 2 : 1; }
 
-double attn_flop(const AttnPlan& ap) { return 4.0 * ap.B * ap.p.nheads * (double)ap.p.NQ * ap.p.NK * kAtHD; }
+double attn_flop(const AttnPlan& ap) {
+  return 2.0 * ap.B * ap.p.nheads * (double)ap.p.NQ * ap.p.NK * 64.0 * (ap.p.kchunks + ap.p.vchunks);
+}
 
 }  // namespace dexb

@@ -13,6 +13,7 @@ struct AttnParams {
   int nheads;
   int nt;                    // key tiles of 64
   int kchunks;               // 64-wide chunks of the Q / K rows (head dim / 64): 2, or 1 for the C = 64 linear attention
+  int vchunks;               // 64-wide chunks of the V rows (output width / 64): 2; C / 64 for the linear-attention context
   int kv_splits;             // > 1: split-KV mode -- blockIdx.x = key split, one 128-row query tile, partial outputs
   int tiles_per_split;
   int q_img_rows;            // Q rows per image (0: the same Q rows for every image)
@@ -65,8 +66,10 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
                       int C);
 // LinearAttention context (diffusion.py:82-95) as attention with the roles swapped: "queries" = the 128 k-channels (rows of the
 // k part of to_qkv, split weights wk [128][hi(C)|lo(C)]), "keys" = the pixels x, softmax over ALL pixels of an image, "values" = v
-// (split rows [b][P][hi(128)|lo(128)] from the GEMM engine, used as an MN-major B operand).  Split over the pixels; partials are merged by launch_la_combine.
-int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, const bf16* vT, float* part_o,
+// = the pixels x AGAIN (MN-major B operand straight from the activation rows): context = softmax(k)^T v = (softmax(k)^T x) W_v^T,
+// so the kernel produces G = softmax(k)^T x (128 x C per image) and the small product with W_v is left to the merge kernel
+// (launch_la_combine) -- v is never materialised.  Split over the pixels; partials [b][split][128][128 (first C used)].
+int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride, int x_hi, int x_lo, float* part_o,
                       float* part_l, float* part_m, int B, int P, int PP, int C, int splits);
 // Balance the last partial wave of the DiT attention (see AttnParams::tail_first).  Returns the number of floats of scratch the
 // partials need (0: the tile count already fills the SMs evenly, nothing to do); call attn_plan_set_tail with that scratch.

@@ -92,6 +92,7 @@ static int bind_la(dexb_handle* h, LinAttW& la, const std::string& p, int C, Are
   NEED_W(g, p + ".fn.g", 1);
   la.C = C;
   la.wq = qkv->p;                       // rows 0..127
+  la.wv = qkv->p + 256L * C;            // rows 256..383
   la.wout = wo->p; la.bout = bo->p; la.g = g->p;
   la.kv_w = ar.get<bf16>(256L * 2 * C);
   return 0;
@@ -343,16 +344,9 @@ static int plan_la(dexb_handle* h, LinAttW& la, const bf16* in, long in_stride, 
     gp_out_f(p, h->kv, 256);
     DEXB_TRY(plan_shared(&la.kv, p));
   }
-  if (h->fused_la) {
-    GemmParams p = gp_base(h->cfg);                   // v = W_v x as split rows for the tensor-core context kernel
-    gp_geom(p, h->B, H, W);
-    gp_a(p, in, in_stride, in_hi, in_lo, la.C);
-    gp_b(p, la.kv_w + 128L * 2 * la.C, la.C, 128);
-    gp_out_s(p, h->la_vT, 256, 0, 128);                // split rows [pixel][hi(128) | lo(128)]
-    DEXB_TRY(plan_shared(&la.vt, p));
-    DEXB_TRY(attn_plan_init_la(&la.ctx_plan, la.kv_w, in, in_stride, in_hi, in_lo, h->la_vT, la.part_o, la.part_l, la.part_m, h->B,
-                               H * W, la.PP, la.C, la.splits));
-  }
+  if (h->fused_la)                                    // G = softmax(k)^T x on the tensor cores; W_v is applied by the merge kernel
+    DEXB_TRY(attn_plan_init_la(&la.ctx_plan, la.kv_w, in, in_stride, in_hi, in_lo, la.part_o, la.part_l, la.part_m, h->B, H * W,
+                               la.PP, la.C, la.splits));
   {
     GemmParams p = gp_base(h->cfg);
     gp_geom(p, h->B, H, W);
@@ -426,8 +420,6 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->A0 = ar.get<bf16>(P0 * 2 * d); h->B0 = ar.get<bf16>(P0 * 2 * d); h->C0 = ar.get<bf16>(P0 * 2 * d);
   h->kv = ar.get<float>(P0 * 256);
   {
-    const long pp0 = (long)(h->H0 * h->W0 + 63) / 64 * 64;
-    h->la_vT = ar.get<bf16>((long)B * pp0 * 256);         // v rows [b][pixel][hi(128)|lo(128)]
     LinAttW* las2[3] = {&h->la0, &h->la1, &h->la2};
     for (LinAttW* la : las2) {
       const int Pl = (la == &h->la0) ? h->H0 * h->W0 : h->H1 * h->W1;
@@ -818,12 +810,11 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
 
 static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
   if (h->fused_la) {
-    GEMM(la.vt, la.vt.p);
     if (h->prof) prof_begin(h, "attn_fwd_kernel(la ctx)", attn_flop(la.ctx_plan), st);
     DEXB_TRY(attn_launch(la.ctx_plan, st));
     if (h->prof) prof_end(h, st);
     ++h->launches;
-    LAUNCH(launch_la_combine(la.part_o, la.part_l, la.part_m, la.ctx, la.ssum, h->B, la.splits, st));
+    LAUNCH(launch_la_combine(la.part_o, la.part_l, la.part_m, la.wv, la.ctx, la.ssum, h->B, la.splits, la.C, st));
   } else {
     GEMM(la.kv, la.kv.p);
     LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));

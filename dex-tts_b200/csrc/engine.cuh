@@ -52,10 +52,9 @@ struct ResnetW {
 
 struct LinAttW {
   bf16* kv_w = nullptr;               // [256][hi(C)|lo(C)]  (rows 128..383 of to_qkv)
-  const float *wq = nullptr, *wout = nullptr, *bout = nullptr, *g = nullptr;
+  const float *wq = nullptr, *wv = nullptr, *wout = nullptr, *bout = nullptr, *g = nullptr;
   int C = 0;
   GemmPlan kv, apply;
-  GemmPlan vt;                        // fused path: v only, split rows for the tensor-core context kernel
   AttnPlan ctx_plan;
   int splits = 1, PP = 0;
   float *part_o = nullptr, *part_l = nullptr, *part_m = nullptr;
@@ -139,7 +138,6 @@ struct dexb_handle {
   dexb::PosConvPlan pc_plan;
   bool fused_attn = false, fused_tv = false, fused_la = false, ws_posconv = false;
   dexb::bf16 *pc_w = nullptr, *pc_in = nullptr;      // weight-stationary pos-conv: packed weights / packed input rows
-  dexb::bf16* la_vT = nullptr;                       // v rows [B][P][hi(128)|lo(128)], shared by the three linear attentions
   // CUDA graph of one whole trajectory
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;

@@ -60,8 +60,9 @@ int la_ctx_blocks(int B, int P);                      // pixel blocks per image 
 void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part /*[B][blocks][4224] scratch*/,
                    float* ctx /*[B][4][32][32]*/, float* ssum /*[B][128]*/, int B, int P, cudaStream_t st);
 // merge of the split-KV partials of the tensor-core context kernel -> ctx, ssum (see attn.cuh: attn_plan_init_la)
-void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, float* ctx, float* ssum, int B, int S,
-                       cudaStream_t st);
+// (also applies W_v: the context kernel computes softmax(k)^T x, see attn.cuh: attn_plan_init_la); wv = v rows of to_qkv [128][C]
+void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, const float* wv, float* ctx, float* ssum,
+                       int B, int S, int C, cudaStream_t st);
 // W_eff[b] = I + g * W_out * ctxn^T * W_q  -> packed split weights [B][C][hi(C)|lo(C)], beff[b] = g * b_out
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq /*[128][C]*/, const float* wout /*[C][128]*/,
                     const float* bout, const float* g, float* m1 /*[B][128][C] scratch*/, bf16* weff, float* beff, int B,

@@ -469,34 +469,60 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float
   k_la_reduce<<<cdiv((long)B * kLaPartial, 256), 256, 0, st>>>(part, ctx, ssum, B, nblk);
 }
 
-// Merge the split-KV partials of the tensor-core context kernel (attn.cu, out_mode 2), in split order:
-//   M[d] = max_s m_s[d];  ctx[b][h][d][e] = sum_s O_s[d][h*32+e] exp(m_s[d] - M[d]);  ssum[b][d] = sum_s l_s[d] exp(m_s[d] - M[d])
-// (only the 4 diagonal 32x32 head blocks of the 128x128 product are context).  One thread per output.
-__global__ void __launch_bounds__(256) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
-                                                    const float* __restrict__ part_m, float* __restrict__ ctx,
-                                                    float* __restrict__ ssum, int B, int S) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = 4096 + 128;
-  if (i >= B * per) return;
-  const int b = i / per, k = i % per;
-  int d, col;
-  if (k < 4096) { const int h = k >> 10, dl = (k >> 5) & 31, el = k & 31; d = h * 32 + dl; col = h * 32 + el; }
-  else { d = k - 4096; col = -1; }
+// Merge the split-KV partials of the tensor-core context kernel (attn.cu, out_mode 2) in split order, then finish the
+// reassociated context:  the kernel produced G = softmax(k)^T x per key range (128 x C, un-normalised), so
+//   M[d] = max_s m_s[d];  G[d][c] = sum_s G_s[d][c] exp(m_s[d] - M[d]);  ssum[b][d] = sum_s l_s[d] exp(m_s[d] - M[d]);
+//   ctx[b][h][d][e] = sum_c G[h*32+d][c] W_v[h*32+e][c]          (= softmax(k)^T v restricted to the 4 diagonal head blocks).
+// One block of 64 threads per (head, group of 8 rows, image); thread = (row d, a contiguous eighth of the C columns).
+template <int C>
+__global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
+                                                    const float* __restrict__ part_m, const float* __restrict__ wv,
+                                                    float* __restrict__ ctx, float* __restrict__ ssum, int S) {
+  __shared__ float Gh[8][C + 1];
+  __shared__ float Wvs[32][C + 1];
+  const int h = blockIdx.x >> 2, rg = blockIdx.x & 3, b = blockIdx.y, tid = threadIdx.x;
+  const int dl = tid >> 3, seg = tid & 7;
+  const int d = rg * 8 + dl;
+  constexpr int CS = C / 8;                                  // columns per thread: 8 or 16
+  const int row = h * 32 + d;
   float M = -INFINITY;
-  for (int s = 0; s < S; ++s) M = fmaxf(M, part_m[((long)b * S + s) * 128 + d]);
-  float acc = 0.f;
+  for (int s = 0; s < S; ++s) M = fmaxf(M, part_m[((long)b * S + s) * 128 + row]);
+  float acc[CS];
+#pragma unroll
+  for (int j = 0; j < CS; ++j) acc[j] = 0.f;
+  float l = 0.f;
+#pragma unroll 4
   for (int s = 0; s < S; ++s) {
-    const long ps = (long)b * S + s;
-    const float w = expf(part_m[ps * 128 + d] - M);          // exp(-inf) = 0 for an empty split
-    const float v = (col >= 0) ? part_o[(ps * 128 + d) * 128 + col] : part_l[ps * 128 + d];
-    acc = fmaf(v, w, acc);
+    const long pi = ((long)b * S + s) * 128 + row;
+    const float w = expf(part_m[pi] - M);                    // exp(-inf) = 0 for an empty split
+    l = fmaf(part_l[pi], w, l);
+    const float4* po = reinterpret_cast<const float4*>(part_o + pi * 128 + seg * CS);
+#pragma unroll
+    for (int j = 0; j < CS / 4; ++j) {
+      const float4 v = po[j];
+      acc[4 * j] = fmaf(v.x, w, acc[4 * j]); acc[4 * j + 1] = fmaf(v.y, w, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(v.z, w, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v.w, w, acc[4 * j + 3]);
+    }
   }
-  if (col >= 0) ctx[(long)b * 4096 + k] = acc;
-  else ssum[b * 128 + d] = acc;
+#pragma unroll
+  for (int j = 0; j < CS; ++j) Gh[dl][seg * CS + j] = acc[j];
+  if (seg == 0) ssum[b * 128 + row] = l;
+  for (int i = tid; i < 32 * C; i += 64) Wvs[i / C][i % C] = wv[(long)(h * 32 + i / C) * C + i % C];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = seg * 4 + i;
+    float a = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) a = fmaf(Gh[dl][c], Wvs[e][c], a);
+    ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] = a;
+  }
 }
-void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, float* ctx, float* ssum, int B, int S,
-                       cudaStream_t st) {
-  k_la_combine<<<cdiv((long)B * (4096 + 128), 256), 256, 0, st>>>(part_o, part_l, part_m, ctx, ssum, B, S);
+void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, const float* wv, float* ctx, float* ssum,
+                       int B, int S, int C, cudaStream_t st) {
+  dim3 grid(16, B);
+  if (C == 64) k_la_combine<64><<<grid, 64, 0, st>>>(part_o, part_l, part_m, wv, ctx, ssum, S);
+  else k_la_combine<128><<<grid, 64, 0, st>>>(part_o, part_l, part_m, wv, ctx, ssum, S);
 }
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
