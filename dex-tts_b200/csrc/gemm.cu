@@ -139,6 +139,7 @@ static bool epi_fast_ok(const GemmParams& p) {
     mode = (e != nullptr) ? atoi(e) : 1;
   }
   if (mode == 0) return false;
+  if (p.dbg != 0 || p.nsplit != 3) return false;          // the FAST kernel also drops the tuning / single-product branches
   const EpiParams& e = p.epi;
   auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
   if (p.N % 32 != 0 || e.out_vt != nullptr || e.colmean != nullptr || e.o_head_stride % 16 != 0) return false;

@@ -397,87 +397,100 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tma_load_3d(smem + it * BB2 + SM::kBBytes, &tmB, b_full, p.b_lo + kc * kTcBlockK, brow, 0);
         }
       }
-      uint32_t g = 0;                                        // ring position, continues across tiles
+      // The two single-thread loops (this one and the MMA issuer) are the serial resource of the kernel: every integer
+      // division / modulo of the ring position or the tap index costs ~25 dependent instructions per stage, and the tensor
+      // pipe retires a 64-wide stage in 473 cycles (tools/mma_bench.cu `kernel pattern`).  Stage index, phase, tap
+      // coordinates and weight rows are therefore carried incrementally.
+      uint32_t s = 0, ph = 0;                                // ring slot and its phase parity, continue across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
         const int bz = (p.b_mode == 0) ? 0 : (p.b_mode == 1 ? tl.z / p.nheads : tl.z);
-        for (int it = 0; it < nk; ++it, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          const int tap = it / kchunks, kc = it % kchunks;
-          const int dy = tap / p.KW + p.offH, dx = (tap % p.KW) * p.tap_sw + p.offW;
-          uint8_t* st = ring + s * stage_bytes;
-          if (p.dbg & 4) { ptx::mbar_arrive(&full_bar[s]); continue; }   // tuning aid: no operand traffic at all
-          ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
-          const int acol = kc * kTcBlockK + tl.head * p.a_head_stride;
-          const int ax = tl.cw0 * p.in_stride + dx, ay = tl.ch0 * p.in_stride + dy;
-          ptx::tma_load_4d(st, &tmA, &full_bar[s], p.a_hi + acol, ax, ay, tl.img_a);
-          if (rb > 0) {
-            ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, ax, ay, tl.img_a);
-            continue;
-          }
-          const int bcol = kc * kTcBlockK + tl.head * p.b_head_stride;
-          const int brow = tap * p.b_rows_per_tap + tl.n0 + tl.head * p.b_head_rows;
-          ptx::tma_load_3d(st + 2 * SM::kABytes, &tmB, &full_bar[s], p.b_hi + bcol, brow, bz);
-          if (p.nsplit == 3) {
-            ptx::tma_load_4d(st + SM::kABytes, &tmA, &full_bar[s], p.a_lo + acol, ax, ay, tl.img_a);
-            ptx::tma_load_3d(st + 2 * SM::kABytes + SM::kBBytes, &tmB, &full_bar[s], p.b_lo + bcol, brow, bz);
+        const int ax0 = tl.cw0 * p.in_stride + p.offW, ay0 = tl.ch0 * p.in_stride + p.offH;
+        const int acol0 = tl.head * p.a_head_stride, bcol0 = tl.head * p.b_head_stride;
+        int brow = tl.n0 + tl.head * p.b_head_rows;          // weight row of the current tap
+        for (int ty = 0; ty < p.KH; ++ty) {
+          for (int tx = 0; tx < p.KW; ++tx, brow += p.b_rows_per_tap) {
+            const int ax = ax0 + tx * p.tap_sw, ay = ay0 + ty;
+            for (int kc = 0; kc < kchunks; ++kc) {
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* st = ring + s * stage_bytes;
+              uint64_t* fb = &full_bar[s];
+              if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+              if (p.dbg & 4) { ptx::mbar_arrive(fb); continue; }   // tuning aid: no operand traffic at all
+              ptx::mbar_expect_tx(fb, tx_bytes);
+              const int acol = kc * kTcBlockK + acol0;
+              ptx::tma_load_4d(st, &tmA, fb, p.a_hi + acol, ax, ay, tl.img_a);
+              if (rb > 0) {
+                ptx::tma_load_4d(st + SM::kABytes, &tmA, fb, p.a_lo + acol, ax, ay, tl.img_a);
+                continue;
+              }
+              const int bcol = kc * kTcBlockK + bcol0;
+              ptx::tma_load_3d(st + 2 * SM::kABytes, &tmB, fb, p.b_hi + bcol, brow, bz);
+              if (p.nsplit == 3) {
+                ptx::tma_load_4d(st + SM::kABytes, &tmA, fb, p.a_lo + acol, ax, ay, tl.img_a);
+                ptx::tma_load_3d(st + 2 * SM::kABytes + SM::kBBytes, &tmB, fb, p.b_lo + bcol, brow, bz);
+              }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
+    // ---------------- MMA issuer: one elected thread runs the whole loop ----------------
     constexpr uint32_t idesc = ptx::make_idesc_bf16(kTcBlockM, BLOCK_N);
     constexpr uint32_t idesc2 = ptx::make_idesc_bf16(kTcBlockM, STACKED ? 2 * BLOCK_N : BLOCK_N);
-    uint32_t g = 0;
-    int li = 0;                                              // local tile counter -> accumulator buffer li & 1
-    if (rb > 0 && blockIdx.x < total_tiles) ptx::mbar_wait(b_full, 0);
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
-      const int buf = li & 1;
-      ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
-      ptx::tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
-      for (int it = 0; it < nk; ++it, ++g) {
-        const int s = g % STAGES;
-        const uint32_t ph = (g / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+    if (ptx::elect_one()) {
+      // K-major SWIZZLE_128B descriptors differ only in their 14-bit start-address field: desc(addr) = kDescBase + (addr >> 4)
+      // (shared-memory addresses are < 256 KiB, so the field never carries)
+      constexpr uint64_t kDescBase = ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint32_t ring_u = ptx::smem_u32(ring) >> 4, stage_u = (uint32_t)stage_bytes >> 4;
+      const uint32_t bres_u = ptx::smem_u32(smem) >> 4;
+      uint32_t s = 0, ph = 0;
+      int li = 0;                                            // local tile counter -> accumulator buffer li & 1
+      if (rb > 0 && blockIdx.x < total_tiles) ptx::mbar_wait(b_full, 0);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+        const int buf = li & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          if (!(p.dbg & 2)) {
-          const uint32_t a_hi = ptx::smem_u32(ring + s * stage_bytes);
-          const uint32_t a_lo = a_hi + SM::kABytes;
-          const uint32_t b_hi = (rb > 0) ? ptx::smem_u32(smem + it * BB2) : a_hi + 2 * SM::kABytes;
-          const uint32_t b_lo = b_hi + SM::kBBytes;
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
+        uint32_t bres = bres_u;                              // resident weight chunk of this iteration
+        for (int it = 0; it < nk; ++it, bres += (uint32_t)(BB2 >> 4)) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ring_u + s * stage_u;
+          const uint32_t a_lo = a_hi + (SM::kABytes >> 4);
+          const uint32_t b_hi = (rb > 0) ? bres : a_hi + (2 * SM::kABytes >> 4);
+          const uint32_t b_lo = b_hi + (SM::kBBytes >> 4);
+          if (FAST || !(p.dbg & 2)) {
 #pragma unroll
-          for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
-            const uint32_t ko = kk * 32;                     // 16 bf16 = 32 B inside the 128 B swizzle span
-            const uint64_t dah = ptx::make_desc_k128(a_hi + ko);
-            const uint64_t dbh = ptx::make_desc_k128(b_hi + ko);
-            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-            if (p.nsplit == 3) {
-              const uint64_t dal = ptx::make_desc_k128(a_lo + ko);
-              if constexpr (STACKED) {
-                ptx::mma_bf16_ss(tacc, dah, dbh, idesc2, acc);            // [A_hi B_hi | A_hi B_lo]
-                ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);              //  + A_lo B_hi
+            for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+              const uint32_t ko = kk * 2;                    // 16 bf16 = 32 B inside the 128 B swizzle span
+              const uint64_t dah = kDescBase + (a_hi + ko);
+              const uint64_t dbh = kDescBase + (b_hi + ko);
+              const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+              if (FAST || p.nsplit == 3) {
+                const uint64_t dal = kDescBase + (a_lo + ko);
+                if constexpr (STACKED) {
+                  ptx::mma_bf16_ss(tacc, dah, dbh, idesc2, acc);            // [A_hi B_hi | A_hi B_lo]
+                  ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);              //  + A_lo B_hi
+                } else {
+                  const uint64_t dbl = kDescBase + (b_lo + ko);
+                  ptx::mma_bf16_ss(tacc, dah, dbh, idesc, acc);
+                  ptx::mma_bf16_ss(tacc, dah, dbl, idesc, 1u);
+                  ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
+                }
               } else {
-                const uint64_t dbl = ptx::make_desc_k128(b_lo + ko);
                 ptx::mma_bf16_ss(tacc, dah, dbh, idesc, acc);
-                ptx::mma_bf16_ss(tacc, dah, dbl, idesc, 1u);
-                ptx::mma_bf16_ss(tacc, dal, dbh, idesc, 1u);
               }
-            } else {
-              ptx::mma_bf16_ss(tacc, dah, dbh, idesc, acc);
             }
-          }
           }
           ptx::mma_commit(&empty_bar[s]);                    // frees the smem stage when these MMAs retire
           if (it == nk - 1) ptx::mma_commit(&acc_full[buf]); // accumulator complete
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     // 8 warps: lane group lg = warp & 3 (the TMEM lanes a warp may touch); the two warps of a lane group take the

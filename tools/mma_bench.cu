@@ -53,6 +53,54 @@ __global__ void __launch_bounds__(128, 1) k_time(int n, int ts_mode, int reps, l
   if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
 }
 
+// The conv / linear kernels' exact per-stage pattern: 4 x { MMA(A_hi, [B_hi|B_lo], N = 2*bn) ; MMA(A_lo, B_hi, N = bn) } then one
+// tcgen05.commit, `stages` times, alternating between two TMEM accumulators every 9 stages.  mode 1 adds nothing else; it shows
+// whether the tensor pipe itself sustains N/2 + 43 cycles per MMA on this mix.
+__global__ void __launch_bounds__(128, 1) k_pattern(int bn, int stages, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar[4];
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) ptx::mbar_init(&bar[i], 1); ptx::fence_barrier_init(); }
+  if (threadIdx.x < 32) ptx::tmem_alloc<512>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  if (threadIdx.x < 32) {
+    const uint32_t idesc = ptx::make_idesc_bf16(128, bn), idesc2 = ptx::make_idesc_bf16(128, 2 * bn);
+    long long t0 = 0, t1 = 0;
+    __syncwarp();
+    if (ptx::elect_one()) {
+      t0 = clock64();
+      for (int st = 0; st < stages; ++st) {
+        const uint32_t base = ptx::smem_u32(smem) + (st % 3) * 65536;
+        const uint32_t a_hi = base, a_lo = base + 16384, b_hi = base + 32768;
+        const uint32_t tacc = tmem + ((st / 9) & 1) * 256;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 32;
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_hi + ko), ptx::make_desc_k128(b_hi + ko), idesc2, (st % 9 || kk) ? 1u : 0u);
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_lo + ko), ptx::make_desc_k128(b_hi + ko), idesc, 1u);
+        }
+        ptx::mma_commit(&bar[1 + (st % 3)]);
+      }
+      ptx::mma_commit(&bar[0]);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&bar[0], 0);                              // only the final commit arrives on bar[0]
+    t1 = clock64();
+    long long mx = t0;
+    for (int o = 16; o > 0; o >>= 1) { long long v = __shfl_xor_sync(0xffffffffu, mx, o); mx = v > mx ? v : mx; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = t1 - mx;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
+}
+
 // A[r][k] = (k == 0) ? r + 1 : 0 for r in [0, 144), written with the TMA 128B swizzle; B[n][k] = (n == 0 && k == 0).
 // D = A_shift B^T  -> D[m][0] must be m + shift + 1.
 __global__ void __launch_bounds__(128, 1) k_shift(int shift, int use_base_offset, float* out) {
@@ -122,6 +170,16 @@ int main() {
                128.0 * n / 256.0);
       }
     }
+  }
+  cudaFuncSetAttribute(k_pattern, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
+  for (int bn : {64, 128}) {
+    const int stages = 9 * 32;
+    k_pattern<<<148, 128, 194 * 1024>>>(bn, stages, d);
+    long long c = 0;
+    cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { printf("pattern error %s\n", cudaGetErrorString(e)); return 1; }
+    printf("kernel pattern  BLOCK_N=%3d: %7.1f cycles per stage (4 x [N=%d + N=%d]); model 4 x (%d/2+43 + %d/2+43) = %d\n", bn,
+           (double)c / stages, 2 * bn, bn, 2 * bn, bn, 4 * (bn + 43 + bn / 2 + 43));
   }
   float* o;
   cudaMalloc(&o, 128 * 4);
