@@ -71,10 +71,22 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
               ((q.a_hi | q.a_lo | q.b_hi | q.b_lo | q.a_head_stride | q.b_head_stride) % 8 == 0);
   if (!gp->tc_ok) return 0;
   {
+    // halo mode (gemm.cuh): 3x3 stride-1 convolution on 1 x 128 pixel tiles, shared weights, stacked-N tile widths
+    static int halo_mode = -1;
+    if (halo_mode < 0) {
+      const char* e = getenv("DEXB_HALO");
+      halo_mode = (e != nullptr) ? atoi(e) : 1;
+    }
+    gp->halo = halo_mode != 0 && q.KH == 3 && q.KW == 3 && q.offH == -1 && q.offW == -1 && q.tap_sw == 1 && q.in_stride == 1 &&
+               q.out_scale == 1 && q.BW == 128 && q.BH == 1 && q.nheads == 1 && q.b_mode == 0 && q.nsplit == 3 && q.dbg == 0 &&
+               gp->block_n <= 128 && q.N % gp->block_n == 0;
+  }
+  {
     const cuuint64_t dims[4] = {(cuuint64_t)q.a_row_stride, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)n_img_a};
     const cuuint64_t str[3] = {(cuuint64_t)q.a_row_stride * 2, (cuuint64_t)q.a_row_stride * 2 * q.W,
                                (cuuint64_t)q.a_row_stride * 2 * q.W * q.H};
-    const cuuint32_t box[4] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(q.BW * q.in_stride), (cuuint32_t)(q.BH * q.in_stride), 1};
+    const cuuint32_t box[4] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(gp->halo ? kTcHaloRows : q.BW * q.in_stride),
+                               (cuuint32_t)(q.BH * q.in_stride), 1};
     const cuuint32_t es[4] = {1, (cuuint32_t)q.in_stride, (cuuint32_t)q.in_stride, 1};
     DEXB_TRY(encode_bf16(&gp->tmA, q.A, 4, dims, str, box, es, "A"));
   }
@@ -160,6 +172,13 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
   const int ntn = cdiv(p.N, BN);
   const long m_tiles = (long)p.nz * p.TH * p.TW;
   const long total = m_tiles * ntn;
+  if (gp.halo && BN <= 128) {                          // the plan encoded 136-row A boxes: halo mode is the only valid launch
+    int nb = (kTcSmemMax - tc_halo_bytes(BN, 0)) / (2 * BN * kTcBlockK * 2);
+    if (nb > kTcMaxStages) nb = kTcMaxStages;
+    const int grid = (int)(total < g_num_sms ? total : g_num_sms);
+    gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, tc_halo_bytes(BN, nb), st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, -nb);
+    return 0;
+  }
   const int rb = rb_stages_for(p, BN, m_tiles, ntn);
   if (rb > 0) {
     const int nk = p.KH * p.KW * (p.K / kTcBlockK);

@@ -311,7 +311,18 @@ struct TcSmem {
 // and the ring only carries A (32 KiB per stage instead of 48-64).  The grid is a multiple of the n-tile count, so t += gridDim.x
 // keeps a CTA on one n-tile for its whole life.  Small-K GEMMs (DiT linears: K = 256) are bound by the SM's L2->SMEM ingest
 // (~64 B/clk: `neither` column of profiles/r01_epilogue_experiments.md), and half of their ingest was the re-streamed weight tile.
-constexpr int kTcMaxStages = 6;
+constexpr int kTcMaxStages = 8;
+// Halo mode (rb < 0, -rb = number of weight stages): 3x3 stride-1 convolutions on tiles of 1 x 128 pixels.  One staged input
+// row slab of 136 pixels (x0 - 1 ... x0 + 134) serves the three dx taps of its dy: the A descriptor of tap dx simply starts dx
+// rows (dx * 128 B) into the slab -- SWIZZLE_128B is a function of the absolute shared-memory address, so a row-shifted start
+// is legal (tools/mma_bench.cu, `row-shifted A descriptor`).  A traffic drops from 9 to 3.2 tile-loads per tile; with the ring
+// at 192 KiB the operand stream of the plain path is latency-bound (bytes in flight / TMA latency ~ 64 B/clk per SM).
+constexpr int kTcHaloRows = 136;                                   // slab rows: 128 + 2 halo, rounded up to 8
+constexpr int kTcHaloSlab = kTcHaloRows * kTcBlockK * 2;           // 17 408 B per (hi | lo) slab, a multiple of 1024
+constexpr int kTcHaloASlots = 3;
+__host__ __device__ constexpr int tc_halo_bytes(int block_n, int nb) {
+  return kTcHaloASlots * 2 * kTcHaloSlab + nb * 2 * block_n * kTcBlockK * 2 + 1024 + 256;
+}
 constexpr int kTcSmemMax = 232448;             // 227 KiB: the most a CTA can opt in to
 __host__ __device__ constexpr int tc_rb_bytes(int block_n, int nk, int rb) {
   return nk * 2 * block_n * kTcBlockK * 2 + rb * 2 * kTcBlockM * kTcBlockK * 2 + 1024 + 256;
@@ -342,7 +353,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p, const int total_tiles, const int ntn, const int rb) {
   using SM = TcSmem<BLOCK_N>;
-  const int STAGES = rb > 0 ? rb : SM::kStages;
+  const bool halo = rb < 0;
+  const int STAGES = rb > 0 ? rb : (halo ? -rb : SM::kStages);
   constexpr int BB2 = 2 * SM::kBBytes;                               // one resident weight chunk: [B_hi | B_lo]
   // Stacked-N split product (BLOCK_N <= 128): B_hi and B_lo tiles are adjacent in shared memory, so ONE MMA with
   // N = 2*BLOCK_N computes A_hi*B_hi (columns [0, BN)) and A_hi*B_lo (columns [BN, 2BN)); a second MMA adds A_lo*B_hi to
@@ -358,14 +370,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kchunks = p.K / kTcBlockK;
   const int nk = p.KH * p.KW * kchunks;
   // ring stage: [A_hi | A_lo | B_hi | B_lo], or [A_hi | A_lo] behind the resident weights
-  const int stage_bytes = rb > 0 ? 2 * SM::kABytes : SM::kStageBytes;
-  uint8_t* ring = smem + (rb > 0 ? nk * BB2 : 0);
+  // halo: [3 A slots of (hi slab | lo slab)] [STAGES weight slots of (B_hi | B_lo)]
+  const int stage_bytes = rb > 0 ? 2 * SM::kABytes : (halo ? BB2 : SM::kStageBytes);
+  uint8_t* ring = smem + (rb > 0 ? nk * BB2 : (halo ? kTcHaloASlots * 2 * kTcHaloSlab : 0));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * stage_bytes);
   uint64_t* empty_bar = full_bar + kTcMaxStages;
   uint64_t* acc_full = empty_bar + kTcMaxStages;  // [2]
   uint64_t* acc_empty = acc_full + 2;             // [2]
   uint64_t* b_full = acc_empty + 2;               // resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* a_full = b_full + 1;                  // [3] halo mode: input row slab landed / consumed
+  uint64_t* a_empty = a_full + kTcHaloASlots;     // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kTcHaloASlots);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -373,6 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kTcEpiThreads); }
     ptx::mbar_init(b_full, 1);
+    for (int s = 0; s < kTcHaloASlots; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -402,6 +418,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // pipe retires a 64-wide stage in 473 cycles (tools/mma_bench.cu `kernel pattern`).  Stage index, phase, tap
       // coordinates and weight rows are therefore carried incrementally.
       uint32_t s = 0, ph = 0;                                // ring slot and its phase parity, continue across tiles
+      if (halo) {
+        uint32_t sa = 0, pa = 0;                             // A slab slot and phase
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+          const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
+          int brow = tl.n0;
+          for (int ty = 0; ty < 3; ++ty) {
+            for (int kc = 0; kc < kchunks; ++kc) {
+              ptx::mbar_wait(&a_empty[sa], pa ^ 1);
+              uint8_t* sl = smem + sa * (2 * kTcHaloSlab);
+              ptx::mbar_expect_tx(&a_full[sa], 2 * kTcHaloSlab);
+              ptx::tma_load_4d(sl, &tmA, &a_full[sa], p.a_hi + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
+              ptx::tma_load_4d(sl + kTcHaloSlab, &tmA, &a_full[sa], p.a_lo + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
+              if (++sa == kTcHaloASlots) { sa = 0; pa ^= 1; }
+              for (int tx = 0; tx < 3; ++tx) {
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = ring + s * BB2;
+                uint64_t* fb = &full_bar[s];
+                if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+                ptx::mbar_expect_tx(fb, BB2);
+                const int br = brow + tx * p.b_rows_per_tap;
+                ptx::tma_load_3d(st, &tmB, fb, p.b_hi + kc * kTcBlockK, br, 0);
+                ptx::tma_load_3d(st + SM::kBBytes, &tmB, fb, p.b_lo + kc * kTcBlockK, br, 0);
+              }
+            }
+            brow += 3 * p.b_rows_per_tap;
+          }
+        }
+      } else
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
         const int bz = (p.b_mode == 0) ? 0 : (p.b_mode == 1 ? tl.z / p.nheads : tl.z);
@@ -448,7 +492,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t s = 0, ph = 0;
       int li = 0;                                            // local tile counter -> accumulator buffer li & 1
       if (rb > 0 && blockIdx.x < total_tiles) ptx::mbar_wait(b_full, 0);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+      if constexpr (STACKED) {
+        if (halo) {
+          uint32_t sa = 0, pa = 0;
+          const uint32_t slab_u = ptx::smem_u32(smem) >> 4;
+          for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
+            const int buf = li & 1;
+            ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
+            const int na = 3 * kchunks;                      // (dy, k-chunk) slab steps of a tile
+            for (int ia = 0; ia < na; ++ia) {
+              ptx::mbar_wait(&a_full[sa], pa);
+              const uint32_t a_base = slab_u + sa * (uint32_t)(2 * kTcHaloSlab >> 4);
+              for (int tx = 0; tx < 3; ++tx) {
+                ptx::mbar_wait(&full_bar[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_hi = a_base + (uint32_t)(tx * 8);          // tap dx: the slab shifted by dx rows of 128 B
+                const uint32_t a_lo = a_hi + (kTcHaloSlab >> 4);
+                const uint32_t b_hi = ring_u + s * stage_u;
+#pragma unroll
+                for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+                  const uint32_t ko = kk * 2;
+                  const uint64_t dbh = kDescBase + (b_hi + ko);
+                  ptx::mma_bf16_ss(tacc, kDescBase + (a_hi + ko), dbh, idesc2, (ia > 0 || tx > 0 || kk > 0) ? 1u : 0u);
+                  ptx::mma_bf16_ss(tacc, kDescBase + (a_lo + ko), dbh, idesc, 1u);
+                }
+                ptx::mma_commit(&empty_bar[s]);
+                if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+              }
+              ptx::mma_commit(&a_empty[sa]);                 // slab free once the MMAs of its three taps have retired
+              if (ia == na - 1) ptx::mma_commit(&acc_full[buf]);
+              if (++sa == kTcHaloASlots) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+      }
+      for (int t = blockIdx.x; t < total_tiles && !halo; t += gridDim.x, ++li) {
         const int buf = li & 1;
         ptx::mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this buffer
         ptx::tc_fence_after();
@@ -537,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float rpre[CW];
         if (!(p.dbg & 1) && !use_vt) epi_load_resid<CW, FAST>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, rpre);
         if (k == 0) {
-          ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);
+          ptx::mbar_wait_backoff(&acc_full[buf], (li >> 1) & 1, 128);
           ptx::tc_fence_after();
         }
         float v[CW];

@@ -86,6 +86,7 @@ struct GemmPlan {
   int block_n;
   int n_img_a;
   bool tc_ok;                  // shape is eligible for the tcgen05 engine
+  bool halo;                   // 3x3 stride-1 convolution in halo mode: tmA boxes are 136-pixel row slabs (gemm.cuh)
 };
 
 // one-off kernel attribute setup + driver entry point resolution (call outside stream capture)

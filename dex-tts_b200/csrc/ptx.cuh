@@ -74,6 +74,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait of a consumer that expects to be blocked for a long time (epilogue warps waiting for a whole tile of MMAs): back off
+// between polls so that 16 polling warps do not compete with the two single-thread pipelines for issue slots / the sync unit.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
