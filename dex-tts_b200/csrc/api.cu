@@ -33,6 +33,8 @@ int dexb_create(const dexb_config* cfg, dexb_handle** out) {
   DEXB_CHECK(cfg->variant == 0 || cfg->variant == 1, "variant must be 0 (GeDEX-TTS) or 1 (DEX-TTS)");
   DEXB_CHECK(cfg->nsplit == 1 || cfg->nsplit == 3, "nsplit must be 1 or 3");
   DEXB_CHECK(cfg->gemm_engine == 0 || cfg->gemm_engine == 1, "gemm_engine must be 0 or 1");
+  DEXB_CHECK(cfg->n_spks <= 1 || (cfg->variant == 0 && cfg->spk_emb_dim >= 1 && cfg->spk_emb_dim <= 1024),
+             "n_spks > 1 is a GeDEX-TTS option (variant 0) and needs 1 <= spk_emb_dim <= 1024");
   dexb_handle* h = new dexb_handle();
   h->cfg = *cfg;
   *out = h;
@@ -89,7 +91,7 @@ int dexb_denoise_once(dexb_handle* h, const float* x_dev, const float* mu_dev, c
 
 int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float* mu_host, const float* mask_host,
                                 const float* sty_host, const int32_t* sty_len_host, const float* const* ref_skips_host, int Tr,
-                                void* stream) {
+                                const float* spk_host, void* stream) {
   DEXB_CHECK(h != nullptr && h->planned, "dexb_reverse_diffusion_host: call dexb_plan first");
   DEXB_CHECK(x_inout_host != nullptr && mu_host != nullptr && mask_host != nullptr, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -111,8 +113,14 @@ int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float
     cond.sty_dev = h->sty; cond.sty_len_dev = h->sty_len; cond.Tr = Tr;
     for (int l = 0; l < 6; ++l) cond.ref_skips_dev[l] = h->refs[l];
   }
+  const bool spk = h->cfg.variant == 0 && h->cfg.n_spks > 1;
+  if (spk) {
+    DEXB_CHECK(spk_host != nullptr, "multi-speaker GeDEX-TTS needs the speaker embedding");
+    DEXB_CUDA_OK(cudaMemcpyAsync(h->spk, spk_host, (long)h->B * h->cfg.spk_emb_dim * 4, cudaMemcpyHostToDevice, st));
+    cond.spk_dev = h->spk;
+  }
   // engine_run's device-to-device staging copies become self-copies (src == dst) and are skipped there
-  DEXB_TRY(engine_run(h, h->x, h->mu, h->mask0, h->cfg.variant == 1 ? &cond : nullptr, -1, nullptr, st));
+  DEXB_TRY(engine_run(h, h->x, h->mu, h->mask0, (h->cfg.variant == 1 || spk) ? &cond : nullptr, -1, nullptr, st));
   DEXB_CUDA_OK(cudaMemcpyAsync(x_inout_host, h->x, n0 * 4, cudaMemcpyDeviceToHost, st));
   DEXB_CUDA_OK(cudaStreamSynchronize(st));
   return 0;

@@ -101,7 +101,8 @@ static int bind_la(dexb_handle* h, LinAttW& la, const std::string& p, int C, Are
 static int layout_weights(dexb_handle* h, Arena& ar) {
   const dexb_config& c = h->cfg;
   const int d = c.dim, mid = 2 * c.dim, hid = c.hidden;
-  DEXB_TRY(bind_resnet(h, h->d00, "downs.0.0", 2, d, ar));
+  h->cin = (c.variant == 0 && c.n_spks > 1) ? 3 : 2;
+  DEXB_TRY(bind_resnet(h, h->d00, "downs.0.0", h->cin, d, ar));
   DEXB_TRY(bind_resnet(h, h->d01, "downs.0.1", d, d, ar));
   DEXB_TRY(bind_la(h, h->la0, "downs.0.2", d, ar));
   DEXB_TRY(bind_resnet(h, h->d10, "downs.1.0", d, mid, ar));
@@ -112,8 +113,16 @@ static int layout_weights(dexb_handle* h, Arena& ar) {
   DEXB_TRY(bind_la(h, h->la2, "ups.0.2", d, ar));
   DEXB_TRY(bind_block(h, h->fin, "final_block", d, d, ar, true));
   {
-    NEED_W(w, "downs.0.0.block1.block.0.weight", d, 2, 3, 3);
+    NEED_W(w, "downs.0.0.block1.block.0.weight", d, h->cin, 3, 3);
     h->conv_in_w = w->p; h->conv_in_b = h->d00.b1.bias;
+    if (h->cin == 3) {
+      const int E = c.spk_emb_dim;
+      NEED_W(s0, "spk_mlp.0.weight", 4 * E, E);
+      NEED_W(s0b, "spk_mlp.0.bias", 4 * E);
+      NEED_W(s2, "spk_mlp.2.weight", c.n_feats, 4 * E);
+      NEED_W(s2b, "spk_mlp.2.bias", c.n_feats);
+      h->spk_w0 = s0->p; h->spk_b0 = s0b->p; h->spk_w2 = s2->p; h->spk_b2 = s2b->p;
+    }
     NEED_W(dw, "downs.0.3.conv.weight", d, d, 3, 3);
     NEED_W(db, "downs.0.3.conv.bias", d);
     (void)dw; h->down_b = db->p; h->down_w = ar.get<bf16>(9L * d * 2 * d);
@@ -373,6 +382,10 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->tab = ar.get<StepScalars>(steps);
   h->x = ar.get<float>(P0); h->mu = ar.get<float>(P0);
   h->mask0 = ar.get<float>((long)B * h->W0); h->mask1 = ar.get<float>((long)B * h->W1);
+  if (h->cin == 3) {
+    h->spk = ar.get<float>((long)B * c.spk_emb_dim); h->spk_hid = ar.get<float>((long)B * 4 * c.spk_emb_dim);
+    h->spk_s = ar.get<float>((long)B * c.n_feats);
+  }
   // per-step zeroed region
   const size_t z0 = (ar.off + 1023) & ~(size_t)1023;
   h->gn_stats = ar.get<double>((long)h->n_slots * B * 16);
@@ -831,7 +844,7 @@ static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const 
                       bool first, cudaStream_t st) {
   const int P = H * W;
   if (first) {
-    LAUNCH(launch_conv_in(h->x, h->mu, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
+    LAUNCH(launch_conv_in(h->x, h->mu, h->cin == 3 ? h->spk_s : nullptr, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
                           h->gn_stats + (long)r.b1.slot * h->B * 16, h->B, H, W, r.co, st));
   } else {
     GEMM(r.b1.conv, r.b1.conv.p);
@@ -847,6 +860,7 @@ static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const 
     GnApplyArgs a = gn_args(h, r.b2, raw, P, W, mask, out, out_stride, 0, (int)(out_stride / 2));
     if (first) {
       a.rin_w = r.rin_w; a.rin_b = r.res_b; a.x = h->x; a.mu = h->mu; a.tab = h->tab; a.step = step;
+      a.spk_s = (h->cin == 3) ? h->spk_s : nullptr; a.H = H;
     } else if (r.res_w != nullptr) {
       a.resid_f = h->resid1; a.resid_f_stride = r.co;
     } else {
@@ -972,6 +986,12 @@ static int run_prepare(dexb_handle* h, cudaStream_t st) {
   const dexb_config& c = h->cfg;
   const int B = h->B, mid = 2 * c.dim, Ts = h->Ts;
   LAUNCH(launch_mask_down(h->mask0, h->mask1, B, h->W0, h->W1, st));
+  if (h->cin == 3) {
+    // s = spk_mlp(spk): Linear -> Mish -> Linear, one value per (utterance, mel bin), constant over time and over the steps
+    const int E = c.spk_emb_dim;
+    LAUNCH(launch_small_linear(h->spk, E, h->spk_w0, h->spk_b0, h->spk_hid, 4 * E, B, 4 * E, E, 0, 1, st));
+    LAUNCH(launch_small_linear(h->spk_hid, 4 * E, h->spk_w2, h->spk_b2, h->spk_s, c.n_feats, B, c.n_feats, 4 * E, 0, 0, st));
+  }
   if (c.variant != 1) return 0;
   LAUNCH(launch_bct_to_btc(h->sty, h->styT, B, mid, Ts, st));
   LAUNCH(launch_small_linear(h->styT, mid, h->tv_wk, nullptr, h->kmat, mid, B * Ts, mid, mid, 0, 0, st));
@@ -1016,6 +1036,11 @@ int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mas
       if (cond->ref_skips_dev[l] != h->refs[l])
         DEXB_CUDA_OK(cudaMemcpyAsync(h->refs[l], cond->ref_skips_dev[l], (long)h->B * mid * h->Tr * 4, cudaMemcpyDeviceToDevice, st));
     }
+  }
+  if (h->cin == 3) {
+    DEXB_CHECK(cond != nullptr && cond->spk_dev != nullptr, "multi-speaker GeDEX-TTS needs the speaker embedding (dexb_cond.spk_dev)");
+    if (cond->spk_dev != h->spk)
+      DEXB_CUDA_OK(cudaMemcpyAsync(h->spk, cond->spk_dev, (long)h->B * c.spk_emb_dim * 4, cudaMemcpyDeviceToDevice, st));
   }
   h->launches = 0;
   if (only_step < 0 && h->use_graph) {

@@ -89,6 +89,9 @@ struct dexb_handle {
   dexb::bf16 *down_w = nullptr, *up_w = nullptr;      // conv 3x3 s2 [9][co][..], convT [4][4][co][..]
   const float *down_b = nullptr, *up_b = nullptr;
   const float *conv_in_w = nullptr, *conv_in_b = nullptr;
+  int cin = 2;                                         // input channels of the first conv: [mu, x] (+ speaker channel)
+  const float *spk_w0 = nullptr, *spk_b0 = nullptr, *spk_w2 = nullptr, *spk_b2 = nullptr;   // spk_mlp (GeDEX-TTS, n_spks > 1)
+  float *spk = nullptr, *spk_hid = nullptr, *spk_s = nullptr;   // staged embedding (B, E), hidden (B, 4E), channel values (B, n_feats)
   const float *fc_w = nullptr, *fc_b = nullptr;
   // TV / TIV adaptors
   float *wqT_s = nullptr;                              // [C][C]  W_q^T / sqrt(C)

@@ -28,7 +28,8 @@ void launch_scale(float* x, long n, float s, cudaStream_t st);
 void launch_mask_down(const float* mask, float* mask1, int B, int T, int W1, cudaStream_t st);
 
 // first conv of the U-Net: conv3x3(2 -> C) on stack[mu, c_in*x] * mask, + bias, raw fp32 out + GroupNorm partial sums
-void launch_conv_in(const float* x, const float* mu, const float* mask, const StepScalars* tab, int step,
+// spk_s != null: third input channel spk_s[b][h] (GeDEX-TTS speaker channel), w is [C][3][3][3]
+void launch_conv_in(const float* x, const float* mu, const float* spk_s, const float* mask, const StepScalars* tab, int step,
                     const float* w /*[C][2][3][3]*/, const float* bias, float* raw /*F[M][C]*/, double* stats, int B,
                     int H, int W, int C, cudaStream_t st);
 
@@ -44,6 +45,7 @@ struct GnApplyArgs {
   // residual computed from the network input (first ResnetBlock, res_conv 1x1 on 2 channels)
   const float* rin_w; const float* rin_b;   // [C][2], [C] or null
   const float* x; const float* mu; const StepScalars* tab; int step;
+  const float* spk_s; int H;                // third input channel spk_s[b][h] of the multi-speaker GeDEX-TTS (rin_w is [C][3] then)
   SView out;
 };
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st);

@@ -39,23 +39,25 @@ void launch_mask_down(const float* mask, float* mask1, int B, int T, int W1, cud
 // Thread = 8 output channels (one GroupNorm group at C == 64) x 4 x-adjacent pixels: the 144 weights of its channel octet
 // come from shared memory as 36 LDS.128 for 576 FMAs (the one-pixel-per-thread version issued one LDS per FMA and was
 // shared-memory bound: 57 us for 0.75 GFLOP).  8 consecutive lanes write the 256 B row of a pixel.
-template <int C>
+template <int C, int CIN>
 __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, const float* __restrict__ mu,
+                                                 const float* __restrict__ spk_s,
                                                  const float* __restrict__ mask, const StepScalars* __restrict__ tab,
                                                  int step, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ raw, double* __restrict__ stats, int B, int H,
                                                  int W) {
   static_assert(C == 64, "one GroupNorm group per channel octet");
-  __shared__ __align__(16) float wsT[18][C];                 // [k][co]
+  constexpr int KT = 9 * CIN;                                // taps x input channels: [mu | c_in x | speaker channel]
+  __shared__ __align__(16) float wsT[KT][C];                 // [k][co]
   __shared__ float red[8][C / 8][2];
-  for (int i = threadIdx.x; i < C * 18; i += 256) wsT[i % 18][i / 18] = w[i];
+  for (int i = threadIdx.x; i < C * KT; i += 256) wsT[i % KT][i / KT] = w[i];
   __syncthreads();
   const int h = blockIdx.y, b = blockIdx.z;
   const int oct = threadIdx.x & 7, quad = threadIdx.x >> 3;
   const int c0 = oct * 8;
   const int x0 = blockIdx.x * 128 + quad * 4;
   const float c_in = tab[step].c_in;
-  float va[3][6], vc[3][6];                                  // mu*mask and c_in*x*mask at rows h-1..h+1, columns x0-1..x0+4
+  float va[3][6], vc[3][6], vs[3][6];                        // mu*mask, c_in*x*mask (and spk*mask) at rows h-1..h+1, columns x0-1..x0+4
 #pragma unroll
   for (int col = 0; col < 6; ++col) {
     const int ww = x0 + col - 1;
@@ -64,14 +66,16 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int hh = h + dy - 1;
-      float a = 0.f, c = 0.f;
+      float a = 0.f, c = 0.f, s3 = 0.f;
       if (cok && hh >= 0 && hh < H) {
         const long idx = ((long)b * H + hh) * W + ww;
         a = mu[idx] * m;
         c = (c_in * x[idx]) * m;
+        if (CIN == 3) s3 = spk_s[b * H + hh] * m;
       }
       va[dy][col] = a;
       vc[dy][col] = c;
+      vs[dy][col] = s3;
     }
   }
   float acc[4][8];
@@ -84,14 +88,14 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
     }
   }
 #pragma unroll
-  for (int k = 0; k < 18; ++k) {                             // same accumulation order as the reference-ordered oracle: mu taps, then x taps
+  for (int k = 0; k < KT; ++k) {                             // accumulation order: mu taps, x taps(, speaker taps)
     const float4 w0 = *reinterpret_cast<const float4*>(&wsT[k][c0]);
     const float4 w1 = *reinterpret_cast<const float4*>(&wsT[k][c0 + 4]);
     const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
     const int dy = (k % 9) / 3, dx = k % 3;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float iv = (k < 9) ? va[dy][p + dx] : vc[dy][p + dx];
+      const float iv = (k < 9) ? va[dy][p + dx] : ((k < 18) ? vc[dy][p + dx] : vs[dy][p + dx]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(wv[i], iv, acc[p][i]);
     }
@@ -122,13 +126,15 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
   }
 }
 
-void launch_conv_in(const float* x, const float* mu, const float* mask, const StepScalars* tab, int step,
+void launch_conv_in(const float* x, const float* mu, const float* spk_s, const float* mask, const StepScalars* tab, int step,
                     const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
                     cudaStream_t st) {
   dim3 grid(cdiv(W, 128), H, B);
   // stats layout is [B][8 groups][2]; only C == 64 (decoder.dim 64, GroupNorm(8, 64): one group per channel octet) is
   // instantiated -- engine_finalize rejects other widths.
-  if (C == 64) k_conv_in<64><<<grid, 256, 0, st>>>(x, mu, mask, tab, step, w, bias, raw, stats, B, H, W);
+  if (C != 64) return;
+  if (spk_s == nullptr) k_conv_in<64, 2><<<grid, 256, 0, st>>>(x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
+  else k_conv_in<64, 3><<<grid, 256, 0, st>>>(x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -230,8 +236,15 @@ __global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
     } else if (a.rin_w != nullptr) {
       // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
       const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
+      if (a.spk_s == nullptr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
+        for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
+      } else {
+        const float in2 = a.spk_s[b * a.H + (int)(p / (unsigned)a.W)] * m;      // speaker channel: constant along time
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 3] * in0 + a.rin_w[(c0 + i) * 3 + 1] * in1 + a.rin_w[(c0 + i) * 3 + 2] * in2) * m;
+      }
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) res[i] = 0.f;

@@ -40,9 +40,9 @@ class ReverseDiffusion:
         c = _lib.DexbConfig(variant=1 if cfg.variant == "dex" else 0, dim=cfg.dim, hidden=cfg.hidden, depth=cfg.depth,
                             heads=cfg.heads, mlp_hidden=int(cfg.hidden * cfg.mlp_ratio), patch=cfg.patch, stride=cfg.stride,
                             conv_pos=cfg.conv_pos, conv_pos_groups=cfg.conv_pos_groups, n_feats=cfg.n_feats,
-                            pe_scale=float(cfg.pe_scale), gemm_engine=gemm_engine, nsplit=nsplit)
-        if cfg.n_spks > 1:
-            raise RuntimeError("multi-speaker GeDEX-TTS (n_spks > 1, extra speaker channel) is not supported by the CUDA path")
+                            pe_scale=float(cfg.pe_scale), gemm_engine=gemm_engine, nsplit=nsplit,
+                            n_spks=int(cfg.n_spks), spk_emb_dim=int(cfg.spk_emb_dim))
+        self.multi_spk = cfg.variant == "gedex" and cfg.n_spks > 1
         h = ctypes.c_void_p()
         _lib.check(self.L.dexb_create(ctypes.byref(c), ctypes.byref(h)), "dexb_create")
         self.h = h
@@ -93,6 +93,13 @@ class ReverseDiffusion:
         self.plan_key = key
 
     def _cond(self, cond, B):
+        if self.multi_spk:                       # GeDEX-TTS speaker embedding (GeDEX-TTS/model/tts.py:30-31,53)
+            if cond is None or cond.get("spk") is None:
+                raise RuntimeError("multi-speaker GeDEX-TTS needs cond['spk'] (B, spk_emb_dim)")
+            spk = cond["spk"].detach().float().reshape(B, self.cfg.spk_emb_dim).contiguous()
+            c = _lib.DexbCond()
+            c.spk_dev = spk.data_ptr()
+            return c, [spk]
         if self.cfg.variant != "dex":
             return None, []
         sty = cond["sty"].float().contiguous()
@@ -147,8 +154,13 @@ class ReverseDiffusion:
             refs_arr = (ctypes.c_void_p * 6)(*[r.data_ptr() for r in refs])
             sty_p, sl_p, Tr = _ptr(sty), _ptr(sl), refs[0].shape[-1]
             keep = [sty, sl] + refs
-        _lib.check(self.L.dexb_reverse_diffusion_host(self.h, _ptr(x), _ptr(mu), _ptr(m), sty_p, sl_p, refs_arr, Tr, _stream()),
-                   "dexb_reverse_diffusion_host")
+        spk_p = None
+        if self.multi_spk:
+            spk = cond["spk"].float().reshape(B, self.cfg.spk_emb_dim).contiguous()
+            spk_p = _ptr(spk)
+            keep.append(spk)
+        _lib.check(self.L.dexb_reverse_diffusion_host(self.h, _ptr(x), _ptr(mu), _ptr(m), sty_p, sl_p, refs_arr, Tr, spk_p,
+                                                      _stream()), "dexb_reverse_diffusion_host")
         del keep
         return x
 

@@ -18,12 +18,13 @@ class DexbConfig(ctypes.Structure):
     _fields_ = [("variant", ctypes.c_int), ("dim", ctypes.c_int), ("hidden", ctypes.c_int), ("depth", ctypes.c_int),
                 ("heads", ctypes.c_int), ("mlp_hidden", ctypes.c_int), ("patch", ctypes.c_int), ("stride", ctypes.c_int),
                 ("conv_pos", ctypes.c_int), ("conv_pos_groups", ctypes.c_int), ("n_feats", ctypes.c_int),
-                ("pe_scale", ctypes.c_float), ("gemm_engine", ctypes.c_int), ("nsplit", ctypes.c_int)]
+                ("pe_scale", ctypes.c_float), ("gemm_engine", ctypes.c_int), ("nsplit", ctypes.c_int),
+                ("n_spks", ctypes.c_int), ("spk_emb_dim", ctypes.c_int)]
 
 
 class DexbCond(ctypes.Structure):
     _fields_ = [("sty_dev", ctypes.c_void_p), ("sty_len_dev", ctypes.c_void_p), ("ref_skips_dev", ctypes.c_void_p * 6),
-                ("Tr", ctypes.c_int)]
+                ("Tr", ctypes.c_int), ("spk_dev", ctypes.c_void_p)]
 
 
 # every symbol include/dexb200.h declares: name -> (restype, argtypes)
@@ -40,7 +41,7 @@ SYMBOLS = {
                                               ctypes.POINTER(DexbCond), ctypes.c_void_p]),
     "dexb_reverse_diffusion_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
-                                                   ctypes.c_int, ctypes.c_void_p]),
+                                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_denoise_once": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.POINTER(DexbCond), ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_gemm_test": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -123,4 +123,6 @@ class GeDiffusion(_DiffusionBase):
     def forward(self, x, mask, mu, n_timesteps=1, spk=None, infer=False, temperature=1.0, mask_ratio=0):
         if not infer:
             raise NotImplementedError("training loss (EDMLoss) is outside the CUDA inference path")
-        return self._run(x, mask, mu, n_timesteps, temperature, None)
+        # n_spks > 1: `spk` is the speaker embedding GeDEXTTS.forward looked up (tts.py:30-31); it becomes the third input channel
+        cond = dict(spk=spk) if self.cfg.n_spks > 1 else None
+        return self._run(x, mask, mu, n_timesteps, temperature, cond)

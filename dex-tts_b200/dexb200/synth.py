@@ -80,4 +80,6 @@ def synth_inputs(cfg, B, T, Ts=259, seed=1234, ragged=False):
             sl = torch.full((B,), Ts, dtype=torch.long)
         smask = (torch.arange(Ts)[None, :] < sl[:, None]).float().unsqueeze(1)
         out.update(sty=sty * smask, sty_lengths=sl, ref_skips=[r * smask for r in refs], ref_lengths=sl.clone())
+    elif cfg.n_spks > 1:                           # GeDEX-TTS speaker embedding (rows of nn.Embedding(n_spks, spk_emb_dim))
+        out["spk"] = torch.randn(B, cfg.spk_emb_dim, generator=g)
     return out

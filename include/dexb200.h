@@ -39,14 +39,18 @@ typedef struct dexb_config {
   float pe_scale;      /* 1000 */
   int gemm_engine;     /* 0 = tcgen05 (product), 1 = CUDA-core cross-check engine */
   int nsplit;          /* 3 = bf16x3 split precision (parity-safe default), 1 = plain bf16 operands */
+  int n_spks;          /* GeDEX-TTS: > 1 adds the speaker channel spk_mlp(spk) as third input (GeDEX-TTS/model/diffusion.py:132-134,170-175) */
+  int spk_emb_dim;     /* 64 */
 } dexb_config;
 
-/* DEX-TTS conditioning that reaches the loop (DEX-TTS/model/diffusion.py:190-196,220-221). */
+/* Conditioning that reaches the loop: DEX-TTS style / reference tensors (DEX-TTS/model/diffusion.py:190-196,220-221) or the
+ * GeDEX-TTS speaker embedding (GeDEX-TTS/model/tts.py:30-31,53; diffusion.py:170-175). */
 typedef struct dexb_cond {
   const float* sty_dev;          /* (B, 2*dim, Ts) fp32: `sty` of DiffusionDenoiser.forward */
   const int32_t* sty_len_dev;    /* (B) */
   const float* ref_skips_dev[6]; /* 6 x (B, 2*dim, Tr) fp32: `ref` skip tensors of the TIV encoder */
   int Tr;
+  const float* spk_dev;          /* (B, spk_emb_dim) fp32: GeDEX-TTS with n_spks > 1 (the other fields are unused then) */
 } dexb_cond;
 
 const char* dexb_last_error(void);
@@ -74,14 +78,14 @@ int dexb_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const f
  * (DEX-TTS/model/edm.py:104-211) over EDMPrecond (edm.py:88-98) over DiffusionDenoiser.forward
  * (DEX-TTS/model/diffusion.py:190-236).
  *   x_inout_dev (B, 80, T): in = z / temperature + mu, out = the generated mel
- *   mu_dev (B, 80, T), mask_dev (B, T) in {0,1}; cond = NULL for GeDEX-TTS. */
+ *   mu_dev (B, 80, T), mask_dev (B, T) in {0,1}; cond = NULL for single-speaker GeDEX-TTS. */
 int dexb_reverse_diffusion(dexb_handle* h, float* x_inout_dev, const float* mu_dev, const float* mask_dev,
                            const dexb_cond* cond, void* stream);
 
 /* Same call with HOST buffers (pinned or pageable): copies in, runs, copies the mel back, synchronises `stream`. */
 int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float* mu_host, const float* mask_host,
                                 const float* sty_host, const int32_t* sty_len_host, const float* const* ref_skips_host,
-                                int Tr, void* stream);
+                                int Tr, const float* spk_host, void* stream);
 
 /* One preconditioned network call D(x; sigma_step) written to out_dev (x untouched) -- unit parity of EDMPrecond. */
 int dexb_denoise_once(dexb_handle* h, const float* x_dev, const float* mu_dev, const float* mask_dev,

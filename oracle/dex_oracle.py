@@ -36,16 +36,19 @@ import torch.nn.functional as F
 # ----------------------------------------------------------------------------------------------
 
 def make_cfg(variant="dex", dim=64, hidden=256, depth=4, heads=2, mlp_ratio=2, patch=None, stride=None,
-             conv_pos=16, conv_pos_groups=8, n_feats=80, pe_scale=1000):
-    """Hyper-parameters of the decoder (DEX-TTS/config/VCTK/base.yaml:56-78, GeDEX-TTS/config/LJSpeech/base.yaml:41-63)."""
+             conv_pos=16, conv_pos_groups=8, n_feats=80, pe_scale=1000, n_spks=None):
+    """Hyper-parameters of the decoder (DEX-TTS/config/VCTK/base.yaml:56-78, GeDEX-TTS/config/LJSpeech/base.yaml:41-63).
+    n_spks > 1 (GeDEX-TTS only) adds the speaker channel of GeDEX-TTS/model/diffusion.py:132-134,170-175."""
     assert variant in ("dex", "gedex")
     if patch is None:
         patch = 3 if variant == "dex" else 7
     if stride is None:
         stride = 2 if variant == "dex" else 4
+    if n_spks is None:
+        n_spks = 0 if variant == "dex" else 1
     return dict(variant=variant, dim=dim, hidden=hidden, depth=depth, heads=heads, mlp_ratio=mlp_ratio,
                 patch=patch, stride=stride, conv_pos=conv_pos, conv_pos_groups=conv_pos_groups,
-                n_feats=n_feats, pe_scale=pe_scale)
+                n_feats=n_feats, pe_scale=pe_scale, n_spks=n_spks)
 
 
 def sequence_mask(lengths, max_len):
@@ -243,7 +246,7 @@ def _dit(w, p, cfg, x, mask, t, taps=None):
 
 def denoiser(w, cfg, x, mask, mu, t, cond=None, prefix="denoise_fn", taps=None):
     """DiffusionDenoiser.forward.  x, mu (B,80,T); mask (B,1,T); t (B,) = c_noise.
-    cond (DEX only) = dict(sty (B,128,Ts), sty_lengths (B,), ref_skips [6 x (B,128,Tr)]).
+    cond: DEX = dict(sty (B,128,Ts), sty_lengths (B,), ref_skips [6 x (B,128,Tr)]); multi-speaker GeDEX = dict(spk (B, spk_emb_dim)).
     DEX-TTS/model/diffusion.py:190-236, GeDEX-TTS/model/diffusion.py:168-207."""
     p = prefix
     dex = cfg["variant"] == "dex"
@@ -255,7 +258,12 @@ def denoiser(w, cfg, x, mask, mu, t, cond=None, prefix="denoise_fn", taps=None):
         t_sty = _lin(w, p + ".mlp_adap_sty.2", mish(_lin(w, p + ".mlp_adap_sty.0", t_init)))
         sty_mask = sequence_mask(cond["sty_lengths"], cond["sty"].shape[2]).to(x.dtype)
         ref_mean, ref_std = ref_stats(cond["ref_skips"])
-    h = torch.stack([mu, x], 1)
+    if not dex and cfg.get("n_spks", 1) > 1:
+        # GeDEX-TTS/model/diffusion.py:170-175: s = spk_mlp(spk) broadcast over time is the third input channel
+        s_ = _lin(w, p + ".spk_mlp.2", mish(_lin(w, p + ".spk_mlp.0", cond["spk"])))
+        h = torch.stack([mu, x, s_.unsqueeze(-1).repeat(1, 1, x.shape[-1])], 1)
+    else:
+        h = torch.stack([mu, x], 1)
     m0 = mask.unsqueeze(1)                                                                     # (B,1,1,T)
     # level 0
     h = _resnet(w, p + ".downs.0.0", h, m0, t_unet)

@@ -34,6 +34,7 @@ CASES = [
     ("gedex_zero", "gedex", 1, 40, 0,  3, False, False, 13),   # reference default-style init (dead DiT branch)
     ("dex_b1",     "dex",   1, 44, 23, 4, False, True, 21),
     ("dex_b2r",    "dex",   2, 48, 19, 3, True,  True, 22),
+    ("gedex_spk_b2r", "gedex", 2, 44, 0, 3, True, True, 14, 4),    # multi-speaker GeDEX-TTS: n_spks = 4 (third input channel)
 ]
 TEMPERATURE = 1.5
 TAP_STRIDE = 16
@@ -47,10 +48,10 @@ def ref_cfgs(cfg):
     return dec, dit
 
 
-def run_case(name, variant, B, T, Ts, steps, ragged, live, seed):
-    cfg = DecoderCfg.make(variant)
+def run_case(name, variant, B, T, Ts, steps, ragged, live, seed, n_spks=None):
+    cfg = DecoderCfg.make(variant, n_spks=n_spks)
     dec_cfg, dit_cfg = ref_cfgs(cfg)
-    dec, mod = ref_loader.build_reference_decoder(variant, dec_cfg, dit_cfg)
+    dec, mod = ref_loader.build_reference_decoder(variant, dec_cfg, dit_cfg, n_spks=n_spks)
     w = synth_decoder_weights(cfg, seed=100, live=live)
     sd = dict(w)
     sd.update({k.replace("denoise_fn.", "precond_model.model."): v for k, v in w.items()})
@@ -90,12 +91,13 @@ def run_case(name, variant, B, T, Ts, steps, ragged, live, seed):
                 y = dec(inp["mu"], inp["mask"], inp["mu"], inp["ref_skips"], inp["ref_lengths"], inp["sty"],
                         inp["sty_lengths"], n_timesteps=steps, infer=True, temperature=TEMPERATURE)
             else:
-                y = dec(inp["mu"], inp["mask"], inp["mu"], n_timesteps=steps, infer=True, temperature=TEMPERATURE)
+                y = dec(inp["mu"], inp["mask"], inp["mu"], n_timesteps=steps, spk=inp.get("spk"), infer=True,
+                        temperature=TEMPERATURE)
     finally:
         torch.randn = real_randn
         for h in hooks:
             h.remove()
-    out = dict(y=y.numpy(), meta=np.array([B, T, Ts, steps, int(ragged), int(live), seed], dtype=np.int64),
+    out = dict(y=y.numpy(), meta=np.array([B, T, Ts, steps, int(ragged), int(live), seed] + ([int(n_spks)] if n_spks else []), dtype=np.int64),
                variant=np.array(variant), temperature=np.array(TEMPERATURE, dtype=np.float32))
     for k, v in taps.items():               # intermediates: channel-strided subsample keeps the fixtures small
         a = v.numpy().astype(np.float32)
@@ -108,5 +110,7 @@ def run_case(name, variant, B, T, Ts, steps, ragged, live, seed):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])                         # optional: names of the cases to (re)generate
     for c in CASES:
-        run_case(*c)
+        if not only or c[0] in only:
+            run_case(*c)

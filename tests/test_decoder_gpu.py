@@ -21,11 +21,13 @@ IDS = [os.path.basename(p)[:-4] for p in GOLD]
 _engines = {}
 
 
-def get_engine(variant, live, gemm_engine):
+def get_engine(variant, live, gemm_engine, n_spks=None):
     from dexb200.engine import ReverseDiffusion
-    key = (variant, live, gemm_engine)
+    if n_spks is None:
+        n_spks = DecoderCfg.make(variant).n_spks
+    key = (variant, live, gemm_engine, n_spks)
     if key not in _engines:
-        cfg = DecoderCfg.make(variant)
+        cfg = DecoderCfg.make(variant, n_spks=n_spks)
         eng = ReverseDiffusion(cfg, gemm_engine=gemm_engine)
         eng.load_state_dict(synth_decoder_weights(cfg, seed=100, live=live))
         _engines[key] = eng
@@ -34,19 +36,24 @@ def get_engine(variant, live, gemm_engine):
 
 def load_case(path):
     g = np.load(path)
-    B, T, Ts, steps, ragged, live, seed = [int(v) for v in g["meta"]]
+    meta = [int(v) for v in g["meta"]]
+    B, T, Ts, steps, ragged, live, seed = meta[:7]
     variant = str(g["variant"])
-    cfg = DecoderCfg.make(variant)
+    cfg = DecoderCfg.make(variant, n_spks=meta[7] if len(meta) > 7 else None)     # 8th entry: multi-speaker GeDEX-TTS
     inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=seed, ragged=bool(ragged))
     cond = None
     if variant == "dex":
         cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"])
+    elif cfg.n_spks > 1:
+        cond = dict(spk=inp["spk"])
     return g, cfg, inp, cond, steps, bool(live)
 
 
 def to_cuda(cond):
     if cond is None:
         return None
+    if "spk" in cond:
+        return dict(spk=cond["spk"].cuda())
     return dict(sty=cond["sty"].cuda(), sty_lengths=cond["sty_lengths"].cuda(), ref_skips=[r.cuda() for r in cond["ref_skips"]])
 
 
@@ -55,12 +62,12 @@ def to_cuda(cond):
 def test_first_network_call_matches_oracle(path, gemm_engine):
     """D(x_0; sigma_0) of the first sampler step against the CPU oracle (one full denoiser evaluation)."""
     g, cfg, inp, cond, steps, live = load_case(path)
-    eng = get_engine(cfg.variant, live, gemm_engine)
+    eng = get_engine(cfg.variant, live, gemm_engine, cfg.n_spks)
     w = synth_decoder_weights(cfg, seed=100, live=live)
     ts = O.sigma_schedule(steps)
     x0 = (inp["z"] / float(g["temperature"]) + inp["mu"]) * ts[0]
     with torch.no_grad():
-        ref = O.edm_precond(w, O.make_cfg(cfg.variant), x0, ts[0], inp["mask"], inp["mu"], cond=cond)
+        ref = O.edm_precond(w, O.make_cfg(cfg.variant, n_spks=cfg.n_spks), x0, ts[0], inp["mask"], inp["mu"], cond=cond)
     out = eng.denoise_once(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, 0, cond=to_cuda(cond)).cpu()
     assert torch.isfinite(out).all()
     assert tensor_rel_err(out, ref) < 2e-4
@@ -73,7 +80,7 @@ def test_first_network_call_matches_oracle(path, gemm_engine):
 def test_trajectory_matches_reference_golden(path, gemm_engine):
     """Full reverse diffusion against the output of the unmodified reference (golden fixture)."""
     g, cfg, inp, cond, steps, live = load_case(path)
-    eng = get_engine(cfg.variant, live, gemm_engine)
+    eng = get_engine(cfg.variant, live, gemm_engine, cfg.n_spks)
     x0 = inp["z"] / float(g["temperature"]) + inp["mu"]
     y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
     y_ref = torch.from_numpy(g["y"])
@@ -85,7 +92,7 @@ def test_trajectory_matches_reference_golden(path, gemm_engine):
 @pytest.mark.parametrize("path", [p for p in GOLD if "b2r" in p], ids=[i for i in IDS if "b2r" in i])
 def test_host_entry_point_equals_device_entry_point(path):
     g, cfg, inp, cond, steps, live = load_case(path)
-    eng = get_engine(cfg.variant, live, 0)
+    eng = get_engine(cfg.variant, live, 0, cfg.n_spks)
     x0 = inp["z"] / float(g["temperature"]) + inp["mu"]
     y_dev = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
     y_host = eng.sample_host(x0, inp["mask"], inp["mu"], steps, cond=cond)

@@ -17,25 +17,28 @@ GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "gold
 
 def load_case(path):
     g = np.load(path)
-    B, T, Ts, steps, ragged, live, seed = [int(v) for v in g["meta"]]
+    meta = [int(v) for v in g["meta"]]
+    B, T, Ts, steps, ragged, live, seed = meta[:7]
     variant = str(g["variant"])
-    cfg = DecoderCfg.make(variant)
+    cfg = DecoderCfg.make(variant, n_spks=meta[7] if len(meta) > 7 else None)     # 8th entry: multi-speaker GeDEX-TTS
     w = synth_decoder_weights(cfg, seed=100, live=bool(live))
     inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=seed, ragged=bool(ragged))
     cond = None
     if variant == "dex":
         cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"])
+    elif cfg.n_spks > 1:
+        cond = dict(spk=inp["spk"])
     return g, cfg, w, inp, cond, steps
 
 
 def test_golden_present():
-    assert len(GOLD) >= 5
+    assert len(GOLD) >= 6
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_matches_reference(path):
     g, cfg, w, inp, cond, steps = load_case(path)
-    ocfg = O.make_cfg(cfg.variant)
+    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks)
     with torch.no_grad():
         y = O.reverse_diffusion(w, ocfg, inp["z"], inp["mask"], inp["mu"], steps,
                                 temperature=float(g["temperature"]), cond=cond)
@@ -48,7 +51,7 @@ def test_oracle_matches_reference(path):
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_intermediates(path):
     g, cfg, w, inp, cond, steps = load_case(path)
-    ocfg = O.make_cfg(cfg.variant)
+    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks)
     taps = {}
     ts = O.sigma_schedule(steps)
     x0 = (inp["z"] / float(g["temperature"]) + inp["mu"]) * ts[0]
