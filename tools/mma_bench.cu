@@ -101,6 +101,73 @@ __global__ void __launch_bounds__(128, 1) k_pattern(int bn, int stages, long lon
   if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
 }
 
+// The same MMA pattern behind a producer / consumer mbarrier ring of depth D (no TMA: the producer thread only waits for `empty`
+// and arrives on `full`): what does the barrier round trip (tcgen05.commit -> empty -> producer -> full -> issuer) cost?
+__global__ void __launch_bounds__(128, 1) k_ring(int bn, int stages, int depth, int flags, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[8], empty[8], done;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(&done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) ptx::tmem_alloc<512>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  const int warp = threadIdx.x >> 5;
+  long long t0 = clock64();
+  if (warp == 1) {                                           // producer
+    if (ptx::elect_one()) {
+      uint32_t s = 0, ph = 0;
+      for (int st = 0; st < stages && !(flags & 2); ++st) {
+        if (!(flags & 4)) ptx::mbar_wait(&empty[s], ph ^ 1);
+        ptx::mbar_arrive(&full[s]);
+        if (++s == (uint32_t)depth) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 0) {                                    // MMA issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, bn), idesc2 = ptx::make_idesc_bf16(128, 2 * bn);
+      uint32_t s = 0, ph = 0;
+      for (int st = 0; st < stages; ++st) {
+        if (flags & 8) {                                     // mbarrier.test_wait (no suspend) instead of try_wait
+          uint32_t ok = 0;
+          while (!ok) {
+            asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}\n"
+                         : "=r"(ok) : "r"(ptx::smem_u32(&full[s])), "r"(ph) : "memory");
+          }
+        } else if (!(flags & 2)) ptx::mbar_wait(&full[s], ph);
+        if (!(flags & 1)) ptx::tc_fence_after();
+        const uint32_t base = ptx::smem_u32(smem) + (st % 3) * 65536;
+        const uint32_t a_hi = base, a_lo = base + 16384, b_hi = base + 32768;
+        const uint32_t tacc = tmem + ((st / 9) & 1) * 256;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 32;
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_hi + ko), ptx::make_desc_k128(b_hi + ko), idesc2, (st % 9 || kk) ? 1u : 0u);
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_lo + ko), ptx::make_desc_k128(b_hi + ko), idesc, 1u);
+        }
+        if (!(flags & 4)) ptx::mma_commit(&empty[s]);
+        if (++s == (uint32_t)depth) { s = 0; ph ^= 1; }
+      }
+      ptx::mma_commit(&done);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&done, 0);
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
+}
+
 // A[r][k] = (k == 0) ? r + 1 : 0 for r in [0, 144), written with the TMA 128B swizzle; B[n][k] = (n == 0 && k == 0).
 // D = A_shift B^T  -> D[m][0] must be m + shift + 1.
 __global__ void __launch_bounds__(128, 1) k_shift(int shift, int use_base_offset, float* out) {
@@ -180,6 +247,18 @@ int main() {
     if (e != cudaSuccess) { printf("pattern error %s\n", cudaGetErrorString(e)); return 1; }
     printf("kernel pattern  BLOCK_N=%3d: %7.1f cycles per stage (4 x [N=%d + N=%d]); model 4 x (%d/2+43 + %d/2+43) = %d\n", bn,
            (double)c / stages, 2 * bn, bn, 2 * bn, bn, 4 * (bn + 43 + bn / 2 + 43));
+  }
+  cudaFuncSetAttribute(k_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
+  for (int cfgi = 0; cfgi < 9; ++cfgi) {
+    const int depths[9] = {1, 2, 4, 8, 4, 4, 4, 4, 4}, flagv[9] = {0, 0, 0, 0, 1, 2, 8, 9, 9};
+    const int depth = depths[cfgi], flags = flagv[cfgi];
+    const int stages = 9 * 32;
+    k_ring<<<148, 128, 194 * 1024>>>(64, stages, depth, flags, d);
+    long long c = 0;
+    cudaError_t e = cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { printf("ring error %s\n", cudaGetErrorString(e)); return 1; }
+    printf("mbarrier ring depth %d flags %d (1 = no fence, 2 = no full wait, 8 = test_wait), BLOCK_N=64 stage (8 MMAs, 473 "
+           "cycles of tensor time): %7.1f cycles per stage\n", depth, flags, (double)c / stages);
   }
   float* o;
   cudaMalloc(&o, 128 * 4);
