@@ -103,6 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tm_o = tmem + kTmO;
+  pdl_wait();                                      // the setup above overlaps the tail of the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -548,13 +549,13 @@ int attn_launch(const AttnPlan& ap, cudaStream_t st) {
   const AttnParams& p = ap.p;
   if (p.tail_splits > 1) {
     const int total = ap.B * p.nheads * p.q_tiles, rem = total - p.tail_first;
-    attn_fwd_kernel<<<p.tail_first + rem * p.tail_splits, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, p);
+    launch_pdl(attn_fwd_kernel, dim3(p.tail_first + rem * p.tail_splits), dim3(kAtThreads), kAtSmem, st, ap.tmK, ap.tmV, p);
     k_attn_tail_merge<<<rem, 256, 0, st>>>(p);
     DEXB_CUDA_OK(cudaGetLastError());
     return 0;
   }
   dim3 grid((unsigned)(ap.p.kv_splits > 1 ? ap.p.kv_splits : (ap.p.NQ + kAtBM - 1) / kAtBM), (unsigned)(ap.B * ap.p.nheads));
-  attn_fwd_kernel<<<grid, kAtThreads, kAtSmem, st>>>(ap.tmK, ap.tmV, ap.p);
+  launch_pdl(attn_fwd_kernel, grid, dim3(kAtThreads), kAtSmem, st, ap.tmK, ap.tmV, ap.p);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -176,18 +176,18 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
     int nb = (kTcSmemMax - tc_halo_bytes(BN, 0)) / (2 * BN * kTcBlockK * 2);
     if (nb > kTcMaxStages) nb = kTcMaxStages;
     const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-    gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, tc_halo_bytes(BN, nb), st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, -nb);
+    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_halo_bytes(BN, nb), st, gp.tmA, gp.tmB, p, (int)total, ntn, -nb);
     return 0;
   }
   const int rb = rb_stages_for(p, BN, m_tiles, ntn);
   if (rb > 0) {
     const int nk = p.KH * p.KW * (p.K / kTcBlockK);
     const int grid = (g_num_sms / ntn) * ntn;            // multiple of ntn: a CTA never changes its n-tile
-    gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, tc_rb_bytes(BN, nk, rb), st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, rb);
+    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_rb_bytes(BN, nk, rb), st, gp.tmA, gp.tmB, p, (int)total, ntn, rb);
     return 0;
   }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  gemm_tc_kernel<BN, FAST><<<grid, kTcThreads, TcSmem<BN>::kBytes, st>>>(gp.tmA, gp.tmB, p, (int)total, ntn, 0);
+  launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), TcSmem<BN>::kBytes, st, gp.tmA, gp.tmB, p, (int)total, ntn, 0);
   return 0;
 }
 

@@ -396,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // everything above overlaps the tail of the previous kernel
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------

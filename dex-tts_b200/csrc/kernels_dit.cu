@@ -218,6 +218,7 @@ __device__ __forceinline__ void ln_mod_row(float (&v)[PER_LANE], const float* sh
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) k_ln_mod(const float* __restrict__ x, const float* __restrict__ shift,
                                                 const float* __restrict__ scale, SView out, long M, int D) {
+  pdl_wait();
   const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -231,8 +232,8 @@ __global__ void __launch_bounds__(256) k_ln_mod(const float* __restrict__ x, con
   ln_mod_row<PER_LANE>(v, shift, scale, out.p + row * out.stride, out.hi, out.lo, lane, D);
 }
 void launch_ln_mod(const float* x, const float* shift, const float* scale, SView out, long M, int D, cudaStream_t st) {
-  if (D == 256) k_ln_mod<8><<<cdiv(M * 32, 256), 256, 0, st>>>(x, shift, scale, out, M, D);
-  else if (D == 384) k_ln_mod<12><<<cdiv(M * 32, 256), 256, 0, st>>>(x, shift, scale, out, M, D);
+  if (D == 256) launch_pdl(k_ln_mod<8>, dim3(cdiv(M * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
+  else if (D == 384) launch_pdl(k_ln_mod<12>, dim3(cdiv(M * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
 }
 
 // pe[b][w][c] = mean over the frequency rows of pg[b][h][w][c] (dit.py:445), summed in a fixed order.  One thread = 4 channels.

@@ -4,7 +4,19 @@
 // DEX-TTS/model/ref_encoder.py:239-273, DEX-TTS/model/dit.py:75-90.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace dexb {
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DEXB_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // InstanceNorm1D.cal_stats over the time axis (lengths ignored, unbiased variance, std = sqrt(var + 1e-5)).

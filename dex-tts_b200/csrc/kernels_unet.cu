@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
                                                  float* __restrict__ raw, double* __restrict__ stats, int B, int H,
                                                  int W) {
   static_assert(C == 64, "one GroupNorm group per channel octet");
+  pdl_wait();
   constexpr int KT = 9 * CIN;                                // taps x input channels: [mu | c_in x | speaker channel]
   __shared__ __align__(16) float wsT[KT][C];                 // [k][co]
   __shared__ float red[8][C / 8][2];
@@ -133,8 +134,8 @@ void launch_conv_in(const float* x, const float* mu, const float* spk_s, const f
   // stats layout is [B][8 groups][2]; only C == 64 (decoder.dim 64, GroupNorm(8, 64): one group per channel octet) is
   // instantiated -- engine_finalize rejects other widths.
   if (C != 64) return;
-  if (spk_s == nullptr) k_conv_in<64, 2><<<grid, 256, 0, st>>>(x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
-  else k_conv_in<64, 3><<<grid, 256, 0, st>>>(x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+  if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
+  else launch_pdl(k_conv_in<64, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -167,6 +168,7 @@ __device__ __forceinline__ float mish_fast(float x) {
 // c0 for all its items (gamma / beta / time bias live in registers).
 template <int ITEMS>
 __global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
+  pdl_wait();
   const int b = blockIdx.y;
   const int cpt = a.C >> 3;                                  // threads per pixel: 8 or 16
   const int cshift = 31 - __clz(cpt);
@@ -264,10 +266,10 @@ void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
   const long ngroups = (long)a.P * (a.C / 8);
   if (ngroups >= 8 * 256) {
     dim3 grid(cdiv(ngroups, 2 * 256), a.B);
-    k_gn_apply<2><<<grid, 256, 0, st>>>(a);
+    launch_pdl(k_gn_apply<2>, grid, dim3(256), 0, st, a);
   } else {
     dim3 grid(cdiv(ngroups, 256), a.B);
-    k_gn_apply<1><<<grid, 256, 0, st>>>(a);
+    launch_pdl(k_gn_apply<1>, grid, dim3(256), 0, st, a);
   }
 }
 
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
                                                   float* __restrict__ x, float* __restrict__ den_out,
                                                   const StepScalars* __restrict__ tab, int step, int B, int P, int W) {
   // grid = (chunks of ITEMS * 256 eight-channel groups, image); C == 64: 8 lanes per pixel (32-bit index math, see k_gn_apply)
+  pdl_wait();
   const int b = blockIdx.y;
   const unsigned ngroups = (unsigned)P << 3;
   const unsigned base = blockIdx.x * (unsigned)(256 * ITEMS);
@@ -345,10 +348,10 @@ void launch_gn_final(const float* raw, int C, int G, const double* stats, const 
   const long ngroups = (long)H * W * 8;                     // C == 64 (engine_finalize)
   if (ngroups >= 8 * 256) {
     dim3 grid(cdiv(ngroups, 2 * 256), B);
-    k_gn_final<2><<<grid, 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
+    launch_pdl(k_gn_final<2>, grid, dim3(256), 0, st, raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
   } else {
     dim3 grid(cdiv(ngroups, 256), B);
-    k_gn_final<1><<<grid, 256, 0, st>>>(raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
+    launch_pdl(k_gn_final<1>, grid, dim3(256), 0, st, raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
   }
 }
 

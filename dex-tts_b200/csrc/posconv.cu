@@ -84,6 +84,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
   const int KG = p.KS / 4;                                  // tap groups of 4 along x
 
   if (warp == 0) {
@@ -322,7 +323,7 @@ int posconv_plan_init(PosConvPlan* pp, const bf16* pin, const bf16* pw, const fl
 }
 
 int posconv_launch(const PosConvPlan& pp, cudaStream_t st) {
-  posconv_kernel<<<pp.grid, kPcThreads, kPcSmem, st>>>(pp.tmIn, pp.tmW, pp.p);
+  launch_pdl(posconv_kernel, dim3(pp.grid), dim3(kPcThreads), kPcSmem, st, pp.tmIn, pp.tmW, pp.p);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
 }
