@@ -21,12 +21,26 @@ static double gemm_flop(const GemmParams& p) {
   return 2.0 * p.nz * p.CH * p.CW * (double)p.N * p.K * p.KH * p.KW;
 }
 
+// DEXB_DEBUG_SYNC=1 (debug aid, un-graphed runs only): synchronise after every launch and name the one that failed
+static int debug_sync_check(const char* tag, cudaStream_t st) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DEXB_DEBUG_SYNC"); on = (e != nullptr && e[0] == '1') ? 1 : 0; }
+  if (!on) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return 0;
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { set_last_error("launch '%s' failed: %s", tag, cudaGetErrorString(e)); return -2; }
+  return 0;
+}
+
 #define LAUNCH(expr)                              \
   do {                                            \
     if (h->prof) prof_begin(h, #expr, 0.0, st);   \
     expr;                                         \
     if (h->prof) prof_end(h, st);                 \
     ++h->launches;                                \
+    DEXB_TRY(debug_sync_check(#expr, st));        \
   } while (0)
 #define GEMM(plan, params)                                            \
   do {                                                                \
@@ -34,6 +48,12 @@ static double gemm_flop(const GemmParams& p) {
     DEXB_TRY(gemm_launch((plan), (params), h->cfg.gemm_engine, st));  \
     if (h->prof) prof_end(h, st);                                     \
     ++h->launches;                                                    \
+    if (debug_sync_check("gemm:" #plan, st) != 0) {                   \
+      fprintf(stderr, "failing GEMM %s: K %d N %d H %d W %d CH %d CW %d KH %d halo %d block_n %d stride %d\n", #plan, (params).K, \
+              (params).N, (params).H, (params).W, (params).CH, (params).CW, (params).KH, (int)(plan).halo, (plan).block_n,      \
+              (params).in_stride);                                    \
+      return -2;                                                      \
+    }                                                                 \
   } while (0)
 
 // ------------------------------------------------------------------------------------------------

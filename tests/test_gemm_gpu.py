@@ -19,6 +19,13 @@ CASES = {
     "lin_fc2": (1, 1, 520, 512, 256, (1, 1), (0, 0), 1),
     "taps2x2_n32": (2, 9, 70, 64, 32, (2, 2), (-1, 0), 1),
     "lin_n260": (1, 3, 130, 128, 260, (1, 1), (0, 0), 1),
+    # several tiles per persistent CTA (more tiles than SMs): ring / accumulator hand-over between tiles, both MMA issuers
+    "conv3_64_many": (4, 80, 256, 64, 64, (3, 3), (-1, -1), 1),
+    "conv3_128_many": (3, 40, 256, 128, 128, (3, 3), (-1, -1), 1),
+    "conv3_256to64_many": (2, 40, 384, 256, 64, (3, 3), (-1, -1), 1),
+    "lin_256_many": (1, 1, 40000, 256, 256, (1, 1), (0, 0), 1),
+    "lin_k64_many": (3, 64, 256, 64, 128, (1, 1), (0, 0), 1),
+    "conv3_stride2_many": (4, 80, 512, 64, 64, (3, 3), (-1, -1), 2),
 }
 
 

@@ -168,6 +168,71 @@ __global__ void __launch_bounds__(128, 1) k_ring(int bn, int stages, int depth, 
   if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
 }
 
+// Two MMA-issuing warps, each with its own accumulator and its own mbarrier ring (a third / fourth warp flips the barriers):
+// does the tensor pipe interleave the two streams so that one issuer's barrier handshake hides behind the other's MMAs?
+__global__ void __launch_bounds__(128, 1) k_ring2(int bn, int stages, int depth, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[2][8], empty[2][8], done[2];
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 192 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    for (int w = 0; w < 2; ++w) {
+      for (int i = 0; i < 8; ++i) { ptx::mbar_init(&full[w][i], 1); ptx::mbar_init(&empty[w][i], 1); }
+      ptx::mbar_init(&done[w], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (threadIdx.x < 32) ptx::tmem_alloc<512>(&slot);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = slot;
+  const int warp = threadIdx.x >> 5;
+  long long t0 = clock64();
+  if (warp >= 2) {                                           // producers: warp 2 feeds issuer 0, warp 3 issuer 1
+    const int w = warp - 2;
+    if (ptx::elect_one()) {
+      uint32_t s = 0, ph = 0;
+      for (int st = 0; st < stages; ++st) {
+        ptx::mbar_wait(&empty[w][s], ph ^ 1);
+        ptx::mbar_arrive(&full[w][s]);
+        if (++s == (uint32_t)depth) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {                                                   // issuers
+    const int w = warp;
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, bn), idesc2 = ptx::make_idesc_bf16(128, 2 * bn);
+      uint32_t s = 0, ph = 0;
+      for (int st = 0; st < stages; ++st) {
+        ptx::mbar_wait(&full[w][s], ph);
+        ptx::tc_fence_after();
+        const uint32_t base = ptx::smem_u32(smem) + ((2 * st + w) % 3) * 65536;
+        const uint32_t a_hi = base, a_lo = base + 16384, b_hi = base + 32768;
+        const uint32_t tacc = tmem + w * 256;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = kk * 32;
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_hi + ko), ptx::make_desc_k128(b_hi + ko), idesc2, (st % 9 || kk) ? 1u : 0u);
+          ptx::mma_bf16_ss(tacc, ptx::make_desc_k128(a_lo + ko), ptx::make_desc_k128(b_hi + ko), idesc, 1u);
+        }
+        ptx::mma_commit(&empty[w][s]);
+        if (++s == (uint32_t)depth) { s = 0; ph ^= 1; }
+      }
+      ptx::mma_commit(&done[w]);
+    }
+    __syncwarp();
+    ptx::mbar_wait(&done[w], 0);
+    long long t1 = clock64();
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) out[w] = t1 - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tmem);
+}
+
 // A[r][k] = (k == 0) ? r + 1 : 0 for r in [0, 144), written with the TMA 128B swizzle; B[n][k] = (n == 0 && k == 0).
 // D = A_shift B^T  -> D[m][0] must be m + shift + 1.
 __global__ void __launch_bounds__(128, 1) k_shift(int shift, int use_base_offset, float* out) {
@@ -259,6 +324,20 @@ int main() {
     if (e != cudaSuccess) { printf("ring error %s\n", cudaGetErrorString(e)); return 1; }
     printf("mbarrier ring depth %d flags %d (1 = no fence, 2 = no full wait, 8 = test_wait), BLOCK_N=64 stage (8 MMAs, 473 "
            "cycles of tensor time): %7.1f cycles per stage\n", depth, flags, (double)c / stages);
+  }
+  cudaFuncSetAttribute(k_ring2, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
+  {
+    long long* d2;
+    cudaMalloc(&d2, 16);
+    for (int bn : {64, 128}) {
+      const int stages = 9 * 16;
+      k_ring2<<<148, 128, 194 * 1024>>>(bn, stages, 2, d2);
+      long long c[2] = {0, 0};
+      cudaError_t e = cudaMemcpy(c, d2, 16, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { printf("ring2 error %s\n", cudaGetErrorString(e)); return 1; }
+      printf("two issuers x mbarrier ring depth 2, BLOCK_N=%d: %7.1f / %7.1f cycles per stage PAIR  (single issuer with ring: %d per stage)\n",
+             bn, (double)c[0] / stages, (double)c[1] / stages, bn == 64 ? 726 : 1020);
+    }
   }
   float* o;
   cudaMalloc(&o, 128 * 4);
