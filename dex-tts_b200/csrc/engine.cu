@@ -421,7 +421,6 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   for (LinAttW* la : las) {
     la->weff = ar.get<bf16>((long)B * la->C * 2 * la->C);
     la->beff = ar.get<float>((long)B * la->C);
-    la->m1 = ar.get<float>((long)B * 128 * la->C);
     la->part = ar.get<float>((long)B * la_ctx_blocks(B, la == &h->la0 ? h->H0 * h->W0 : h->H1 * h->W1) * 4224);
   }
   // tables
@@ -853,7 +852,7 @@ static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
     LAUNCH(launch_la_colmax(h->kv, la.kmax, h->B, P, st));
     LAUNCH(launch_la_ctx(h->kv, la.kmax, la.part, la.ctx, la.ssum, h->B, P, st));
   }
-  LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.m1, la.weff, la.beff, h->B, la.C, st));
+  LAUNCH(launch_la_weff(la.ctx, la.ssum, la.wq, la.wout, la.bout, la.g, la.weff, la.beff, h->B, la.C, st));
   GEMM(la.apply, la.apply.p);
   return 0;
 }

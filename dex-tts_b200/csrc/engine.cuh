@@ -59,7 +59,7 @@ struct LinAttW {
   int splits = 1, PP = 0;
   float *part_o = nullptr, *part_l = nullptr, *part_m = nullptr;
   unsigned* kmax = nullptr;           // [B][128]
-  float *ctx = nullptr, *ssum = nullptr, *beff = nullptr, *m1 = nullptr, *part = nullptr;
+  float *ctx = nullptr, *ssum = nullptr, *beff = nullptr, *part = nullptr;
   bf16* weff = nullptr;               // [B][C][hi(C)|lo(C)]
 };
 

@@ -67,7 +67,7 @@ void launch_la_combine(const float* part_o, const float* part_l, const float* pa
                        int B, int S, int C, cudaStream_t st);
 // W_eff[b] = I + g * W_out * ctxn^T * W_q  -> packed split weights [B][C][hi(C)|lo(C)], beff[b] = g * b_out
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq /*[128][C]*/, const float* wout /*[C][128]*/,
-                    const float* bout, const float* g, float* m1 /*[B][128][C] scratch*/, bf16* weff, float* beff, int B,
+                    const float* bout, const float* g, bf16* weff, float* beff, int B,
                     int C, cudaStream_t st);
 
 // per-(image, channel) sum / sumsq over all pixels of an S tensor (InstanceNorm2D statistics)

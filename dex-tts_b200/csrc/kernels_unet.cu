@@ -598,8 +598,7 @@ __global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, 
 }
 int kernels_global_init() { return 0; }
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq, const float* wout, const float* bout,
-                    const float* g, float* m1, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
-  (void)m1;
+                    const float* g, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
   dim3 grid(C / 8, B);
   k_la_weff<<<grid, 256, 0, st>>>(ctx, ssum, wq, wout, bout, g, weff, beff, C);
 }
