@@ -55,6 +55,13 @@ SYMBOLS = {
     "dexb_profile_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dexb_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "dexb_simt_fallbacks": (ctypes.c_int, [ctypes.c_void_p]),
+    "dexb_tiv_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+    "dexb_tiv_destroy": (None, [ctypes.c_void_p]),
+    "dexb_tiv_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, c_int64_p, ctypes.c_int]),
+    "dexb_tiv_finalize_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_tiv_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    "dexb_tiv_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
 }
 
 _lib = None

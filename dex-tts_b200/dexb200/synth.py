@@ -83,3 +83,59 @@ def synth_inputs(cfg, B, T, Ts=259, seed=1234, ragged=False):
     elif cfg.n_spks > 1:                           # GeDEX-TTS speaker embedding (rows of nn.Embedding(n_spks, spk_emb_dim))
         out["spk"] = torch.randn(B, cfg.spk_emb_dim, generator=g)
     return out
+
+
+def tiv_manifest(c_in=80, c_out=64, num_layer=6, c_h=128):
+    """[(name relative to ``tiv_encoder.``, shape, kind)] -- the ``state_dict`` of the reference TIVEncoder
+    (DEX-TTS/model/ref_encoder.py:83-93 over BasicConv, DEX-TTS/model/base.py:33-50), in its own order."""
+    out = []
+
+    def basic(p, ci, co, bn):
+        out.append((p + ".conv.weight", (co, ci, 3), "conv"))
+        if bn:
+            out.extend([(p + ".bn.weight", (co,), "bn_w"), (p + ".bn.bias", (co,), "bn_b"),
+                        (p + ".bn.running_mean", (co,), "bn_rm"), (p + ".bn.running_var", (co,), "bn_rv"),
+                        (p + ".bn.num_batches_tracked", (), "bn_n")])
+    basic("in_conv", c_in, c_h, True)
+    for i in range(num_layer):
+        basic(f"conv_blocks.{i}.conv_block.0", c_h, c_h, True)
+        basic(f"conv_blocks.{i}.conv_block.1", c_h, c_h, False)
+    basic("out_conv", c_h, c_out, True)
+    return out
+
+
+def synth_tiv_weights(c_in=80, c_out=64, num_layer=6, c_h=128, seed=100, prefix="tiv_encoder."):
+    """Seeded TIV-encoder tensors.  The BatchNorm running statistics are drawn away from their (0, 1) initial values so the
+    eval-mode normalisation is really exercised."""
+    out = {}
+    for name, shape, kind in tiv_manifest(c_in, c_out, num_layer, c_h):
+        g = _gen(seed, "tiv_encoder." + name)
+        if kind == "conv":
+            bound = 1.0 / (shape[1] * shape[2]) ** 0.5
+            t = (torch.rand(shape, generator=g) * 2 - 1) * bound * 1.7
+        elif kind == "bn_w":
+            t = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_b":
+            t = 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_rm":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_rv":
+            t = 0.3 + 0.4 * torch.rand(shape, generator=g)
+        else:
+            t = torch.tensor(1000, dtype=torch.long)
+        out[prefix + name] = t if kind == "bn_n" else t.float().contiguous()
+    return out
+
+
+def synth_ref_mel(B, T, n_feats=80, seed=77, ragged=False):
+    """Seeded stand-in for a reference log-mel (B, n_feats, T) with lengths and mask (B,1,T)."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    ref = torch.randn(B, n_feats, T, generator=g) * 1.5 - 4.0            # log-mel-like range
+    if ragged:
+        lens = ((torch.rand(B, generator=g) * 0.4 + 0.6) * T).long().clamp(2, T)
+        lens[0] = T
+    else:
+        lens = torch.full((B,), T, dtype=torch.long)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
+    return dict(ref=ref, ref_lengths=lens, mask=mask)

@@ -121,6 +121,34 @@ long dexb_last_launch_count(const dexb_handle* h);
 /* Number of GEMMs per step that the tcgen05 engine could not take (shape ineligible) and ran on CUDA cores instead. */
 int dexb_simt_fallbacks(const dexb_handle* h);
 
+/* ---- TIV encoder (the once-per-utterance stage that feeds the loop) ---------------------------------
+ * replaces: TIVEncoder (DEX-TTS/model/ref_encoder.py:83-107; attached as DeXTTS.tiv_encoder, DEX-TTS/model/tts.py:28,50) in
+ * eval mode: in_conv -> num_layer x { residual conv block, skip, InstanceNorm1D } -> out_conv, BatchNorm1d on running statistics.
+ * Its six skip tensors are the `ref_skips_dev` of dexb_cond. */
+typedef struct dexb_tiv dexb_tiv;
+#define DEXB_TIV_MAX_LAYERS 16
+
+/* replaces: TIVEncoder.__init__(c_in, c_out, num_layer, c_h) (ref_encoder.py:84-93).  c_h % 64 == 0, c_out % 32 == 0. */
+int dexb_tiv_create(int c_in, int c_h, int c_out, int num_layer, dexb_tiv** out);
+void dexb_tiv_destroy(dexb_tiv* h);
+
+/* replaces: load_state_dict for the `tiv_encoder.*` tensors.  `name` is the reference key relative to `tiv_encoder.`
+ * ("in_conv.conv.weight", "in_conv.bn.running_var", "conv_blocks.3.conv_block.1.conv.weight", ...); the tensor is copied.
+ * Call dexb_tiv_finalize_weights once after the last tensor (packs the split-bf16 weights, folds the BatchNorm affine). */
+int dexb_tiv_load_weight(dexb_tiv* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_tiv_finalize_weights(dexb_tiv* h, void* stream);
+
+/* replaces: TIVEncoder.forward(x, mask) (ref_encoder.py:95-107).
+ *   ref_dev (B, c_in, T) fp32 reference mel, mask_dev (B, T) in {0,1}
+ *   skips_dev: HOST array of num_layer device pointers, each (B, c_h, T) fp32 -- the `skips` list
+ *   out_dev (B, c_out, T) fp32 -- the first return value (unused by DeXTTS.forward); may be NULL to skip out_conv.
+ * The first call for a new (B, T) allocates the workspace and encodes the TMA descriptors; later calls with the same (B, T)
+ * only enqueue kernels on `stream` (no allocation, no host synchronisation). */
+int dexb_tiv_forward(dexb_tiv* h, const float* ref_dev, const float* mask_dev, int B, int T, float* out_dev,
+                     float* const* skips_dev, void* stream);
+/* Number of kernels the last dexb_tiv_forward enqueued. */
+long dexb_tiv_last_launch_count(const dexb_tiv* h);
+
 #ifdef __cplusplus
 }
 #endif

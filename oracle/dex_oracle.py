@@ -13,6 +13,8 @@ reference's own ``state_dict`` names) of:
     DiffusionDenoiser.forward          DEX-TTS/model/diffusion.py:190-236   (GeDEX-TTS/model/diffusion.py:168-207)
     DiTMask.forward                    DEX-TTS/model/dit.py:479-519
     TVAdaptor / TIVAdaptor             DEX-TTS/model/ref_encoder.py:142-179, 239-273
+    TIVEncoder.forward (eval)          DEX-TTS/model/ref_encoder.py:83-107  (pre-loop stage, SURVEY.md §8f rank 1;
+                                       pinned by tests/golden/tiv_*.npz from oracle/make_golden_tiv.py)
 
 Third-party arithmetic on the path: ``timm`` (un-pinned, DEX-TTS/requirements.txt:16) ``Attention`` and ``Mlp``
 (call sites DEX-TTS/model/dit.py:270,274); their published algorithm is restated in ``_dit_block``.
@@ -341,6 +343,45 @@ def reverse_diffusion(w, cfg, z, mask, mu, num_steps, temperature=1.0, cond=None
     DEX-TTS/model/diffusion.py:255-259:  x = z / temperature + mu ; x = sampler(x, ...)."""
     x = z / temperature + mu
     return sampler(w, cfg, x, mask, mu, num_steps, cond=cond, trace=trace)
+
+
+# ----------------------------------------------------------------------------------------------
+# pre-loop stage: TIV encoder (produces the six `ref` skip tensors of the loop's TIVAdaptor)
+# ----------------------------------------------------------------------------------------------
+
+def _basic_conv_bn(w, p, x, relu=True, norm=True):
+    """BasicConv(norm_type='bn') in eval mode, DEX-TTS/model/base.py:33-63: conv1d(k=3, pad 1, no bias) -> BatchNorm1d on
+    running statistics (eps 1e-5) -> ReLU."""
+    x = F.conv1d(x, w[p + ".conv.weight"], None, padding=1)
+    if norm:
+        x = F.batch_norm(x, w[p + ".bn.running_mean"], w[p + ".bn.running_var"], w[p + ".bn.weight"], w[p + ".bn.bias"],
+                         training=False, momentum=0.01, eps=1e-5)
+    return torch.relu(x) if relu else x
+
+
+def _instance_norm_1d(x, eps=1e-5):
+    """InstanceNorm1D.forward, DEX-TTS/model/base.py:66-93: statistics over ALL frames (x_lengths ignored), unbiased variance."""
+    mean = x.mean(-1, keepdim=True)
+    std = (x.var(-1, keepdim=True) + eps).sqrt()
+    return (x - mean) / std
+
+
+def tiv_encoder(w, ref, mask, num_layer=6, prefix="tiv_encoder"):
+    """TIVEncoder.forward(x, mask), DEX-TTS/model/ref_encoder.py:95-107 (eval).  ref (B,80,T) or (B,1,80,T), mask (B,1,T)
+    -> (out (B,c_out,T), [num_layer x (B,c_h,T)])."""
+    if ref.dim() == 4:
+        ref = ref.squeeze(1)
+    x = _basic_conv_bn(w, prefix + ".in_conv", ref * mask) * mask                                   # :97
+    skips = []
+    for i in range(num_layer):
+        p = f"{prefix}.conv_blocks.{i}.conv_block"
+        xin = x * mask
+        h = _basic_conv_bn(w, p + ".0", xin)                                                         # :61
+        x = (xin + _basic_conv_bn(w, p + ".1", h, relu=False, norm=False)) * mask                    # :62,66,101
+        skips.append(x)
+        x = _instance_norm_1d(x)                                                                     # :103
+    out = _basic_conv_bn(w, prefix + ".out_conv", x * mask) * mask                                   # :104
+    return out, skips
 
 
 def decoder_weights(state_dict, dtype=torch.float32):
