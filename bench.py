@@ -199,12 +199,30 @@ def main():
         except Exception:
             fb = torch.rand(80, 513) * 0.01
         fb_d = dev(fb)
-        config["stft"] = "dexb_stft_mel on (B, 66150) synthetic audio inside every bench step (its mel is not fed back: the style encoders are out of scope)"
+        # ... and the reference-speech encoders on that mel: the TIV encoder's six skip tensors are what the loop consumes as
+        # `ref_skips` in this workload; the TV encoder runs too (its z_dec still needs the LF0 encoder + conv_sty of the reference to
+        # become `sty`, so `sty` stays synthetic)
+        from dexb200.model import TIVEncoder, TVEncoder
+        from dexb200.synth import synth_tiv_weights, synth_tv_weights
+        tiv = TIVEncoder(c_in=80, c_out=64, num_layer=6, c_h=128)
+        tiv.load_state_dict(synth_tiv_weights(prefix=""), strict=True)
+        tiv = tiv.cuda().eval()
+        tv = TVEncoder(c_in=80, c_out=192, c_out_g=192, num_layer=6, c_h=128, n_emb=512, commit_w=0.25)
+        tv.load_state_dict(synth_tv_weights(prefix=""), strict=True)
+        tv = tv.cuda().eval()
+        ref_mask_d = torch.ones(B, 1, 66150 // 256 + 1, device="cuda")
+        config["stft"] = ("every bench step runs dexb_stft_mel on (B, 66150) synthetic audio -> (B, 80, 259) log-mel -> dexb_tiv_forward "
+                          "(its six skips are the loop's ref_skips) and dexb_tv_forward (z_dec; sty stays synthetic: LF0 encoder + "
+                          "conv_sty are not built)")
 
     def one_pass():
+        cond = cond_d
         if audio_d is not None:
-            stft_mel(audio_d, win_d, fb_d)
-        y = eng.sample(x0_d, mask_d, mu_d, n_steps, cond=cond_d)
+            mel = stft_mel(audio_d, win_d, fb_d)
+            _, skips = tiv(mel, ref_mask_d)
+            tv(mel, ref_mask_d)
+            cond = dict(cond_d, ref_skips=skips)
+        y = eng.sample(x0_d, mask_d, mu_d, n_steps, cond=cond)
         if world > 1:
             dist.all_gather_into_tensor(gathered, y)        # the path's only collective: finished mels (SURVEY.md 8e,
         return y                                            # dexb200.parallel.gather_mels does the same for ragged shards)
@@ -236,6 +254,8 @@ def main():
     ms_per = ms / args.steps
     value = world * B * T / (ms_per * 1e-3)
     launches = eng.launches * args.steps
+    if audio_d is not None:                               # C3: + the STFT kernel and the two encoders of every step
+        launches += (1 + tiv.cuda_engine().launches + tv.cuda_engine().launches) * args.steps
 
     # ---- e2e: host buffers in, host mel out, through the host entry point (pinned memory)
     pin = lambda t: t.contiguous().pin_memory()

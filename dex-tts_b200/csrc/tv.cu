@@ -1,0 +1,535 @@
+// TV encoder of DEX-TTS (once-per-utterance stage; its z_dec becomes the loop's `sty` after conv_sty):
+// TVEncoder.forward, DEX-TTS/model/ref_encoder.py:109-140, over BasicConv (model/base.py:33-63), Projection (:8-34),
+// VQEmbeddingEMA (:181-235, eval branch) and model.base.LayerNorm (base.py:139-159).
+//
+//   x = ln(relu(conv3(sty * mask))) * mask                                              in_conv        (:128)
+//   6x  x = (x*mask + conv3(ln(relu(conv3(x*mask))))) * mask                            conv_blocks    (:131-133, :70-81)
+//   z_beforeVQ = conv3(x * mask) * mask                                                 out_conv       (:134)
+//   z = nearest code of z_beforeVQ per frame (fp32 CUDA cores), vq_loss                 vq             (:135, :199-235)
+//   z_dec = proj(cln(relu(conv3(cln(relu(conv3(z)))))))  (mask before every conv)       proj_0         (:137-138, :24-34)
+//   z_dec = relu(bn(conv3(z_dec * mask))) * mask                                        proj_1         (:139)
+//
+// Same construction as the TIV encoder (tiv.cu): rows [B*T][C], one image row per utterance, every Conv1d a 1 x k-tap implicit
+// GEMM on the tcgen05 engine (split-bf16 x3; conv biases in the GEMM epilogue), and ONE fused row kernel between two
+// convolutions (BatchNorm-eval | ReLU | LayerNorm over channels | residual | mask | split-operand store).  The nearest-code
+// search stays in fp32 on the CUDA cores: an argmin must not see split-bf16 noise, and it is 0.2 GFLOP per 8 utterances.
+#include <string.h>
+
+#include <initializer_list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dexb200.h"
+#include "gemm_host.cuh"
+
+namespace dexb {
+
+struct TvTensor {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  size_t n = 0;
+};
+
+struct TvConv {
+  bf16* w = nullptr;                          // [taps][co][hi(K)|lo(K)], K = ci padded to a multiple of 64
+  const float* bias = nullptr;                // conv bias (GEMM epilogue) or null
+  float *bn_a = nullptr, *bn_b = nullptr;     // eval BatchNorm as y = x * a + b, or null
+  const float *ln_g = nullptr, *ln_b = nullptr;
+  int ci = 0, co = 0, K = 0, taps = 3;
+  GemmPlan plan;
+};
+
+// what the fused row kernel does after a convolution
+struct TvPost {
+  const float* acc;          // [rows][C] raw conv output (bias already added by the GEMM epilogue)
+  const float *bn_a, *bn_b;  // [C] or null
+  int relu;
+  int ln_mode;               // 0 none, 1 nn.LayerNorm (1 / sqrt(var + eps)), 2 model.base.LayerNorm (rsqrt(var + eps))
+  float ln_eps;
+  const float *ln_g, *ln_b;  // [C]
+  const float* resid;        // fp32 rows added after the norm, or null
+  const float* mask;         // [rows] or null
+  bf16* os;                  // split rows [rows][hi(C)|lo(C)] or null
+  float* of;                 // fp32 rows or null
+  float* ocm;                // channel-major (B, C, T) or null
+  long rows;
+  int C, T;
+};
+
+}  // namespace dexb
+
+struct dexb_tv {
+  int c_in = 0, c_h = 0, c_out = 0, c_g = 0, L = 0, n_emb = 0;
+  float commit_w = 0.25f;
+  std::map<std::string, dexb::TvTensor> w;
+  bool finalized = false;
+  dexb::TvConv in_conv, out_conv, p_conv1, p_conv2, p_proj, proj1;
+  std::vector<dexb::TvConv> conv_a, conv_b;
+  const float* codebook = nullptr;             // (n_emb, c_out)
+  // plan (B, T)
+  int B = 0, T = 0;
+  dexb::bf16 *xs = nullptr, *hs = nullptr;     // split rows, up to 2 * max(K) columns
+  float *acc = nullptr, *xf = nullptr;         // fp32 rows, up to max(C) columns
+  double* loss_acc = nullptr;                  // [2]: sum of squared code distances over valid frames, number of valid frames
+  long launches = 0;
+};
+
+namespace dexb {
+
+static inline int tv_pad64(int k) { return (k + 63) / 64 * 64; }
+constexpr int kTvMaxC = 256;                   // channels per row the fused row kernel keeps in registers (8 per lane)
+
+// ---- weight packing ------------------------------------------------------------------------------------------------------------
+__global__ void k_tv_pack_w(const float* __restrict__ w, bf16* __restrict__ out, int co, int ci, int K, int taps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= taps * co * K) return;
+  const int k = i % K, n = (i / K) % co, tap = i / (K * co);
+  const float v = k < ci ? w[((long)n * ci + k) * taps + tap] : 0.f;
+  bf16 hi, lo;
+  split2(v, hi, lo);
+  out[((long)tap * co + n) * 2 * K + k] = hi;
+  out[((long)tap * co + n) * 2 * K + K + k] = lo;
+}
+__global__ void k_tv_bn_fold(const float* __restrict__ g, const float* __restrict__ b, const float* __restrict__ rm,
+                             const float* __restrict__ rv, float* __restrict__ alpha, float* __restrict__ beta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float a = g[c] * (1.f / sqrtf(rv[c] + 1e-5f));
+  alpha[c] = a;
+  beta[c] = b[c] - rm[c] * a;
+}
+
+// ---- activations ---------------------------------------------------------------------------------------------------------------
+// sty (B, c_in, T) channel-major, mask (B, T) -> split rows of sty * mask (columns >= c_in zeroed by the caller)
+__global__ void k_tv_in(const float* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xs, int B, int C, int T,
+                        int K) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)B * C * T) return;
+  const int t = (int)(i % T), c = (int)((i / T) % C), b = (int)(i / ((long)T * C));
+  const float v = x[i] * mask[(long)b * T + t];
+  bf16 hi, lo;
+  split2(v, hi, lo);
+  bf16* row = xs + ((long)b * T + t) * 2 * K;
+  row[c] = hi;
+  row[K + c] = lo;
+}
+
+// one warp per row (frame): everything between two convolutions
+__global__ void __launch_bounds__(256) k_tv_post(const TvPost p) {
+  const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  const int C = p.C;
+  float v[kTvMaxC / 32];
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    float x = 0.f;
+    if (c < C) {
+      x = p.acc[r * C + c];
+      if (p.bn_a != nullptr) x = fmaf(x, p.bn_a[c], p.bn_b[c]);
+      if (p.relu) x = fmaxf(x, 0.f);
+    }
+    v[j] = x;
+  }
+  if (p.ln_mode != 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) s += v[j];                 // lanes beyond C hold zeros
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const float d = (lane + 32 * j < C) ? v[j] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float var = warp_sum(q) / (float)C;                         // biased, as both LayerNorm flavours use
+    const float rstd = p.ln_mode == 1 ? 1.f / sqrtf(var + p.ln_eps) : rsqrtf(var + p.ln_eps);
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) v[j] = (v[j] - mean) * rstd * p.ln_g[c] + p.ln_b[c];
+    }
+  }
+  const float m = p.mask != nullptr ? p.mask[r] : 1.f;
+  const long b = r / p.T;
+  const int t = (int)(r % p.T);
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    if (c >= C) continue;
+    float x = v[j];
+    if (p.resid != nullptr) x += p.resid[r * C + c];
+    x *= m;
+    if (p.os != nullptr) {
+      bf16 hi, lo;
+      split2(x, hi, lo);
+      p.os[r * 2 * C + c] = hi;
+      p.os[r * 2 * C + C + c] = lo;
+    }
+    if (p.of != nullptr) p.of[r * C + c] = x;
+    if (p.ocm != nullptr) p.ocm[(b * C + c) * p.T + t] = x;
+  }
+}
+
+// Nearest-code search, VQEmbeddingEMA.forward (ref_encoder.py:199-231), eval mode.  One warp = 4 frames; the codebook streams
+// through every warp once (coalesced rows, L2 resident: n_emb * D * 4 B = 393 KB).  Distances are the direct fp32 sums
+// sum_d (x_d - e_d)^2 (the reference expands them to |e|^2 + |x|^2 - 2 x.e; both orderings agree far below the code gaps);
+// ties resolve to the lowest index like torch.argmin.  Output rows: (x + (e - x)) * mask as the split operand of proj_0.conv_1.
+constexpr int kVqRows = 4;
+__global__ void __launch_bounds__(256) k_tv_vq(const float* __restrict__ zf, const float* __restrict__ code,
+                                               const float* __restrict__ mask, bf16* __restrict__ os, int* __restrict__ idx_out,
+                                               double* __restrict__ loss_acc, long rows, int D, int M) {
+  const long r0 = (blockIdx.x * 8L + (threadIdx.x >> 5)) * kVqRows;
+  if (r0 >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float x[kVqRows][kTvMaxC / 32];
+#pragma unroll
+  for (int i = 0; i < kVqRows; ++i)
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int d = lane + 32 * j;
+      x[i][j] = (r0 + i < rows && d < D) ? zf[(r0 + i) * D + d] : 0.f;     // zf is z_beforeVQ * mask already
+    }
+  float best[kVqRows];
+  int bi[kVqRows];
+#pragma unroll
+  for (int i = 0; i < kVqRows; ++i) { best[i] = INFINITY; bi[i] = 0; }
+  for (int m = 0; m < M; ++m) {
+    float e[kTvMaxC / 32];
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int d = lane + 32 * j;
+      e[j] = d < D ? code[(long)m * D + d] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < kVqRows; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTvMaxC / 32; ++j) {
+        const float df = x[i][j] - e[j];
+        s = fmaf(df, df, s);
+      }
+      s = warp_sum(s);
+      if (s < best[i]) { best[i] = s; bi[i] = m; }
+    }
+  }
+  double lsum = 0.0, lcnt = 0.0;
+#pragma unroll
+  for (int i = 0; i < kVqRows; ++i) {
+    const long r = r0 + i;
+    if (r >= rows) continue;
+    const float mk = mask[r];
+    if (idx_out != nullptr && lane == 0) idx_out[r] = bi[i];
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int d = lane + 32 * j;
+      if (d >= D) continue;
+      const float q = code[(long)bi[i] * D + d];
+      const float dl = x[i][j] * mk - q * mk;                           // e_latent_loss term (:223)
+      sq = fmaf(dl, dl, sq);
+      const float o = (x[i][j] + (q - x[i][j])) * mk;                   // straight-through value, then mask (:227,233)
+      bf16 hi, lo;
+      split2(o, hi, lo);
+      os[r * 2 * D + d] = hi;
+      os[r * 2 * D + D + d] = lo;
+    }
+    sq = warp_sum(sq);
+    lsum += (double)sq;
+    lcnt += (double)mk;
+  }
+  if (lane == 0) {
+    atomicAdd(&loss_acc[0], lsum);
+    atomicAdd(&loss_acc[1], lcnt);
+  }
+}
+__global__ void k_tv_loss(const double* __restrict__ loss_acc, float* __restrict__ out, float commit_w, int D) {
+  // commitment_cost * sum((x*m - q*m)^2) / (sum(m) * D)   (:223-224)
+  out[0] = commit_w * (float)(loss_acc[0] / (loss_acc[1] * (double)D));
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------------------
+static int tv_get(dexb_tv* h, const std::string& name, std::initializer_list<int64_t> shape, const float** out) {
+  auto it = h->w.find(name);
+  DEXB_CHECK(it != h->w.end(), "tv encoder: weight '%s' was not loaded", name.c_str());
+  const std::vector<int64_t> want(shape);
+  DEXB_CHECK(it->second.shape == want, "tv encoder: weight '%s' has the wrong shape", name.c_str());
+  *out = it->second.p;
+  return 0;
+}
+
+// norm: 0 none, 1 ".ln" (nn.LayerNorm of BasicConv), 2 ".bn" (eval BatchNorm of BasicConv)
+static int tv_pack_conv(dexb_tv* h, const std::string& wname, const std::string& bname, int ci, int co, int taps, TvConv* c,
+                        cudaStream_t st) {
+  c->ci = ci; c->co = co; c->K = tv_pad64(ci); c->taps = taps;
+  const float* w = nullptr;
+  DEXB_TRY(tv_get(h, wname, {co, ci, taps}, &w));
+  if (c->w == nullptr) DEXB_CUDA_OK(cudaMalloc(&c->w, (size_t)taps * co * 2 * c->K * sizeof(bf16)));
+  k_tv_pack_w<<<cdiv((long)taps * co * c->K, 256), 256, 0, st>>>(w, c->w, co, ci, c->K, taps);
+  c->bias = nullptr;
+  if (!bname.empty()) DEXB_TRY(tv_get(h, bname, {co}, &c->bias));
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int tv_basic_conv(dexb_tv* h, const std::string& p, int ci, int co, int norm, TvConv* c, cudaStream_t st) {
+  DEXB_TRY(tv_pack_conv(h, p + ".conv.weight", "", ci, co, 3, c, st));
+  if (norm == 1) {
+    DEXB_TRY(tv_get(h, p + ".ln.weight", {co}, &c->ln_g));
+    DEXB_TRY(tv_get(h, p + ".ln.bias", {co}, &c->ln_b));
+  } else if (norm == 2) {
+    const float *g, *b, *rm, *rv;
+    DEXB_TRY(tv_get(h, p + ".bn.weight", {co}, &g));
+    DEXB_TRY(tv_get(h, p + ".bn.bias", {co}, &b));
+    DEXB_TRY(tv_get(h, p + ".bn.running_mean", {co}, &rm));
+    DEXB_TRY(tv_get(h, p + ".bn.running_var", {co}, &rv));
+    if (c->bn_a == nullptr) {
+      DEXB_CUDA_OK(cudaMalloc(&c->bn_a, (size_t)co * sizeof(float)));
+      DEXB_CUDA_OK(cudaMalloc(&c->bn_b, (size_t)co * sizeof(float)));
+    }
+    k_tv_bn_fold<<<cdiv(co, 128), 128, 0, st>>>(g, b, rm, rv, c->bn_a, c->bn_b, co);
+    DEXB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+static void tv_free_conv(TvConv* c) {
+  cudaFree(c->w); cudaFree(c->bn_a); cudaFree(c->bn_b);
+  c->w = nullptr; c->bn_a = c->bn_b = nullptr;
+}
+
+static void tv_release_plan(dexb_tv* h) {
+  cudaFree(h->xs); cudaFree(h->hs); cudaFree(h->acc); cudaFree(h->xf); cudaFree(h->loss_acc);
+  h->xs = h->hs = nullptr;
+  h->acc = h->xf = nullptr;
+  h->loss_acc = nullptr;
+  h->B = h->T = 0;
+}
+
+// Conv1d(k = taps, padding taps / 2) as a 1 x taps implicit GEMM: A = split rows [B][1][T][2K], output fp32 rows [B*T][co]
+static int tv_plan_conv(dexb_tv* h, TvConv* c, const bf16* a, float* out) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.nz = h->B; p.nheads = 1;
+  p.H = 1; p.W = h->T;
+  p.in_stride = 1;
+  p.CH = 1; p.CW = h->T; p.OH = 1; p.OW = h->T;
+  p.out_scale = 1; p.tap_sw = 1;
+  p.KH = 1; p.KW = c->taps; p.offH = 0; p.offW = -(c->taps / 2);
+  p.K = c->K; p.N = c->co;
+  p.A = a; p.a_row_stride = 2L * c->K; p.a_hi = 0; p.a_lo = c->K;
+  p.Bw = c->w; p.b_row_stride = 2L * c->K; p.b_hi = 0; p.b_lo = c->K; p.b_rows_per_tap = c->co;
+  p.nsplit = 3;
+  p.epi.alpha = 1.f; p.epi.out_s_ncols = 1 << 30;
+  p.epi.bias = c->bias;
+  p.epi.out_f32 = out; p.epi.out_f32_stride = c->co;
+  p.BW = 128; p.BH = 1;                     // one image row per utterance: 1 x 128-frame tiles (frames beyond T are zero-filled by TMA)
+  DEXB_TRY(gemm_plan_init(&c->plan, p, h->B, (long)c->taps * c->co, 1));
+  DEXB_CHECK(c->plan.tc_ok, "tv encoder: convolution %d -> %d is not eligible for the tcgen05 engine", c->ci, c->co);
+  return 0;
+}
+
+static int tv_plan(dexb_tv* h, int B, int T) {
+  if (B == h->B && T == h->T) return 0;
+  tv_release_plan(h);
+  DEXB_TRY(gemm_global_init());
+  int Kmax = h->in_conv.K, Cmax = h->c_h;
+  if (h->c_h > Kmax) Kmax = h->c_h;
+  if (tv_pad64(h->c_out) > Kmax) Kmax = tv_pad64(h->c_out);
+  if (tv_pad64(h->c_g) > Kmax) Kmax = tv_pad64(h->c_g);
+  if (h->c_out > Cmax) Cmax = h->c_out;
+  if (h->c_g > Cmax) Cmax = h->c_g;
+  const long rows = (long)B * T;
+  DEXB_CUDA_OK(cudaMalloc(&h->xs, rows * 2 * Kmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->hs, rows * 2 * Kmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->acc, rows * Cmax * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->xf, rows * Cmax * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->loss_acc, 2 * sizeof(double)));
+  h->B = B; h->T = T;
+  DEXB_TRY(tv_plan_conv(h, &h->in_conv, h->xs, h->acc));
+  for (int l = 0; l < h->L; ++l) {
+    DEXB_TRY(tv_plan_conv(h, &h->conv_a[l], h->xs, h->acc));
+    DEXB_TRY(tv_plan_conv(h, &h->conv_b[l], h->hs, h->acc));
+  }
+  DEXB_TRY(tv_plan_conv(h, &h->out_conv, h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_conv1, h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_conv2, h->hs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_proj, h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->proj1, h->hs, h->acc));
+  return 0;
+}
+
+static TvPost tv_post(const dexb_tv* h, const TvConv& c, int relu, int ln_mode, float ln_eps) {
+  TvPost p;
+  memset(&p, 0, sizeof(p));
+  p.acc = h->acc;
+  p.bn_a = c.bn_a; p.bn_b = c.bn_b;
+  p.relu = relu;
+  p.ln_mode = ln_mode; p.ln_eps = ln_eps; p.ln_g = c.ln_g; p.ln_b = c.ln_b;
+  p.rows = (long)h->B * h->T;
+  p.C = c.co; p.T = h->T;
+  return p;
+}
+static void tv_launch_post(const TvPost& p, cudaStream_t st) { k_tv_post<<<cdiv(p.rows, 8), 256, 0, st>>>(p); }
+
+}  // namespace dexb
+
+using namespace dexb;
+
+extern "C" {
+
+int dexb_tv_create(int c_in, int c_h, int c_out, int c_out_g, int num_layer, int n_emb, float commit_w, dexb_tv** out) {
+  DEXB_CHECK(out != nullptr, "dexb_tv_create: null argument");
+  int dev = 0, major = 0;
+  DEXB_CUDA_OK(cudaGetDevice(&dev));
+  DEXB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DEXB_CHECK(major == 10, "dexb200 is built for sm_100a only (device %d has compute capability major %d); there is no fallback",
+             dev, major);
+  DEXB_CHECK(c_in >= 1 && c_in <= kTvMaxC && num_layer >= 1 && num_layer <= DEXB_TIV_MAX_LAYERS && n_emb >= 1,
+             "dexb_tv_create: c_in %d / num_layer %d / n_emb %d out of range", c_in, num_layer, n_emb);
+  DEXB_CHECK(c_h >= 64 && c_h % 64 == 0 && c_h <= kTvMaxC, "dexb_tv_create: c_h = %d must be a multiple of 64 (<= %d)", c_h, kTvMaxC);
+  DEXB_CHECK(c_out >= 64 && c_out % 64 == 0 && c_out <= kTvMaxC && c_out_g >= 64 && c_out_g % 64 == 0 && c_out_g <= kTvMaxC,
+             "dexb_tv_create: c_out = %d / c_out_g = %d must be multiples of 64 (<= %d)", c_out, c_out_g, kTvMaxC);
+  dexb_tv* h = new dexb_tv();
+  h->c_in = c_in; h->c_h = c_h; h->c_out = c_out; h->c_g = c_out_g; h->L = num_layer; h->n_emb = n_emb; h->commit_w = commit_w;
+  h->conv_a.resize(num_layer);
+  h->conv_b.resize(num_layer);
+  *out = h;
+  return 0;
+}
+
+void dexb_tv_destroy(dexb_tv* h) {
+  if (h == nullptr) return;
+  tv_release_plan(h);
+  TvConv* cs[6] = {&h->in_conv, &h->out_conv, &h->p_conv1, &h->p_conv2, &h->p_proj, &h->proj1};
+  for (TvConv* c : cs) tv_free_conv(c);
+  for (auto& c : h->conv_a) tv_free_conv(&c);
+  for (auto& c : h->conv_b) tv_free_conv(&c);
+  for (auto& kv : h->w) cudaFree(kv.second.p);
+  delete h;
+}
+
+int dexb_tv_load_weight(dexb_tv* h, const char* name, const float* data_dev, const int64_t* shape, int ndim) {
+  DEXB_CHECK(h != nullptr && name != nullptr && data_dev != nullptr && shape != nullptr && ndim >= 1 && ndim <= 4,
+             "dexb_tv_load_weight: bad argument");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DEXB_CHECK(shape[i] >= 1, "dexb_tv_load_weight(%s): empty dimension", name);
+    n *= (size_t)shape[i];
+  }
+  TvTensor& t = h->w[name];
+  if (t.p != nullptr && t.n != n) { cudaFree(t.p); t.p = nullptr; }
+  if (t.p == nullptr) DEXB_CUDA_OK(cudaMalloc(&t.p, n * sizeof(float)));
+  t.n = n;
+  t.shape.assign(shape, shape + ndim);
+  DEXB_CUDA_OK(cudaMemcpy(t.p, data_dev, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->finalized = false;
+  return 0;
+}
+
+int dexb_tv_finalize_weights(dexb_tv* h, void* stream) {
+  DEXB_CHECK(h != nullptr, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(tv_basic_conv(h, "in_conv", h->c_in, h->c_h, 1, &h->in_conv, st));
+  for (int l = 0; l < h->L; ++l) {
+    const std::string p = "conv_blocks." + std::to_string(l) + ".conv_block.";
+    DEXB_TRY(tv_basic_conv(h, p + "0", h->c_h, h->c_h, 1, &h->conv_a[l], st));
+    DEXB_TRY(tv_basic_conv(h, p + "1", h->c_h, h->c_h, 0, &h->conv_b[l], st));
+  }
+  DEXB_TRY(tv_basic_conv(h, "out_conv", h->c_h, h->c_out, 0, &h->out_conv, st));
+  DEXB_TRY(tv_get(h, "vq.embedding", {h->n_emb, h->c_out}, &h->codebook));
+  DEXB_TRY(tv_pack_conv(h, "proj_0.conv_1.weight", "proj_0.conv_1.bias", h->c_out, h->c_g, 3, &h->p_conv1, st));
+  DEXB_TRY(tv_get(h, "proj_0.norm_1.gamma", {h->c_g}, &h->p_conv1.ln_g));
+  DEXB_TRY(tv_get(h, "proj_0.norm_1.beta", {h->c_g}, &h->p_conv1.ln_b));
+  DEXB_TRY(tv_pack_conv(h, "proj_0.conv_2.weight", "proj_0.conv_2.bias", h->c_g, h->c_g, 3, &h->p_conv2, st));
+  DEXB_TRY(tv_get(h, "proj_0.norm_2.gamma", {h->c_g}, &h->p_conv2.ln_g));
+  DEXB_TRY(tv_get(h, "proj_0.norm_2.beta", {h->c_g}, &h->p_conv2.ln_b));
+  DEXB_TRY(tv_pack_conv(h, "proj_0.proj.weight", "proj_0.proj.bias", h->c_g, h->c_g, 1, &h->p_proj, st));
+  DEXB_TRY(tv_basic_conv(h, "proj_1", h->c_g, h->c_g, 2, &h->proj1, st));
+  DEXB_CUDA_OK(cudaStreamSynchronize(st));
+  tv_release_plan(h);                       // plans hold the packed-weight pointers of the previous finalize
+  h->finalized = true;
+  return 0;
+}
+
+int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int B, int T, float* z_before_dev, float* z_dec_dev,
+                    float* vq_loss_dev, int32_t* idx_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && sty_dev != nullptr && mask_dev != nullptr && z_dec_dev != nullptr, "dexb_tv_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_tv_forward: call dexb_tv_finalize_weights first");
+  DEXB_CHECK(B >= 1 && T >= 1, "dexb_tv_forward: B = %d, T = %d", B, T);
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(tv_plan(h, B, T));
+  const long rows = (long)B * T;
+  h->launches = 0;
+  // in_conv(sty * mask) * mask
+  if (h->in_conv.K != h->c_in) DEXB_CUDA_OK(cudaMemsetAsync(h->xs, 0, rows * 2 * h->in_conv.K * sizeof(bf16), st));
+  DEXB_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, 2 * sizeof(double), st));
+  k_tv_in<<<cdiv(rows * h->c_in, 256), 256, 0, st>>>(sty_dev, mask_dev, h->xs, B, h->c_in, T, h->in_conv.K);
+  DEXB_TRY(gemm_launch(h->in_conv.plan, h->in_conv.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->in_conv, 1, 1, 1e-5f);
+    p.mask = mask_dev; p.os = h->xs; p.of = h->xf;
+    tv_launch_post(p, st);
+  }
+  h->launches += 3;
+  for (int l = 0; l < h->L; ++l) {
+    DEXB_TRY(gemm_launch(h->conv_a[l].plan, h->conv_a[l].plan.p, 0, st));
+    TvPost pa = tv_post(h, h->conv_a[l], 1, 1, 1e-5f);
+    pa.os = h->hs;
+    tv_launch_post(pa, st);
+    DEXB_TRY(gemm_launch(h->conv_b[l].plan, h->conv_b[l].plan.p, 0, st));
+    TvPost pb = tv_post(h, h->conv_b[l], 0, 0, 0.f);
+    pb.resid = h->xf; pb.mask = mask_dev; pb.os = h->xs; pb.of = h->xf;      // in place: every element is read and written by one lane
+    tv_launch_post(pb, st);
+    h->launches += 4;
+  }
+  // z_beforeVQ = out_conv(x * mask) * mask
+  DEXB_TRY(gemm_launch(h->out_conv.plan, h->out_conv.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->out_conv, 0, 0, 0.f);
+    p.mask = mask_dev; p.of = h->xf; p.ocm = z_before_dev;
+    tv_launch_post(p, st);
+  }
+  // vector quantisation -> split operand of proj_0.conv_1, loss
+  k_tv_vq<<<cdiv(cdiv(rows, kVqRows), 8), 256, 0, st>>>(h->xf, h->codebook, mask_dev, h->xs, idx_dev, h->loss_acc, rows, h->c_out,
+                                                       h->n_emb);
+  h->launches += 3;
+  if (vq_loss_dev != nullptr) {
+    k_tv_loss<<<1, 1, 0, st>>>(h->loss_acc, vq_loss_dev, h->commit_w, h->c_out);
+    h->launches += 1;
+  }
+  // proj_0: conv_1 -> relu -> norm_1 -> (mask) conv_2 -> relu -> norm_2 -> (mask) proj -> mask
+  DEXB_TRY(gemm_launch(h->p_conv1.plan, h->p_conv1.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_conv1, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.os = h->hs;
+    tv_launch_post(p, st);
+  }
+  DEXB_TRY(gemm_launch(h->p_conv2.plan, h->p_conv2.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_conv2, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.os = h->xs;
+    tv_launch_post(p, st);
+  }
+  DEXB_TRY(gemm_launch(h->p_proj.plan, h->p_proj.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_proj, 0, 0, 0.f);
+    p.mask = mask_dev; p.os = h->hs;
+    tv_launch_post(p, st);
+  }
+  // proj_1: relu(bn(conv3(z_dec * mask))) * mask
+  DEXB_TRY(gemm_launch(h->proj1.plan, h->proj1.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->proj1, 1, 0, 0.f);
+    p.mask = mask_dev; p.ocm = z_dec_dev;
+    tv_launch_post(p, st);
+  }
+  h->launches += 8;
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+long dexb_tv_last_launch_count(const dexb_tv* h) { return h != nullptr ? h->launches : 0; }
+
+}  // extern "C"

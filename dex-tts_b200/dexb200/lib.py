@@ -62,6 +62,14 @@ SYMBOLS = {
     "dexb_tiv_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                         ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
     "dexb_tiv_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
+    "dexb_tv_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_float, ctypes.POINTER(ctypes.c_void_p)]),
+    "dexb_tv_destroy": (None, [ctypes.c_void_p]),
+    "dexb_tv_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, c_int64_p, ctypes.c_int]),
+    "dexb_tv_finalize_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_tv_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_tv_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
 }
 
 _lib = None

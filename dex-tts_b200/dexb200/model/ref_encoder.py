@@ -1,10 +1,11 @@
-"""``TIVEncoder`` -- the time-invariant reference encoder of DeXTTS with its forward pass on hand-written sm_100a CUDA.
+"""``TIVEncoder`` / ``TVEncoder`` -- the reference-speech encoders of DeXTTS with their forward passes on hand-written sm_100a CUDA.
 
-Replaces (same constructor arguments, same ``forward`` signature and return value, same ``state_dict`` keys):
-    DEX-TTS/model/ref_encoder.py:83-107   class TIVEncoder   (attached as ``DeXTTS.tiv_encoder``, DEX-TTS/model/tts.py:28,50)
+Replace (same constructor arguments, same ``forward`` signature and return value, same ``state_dict`` keys):
+    DEX-TTS/model/ref_encoder.py:83-107    class TIVEncoder  (attached as ``DeXTTS.tiv_encoder``, DEX-TTS/model/tts.py:28,50)
+    DEX-TTS/model/ref_encoder.py:109-140   class TVEncoder   (attached as ``DeXTTS.tv_encoder``,  DEX-TTS/model/tts.py:26,43)
 
-This is the once-per-utterance stage right in front of the reverse-diffusion loop: its six skip tensors
-are the ``ref`` argument of ``Diffusion.forward``.  Parameters and BatchNorm buffers are registered under the reference's names
+This is the once-per-utterance stage right in front of the reverse-diffusion loop: the TIV encoder's six
+skip tensors are the ``ref`` argument of ``Diffusion.forward``, the TV encoder's ``z_dec`` becomes its ``sty`` (tts.py:48-49).  Parameters and BatchNorm buffers are registered under the reference's names
 (``in_conv.conv.weight``, ``in_conv.bn.running_mean``, ``conv_blocks.3.conv_block.1.conv.weight`` ...), so upstream checkpoints
 load with ``strict=True``.  Inference (eval mode) only: BatchNorm uses its running statistics.
 """
@@ -14,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import lib as _lib
-from ..synth import tiv_manifest
+from ..synth import tiv_manifest, tv_manifest
 from .diffusion import _Node
 
 
@@ -134,4 +135,138 @@ class TIVEncoder(nn.Module):
             raise RuntimeError("dexb200.TIVEncoder runs on CUDA (sm_100a) only; move the model and inputs to the GPU")
         if x.dim() == 4:
             x = x.squeeze(1)                                # ref_encoder.py:97
+        return self.cuda_engine().forward(x, mask)
+
+
+def _register(root, manifest):
+    """Rebuild a reference module tree (parameters and buffers under their upstream names) from a manifest."""
+    for name, shape, kind in manifest:
+        parts = name.split(".")
+        mod = root
+        for p in parts[:-1]:
+            if p not in mod._modules:
+                mod.add_module(p, _Node())
+            mod = mod._modules[p]
+        if kind == "conv":                                  # nn.Conv1d default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+            bound = 1.0 / (shape[1] * shape[2]) ** 0.5
+            mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape).uniform_(-bound, bound)))
+        elif kind == "bias":
+            mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape)))
+        elif kind == "bn_w":
+            mod.register_parameter(parts[-1], nn.Parameter(torch.ones(shape)))
+        elif kind == "bn_b":
+            mod.register_parameter(parts[-1], nn.Parameter(torch.zeros(shape)))
+        elif kind == "bn_rm":
+            mod.register_buffer(parts[-1], torch.zeros(shape))
+        elif kind == "bn_rv":
+            mod.register_buffer(parts[-1], torch.ones(shape))
+        elif kind == "code":                                # VQEmbeddingEMA: U(-1/n_emb, 1/n_emb) buffers (ref_encoder.py:192-197)
+            mod.register_buffer(parts[-1], torch.empty(shape).uniform_(-1.0 / shape[0], 1.0 / shape[0]))
+        elif kind == "ema_n":
+            mod.register_buffer(parts[-1], torch.zeros(shape))
+        else:
+            mod.register_buffer(parts[-1], torch.tensor(0, dtype=torch.long))
+
+
+class TVEncoderEngine:
+    """ctypes driver of the ``dexb_tv_*`` entry points (include/dexb200.h)."""
+
+    SKIP = ("bn_n", "ema_n")                                # training bookkeeping the forward pass never reads
+
+    def __init__(self, c_in, c_out, c_out_g, num_layer, c_h, n_emb, commit_w):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dexb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.dims = (int(c_in), int(c_out), int(c_out_g), int(num_layer), int(c_h), int(n_emb))
+        self.L = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self.L.dexb_tv_create(self.dims[0], self.dims[4], self.dims[1], self.dims[2], self.dims[3], self.dims[5],
+                                         float(commit_w), ctypes.byref(h)), "dexb_tv_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.dexb_tv_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd, prefix="tv_encoder."):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        for name, shape, kind in tv_manifest(*self.dims):
+            if kind in self.SKIP or name == "vq.ema_weight":
+                continue
+            key = prefix + name
+            if key not in sd:
+                raise RuntimeError(f"state dict is missing '{key}'")
+            t = sd[key].detach().to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != tuple(shape):
+                raise RuntimeError(f"'{key}' has shape {tuple(t.shape)}, expected {tuple(shape)}")
+            shp = (ctypes.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.L.dexb_tv_load_weight(self.h, name.encode(), ctypes.c_void_p(t.data_ptr()), shp, t.dim()),
+                       f"dexb_tv_load_weight({name})")
+        torch.cuda.synchronize()
+        _lib.check(self.L.dexb_tv_finalize_weights(self.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "dexb_tv_finalize_weights")
+
+    def forward(self, sty, mask, return_indices=False):
+        """sty (B, c_in, T) CUDA fp32, mask (B,1,T) or (B,T) -> (z_beforeVQ (B,c_out,T), z_dec (B,c_out_g,T), vq_loss 0-dim)
+        [+ code indices (B,T) int32]."""
+        c_in, c_out, c_out_g = self.dims[:3]
+        B, C, T = sty.shape
+        if C != c_in:
+            raise RuntimeError(f"style features have {C} channels, the encoder expects {c_in}")
+        sty = sty.detach().float().contiguous()
+        m = mask.detach().float().reshape(B, T).contiguous()
+        z_before = torch.empty(B, c_out, T, device=sty.device, dtype=torch.float32)
+        z_dec = torch.empty(B, c_out_g, T, device=sty.device, dtype=torch.float32)
+        loss = torch.empty((), device=sty.device, dtype=torch.float32)
+        idx = torch.empty(B, T, device=sty.device, dtype=torch.int32) if return_indices else None
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(self.L.dexb_tv_forward(self.h, p(sty), p(m), B, T, p(z_before), p(z_dec), p(loss), p(idx) if return_indices else None,
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dexb_tv_forward")
+        self._keep = (sty, m)
+        return (z_before, z_dec, loss, idx) if return_indices else (z_before, z_dec, loss)
+
+    @property
+    def launches(self):
+        return int(self.L.dexb_tv_last_launch_count(self.h))
+
+
+class TVEncoder(nn.Module):
+    """DEX-TTS/model/ref_encoder.py:109-140."""
+
+    def __init__(self, c_in, c_out, c_out_g, num_layer, c_h, n_emb, commit_w):
+        super().__init__()
+        self.dims = (int(c_in), int(c_out), int(c_out_g), int(num_layer), int(c_h), int(n_emb))
+        self.commit_w = float(commit_w)
+        _register(self, tv_manifest(*self.dims))
+        self._engine = None
+        self._sig = None
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def cuda_engine(self):
+        sig = self._signature()
+        if self._engine is None:
+            self._engine = TVEncoderEngine(*self.dims, self.commit_w)
+            self._sig = None
+        if sig != self._sig:
+            self._engine.load_state_dict(self.state_dict(), prefix="")
+            self._sig = sig
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x, mask):
+        if self.training:
+            raise NotImplementedError("the CUDA TV encoder implements eval mode (no EMA codebook update, BatchNorm on running "
+                                      "statistics) only")
+        if not x.is_cuda:
+            raise RuntimeError("dexb200.TVEncoder runs on CUDA (sm_100a) only; move the model and inputs to the GPU")
+        if x.dim() == 4:
+            x = x.squeeze(1)                                # ref_encoder.py:128
         return self.cuda_engine().forward(x, mask)

@@ -139,3 +139,64 @@ def synth_ref_mel(B, T, n_feats=80, seed=77, ragged=False):
         lens = torch.full((B,), T, dtype=torch.long)
     mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
     return dict(ref=ref, ref_lengths=lens, mask=mask)
+
+
+def tv_manifest(c_in=80, c_out=192, c_out_g=192, num_layer=6, c_h=128, n_emb=512):
+    """[(name relative to ``tv_encoder.``, shape, kind)] -- the ``state_dict`` of the reference TVEncoder
+    (DEX-TTS/model/ref_encoder.py:109-140 over BasicConv / Projection / VQEmbeddingEMA), in its own order."""
+    out = []
+
+    def basic(p, ci, co, norm):
+        out.append((p + ".conv.weight", (co, ci, 3), "conv"))
+        if norm == "ln":
+            out.extend([(p + ".ln.weight", (co,), "bn_w"), (p + ".ln.bias", (co,), "bn_b")])
+        elif norm == "bn":
+            out.extend([(p + ".bn.weight", (co,), "bn_w"), (p + ".bn.bias", (co,), "bn_b"),
+                        (p + ".bn.running_mean", (co,), "bn_rm"), (p + ".bn.running_var", (co,), "bn_rv"),
+                        (p + ".bn.num_batches_tracked", (), "bn_n")])
+    basic("in_conv", c_in, c_h, "ln")
+    for i in range(num_layer):
+        basic(f"conv_blocks.{i}.conv_block.0", c_h, c_h, "ln")
+        basic(f"conv_blocks.{i}.conv_block.1", c_h, c_h, None)
+    basic("out_conv", c_h, c_out, None)
+    out.extend([("vq.embedding", (n_emb, c_out), "code"), ("vq.ema_count", (n_emb,), "ema_n"), ("vq.ema_weight", (n_emb, c_out), "code")])
+    for j, (ci, k) in zip((1, 2), ((c_out, 3), (c_out_g, 3))):
+        out.extend([(f"proj_0.conv_{j}.weight", (c_out_g, ci, k), "conv"), (f"proj_0.conv_{j}.bias", (c_out_g,), "bias")])
+    # registration order of Projection.__init__ (ref_encoder.py:16-22): conv_1, norm_1, conv_2, norm_2, proj
+    proj = [e for e in out if e[0].startswith("proj_0.")]
+    out = [e for e in out if not e[0].startswith("proj_0.")]
+    out.extend(proj[0:2])
+    out.extend([("proj_0.norm_1.gamma", (c_out_g,), "bn_w"), ("proj_0.norm_1.beta", (c_out_g,), "bn_b")])
+    out.extend(proj[2:4])
+    out.extend([("proj_0.norm_2.gamma", (c_out_g,), "bn_w"), ("proj_0.norm_2.beta", (c_out_g,), "bn_b")])
+    out.extend([("proj_0.proj.weight", (c_out_g, c_out_g, 1), "conv"), ("proj_0.proj.bias", (c_out_g,), "bias")])
+    basic("proj_1", c_out_g, c_out_g, "bn")
+    return out
+
+
+def synth_tv_weights(c_in=80, c_out=192, c_out_g=192, num_layer=6, c_h=128, n_emb=512, seed=100, prefix="tv_encoder."):
+    """Seeded TV-encoder tensors.  The codebook is drawn at the scale of the encoder output (the reference's 1/n_emb uniform
+    init would put all 512 codes at the origin relative to the activations and make the argmin degenerate)."""
+    out = {}
+    for name, shape, kind in tv_manifest(c_in, c_out, c_out_g, num_layer, c_h, n_emb):
+        g = _gen(seed, "tv_encoder." + name)
+        if kind == "conv":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 1.7 / (shape[1] * shape[2]) ** 0.5
+        elif kind == "bias":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_w":
+            t = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_b":
+            t = 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_rm":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_rv":
+            t = 0.3 + 0.4 * torch.rand(shape, generator=g)
+        elif kind == "code":
+            t = 0.6 * torch.randn(shape, generator=_gen(seed, "tv_encoder.vq.embedding"))     # ema_weight == embedding clone
+        elif kind == "ema_n":
+            t = torch.rand(shape, generator=g)
+        else:
+            t = torch.tensor(1000, dtype=torch.long)
+        out[prefix + name] = t if kind == "bn_n" else t.float().contiguous()
+    return out

@@ -149,6 +149,33 @@ int dexb_tiv_forward(dexb_tiv* h, const float* ref_dev, const float* mask_dev, i
 /* Number of kernels the last dexb_tiv_forward enqueued. */
 long dexb_tiv_last_launch_count(const dexb_tiv* h);
 
+/* ---- TV encoder (second piece) ---------------------------------------------------------------------
+ * replaces: TVEncoder (DEX-TTS/model/ref_encoder.py:109-140; attached as DeXTTS.tv_encoder, DEX-TTS/model/tts.py:26,43) in eval
+ * mode: in_conv -> num_layer residual conv blocks (channel LayerNorm) -> out_conv -> VQEmbeddingEMA nearest-code search ->
+ * Projection (proj_0) -> proj_1.  z_dec is what DeXTTS.forward turns into the loop's `sty` (tts.py:48-49). */
+typedef struct dexb_tv dexb_tv;
+
+/* replaces: TVEncoder.__init__(c_in, c_out, c_out_g, num_layer, c_h, n_emb, commit_w) (ref_encoder.py:110-122).
+ * c_h, c_out, c_out_g: multiples of 64, at most 256. */
+int dexb_tv_create(int c_in, int c_h, int c_out, int c_out_g, int num_layer, int n_emb, float commit_w, dexb_tv** out);
+void dexb_tv_destroy(dexb_tv* h);
+
+/* replaces: load_state_dict for the `tv_encoder.*` tensors; `name` relative to `tv_encoder.` ("in_conv.ln.weight",
+ * "vq.embedding", "proj_0.norm_1.gamma", "proj_1.bn.running_var", ...).  vq.ema_count / vq.ema_weight / num_batches_tracked are
+ * training bookkeeping and need not be loaded.  Call dexb_tv_finalize_weights once after the last tensor. */
+int dexb_tv_load_weight(dexb_tv* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_tv_finalize_weights(dexb_tv* h, void* stream);
+
+/* replaces: TVEncoder.forward(x, mask) (ref_encoder.py:124-140).
+ *   sty_dev (B, c_in, T) fp32 style mel, mask_dev (B, T) in {0,1}
+ *   z_before_dev (B, c_out, T) = z_beforeVQ (may be NULL), z_dec_dev (B, c_out_g, T) = z_dec,
+ *   vq_loss_dev: one float = commit_w * e_latent_loss (may be NULL), idx_dev (B, T) int32 = the chosen code per frame (may be
+ *   NULL; a test / inspection aid, the reference does not return it).
+ * Allocation behaviour as dexb_tiv_forward: only the first call of a (B, T) shape allocates. */
+int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int B, int T, float* z_before_dev, float* z_dec_dev,
+                    float* vq_loss_dev, int32_t* idx_dev, void* stream);
+long dexb_tv_last_launch_count(const dexb_tv* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ reference's own ``state_dict`` names) of:
     TVAdaptor / TIVAdaptor             DEX-TTS/model/ref_encoder.py:142-179, 239-273
     TIVEncoder.forward (eval)          DEX-TTS/model/ref_encoder.py:83-107  (pre-loop stage, SURVEY.md §8f rank 1;
                                        pinned by tests/golden/tiv_*.npz from oracle/make_golden_tiv.py)
+    TVEncoder.forward (eval)           DEX-TTS/model/ref_encoder.py:109-140 (same stage; tests/golden/tv_*.npz)
 
 Third-party arithmetic on the path: ``timm`` (un-pinned, DEX-TTS/requirements.txt:16) ``Attention`` and ``Mlp``
 (call sites DEX-TTS/model/dit.py:270,274); their published algorithm is restated in ``_dit_block``.
@@ -382,6 +383,76 @@ def tiv_encoder(w, ref, mask, num_layer=6, prefix="tiv_encoder"):
         x = _instance_norm_1d(x)                                                                     # :103
     out = _basic_conv_bn(w, prefix + ".out_conv", x * mask) * mask                                   # :104
     return out, skips
+
+
+# ----------------------------------------------------------------------------------------------
+# pre-loop stage: TV encoder (produces z_dec, from which DeXTTS.forward builds the loop's `sty`)
+# ----------------------------------------------------------------------------------------------
+
+def _basic_conv_ln(w, p, x):
+    """BasicConv(norm_type='ln'), DEX-TTS/model/base.py:33-63: conv1d(k=3, pad 1, no bias) -> ReLU -> nn.LayerNorm over channels
+    (eps 1e-5, affine)."""
+    x = torch.relu(F.conv1d(x, w[p + ".conv.weight"], None, padding=1))
+    c = x.shape[1]
+    return F.layer_norm(x.transpose(1, 2), (c,), w[p + ".ln.weight"], w[p + ".ln.bias"], 1e-5).transpose(1, 2)
+
+
+def _channel_layer_norm(w, p, x, eps=1e-4):
+    """model.base.LayerNorm, DEX-TTS/model/base.py:139-159 (channel axis of (B,C,T), biased variance, rsqrt, eps 1e-4)."""
+    mean = torch.mean(x, 1, keepdim=True)
+    variance = torch.mean((x - mean) ** 2, 1, keepdim=True)
+    x = (x - mean) * torch.rsqrt(variance + eps)
+    return x * w[p + ".gamma"].view(1, -1, 1) + w[p + ".beta"].view(1, -1, 1)
+
+
+def _projection(w, p, x, mask):
+    """Projection.forward (eval: dropout = identity), DEX-TTS/model/ref_encoder.py:24-34."""
+    x = F.conv1d(x * mask, w[p + ".conv_1.weight"], w[p + ".conv_1.bias"], padding=1)
+    x = _channel_layer_norm(w, p + ".norm_1", torch.relu(x))
+    x = F.conv1d(x * mask, w[p + ".conv_2.weight"], w[p + ".conv_2.bias"], padding=1)
+    x = _channel_layer_norm(w, p + ".norm_2", torch.relu(x))
+    x = F.conv1d(x * mask, w[p + ".proj.weight"], w[p + ".proj.bias"])
+    return x * mask
+
+
+def vq_indices(w, p, x_flat):
+    """Nearest-code search of VQEmbeddingEMA.forward, DEX-TTS/model/ref_encoder.py:206-211."""
+    emb = w[p + ".embedding"]
+    distances = torch.addmm(torch.sum(emb ** 2, dim=1) + torch.sum(x_flat ** 2, dim=1, keepdim=True), x_flat, emb.t(),
+                            alpha=-2.0, beta=1.0)
+    return torch.argmin(distances.float(), dim=-1), distances
+
+
+def _vq(w, p, x, mask, commit_w=0.25):
+    """VQEmbeddingEMA.forward in eval mode, DEX-TTS/model/ref_encoder.py:199-235.  x (B,T,D), mask (B,1,T)."""
+    m = mask.transpose(1, 2)
+    x = x * m
+    D = x.shape[-1]
+    idx, _ = vq_indices(w, p, x.reshape(-1, D))
+    quantized = F.embedding(idx, w[p + ".embedding"]).view_as(x)
+    loss = commit_w * torch.sum(((x * m) - (quantized * m)) ** 2) / (torch.sum(m) * D)
+    quantized = x + (quantized - x)
+    return quantized * m, loss, idx.view(x.shape[:2])
+
+
+def tv_encoder(w, sty, mask, num_layer=6, commit_w=0.25, prefix="tv_encoder", return_indices=False):
+    """TVEncoder.forward(x, mask), DEX-TTS/model/ref_encoder.py:124-140 (eval).  sty (B,80,T) or (B,1,80,T), mask (B,1,T)
+    -> (z_beforeVQ (B,c_out,T), z_dec (B,c_out_g,T), vq_loss)."""
+    if sty.dim() == 4:
+        sty = sty.squeeze(1)
+    x = _basic_conv_ln(w, prefix + ".in_conv", sty * mask) * mask                                     # :128
+    for i in range(num_layer):
+        p = f"{prefix}.conv_blocks.{i}.conv_block"
+        xin = x * mask
+        h = _basic_conv_ln(w, p + ".0", xin)
+        x = (xin + F.conv1d(h, w[p + ".1.conv.weight"], None, padding=1)) * mask                     # :73-79,132
+    z_before = F.conv1d(x * mask, w[prefix + ".out_conv.conv.weight"], None, padding=1) * mask        # :134
+    z, loss, idx = _vq(w, prefix + ".vq", z_before.transpose(1, 2), mask, commit_w)                   # :135
+    z_dec = _projection(w, prefix + ".proj_0", z.transpose(1, 2), mask)                               # :137-138
+    z_dec = _basic_conv_bn(w, prefix + ".proj_1", z_dec * mask) * mask                                # :139
+    if return_indices:
+        return z_before, z_dec, loss, idx
+    return z_before, z_dec, loss
 
 
 def decoder_weights(state_dict, dtype=torch.float32):
