@@ -15,5 +15,6 @@ for f in api engine gemm attn posconv kernels_unet kernels_dit kernels_misc kern
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$OBJ"/*.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT.tmp" "$OBJ"/*.o -lcudart
+mv -f "$OUT.tmp" "$OUT"          # atomic replace: a snapshot of the tree never sees a half-written library
 echo "built $OUT"

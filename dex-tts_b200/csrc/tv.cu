@@ -1,4 +1,6 @@
-// TV encoder of DEX-TTS (once-per-utterance stage; its z_dec becomes the loop's `sty` after conv_sty):
+// TV encoder, LF0 encoder and style fusion of DEX-TTS: the once-per-utterance stage that builds the loop's `sty`
+// (DeXTTS.forward, DEX-TTS/model/tts.py:42-49).  Part 1: the TV encoder; part 2 (end of file): LF0 encoder + fusion.
+//
 // TVEncoder.forward, DEX-TTS/model/ref_encoder.py:109-140, over BasicConv (model/base.py:33-63), Projection (:8-34),
 // VQEmbeddingEMA (:181-235, eval branch) and model.base.LayerNorm (base.py:139-159).
 //
@@ -57,22 +59,25 @@ struct TvPost {
   int C, T;
 };
 
+// state every encoder handle of this file shares: loaded tensors, the (B, T) plan and its row buffers
+struct EncBase {
+  std::map<std::string, TvTensor> w;
+  bool finalized = false;
+  int B = 0, T = 0;
+  bf16 *xs = nullptr, *hs = nullptr;           // split rows, up to 2 * max(K) columns
+  float *acc = nullptr, *xf = nullptr;         // fp32 rows, up to max(C) columns
+  long launches = 0;
+};
+
 }  // namespace dexb
 
-struct dexb_tv {
+struct dexb_tv : dexb::EncBase {
   int c_in = 0, c_h = 0, c_out = 0, c_g = 0, L = 0, n_emb = 0;
   float commit_w = 0.25f;
-  std::map<std::string, dexb::TvTensor> w;
-  bool finalized = false;
   dexb::TvConv in_conv, out_conv, p_conv1, p_conv2, p_proj, proj1;
   std::vector<dexb::TvConv> conv_a, conv_b;
   const float* codebook = nullptr;             // (n_emb, c_out)
-  // plan (B, T)
-  int B = 0, T = 0;
-  dexb::bf16 *xs = nullptr, *hs = nullptr;     // split rows, up to 2 * max(K) columns
-  float *acc = nullptr, *xf = nullptr;         // fp32 rows, up to max(C) columns
   double* loss_acc = nullptr;                  // [2]: sum of squared code distances over valid frames, number of valid frames
-  long launches = 0;
 };
 
 namespace dexb {
@@ -251,17 +256,17 @@ __global__ void k_tv_loss(const double* __restrict__ loss_acc, float* __restrict
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------------------
-static int tv_get(dexb_tv* h, const std::string& name, std::initializer_list<int64_t> shape, const float** out) {
+static int tv_get(EncBase* h, const std::string& name, std::initializer_list<int64_t> shape, const float** out) {
   auto it = h->w.find(name);
-  DEXB_CHECK(it != h->w.end(), "tv encoder: weight '%s' was not loaded", name.c_str());
+  DEXB_CHECK(it != h->w.end(), "style encoders: weight '%s' was not loaded", name.c_str());
   const std::vector<int64_t> want(shape);
-  DEXB_CHECK(it->second.shape == want, "tv encoder: weight '%s' has the wrong shape", name.c_str());
+  DEXB_CHECK(it->second.shape == want, "style encoders: weight '%s' has the wrong shape", name.c_str());
   *out = it->second.p;
   return 0;
 }
 
 // norm: 0 none, 1 ".ln" (nn.LayerNorm of BasicConv), 2 ".bn" (eval BatchNorm of BasicConv)
-static int tv_pack_conv(dexb_tv* h, const std::string& wname, const std::string& bname, int ci, int co, int taps, TvConv* c,
+static int tv_pack_conv(EncBase* h, const std::string& wname, const std::string& bname, int ci, int co, int taps, TvConv* c,
                         cudaStream_t st) {
   c->ci = ci; c->co = co; c->K = tv_pad64(ci); c->taps = taps;
   const float* w = nullptr;
@@ -273,7 +278,7 @@ static int tv_pack_conv(dexb_tv* h, const std::string& wname, const std::string&
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
 }
-static int tv_basic_conv(dexb_tv* h, const std::string& p, int ci, int co, int norm, TvConv* c, cudaStream_t st) {
+static int tv_basic_conv(EncBase* h, const std::string& p, int ci, int co, int norm, TvConv* c, cudaStream_t st) {
   DEXB_TRY(tv_pack_conv(h, p + ".conv.weight", "", ci, co, 3, c, st));
   if (norm == 1) {
     DEXB_TRY(tv_get(h, p + ".ln.weight", {co}, &c->ln_g));
@@ -299,16 +304,20 @@ static void tv_free_conv(TvConv* c) {
   c->w = nullptr; c->bn_a = c->bn_b = nullptr;
 }
 
-static void tv_release_plan(dexb_tv* h) {
-  cudaFree(h->xs); cudaFree(h->hs); cudaFree(h->acc); cudaFree(h->xf); cudaFree(h->loss_acc);
+static void enc_release_rows(EncBase* h) {
+  cudaFree(h->xs); cudaFree(h->hs); cudaFree(h->acc); cudaFree(h->xf);
   h->xs = h->hs = nullptr;
   h->acc = h->xf = nullptr;
-  h->loss_acc = nullptr;
   h->B = h->T = 0;
+}
+static void tv_release_plan(dexb_tv* h) {
+  enc_release_rows(h);
+  cudaFree(h->loss_acc);
+  h->loss_acc = nullptr;
 }
 
 // Conv1d(k = taps, padding taps / 2) as a 1 x taps implicit GEMM: A = split rows [B][1][T][2K], output fp32 rows [B*T][co]
-static int tv_plan_conv(dexb_tv* h, TvConv* c, const bf16* a, float* out) {
+static int tv_plan_conv(EncBase* h, TvConv* c, const bf16* a, float* out) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.nz = h->B; p.nheads = 1;
@@ -326,7 +335,7 @@ static int tv_plan_conv(dexb_tv* h, TvConv* c, const bf16* a, float* out) {
   p.epi.out_f32 = out; p.epi.out_f32_stride = c->co;
   p.BW = 128; p.BH = 1;                     // one image row per utterance: 1 x 128-frame tiles (frames beyond T are zero-filled by TMA)
   DEXB_TRY(gemm_plan_init(&c->plan, p, h->B, (long)c->taps * c->co, 1));
-  DEXB_CHECK(c->plan.tc_ok, "tv encoder: convolution %d -> %d is not eligible for the tcgen05 engine", c->ci, c->co);
+  DEXB_CHECK(c->plan.tc_ok, "style encoders: convolution %d -> %d is not eligible for the tcgen05 engine", c->ci, c->co);
   return 0;
 }
 
@@ -360,7 +369,7 @@ static int tv_plan(dexb_tv* h, int B, int T) {
   return 0;
 }
 
-static TvPost tv_post(const dexb_tv* h, const TvConv& c, int relu, int ln_mode, float ln_eps) {
+static TvPost tv_post(const EncBase* h, const TvConv& c, int relu, int ln_mode, float ln_eps) {
   TvPost p;
   memset(&p, 0, sizeof(p));
   p.acc = h->acc;
@@ -531,5 +540,380 @@ int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int
 }
 
 long dexb_tv_last_launch_count(const dexb_tv* h) { return h != nullptr ? h->launches : 0; }
+
+}  // extern "C"
+
+
+// ================================================================================================================================
+// Part 2: LF0 encoder (LF0Encoder.forward, DEX-TTS/model/ref_encoder.py:36-56, eval) and the style fusion of DeXTTS.forward
+// (DEX-TTS/model/tts.py:45-49).
+//
+//   x = ln(relu(conv3(lf0 * mask))) * mask                       in_conv, 1 -> c_h channels: CUDA cores, fused   (:49)
+//   x = BiGRU_{num_layer}(x)  over ALL T frames (no packing)     input projections on the tcgen05 engine (both directions in one
+//                                                                GEMM, b_ih in the epilogue), recurrence in fp32 on CUDA cores:
+//                                                                one CTA per (utterance, direction), W_hh in registers   (:50)
+//   lf0_enc = ln(relu(conv3(x * mask))) * mask                   out_conv                                          (:51)
+//   lf0_dec = Projection(lf0_enc)                                proj                                              (:53-54)
+// ================================================================================================================================
+struct dexb_lf0 : dexb::EncBase {
+  int c_h = 0, c_out = 0, c_g = 0, L = 0, H = 0;
+  const float *in_w = nullptr, *in_g = nullptr, *in_b = nullptr;     // in_conv (c_h, 1, 3), ln affine
+  std::vector<dexb::TvConv> ih;                                      // per layer: [fwd | bwd] input projection (6H x c_h), b_ih
+  std::vector<float*> ih_w, ih_b;                                    // their fp32 sources: concatenated weights / biases
+  std::vector<const float*> hh_w[2], hh_b[2];                        // per direction, per layer: W_hh (3H, H), b_hh (3H)
+  dexb::TvConv out_conv, p_conv1, p_conv2, p_proj;
+  float* gi = nullptr;                                               // [B*T][6H] input projections of the current layer
+};
+
+namespace dexb {
+
+// in_conv of the LF0 encoder: one warp per frame; 1 input channel, 3 taps, ReLU, nn.LayerNorm(eps 1e-5), mask -> split rows
+__global__ void __launch_bounds__(256) k_lf0_in(const float* __restrict__ lf0, const float* __restrict__ mask,
+                                                const float* __restrict__ w, const float* __restrict__ g,
+                                                const float* __restrict__ bta, bf16* __restrict__ os, long rows, int C, int T) {
+  const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(r % T);
+  const float x0 = t > 0 ? lf0[r - 1] * mask[r - 1] : 0.f;           // zero padding at both ends of the utterance
+  const float x1 = lf0[r] * mask[r];
+  const float x2 = t + 1 < T ? lf0[r + 1] * mask[r + 1] : 0.f;
+  float v[kTvMaxC / 32];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    float y = 0.f;
+    if (c < C) y = fmaxf(fmaf(w[c * 3 + 2], x2, fmaf(w[c * 3 + 1], x1, w[c * 3] * x0)), 0.f);
+    v[j] = y;
+    s += y;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const float d = (lane + 32 * j < C) ? v[j] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)C + 1e-5f);
+  const float m = mask[r];
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    if (c >= C) continue;
+    const float y = ((v[j] - mean) * rstd * g[c] + bta[c]) * m;
+    bf16 hi, lo;
+    split2(y, hi, lo);
+    os[r * 2 * C + c] = hi;
+    os[r * 2 * C + C + c] = lo;
+  }
+}
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// GRU recurrence of one layer, both directions: grid (B, 2), 3H threads.  Thread j keeps row j of W_hh (gate order r, z, n) in
+// registers; h lives in shared memory.  gi = x W_ih^T + b_ih comes from the GEMM ([B*T][6H]: forward gates, then backward gates).
+// Output h_t (times omask[t] when given -- the mask the reference applies before out_conv) -> split rows, columns dir*H .. +H.
+template <int H>
+__global__ void __launch_bounds__(3 * H) k_gru_rec(const float* __restrict__ gi, const float* __restrict__ whh_f,
+                                                   const float* __restrict__ bhh_f, const float* __restrict__ whh_b,
+                                                   const float* __restrict__ bhh_b, const float* __restrict__ omask,
+                                                   bf16* __restrict__ os, int T) {
+  __shared__ __align__(16) float h[H];
+  __shared__ float gh[3 * H];
+  const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
+  const float* whh = dir == 0 ? whh_f : whh_b;
+  float wr[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) wr[k] = whh[j * H + k];
+  const float bj = (dir == 0 ? bhh_f : bhh_b)[j];
+  if (j < H) h[j] = 0.f;
+  __syncthreads();
+  for (int s = 0; s < T; ++s) {
+    const int t = dir == 0 ? s : T - 1 - s;
+    const long row = (long)b * T + t;
+    float gr = 0.f, gz = 0.f, gn = 0.f;
+    if (j < H) {                                  // issued before the mat-vec so their latency hides behind it
+      const float* g = gi + row * (6 * H) + dir * 3 * H;
+      gr = g[j]; gz = g[H + j]; gn = g[2 * H + j];
+    }
+    float a0 = bj, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(&h[k]);
+      a0 = fmaf(wr[k], hv.x, a0);
+      a1 = fmaf(wr[k + 1], hv.y, a1);
+      a2 = fmaf(wr[k + 2], hv.z, a2);
+      a3 = fmaf(wr[k + 3], hv.w, a3);
+    }
+    gh[j] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (j < H) {
+      const float r = sigmoid_f(gr + gh[j]);
+      const float z = sigmoid_f(gz + gh[H + j]);
+      const float n = tanhf(gn + r * gh[2 * H + j]);
+      const float hn = (1.f - z) * n + z * h[j];
+      h[j] = hn;
+      const float o = omask != nullptr ? hn * omask[row] : hn;
+      bf16 hi, lo;
+      split2(o, hi, lo);
+      os[row * (4 * H) + dir * H + j] = hi;       // row = [hi(2H) | lo(2H)]
+      os[row * (4 * H) + 2 * H + dir * H + j] = lo;
+    }
+    __syncthreads();
+  }
+}
+
+// rows [2][R][C] -> [2R][C] concatenation helper for the per-layer [forward | backward] input projection
+__global__ void k_cat2(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long na, long nb) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i < na) out[i] = a[i];
+  else if (i < na + nb) out[i] = b[i - na];
+}
+
+// time mean used by the fusion: out[b][c] (+)= sum_t x[b][c][t] / sum_t mask[b][t]   (x is already masked; tts.py:45,48)
+__global__ void __launch_bounds__(256) k_time_mean(const float* __restrict__ x, const float* __restrict__ mask,
+                                                   float* __restrict__ out, int C, int T, int accumulate) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;      // one warp per (b, c)
+  const int b = blockIdx.y;
+  if (w >= C) return;
+  float s = 0.f, m = 0.f;
+  for (int t = lane; t < T; t += 32) {
+    s += x[((long)b * C + w) * T + t];
+    m += mask[(long)b * T + t];
+  }
+  s = warp_sum(s);
+  m = warp_sum(m);
+  if (lane == 0) out[(long)b * C + w] = (accumulate ? out[(long)b * C + w] : 0.f) + s / m;
+}
+
+// sty[b][n][t] = bias[n] + sum_k W[n][k] * (z_dec[b][k][t] + v[b][k]),  v = time mean of lf0_dec   (tts.py:48-49; conv_sty is 1x1)
+// One CTA = (utterance, 32 frames): the [C][32] input tile (+ v) in shared memory, thread = one frame x N/8 output channels.
+__global__ void __launch_bounds__(256) k_conv_sty(const float* __restrict__ z, const float* __restrict__ v,
+                                                  const float* __restrict__ w, const float* __restrict__ bias,
+                                                  float* __restrict__ out, int C, int N, int T) {
+  extern __shared__ float zt[];                  // [C][33]
+  const int b = blockIdx.y, t0 = blockIdx.x * 32, tt = threadIdx.x & 31, ng = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < C * 32; i += 256) {
+    const int k = i >> 5, x = i & 31;
+    zt[k * 33 + x] = (t0 + x < T) ? z[((long)b * C + k) * T + t0 + x] + v[(long)b * C + k] : 0.f;
+  }
+  __syncthreads();
+  if (t0 + tt >= T) return;
+  for (int n = ng; n < N; n += 8) {
+    const float* wn = w + (long)n * C;
+    float a0 = bias[n], a1 = 0.f;
+    for (int k = 0; k < C; k += 2) {
+      a0 = fmaf(__ldg(wn + k), zt[k * 33 + tt], a0);
+      a1 = fmaf(__ldg(wn + k + 1), zt[(k + 1) * 33 + tt], a1);
+    }
+    out[((long)b * N + n) * T + t0 + tt] = a0 + a1;
+  }
+}
+
+static void lf0_release_plan(dexb_lf0* h) {
+  enc_release_rows(h);
+  cudaFree(h->gi);
+  h->gi = nullptr;
+}
+
+static int lf0_plan(dexb_lf0* h, int B, int T) {
+  if (B == h->B && T == h->T) return 0;
+  lf0_release_plan(h);
+  DEXB_TRY(gemm_global_init());
+  int Cmax = h->c_h;
+  if (h->c_out > Cmax) Cmax = h->c_out;
+  if (h->c_g > Cmax) Cmax = h->c_g;
+  const long rows = (long)B * T;
+  DEXB_CUDA_OK(cudaMalloc(&h->xs, rows * 2 * Cmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->hs, rows * 2 * Cmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->acc, rows * Cmax * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->gi, rows * 6 * h->H * sizeof(float)));
+  h->B = B; h->T = T;
+  // layer l reads xs (l even) / hs (l odd) and its recurrence writes the other one; out_conv reads what the last layer wrote
+  for (int l = 0; l < h->L; ++l) DEXB_TRY(tv_plan_conv(h, &h->ih[l], (l & 1) ? h->hs : h->xs, h->gi));
+  bf16* gru_out = (h->L & 1) ? h->hs : h->xs;
+  bf16* other = (h->L & 1) ? h->xs : h->hs;
+  DEXB_TRY(tv_plan_conv(h, &h->out_conv, gru_out, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_conv1, other, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_conv2, gru_out, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->p_proj, other, h->acc));
+  return 0;
+}
+
+}  // namespace dexb
+
+extern "C" {
+
+int dexb_lf0_create(int c_h, int c_out, int c_out_g, int num_layer, dexb_lf0** out) {
+  DEXB_CHECK(out != nullptr, "dexb_lf0_create: null argument");
+  int dev = 0, major = 0;
+  DEXB_CUDA_OK(cudaGetDevice(&dev));
+  DEXB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DEXB_CHECK(major == 10, "dexb200 is built for sm_100a only (device %d has compute capability major %d); there is no fallback",
+             dev, major);
+  DEXB_CHECK(c_h == 192, "dexb_lf0_create: the GRU recurrence kernel is instantiated for c_h = 192 (hidden 96 per direction), got %d", c_h);
+  DEXB_CHECK(c_out >= 64 && c_out % 64 == 0 && c_out <= kTvMaxC && c_out_g >= 64 && c_out_g % 64 == 0 && c_out_g <= kTvMaxC,
+             "dexb_lf0_create: c_out = %d / c_out_g = %d must be multiples of 64 (<= %d)", c_out, c_out_g, kTvMaxC);
+  DEXB_CHECK(num_layer >= 1 && num_layer <= 8, "dexb_lf0_create: num_layer = %d", num_layer);
+  dexb_lf0* h = new dexb_lf0();
+  h->c_h = c_h; h->c_out = c_out; h->c_g = c_out_g; h->L = num_layer; h->H = c_h / 2;
+  h->ih.resize(num_layer);
+  h->ih_w.assign(num_layer, nullptr);
+  h->ih_b.assign(num_layer, nullptr);
+  for (int d = 0; d < 2; ++d) { h->hh_w[d].assign(num_layer, nullptr); h->hh_b[d].assign(num_layer, nullptr); }
+  *out = h;
+  return 0;
+}
+
+void dexb_lf0_destroy(dexb_lf0* h) {
+  if (h == nullptr) return;
+  lf0_release_plan(h);
+  TvConv* cs[4] = {&h->out_conv, &h->p_conv1, &h->p_conv2, &h->p_proj};
+  for (TvConv* c : cs) tv_free_conv(c);
+  for (auto& c : h->ih) tv_free_conv(&c);
+  for (float* p : h->ih_w) cudaFree(p);
+  for (float* p : h->ih_b) cudaFree(p);
+  for (auto& kv : h->w) cudaFree(kv.second.p);
+  delete h;
+}
+
+int dexb_lf0_load_weight(dexb_lf0* h, const char* name, const float* data_dev, const int64_t* shape, int ndim) {
+  DEXB_CHECK(h != nullptr && name != nullptr && data_dev != nullptr && shape != nullptr && ndim >= 1 && ndim <= 4,
+             "dexb_lf0_load_weight: bad argument");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DEXB_CHECK(shape[i] >= 1, "dexb_lf0_load_weight(%s): empty dimension", name);
+    n *= (size_t)shape[i];
+  }
+  TvTensor& t = h->w[name];
+  if (t.p != nullptr && t.n != n) { cudaFree(t.p); t.p = nullptr; }
+  if (t.p == nullptr) DEXB_CUDA_OK(cudaMalloc(&t.p, n * sizeof(float)));
+  t.n = n;
+  t.shape.assign(shape, shape + ndim);
+  DEXB_CUDA_OK(cudaMemcpy(t.p, data_dev, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->finalized = false;
+  return 0;
+}
+
+int dexb_lf0_finalize_weights(dexb_lf0* h, void* stream) {
+  DEXB_CHECK(h != nullptr, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->H, C = h->c_h;
+  DEXB_TRY(tv_get(h, "in_conv.conv.weight", {C, 1, 3}, &h->in_w));
+  DEXB_TRY(tv_get(h, "in_conv.ln.weight", {C}, &h->in_g));
+  DEXB_TRY(tv_get(h, "in_conv.ln.bias", {C}, &h->in_b));
+  for (int l = 0; l < h->L; ++l) {
+    const std::string p = "rnn_layer.", s = "_l" + std::to_string(l);
+    const float *wf, *wb, *bf, *bb;
+    DEXB_TRY(tv_get(h, p + "weight_ih" + s, {3 * H, C}, &wf));
+    DEXB_TRY(tv_get(h, p + "weight_ih" + s + "_reverse", {3 * H, C}, &wb));
+    DEXB_TRY(tv_get(h, p + "bias_ih" + s, {3 * H}, &bf));
+    DEXB_TRY(tv_get(h, p + "bias_ih" + s + "_reverse", {3 * H}, &bb));
+    DEXB_TRY(tv_get(h, p + "weight_hh" + s, {3 * H, H}, &h->hh_w[0][l]));
+    DEXB_TRY(tv_get(h, p + "weight_hh" + s + "_reverse", {3 * H, H}, &h->hh_w[1][l]));
+    DEXB_TRY(tv_get(h, p + "bias_hh" + s, {3 * H}, &h->hh_b[0][l]));
+    DEXB_TRY(tv_get(h, p + "bias_hh" + s + "_reverse", {3 * H}, &h->hh_b[1][l]));
+    if (h->ih_w[l] == nullptr) {
+      DEXB_CUDA_OK(cudaMalloc(&h->ih_w[l], (size_t)6 * H * C * sizeof(float)));
+      DEXB_CUDA_OK(cudaMalloc(&h->ih_b[l], (size_t)6 * H * sizeof(float)));
+    }
+    k_cat2<<<cdiv(6L * H * C, 256), 256, 0, st>>>(wf, wb, h->ih_w[l], 3L * H * C, 3L * H * C);
+    k_cat2<<<cdiv(6L * H, 256), 256, 0, st>>>(bf, bb, h->ih_b[l], 3L * H, 3L * H);
+    TvConv& c = h->ih[l];
+    c.ci = C; c.co = 6 * H; c.K = tv_pad64(C); c.taps = 1;
+    if (c.w == nullptr) DEXB_CUDA_OK(cudaMalloc(&c.w, (size_t)c.co * 2 * c.K * sizeof(bf16)));
+    k_tv_pack_w<<<cdiv((long)c.co * c.K, 256), 256, 0, st>>>(h->ih_w[l], c.w, c.co, C, c.K, 1);
+    c.bias = h->ih_b[l];
+    DEXB_CUDA_OK(cudaGetLastError());
+  }
+  DEXB_TRY(tv_basic_conv(h, "out_conv", C, h->c_out, 1, &h->out_conv, st));
+  DEXB_TRY(tv_pack_conv(h, "proj.conv_1.weight", "proj.conv_1.bias", h->c_out, h->c_g, 3, &h->p_conv1, st));
+  DEXB_TRY(tv_get(h, "proj.norm_1.gamma", {h->c_g}, &h->p_conv1.ln_g));
+  DEXB_TRY(tv_get(h, "proj.norm_1.beta", {h->c_g}, &h->p_conv1.ln_b));
+  DEXB_TRY(tv_pack_conv(h, "proj.conv_2.weight", "proj.conv_2.bias", h->c_g, h->c_g, 3, &h->p_conv2, st));
+  DEXB_TRY(tv_get(h, "proj.norm_2.gamma", {h->c_g}, &h->p_conv2.ln_g));
+  DEXB_TRY(tv_get(h, "proj.norm_2.beta", {h->c_g}, &h->p_conv2.ln_b));
+  DEXB_TRY(tv_pack_conv(h, "proj.proj.weight", "proj.proj.bias", h->c_g, h->c_g, 1, &h->p_proj, st));
+  DEXB_CUDA_OK(cudaStreamSynchronize(st));
+  lf0_release_plan(h);
+  h->finalized = true;
+  return 0;
+}
+
+int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, int B, int T, float* lf0_enc_dev, float* lf0_dec_dev,
+                     void* stream) {
+  DEXB_CHECK(h != nullptr && lf0_dev != nullptr && mask_dev != nullptr && lf0_enc_dev != nullptr && lf0_dec_dev != nullptr,
+             "dexb_lf0_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_lf0_forward: call dexb_lf0_finalize_weights first");
+  DEXB_CHECK(B >= 1 && T >= 1, "dexb_lf0_forward: B = %d, T = %d", B, T);
+  DEXB_CHECK(h->c_out == h->c_h, "dexb_lf0_forward: out_conv must keep the channel count of the GRU (c_out == c_h)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(lf0_plan(h, B, T));
+  const long rows = (long)B * T;
+  h->launches = 0;
+  k_lf0_in<<<cdiv(rows, 8), 256, 0, st>>>(lf0_dev, mask_dev, h->in_w, h->in_g, h->in_b, h->xs, rows, h->c_h, T);
+  h->launches += 1;
+  for (int l = 0; l < h->L; ++l) {
+    bf16* dst = (l & 1) ? h->xs : h->hs;
+    DEXB_TRY(gemm_launch(h->ih[l].plan, h->ih[l].plan.p, 0, st));
+    k_gru_rec<96><<<dim3(B, 2), 3 * 96, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
+                                                 l == h->L - 1 ? mask_dev : nullptr, dst, T);
+    h->launches += 2;
+  }
+  bf16* gru_out = (h->L & 1) ? h->hs : h->xs;
+  bf16* other = (h->L & 1) ? h->xs : h->hs;
+  // lf0_enc = out_conv(x * mask) * mask
+  DEXB_TRY(gemm_launch(h->out_conv.plan, h->out_conv.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->out_conv, 1, 1, 1e-5f);
+    p.mask = mask_dev; p.os = other; p.ocm = lf0_enc_dev;
+    tv_launch_post(p, st);
+  }
+  // lf0_dec = proj(lf0_enc, mask)
+  DEXB_TRY(gemm_launch(h->p_conv1.plan, h->p_conv1.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_conv1, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.os = gru_out;
+    tv_launch_post(p, st);
+  }
+  DEXB_TRY(gemm_launch(h->p_conv2.plan, h->p_conv2.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_conv2, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.os = other;
+    tv_launch_post(p, st);
+  }
+  DEXB_TRY(gemm_launch(h->p_proj.plan, h->p_proj.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->p_proj, 0, 0, 0.f);
+    p.mask = mask_dev; p.ocm = lf0_dec_dev;
+    tv_launch_post(p, st);
+  }
+  h->launches += 8;
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+long dexb_lf0_last_launch_count(const dexb_lf0* h) { return h != nullptr ? h->launches : 0; }
+
+int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const float* sty_mask_dev, int Ts, const float* lf0_enc_dev,
+                    const float* lf0_dec_dev, const float* lf0_mask_dev, int Tl, int B, int C, const float* conv_sty_w_dev,
+                    const float* conv_sty_b_dev, int N, float* lf0_mean_scratch_dev, float* sty_enc_dev, float* sty_dev, void* stream) {
+  DEXB_CHECK(z_dec_dev != nullptr && lf0_dec_dev != nullptr && lf0_mask_dev != nullptr && conv_sty_w_dev != nullptr &&
+                 conv_sty_b_dev != nullptr && lf0_mean_scratch_dev != nullptr && sty_dev != nullptr,
+             "dexb_style_fuse: null argument");
+  DEXB_CHECK(B >= 1 && Ts >= 1 && Tl >= 1 && C >= 2 && C % 2 == 0 && C <= 1024 && N >= 1, "dexb_style_fuse: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sty_enc_dev != nullptr) {                 // text-encoder conditioning (tts.py:45-46): both masked time means added
+    DEXB_CHECK(z_before_dev != nullptr && sty_mask_dev != nullptr && lf0_enc_dev != nullptr, "dexb_style_fuse: sty_enc needs its inputs");
+    k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(z_before_dev, sty_mask_dev, sty_enc_dev, C, Ts, 0);
+    k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(lf0_enc_dev, lf0_mask_dev, sty_enc_dev, C, Tl, 1);
+  }
+  k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(lf0_dec_dev, lf0_mask_dev, lf0_mean_scratch_dev, C, Tl, 0);
+  k_conv_sty<<<dim3(cdiv(Ts, 32), B), 256, (size_t)C * 33 * sizeof(float), st>>>(z_dec_dev, lf0_mean_scratch_dev, conv_sty_w_dev,
+                                                                                 conv_sty_b_dev, sty_dev, C, N, Ts);
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 }  // extern "C"

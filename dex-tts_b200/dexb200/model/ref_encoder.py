@@ -3,6 +3,8 @@
 Replace (same constructor arguments, same ``forward`` signature and return value, same ``state_dict`` keys):
     DEX-TTS/model/ref_encoder.py:83-107    class TIVEncoder  (attached as ``DeXTTS.tiv_encoder``, DEX-TTS/model/tts.py:28,50)
     DEX-TTS/model/ref_encoder.py:109-140   class TVEncoder   (attached as ``DeXTTS.tv_encoder``,  DEX-TTS/model/tts.py:26,43)
+    DEX-TTS/model/ref_encoder.py:36-56     class LF0Encoder  (attached as ``DeXTTS.lf0_encoder``, DEX-TTS/model/tts.py:27,42)
+    DEX-TTS/model/tts.py:45-49             the style fusion lines of ``DeXTTS.forward`` -> ``style_fusion(conv_sty, ...)``
 
 This is the once-per-utterance stage right in front of the reverse-diffusion loop: the TIV encoder's six
 skip tensors are the ``ref`` argument of ``Diffusion.forward``, the TV encoder's ``z_dec`` becomes its ``sty`` (tts.py:48-49).  Parameters and BatchNorm buffers are registered under the reference's names
@@ -15,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .. import lib as _lib
-from ..synth import tiv_manifest, tv_manifest
+from ..synth import lf0_manifest, tiv_manifest, tv_manifest
 from .diffusion import _Node
 
 
@@ -162,6 +164,8 @@ def _register(root, manifest):
             mod.register_buffer(parts[-1], torch.ones(shape))
         elif kind == "code":                                # VQEmbeddingEMA: U(-1/n_emb, 1/n_emb) buffers (ref_encoder.py:192-197)
             mod.register_buffer(parts[-1], torch.empty(shape).uniform_(-1.0 / shape[0], 1.0 / shape[0]))
+        elif kind == "gru":                                 # nn.GRU: U(-1/sqrt(hidden), 1/sqrt(hidden)), hidden = weight_hh.shape[1]
+            mod.register_parameter(parts[-1], nn.Parameter(torch.empty(shape).uniform_(-1.0, 1.0) / (shape[0] // 3) ** 0.5))
         elif kind == "ema_n":
             mod.register_buffer(parts[-1], torch.zeros(shape))
         else:
@@ -270,3 +274,122 @@ class TVEncoder(nn.Module):
         if x.dim() == 4:
             x = x.squeeze(1)                                # ref_encoder.py:128
         return self.cuda_engine().forward(x, mask)
+
+
+class LF0EncoderEngine:
+    """ctypes driver of the ``dexb_lf0_*`` entry points (include/dexb200.h)."""
+
+    def __init__(self, c_h, c_out, c_out_g, num_layer):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dexb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.dims = (int(c_h), int(c_out), int(c_out_g), int(num_layer))
+        self.L = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self.L.dexb_lf0_create(*self.dims, ctypes.byref(h)), "dexb_lf0_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.dexb_lf0_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd, prefix="lf0_encoder."):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        for name, shape, _ in lf0_manifest(*self.dims):
+            key = prefix + name
+            if key not in sd:
+                raise RuntimeError(f"state dict is missing '{key}'")
+            t = sd[key].detach().to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != tuple(shape):
+                raise RuntimeError(f"'{key}' has shape {tuple(t.shape)}, expected {tuple(shape)}")
+            shp = (ctypes.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.L.dexb_lf0_load_weight(self.h, name.encode(), ctypes.c_void_p(t.data_ptr()), shp, t.dim()),
+                       f"dexb_lf0_load_weight({name})")
+        torch.cuda.synchronize()
+        _lib.check(self.L.dexb_lf0_finalize_weights(self.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "dexb_lf0_finalize_weights")
+
+    def forward(self, lf0, mask):
+        """lf0 (B, T) CUDA fp32, mask (B,1,T) or (B,T) -> (lf0_enc (B,c_out,T), lf0_dec (B,c_out_g,T))."""
+        B, T = lf0.shape
+        lf0 = lf0.detach().float().contiguous()
+        m = mask.detach().float().reshape(B, T).contiguous()
+        enc = torch.empty(B, self.dims[1], T, device=lf0.device, dtype=torch.float32)
+        dec = torch.empty(B, self.dims[2], T, device=lf0.device, dtype=torch.float32)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(self.L.dexb_lf0_forward(self.h, p(lf0), p(m), B, T, p(enc), p(dec),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dexb_lf0_forward")
+        self._keep = (lf0, m)
+        return enc, dec
+
+    @property
+    def launches(self):
+        return int(self.L.dexb_lf0_last_launch_count(self.h))
+
+
+class LF0Encoder(nn.Module):
+    """DEX-TTS/model/ref_encoder.py:36-56."""
+
+    def __init__(self, c_h, c_out, c_out_g, num_layer, c_in=1):
+        super().__init__()
+        if c_in != 1:
+            raise NotImplementedError("the CUDA LF0 encoder implements the one-channel contour input of the shipped configs")
+        self.dims = (int(c_h), int(c_out), int(c_out_g), int(num_layer))
+        _register(self, lf0_manifest(*self.dims))
+        self._engine = None
+        self._sig = None
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def cuda_engine(self):
+        sig = self._signature()
+        if self._engine is None:
+            self._engine = LF0EncoderEngine(*self.dims)
+            self._sig = None
+        if sig != self._sig:
+            self._engine.load_state_dict(self.state_dict(), prefix="")
+            self._sig = sig
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, lf0, mask):
+        if not lf0.is_cuda:
+            raise RuntimeError("dexb200.LF0Encoder runs on CUDA (sm_100a) only; move the model and inputs to the GPU")
+        return self.cuda_engine().forward(lf0, mask)
+
+
+@torch.no_grad()
+def style_fusion(conv_sty, sty_enc, sty_dec, sty_mask, lf0_enc, lf0_dec, lf0_mask, want_sty_enc=True):
+    """The four fusion lines of ``DeXTTS.forward`` (DEX-TTS/model/tts.py:45-49) as one C-ABI call (``dexb_style_fuse``):
+
+        sty_enc = (sty_enc.sum(-1) / sty_mask.sum(-1)) + (lf0_enc.sum(-1) / lf0_mask.sum(-1));  sty_enc = sty_enc.squeeze(1)
+        sty_dec = sty_dec + (lf0_dec.sum(-1) / lf0_mask.sum(-1)).unsqueeze(-1);                 sty_dec = self.conv_sty(sty_dec)
+
+    ``conv_sty`` is the module's own ``nn.Conv1d(c_out_g, 2 * dim, 1)`` (tts.py:31; only its weight / bias tensors are read).
+    -> (sty_enc (B, C) or None, sty_dec (B, 2*dim, Ts) = the ``sty`` argument of the decoder)."""
+    if not sty_dec.is_cuda:
+        raise RuntimeError("dexb200.style_fusion runs on CUDA (sm_100a) only")
+    L = _lib.load()
+    f = lambda t: t.detach().float().contiguous()
+    B, C, Ts = sty_dec.shape
+    Tl = lf0_dec.shape[-1]
+    w, b = f(conv_sty.weight), f(conv_sty.bias)
+    N = w.shape[0]
+    if tuple(w.shape) != (N, C, 1):
+        raise RuntimeError(f"conv_sty.weight has shape {tuple(w.shape)}, expected ({N}, {C}, 1)")
+    z_before, z_dec, le, ld = f(sty_enc), f(sty_dec), f(lf0_enc), f(lf0_dec)
+    sm, lm = f(sty_mask).reshape(B, Ts), f(lf0_mask).reshape(B, Tl)
+    scratch = torch.empty(B, C, device=z_dec.device, dtype=torch.float32)
+    out_enc = torch.empty(B, C, device=z_dec.device, dtype=torch.float32) if want_sty_enc else None
+    sty = torch.empty(B, N, Ts, device=z_dec.device, dtype=torch.float32)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(L.dexb_style_fuse(p(z_before), p(z_dec), p(sm), Ts, p(le), p(ld), p(lm), Tl, B, C, p(w), p(b), N, p(scratch),
+                                 p(out_enc), p(sty), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dexb_style_fuse")
+    return out_enc, sty

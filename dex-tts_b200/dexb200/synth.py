@@ -200,3 +200,63 @@ def synth_tv_weights(c_in=80, c_out=192, c_out_g=192, num_layer=6, c_h=128, n_em
             t = torch.tensor(1000, dtype=torch.long)
         out[prefix + name] = t if kind == "bn_n" else t.float().contiguous()
     return out
+
+
+def lf0_manifest(c_h=192, c_out=192, c_out_g=192, num_layer=2, c_in=1):
+    """[(name relative to ``lf0_encoder.``, shape, kind)] -- the ``state_dict`` of the reference LF0Encoder
+    (DEX-TTS/model/ref_encoder.py:36-56: BasicConv, nn.GRU(bidirectional), BasicConv, Projection), in its own order."""
+    hid = c_h // 2
+    out = [("in_conv.conv.weight", (c_h, c_in, 3), "conv"), ("in_conv.ln.weight", (c_h,), "bn_w"), ("in_conv.ln.bias", (c_h,), "bn_b")]
+    for l in range(num_layer):
+        for sfx in ("", "_reverse"):
+            out.extend([(f"rnn_layer.weight_ih_l{l}{sfx}", (3 * hid, c_h), "gru"), (f"rnn_layer.weight_hh_l{l}{sfx}", (3 * hid, hid), "gru"),
+                        (f"rnn_layer.bias_ih_l{l}{sfx}", (3 * hid,), "gru"), (f"rnn_layer.bias_hh_l{l}{sfx}", (3 * hid,), "gru")])
+    out.extend([("out_conv.conv.weight", (c_out, c_h, 3), "conv"), ("out_conv.ln.weight", (c_out,), "bn_w"),
+                ("out_conv.ln.bias", (c_out,), "bn_b")])
+    out.extend([("proj.conv_1.weight", (c_out_g, c_out, 3), "conv"), ("proj.conv_1.bias", (c_out_g,), "bias"),
+                ("proj.norm_1.gamma", (c_out_g,), "bn_w"), ("proj.norm_1.beta", (c_out_g,), "bn_b"),
+                ("proj.conv_2.weight", (c_out_g, c_out_g, 3), "conv"), ("proj.conv_2.bias", (c_out_g,), "bias"),
+                ("proj.norm_2.gamma", (c_out_g,), "bn_w"), ("proj.norm_2.beta", (c_out_g,), "bn_b"),
+                ("proj.proj.weight", (c_out_g, c_out_g, 1), "conv"), ("proj.proj.bias", (c_out_g,), "bias")])
+    return out
+
+
+def synth_lf0_weights(c_h=192, c_out=192, c_out_g=192, num_layer=2, c_in=1, seed=100, prefix="lf0_encoder."):
+    """Seeded LF0-encoder tensors (GRU tensors: nn.GRU's U(-1/sqrt(hidden), 1/sqrt(hidden)) init, slightly widened)."""
+    out = {}
+    hid = c_h // 2
+    for name, shape, kind in lf0_manifest(c_h, c_out, c_out_g, num_layer, c_in):
+        g = _gen(seed, "lf0_encoder." + name)
+        if kind == "conv":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 1.7 / (shape[1] * shape[2]) ** 0.5
+        elif kind == "gru":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 1.5 / hid ** 0.5
+        elif kind == "bias":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_w":
+            t = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        else:
+            t = 0.2 * torch.randn(shape, generator=g)
+        out[prefix + name] = t.float().contiguous()
+    return out
+
+
+def synth_lf0(B, T, seed=55, ragged=False):
+    """Seeded stand-in for a normalised log-F0 contour (B, T) with unvoiced (zero) stretches, lengths and mask (B,1,T)
+    (lf0 ~ N(0,1) * (rand > 0.3))."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    lf0 = torch.randn(B, T, generator=g) * (torch.rand(B, T, generator=g) > 0.3).float()
+    if ragged:
+        lens = ((torch.rand(B, generator=g) * 0.4 + 0.6) * T).long().clamp(1, T)
+        lens[0] = T
+    else:
+        lens = torch.full((B,), T, dtype=torch.long)
+    mask = (torch.arange(T)[None, :] < lens[:, None]).float().unsqueeze(1)
+    return dict(lf0=lf0, lf0_lengths=lens, mask=mask)
+
+
+def synth_conv_sty_weights(c_in=192, c_out=128, seed=100):
+    """Seeded tensors of DeXTTS.conv_sty = nn.Conv1d(tv_encoder.c_out_g, 2 * decoder.dim, 1) (DEX-TTS/model/tts.py:31)."""
+    w = (torch.rand(c_out, c_in, 1, generator=_gen(seed, "conv_sty.weight")) * 2 - 1) * 1.7 / c_in ** 0.5
+    return {"conv_sty.weight": w.contiguous(), "conv_sty.bias": 0.1 * torch.randn(c_out, generator=_gen(seed, "conv_sty.bias"))}

@@ -176,6 +176,35 @@ int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int
                     float* vq_loss_dev, int32_t* idx_dev, void* stream);
 long dexb_tv_last_launch_count(const dexb_tv* h);
 
+/* ---- LF0 encoder and style fusion (last pieces) ------------------------------------------------------
+ * replaces: LF0Encoder (DEX-TTS/model/ref_encoder.py:36-56; attached as DeXTTS.lf0_encoder, DEX-TTS/model/tts.py:27,42) in eval
+ * mode: in_conv (1 -> c_h) -> bidirectional nn.GRU(c_h, c_h/2, num_layer) over all T frames -> out_conv -> Projection. */
+typedef struct dexb_lf0 dexb_lf0;
+
+/* replaces: LF0Encoder.__init__(c_h, c_out, c_out_g, num_layer, c_in=1) (ref_encoder.py:37-44).  c_h must be 192 (the GRU
+ * recurrence kernel is instantiated for 96 hidden units per direction) and c_out == c_h. */
+int dexb_lf0_create(int c_h, int c_out, int c_out_g, int num_layer, dexb_lf0** out);
+void dexb_lf0_destroy(dexb_lf0* h);
+/* `name` relative to `lf0_encoder.` ("in_conv.conv.weight", "rnn_layer.weight_hh_l1_reverse", "proj.norm_2.beta", ...). */
+int dexb_lf0_load_weight(dexb_lf0* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_lf0_finalize_weights(dexb_lf0* h, void* stream);
+/* replaces: LF0Encoder.forward(lf0, mask) (ref_encoder.py:46-56).  lf0_dev (B, T) fp32, mask_dev (B, T) in {0,1} ->
+ * lf0_enc_dev (B, c_out, T), lf0_dec_dev (B, c_out_g, T).  Allocation behaviour as dexb_tiv_forward. */
+int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, int B, int T, float* lf0_enc_dev, float* lf0_dec_dev,
+                     void* stream);
+long dexb_lf0_last_launch_count(const dexb_lf0* h);
+
+/* replaces: the style fusion of DeXTTS.forward (DEX-TTS/model/tts.py:45-49), stateless:
+ *   sty_enc = sum_t z_before / sum_t sty_mask + sum_t lf0_enc / sum_t lf0_mask                    (B, C)      [optional]
+ *   sty     = conv_sty(z_dec + (sum_t lf0_dec / sum_t lf0_mask)[:, :, None])                      (B, N, Ts)  = the loop's `sty`
+ * z_before_dev / z_dec_dev (B, C, Ts) and sty_mask_dev (B, Ts) come from dexb_tv_forward, lf0_enc_dev / lf0_dec_dev (B, C, Tl)
+ * and lf0_mask_dev (B, Tl) from dexb_lf0_forward; conv_sty_w_dev (N, C, 1), conv_sty_b_dev (N) are DeXTTS.conv_sty's tensors
+ * (tts.py:31).  lf0_mean_scratch_dev: (B, C) floats of caller-owned scratch.  sty_enc_dev may be NULL (then z_before_dev,
+ * sty_mask_dev and lf0_enc_dev are not read).  fp32 on the CUDA cores; never allocates or synchronises. */
+int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const float* sty_mask_dev, int Ts, const float* lf0_enc_dev,
+                    const float* lf0_dec_dev, const float* lf0_mask_dev, int Tl, int B, int C, const float* conv_sty_w_dev,
+                    const float* conv_sty_b_dev, int N, float* lf0_mean_scratch_dev, float* sty_enc_dev, float* sty_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

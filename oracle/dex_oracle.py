@@ -16,6 +16,8 @@ reference's own ``state_dict`` names) of:
     TIVEncoder.forward (eval)          DEX-TTS/model/ref_encoder.py:83-107  (pre-loop stage, SURVEY.md §8f rank 1;
                                        pinned by tests/golden/tiv_*.npz from oracle/make_golden_tiv.py)
     TVEncoder.forward (eval)           DEX-TTS/model/ref_encoder.py:109-140 (same stage; tests/golden/tv_*.npz)
+    LF0Encoder.forward (eval)          DEX-TTS/model/ref_encoder.py:36-56   (same stage; tests/golden/lf0_*.npz)
+    style fusion + conv_sty            DEX-TTS/model/tts.py:45-49           (same fixtures)
 
 Third-party arithmetic on the path: ``timm`` (un-pinned, DEX-TTS/requirements.txt:16) ``Attention`` and ``Mlp``
 (call sites DEX-TTS/model/dit.py:270,274); their published algorithm is restated in ``_dit_block``.
@@ -453,6 +455,58 @@ def tv_encoder(w, sty, mask, num_layer=6, commit_w=0.25, prefix="tv_encoder", re
     if return_indices:
         return z_before, z_dec, loss, idx
     return z_before, z_dec, loss
+
+
+# ----------------------------------------------------------------------------------------------
+# pre-loop stage: LF0 encoder and the style fusion of DeXTTS.forward
+# ----------------------------------------------------------------------------------------------
+
+def _gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse):
+    """One direction of one nn.GRU layer (PyTorch gate order r, z, n; h0 = 0).  x (B,T,I) -> (B,T,H)."""
+    B, T, _ = x.shape
+    H = w_hh.shape[1]
+    gi = x @ w_ih.t() + b_ih                                  # (B,T,3H)
+    h = x.new_zeros(B, H)
+    out = x.new_zeros(B, T, H)
+    for t in (range(T - 1, -1, -1) if reverse else range(T)):
+        gh = h @ w_hh.t() + b_hh
+        r = torch.sigmoid(gi[:, t, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, t, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, t, 2 * H:] + r * gh[:, 2 * H:])
+        h = (1 - z) * n + z * h
+        out[:, t] = h
+    return out
+
+
+def _bigru(w, p, x, num_layer):
+    """nn.GRU(c_h, c_h // 2, num_layer, batch_first=True, bidirectional=True) in eval mode, DEX-TTS/model/ref_encoder.py:41,50:
+    no packing -- both directions run over all T frames, padding included."""
+    for l in range(num_layer):
+        outs = []
+        for sfx, rev in (("", False), ("_reverse", True)):
+            outs.append(_gru_direction(x, w[f"{p}.weight_ih_l{l}{sfx}"], w[f"{p}.weight_hh_l{l}{sfx}"],
+                                       w[f"{p}.bias_ih_l{l}{sfx}"], w[f"{p}.bias_hh_l{l}{sfx}"], rev))
+        x = torch.cat(outs, dim=-1)
+    return x
+
+
+def lf0_encoder(w, lf0, mask, num_layer=2, prefix="lf0_encoder"):
+    """LF0Encoder.forward(lf0, mask), DEX-TTS/model/ref_encoder.py:46-56 (eval).  lf0 (B,T), mask (B,1,T)
+    -> (lf0_enc (B,c_out,T), lf0_dec (B,c_out_g,T))."""
+    x = lf0.unsqueeze(1)
+    x = _basic_conv_ln(w, prefix + ".in_conv", x * mask) * mask                                       # :49
+    x = _bigru(w, prefix + ".rnn_layer", x.transpose(1, 2), num_layer)                               # :50
+    x = _basic_conv_ln(w, prefix + ".out_conv", x.transpose(1, 2) * mask) * mask                     # :51
+    return x, _projection(w, prefix + ".proj", x, mask)                                              # :53-54
+
+
+def style_fusion(w, sty_enc_tv, sty_dec_tv, lf0_enc, lf0_dec, sty_mask, lf0_mask):
+    """DeXTTS.forward, DEX-TTS/model/tts.py:45-49: masked time means of the LF0 branch added to the TV branch, then conv_sty.
+    -> (sty_enc (B,c_out) for the text encoder, sty_dec (B,2*dim,Ts) = the loop's `sty`)."""
+    sty_enc = (sty_enc_tv.sum(dim=-1) / sty_mask.sum(dim=-1)) + (lf0_enc.sum(dim=-1) / lf0_mask.sum(dim=-1))
+    sty_dec = sty_dec_tv + (lf0_dec.sum(dim=-1) / lf0_mask.sum(dim=-1)).unsqueeze(-1)
+    sty_dec = F.conv1d(sty_dec, w["conv_sty.weight"], w["conv_sty.bias"])
+    return sty_enc, sty_dec
 
 
 def decoder_weights(state_dict, dtype=torch.float32):
