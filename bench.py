@@ -199,29 +199,39 @@ def main():
         except Exception:
             fb = torch.rand(80, 513) * 0.01
         fb_d = dev(fb)
-        # ... and the reference-speech encoders on that mel: the TIV encoder's six skip tensors are what the loop consumes as
-        # `ref_skips` in this workload; the TV encoder runs too (its z_dec still needs the LF0 encoder + conv_sty of the reference to
-        # become `sty`, so `sty` stays synthetic)
-        from dexb200.model import TIVEncoder, TVEncoder
-        from dexb200.synth import synth_tiv_weights, synth_tv_weights
+        # ... and the whole style stage of DeXTTS.forward (tts.py:42-50) on that mel: TIV encoder -> the loop's `ref_skips`;
+        # TV encoder + LF0 encoder (synthetic log-F0 contour: pitch extraction is CPU pre-processing upstream) -> style fusion +
+        # conv_sty -> the loop's `sty`
+        from dexb200.model import LF0Encoder, TIVEncoder, TVEncoder, style_fusion
+        from dexb200.synth import synth_conv_sty_weights, synth_lf0, synth_lf0_weights, synth_tiv_weights, synth_tv_weights
         tiv = TIVEncoder(c_in=80, c_out=64, num_layer=6, c_h=128)
         tiv.load_state_dict(synth_tiv_weights(prefix=""), strict=True)
         tiv = tiv.cuda().eval()
         tv = TVEncoder(c_in=80, c_out=192, c_out_g=192, num_layer=6, c_h=128, n_emb=512, commit_w=0.25)
         tv.load_state_dict(synth_tv_weights(prefix=""), strict=True)
         tv = tv.cuda().eval()
-        ref_mask_d = torch.ones(B, 1, 66150 // 256 + 1, device="cuda")
+        lf0e = LF0Encoder(c_h=192, c_out=192, c_out_g=192, num_layer=2, c_in=1)
+        lf0e.load_state_dict(synth_lf0_weights(prefix=""), strict=True)
+        lf0e = lf0e.cuda().eval()
+        conv_sty = torch.nn.Conv1d(192, 128, 1, 1)
+        cw = synth_conv_sty_weights()
+        conv_sty.load_state_dict({"weight": cw["conv_sty.weight"], "bias": cw["conv_sty.bias"]})
+        conv_sty = conv_sty.cuda().eval()
+        n_ref = 66150 // 256 + 1
+        ref_mask_d = torch.ones(B, 1, n_ref, device="cuda")
+        lf0_d = dev(synth_lf0(B, n_ref, seed=77 + rank)["lf0"])
         config["stft"] = ("every bench step runs dexb_stft_mel on (B, 66150) synthetic audio -> (B, 80, 259) log-mel -> dexb_tiv_forward "
-                          "(its six skips are the loop's ref_skips) and dexb_tv_forward (z_dec; sty stays synthetic: LF0 encoder + "
-                          "conv_sty are not built)")
+                          "(ref_skips), dexb_tv_forward + dexb_lf0_forward (synthetic log-F0) + dexb_style_fuse (sty) -> the loop")
 
     def one_pass():
         cond = cond_d
         if audio_d is not None:
             mel = stft_mel(audio_d, win_d, fb_d)
             _, skips = tiv(mel, ref_mask_d)
-            tv(mel, ref_mask_d)
-            cond = dict(cond_d, ref_skips=skips)
+            z_before, z_dec, _ = tv(mel, ref_mask_d)
+            lf0_enc, lf0_dec = lf0e(lf0_d, ref_mask_d)
+            _, sty = style_fusion(conv_sty, z_before, z_dec, ref_mask_d, lf0_enc, lf0_dec, ref_mask_d, want_sty_enc=False)
+            cond = dict(cond_d, ref_skips=skips, sty=sty)
         y = eng.sample(x0_d, mask_d, mu_d, n_steps, cond=cond)
         if world > 1:
             dist.all_gather_into_tensor(gathered, y)        # the path's only collective: finished mels (SURVEY.md 8e,
@@ -254,8 +264,8 @@ def main():
     ms_per = ms / args.steps
     value = world * B * T / (ms_per * 1e-3)
     launches = eng.launches * args.steps
-    if audio_d is not None:                               # C3: + the STFT kernel and the two encoders of every step
-        launches += (1 + tiv.cuda_engine().launches + tv.cuda_engine().launches) * args.steps
+    if audio_d is not None:                               # C3: + the STFT kernel, the three encoders and the fusion of every step
+        launches += (1 + tiv.cuda_engine().launches + tv.cuda_engine().launches + lf0e.cuda_engine().launches + 2) * args.steps
 
     # ---- e2e: host buffers in, host mel out, through the host entry point (pinned memory)
     pin = lambda t: t.contiguous().pin_memory()

@@ -12,7 +12,7 @@ from dexb200.manifest import DecoderCfg
 from dexb200.synth import synth_decoder_weights, synth_inputs
 from parity import per_bin_violation, tensor_rel_err
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("stft_", "tiv_", "tv_", "lf0_")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("dex_", "gedex_")))
 
 
 def load_case(path):
