@@ -18,21 +18,24 @@
 
 namespace dexb {
 
-// one warp per utterance; lane 0 walks the tokens in order (same fp32 addition order as torch.cumsum on the CPU)
+// one thread per utterance walks the tokens in order (same fp32 addition order as torch.cumsum on the CPU)
 __global__ void k_align_len(const float* __restrict__ logw, const float* __restrict__ x_mask, float length_scale,
                             float* __restrict__ cum, long long* __restrict__ y_len, int B, int Tx) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float c = 0.f;
   for (int i = 0; i < Tx; ++i) {
-    const float w = expf(logw[(long)b * Tx + i]) * x_mask[(long)b * Tx + i];
-    c += ceilf(w) * length_scale;
+    const float w = __fmul_rn(expf(logw[(long)b * Tx + i]), x_mask[(long)b * Tx + i]);
+    c = __fadd_rn(c, __fmul_rn(ceilf(w), length_scale));     // separate mul and add (no fma contraction), as the reference's two ops
     cum[(long)b * Tx + i] = c;
   }
   y_len[b] = (long long)fmaxf(c, 1.f);                       // clamp_min(sum, 1).long(): truncation
 }
 
-// one thread per (utterance, output frame): token i with cum[i-1] <= t < cum[i]
+// one thread per (utterance, output frame, group of ALIGN_FG features): token i with cum[i-1] <= t < cum[i].  The feature groups
+// (blockIdx.y) put B*Ty/256 * F/8 CTAs on the machine (160 at B = 8, Ty = 512, F = 80: one wave of the 148 SMs) instead of 16;
+// each repeats the 9-step search in the L1-resident cum row, group 0 also writes the alignment column and the frame mask.
+constexpr int ALIGN_FG = 8;
 __global__ void k_align_expand(const float* __restrict__ cum, const float* __restrict__ x_mask, const long long* __restrict__ y_len,
                                const float* __restrict__ mu_x, float* __restrict__ attn, float* __restrict__ y_mask,
                                float* __restrict__ mu_y, int B, int Tx, int F, int Ty) {
@@ -40,7 +43,6 @@ __global__ void k_align_expand(const float* __restrict__ cum, const float* __res
   if (idx >= (long)B * Ty) return;
   const int b = (int)(idx / Ty), t = (int)(idx % Ty);
   const float ym = (long long)t < y_len[b] ? 1.f : 0.f;
-  y_mask[idx] = ym;
   // first i with t < cum[i] (cum is non-decreasing): binary search
   const float* cb = cum + (long)b * Tx;
   const float ft = (float)t;
@@ -50,8 +52,12 @@ __global__ void k_align_expand(const float* __restrict__ cum, const float* __res
     if (ft < cb[mid]) hi = mid; else lo = mid + 1;
   }
   const float a = lo < Tx ? x_mask[(long)b * Tx + lo] * ym : 0.f;      // path * (x_mask (x) y_mask)
-  if (attn != nullptr && lo < Tx) attn[((long)b * Tx + lo) * Ty + t] = a;   // the rest of the column was zeroed by the caller
-  for (int f = 0; f < F; ++f)
+  if (blockIdx.y == 0) {
+    y_mask[idx] = ym;
+    if (attn != nullptr && lo < Tx) attn[((long)b * Tx + lo) * Ty + t] = a;   // the rest of the column was zeroed by the caller
+  }
+  const int f0 = blockIdx.y * ALIGN_FG, f1 = min(F, f0 + ALIGN_FG);
+  for (int f = f0; f < f1; ++f)                                         // stores coalesced over t; the mu_x column is a broadcast
     mu_y[((long)b * F + f) * Ty + t] = lo < Tx ? a * mu_x[((long)b * F + f) * Tx + lo] : 0.f;
 }
 
@@ -79,10 +85,11 @@ int dexb_align_expand(const float* cum_dev, const float* x_mask_dev, const int64
                       int Tx, int n_feats, int Ty, float* attn_dev, float* y_mask_dev, float* mu_y_dev, void* stream) {
   DEXB_CHECK(cum_dev != nullptr && x_mask_dev != nullptr && y_lengths_dev != nullptr && mu_x_dev != nullptr && y_mask_dev != nullptr &&
                  mu_y_dev != nullptr, "dexb_align_expand: null argument");
-  DEXB_CHECK(B >= 1 && Tx >= 1 && n_feats >= 1 && Ty >= 1, "dexb_align_expand: bad shape");
+  DEXB_CHECK(B >= 1 && Tx >= 1 && n_feats >= 1 && Ty >= 1 && cdiv(n_feats, ALIGN_FG) <= 65535,
+             "dexb_align_expand: B = %d, Tx = %d, n_feats = %d, Ty = %d", B, Tx, n_feats, Ty);
   cudaStream_t st = (cudaStream_t)stream;
   if (attn_dev != nullptr) DEXB_CUDA_OK(cudaMemsetAsync(attn_dev, 0, (size_t)B * Tx * Ty * sizeof(float), st));
-  k_align_expand<<<cdiv((long)B * Ty, 256), 256, 0, st>>>(cum_dev, x_mask_dev, reinterpret_cast<const long long*>(y_lengths_dev), mu_x_dev,
+  k_align_expand<<<dim3(cdiv((long)B * Ty, 256), cdiv(n_feats, ALIGN_FG)), 256, 0, st>>>(cum_dev, x_mask_dev, reinterpret_cast<const long long*>(y_lengths_dev), mu_x_dev,
                                                           attn_dev, y_mask_dev, mu_y_dev, B, Tx, n_feats, Ty);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;

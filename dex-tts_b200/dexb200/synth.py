@@ -260,3 +260,17 @@ def synth_conv_sty_weights(c_in=192, c_out=128, seed=100):
     """Seeded tensors of DeXTTS.conv_sty = nn.Conv1d(tv_encoder.c_out_g, 2 * decoder.dim, 1) (DEX-TTS/model/tts.py:31)."""
     w = (torch.rand(c_out, c_in, 1, generator=_gen(seed, "conv_sty.weight")) * 2 - 1) * 1.7 / c_in ** 0.5
     return {"conv_sty.weight": w.contiguous(), "conv_sty.bias": 0.1 * torch.randn(c_out, generator=_gen(seed, "conv_sty.bias"))}
+
+
+def synth_align_inputs(B, Tx, n_feats=80, seed=61, ragged=False, mean_dur=4.0):
+    """Text-encoder outputs for the duration / alignment glue (DEX-TTS/model/tts.py:52-56): mu_x (B, n_feats, Tx), logw and x_mask
+    (B, 1, Tx).  Durations exp(logw) are drawn as integer + U(0.15, 0.85), so ceil() never sits on a rounding boundary of exp()."""
+    g = _gen(seed, "align")
+    x_lengths = torch.full((B,), Tx, dtype=torch.long)
+    if ragged and B > 1:
+        x_lengths[1:] = torch.randint(max(1, int(0.5 * Tx)), Tx + 1, (B - 1,), generator=g)
+    x_mask = (torch.arange(Tx)[None, :] < x_lengths[:, None]).float().unsqueeze(1)
+    dur = torch.floor(torch.rand(B, 1, Tx, generator=g) * 2 * mean_dur) + 0.15 + 0.7 * torch.rand(B, 1, Tx, generator=g)
+    logw = torch.log(dur) + (1 - x_mask) * torch.randn(B, 1, Tx, generator=g)      # padded tokens carry arbitrary logw
+    mu_x = torch.randn(B, n_feats, Tx, generator=g) * x_mask                       # TextEncoder: mu = proj_m(x) * x_mask
+    return dict(logw=logw, x_mask=x_mask, mu_x=mu_x, x_lengths=x_lengths)

@@ -205,6 +205,27 @@ int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const flo
                     const float* lf0_dec_dev, const float* lf0_mask_dev, int Tl, int B, int C, const float* conv_sty_w_dev,
                     const float* conv_sty_b_dev, int N, float* lf0_mean_scratch_dev, float* sty_enc_dev, float* sty_dev, void* stream);
 
+/* replaces: the duration / alignment glue of DeXTTS.forward between the text encoder and the decoder (DEX-TTS/model/tts.py:55-68,
+ * GeDEX-TTS/model/tts.py:37-50) over model.utils.sequence_mask / generate_path (DEX-TTS/model/utils.py:6-39).  Two calls around
+ * the reference's own host round trip (`int(y_lengths.max())`, tts.py:58), which decides the size of the outputs:
+ *
+ *   dexb_align_lengths:  w_ceil = ceil(exp(logw) * x_mask) * length_scale;  cum = cumsum_i(w_ceil)   (utils.py:30)
+ *                        y_lengths = clamp_min(sum_i w_ceil, 1).long()                               (tts.py:57)
+ *     logw_dev, x_mask_dev (B, Tx) fp32 -> cum_dev (B, Tx) fp32 scratch kept for the second call, y_lengths_dev (B) int64, and a
+ *     copy in y_lengths_host (B int64, pinned or pageable).  SYNCHRONISES the stream (the one host sync of the path, as upstream).
+ *     Additions run in token order without fma contraction (torch.cumsum's CPU order): bit-exact y_lengths whenever the partial
+ *     sums are exact in fp32 -- always for the default length_scale = 1 (integers) and for dyadic scales.
+ *   host:                Ty = fix_len_compatibility(max_b y_lengths)   (utils.py:13-17; an integer loop, stays in the caller)
+ *   dexb_align_expand:   y_mask[b, t] = t < y_lengths[b]                                             (tts.py:62)
+ *                        attn[b, i, t] = (cum[b, i-1] <= t < cum[b, i]) * x_mask[b, i] * y_mask[b, t]   (utils.py:26-39, tts.py:63-64)
+ *                        mu_y[b, f, t] = sum_i attn[b, i, t] * mu_x[b, f, i]   -- one-hot in i, so a gather (tts.py:67-68)
+ *     mu_x_dev (B, n_feats, Tx) -> attn_dev (B, Tx, Ty) or NULL, y_mask_dev (B, Ty), mu_y_dev (B, n_feats, Ty), all fp32.
+ *     Never allocates or synchronises.  HBM-bound: one coalesced pass over the outputs. */
+int dexb_align_lengths(const float* logw_dev, const float* x_mask_dev, int B, int Tx, float length_scale, float* cum_dev,
+                       int64_t* y_lengths_dev, int64_t* y_lengths_host, void* stream);
+int dexb_align_expand(const float* cum_dev, const float* x_mask_dev, const int64_t* y_lengths_dev, const float* mu_x_dev, int B,
+                      int Tx, int n_feats, int Ty, float* attn_dev, float* y_mask_dev, float* mu_y_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@ reference's own ``state_dict`` names) of:
     TVEncoder.forward (eval)           DEX-TTS/model/ref_encoder.py:109-140 (same stage; tests/golden/tv_*.npz)
     LF0Encoder.forward (eval)          DEX-TTS/model/ref_encoder.py:36-56   (same stage; tests/golden/lf0_*.npz)
     style fusion + conv_sty            DEX-TTS/model/tts.py:45-49           (same fixtures)
+    duration / alignment glue          DEX-TTS/model/tts.py:55-68, DEX-TTS/model/utils.py:6-39  (first
+                                       piece; tests/golden/align_*.npz from oracle/make_golden_align.py)
 
 Third-party arithmetic on the path: ``timm`` (un-pinned, DEX-TTS/requirements.txt:16) ``Attention`` and ``Mlp``
 (call sites DEX-TTS/model/dit.py:270,274); their published algorithm is restated in ``_dit_block``.
@@ -507,6 +509,28 @@ def style_fusion(w, sty_enc_tv, sty_dec_tv, lf0_enc, lf0_dec, sty_mask, lf0_mask
     sty_dec = sty_dec_tv + (lf0_dec.sum(dim=-1) / lf0_mask.sum(dim=-1)).unsqueeze(-1)
     sty_dec = F.conv1d(sty_dec, w["conv_sty.weight"], w["conv_sty.bias"])
     return sty_enc, sty_dec
+
+
+def align_durations(logw, x_mask, mu_x, length_scale=1.0):
+    """Duration / alignment glue of DeXTTS.forward, DEX-TTS/model/tts.py:55-68 (GeDEX-TTS/model/tts.py:37-50), with
+    sequence_mask / fix_len_compatibility / generate_path of DEX-TTS/model/utils.py:6-39 written out as index arithmetic
+    (pinned against those functions themselves by tests/golden/align_*.npz, oracle/make_golden_align.py).
+    logw, x_mask (B,1,Tx), mu_x (B,F,Tx) -> (mu_y (B,F,Ty_), y_mask (B,1,Ty_), attn (B,1,Tx,Ty_), y_lengths (B,), y_max_length)."""
+    w_ceil = torch.ceil(torch.exp(logw) * x_mask) * length_scale                                      # tts.py:55-56
+    y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()                                  # :57
+    y_max = int(y_lengths.max())                                                                      # :58
+    Ty = y_max
+    while Ty % 4:                                                                                     # utils.py:13-17
+        Ty += 1
+    t = torch.arange(Ty, dtype=torch.float32)
+    y_mask = (t[None, :] < y_lengths[:, None].float()).float().unsqueeze(1)                           # :62 (lengths < 2^24: exact)
+    cum = torch.cumsum(w_ceil.squeeze(1), 1)                                                          # utils.py:30
+    start = torch.cat([torch.zeros_like(cum[:, :1]), cum[:, :-1]], 1)
+    # generate_path: row i of `t < cum[i]` minus row i-1 (utils.py:34-37)  ==  cum[i-1] <= t < cum[i] for a non-decreasing cum
+    path = ((t[None, None, :] < cum[:, :, None]) & (t[None, None, :] >= start[:, :, None])).float()
+    attn = path * (x_mask.squeeze(1)[:, :, None] * y_mask)                                            # utils.py:38, tts.py:63
+    mu_y = torch.matmul(attn.transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)                   # :67-68
+    return mu_y, y_mask, attn.unsqueeze(1), y_lengths, y_max
 
 
 def decoder_weights(state_dict, dtype=torch.float32):
