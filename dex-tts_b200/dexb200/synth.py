@@ -274,3 +274,78 @@ def synth_align_inputs(B, Tx, n_feats=80, seed=61, ragged=False, mean_dur=4.0):
     logw = torch.log(dur) + (1 - x_mask) * torch.randn(B, 1, Tx, generator=g)      # padded tokens carry arbitrary logw
     mu_x = torch.randn(B, n_feats, Tx, generator=g) * x_mask                       # TextEncoder: mu = proj_m(x) * x_mask
     return dict(logw=logw, x_mask=x_mask, mu_x=mu_x, x_lengths=x_lengths)
+
+
+def text_manifest(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8,
+                  kernel_size=3):
+    """[(name relative to ``encoder.``, shape, kind)] -- the ``state_dict`` of the reference TextEncoder for n_spks <= 1
+    (DEX-TTS/model/text_encoder.py:97-142: Embedding, ConvReluNorm prenet, RetNetModel, proj_m, DurationPredictor), in its order."""
+    C, Fc, Fd = n_channels, filter_channels, filter_channels_dp
+    out = [("emb.weight", (n_vocab, C), "emb")]
+    for i in range(3):                                                               # prenet: kernel 5, 3 layers (:116-117)
+        out.extend([(f"prenet.conv_layers.{i}.weight", (C, C, 5), "conv"), (f"prenet.conv_layers.{i}.bias", (C,), "bias")])
+    for i in range(3):
+        out.extend([(f"prenet.norm_layers.{i}.gamma", (C,), "bn_w"), (f"prenet.norm_layers.{i}.beta", (C,), "bn_b")])
+    out.extend([("prenet.proj.weight", (C, C, 1), "conv"), ("prenet.proj.bias", (C,), "bias")])
+    for l in range(n_layers):                                                        # RetNetDecoderLayer (retention.py:396-513)
+        p = f"encoder.layers.{l}."
+        out.extend([(p + f"retention.{n}_proj.weight", (C, C), "lin") for n in ("q", "k", "v", "g", "out")])
+        out.append((p + "retention_layer_norm.weight", (C,), "bn_w"))
+        out.extend([(p + "ffn.fc1.weight", (Fc, C), "lin"), (p + "ffn.fc2.weight", (C, Fc), "lin"), (p + "ffn.gate.weight", (Fc, C), "lin"),
+                    (p + "final_layer_norm.weight", (C,), "bn_w")])
+        for a in ("adaln_1", "adaln_2"):
+            out.extend([(p + a + ".W_scale.weight", (C, C), "ada"), (p + a + ".W_scale.bias", (C,), "bn_w"),
+                        (p + a + ".W_bias.weight", (C, C), "ada"), (p + a + ".W_bias.bias", (C,), "bn_b")])
+    out.extend([("encoder.layer_norm.weight", (C,), "bn_w"),
+                ("encoder.retnet_rel_pos.angle", (C // n_heads,), "angle"), ("encoder.retnet_rel_pos.decay", (n_heads,), "decay"),
+                ("proj_m.weight", (n_feats, C, 1), "conv"), ("proj_m.bias", (n_feats,), "bias"),
+                ("proj_w.conv_1.weight", (Fd, C, kernel_size), "conv"), ("proj_w.conv_1.bias", (Fd,), "bias"),
+                ("proj_w.norm_1.gamma", (Fd,), "bn_w"), ("proj_w.norm_1.beta", (Fd,), "bn_b"),
+                ("proj_w.conv_2.weight", (Fd, Fd, kernel_size), "conv"), ("proj_w.conv_2.bias", (Fd,), "bias"),
+                ("proj_w.norm_2.gamma", (Fd,), "bn_w"), ("proj_w.norm_2.beta", (Fd,), "bn_b"),
+                ("proj_w.proj.weight", (1, Fd, 1), "conv"), ("proj_w.proj.bias", (1,), "bias")])
+    return out
+
+
+def synth_text_weights(seed=100, prefix="encoder.", **dims):
+    """Seeded TextEncoder tensors.  The tensors the reference zero-initialises (prenet.proj, the AdaLN W_scale / W_bias weights:
+    text_encoder.py:52-53, base.py:174-178) are re-drawn so the style conditioning and the prenet residual branch are live; the two
+    RetNetRelPos buffers keep the reference's closed forms (retention.py:75-86)."""
+    man = text_manifest(**dims)
+    n_heads = [shape[0] for _, shape, kind in man if kind == "decay"][0]
+    out = {}
+    for name, shape, kind in man:
+        g = _gen(seed, "encoder." + name)
+        if kind == "emb":
+            t = torch.randn(shape, generator=g) * shape[1] ** -0.5
+        elif kind == "conv":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 1.7 / (shape[1] * shape[2]) ** 0.5
+        elif kind == "lin":
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 1.7 / shape[1] ** 0.5
+        elif kind == "ada":
+            t = 0.02 * torch.randn(shape, generator=g)
+        elif kind == "bias":
+            t = 0.1 * torch.randn(shape, generator=g)
+        elif kind == "bn_w":
+            t = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif kind == "bn_b":
+            t = 0.2 * torch.randn(shape, generator=g)
+        elif kind == "angle":
+            a = 1.0 / (10000 ** torch.linspace(0, 1, shape[0] // 2))
+            t = a.unsqueeze(-1).repeat(1, 2).flatten()
+        else:
+            t = torch.log(1 - 2 ** (-5 - torch.arange(n_heads, dtype=torch.float)))
+        out[prefix + name] = t.float().contiguous()
+    return out
+
+
+def synth_text(B, Tx, n_vocab=149, c_sty=192, seed=81, ragged=False):
+    """Seeded phoneme ids (B, Tx) in [0, n_vocab), lengths, and the style vector (B, c_sty) the AdaLN layers take
+    (randint(0, 149) of length 128 / 512)."""
+    g = _gen(seed, "text")
+    x = torch.randint(0, n_vocab, (B, Tx), generator=g)
+    x_lengths = torch.full((B,), Tx, dtype=torch.long)
+    if ragged and B > 1:
+        x_lengths[1:] = torch.randint(max(1, int(0.5 * Tx)), Tx + 1, (B - 1,), generator=g)
+    x = x * (torch.arange(Tx)[None, :] < x_lengths[:, None])                       # the collate pads ids with 0
+    return dict(x=x, x_lengths=x_lengths, sty=torch.randn(B, c_sty, generator=g))
