@@ -66,3 +66,23 @@ def test_module_state_dict_matches_manifest(variant):
             m(None, None, None, None, None, None, None, infer=False)
         else:
             m(None, None, None, infer=False)
+
+
+def test_align_entry_points_validate_arguments_before_touching_the_gpu():
+    """dexb_align_*: null pointers and bad shapes come back as -1 with a message in dexb_last_error (no CUDA call is made first,
+    so this runs without a device)."""
+    import ctypes
+    from dexb200 import lib
+    L = lib.load()
+    buf = (ctypes.c_float * 16)()
+    ibuf = (ctypes.c_int64 * 4)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    ip = ctypes.cast(ibuf, ctypes.c_void_p)
+    assert L.dexb_align_lengths(None, p, 1, 4, 1.0, p, ip, ip, None) == -1
+    assert b"null" in L.dexb_last_error()
+    assert L.dexb_align_lengths(p, p, 0, 4, 1.0, p, ip, ip, None) == -1
+    assert L.dexb_align_lengths(p, p, 1, 4, 0.0, p, ip, ip, None) == -1          # length_scale must be positive
+    assert b"length_scale" in L.dexb_last_error()
+    assert L.dexb_align_expand(p, p, ip, None, 1, 4, 80, 8, None, p, p, None) == -1
+    assert L.dexb_align_expand(p, p, ip, p, 1, 4, 80, 0, None, p, p, None) == -1
+    assert b"Ty = 0" in L.dexb_last_error()

@@ -56,6 +56,37 @@ def test_oracle_matches_reference_bit_exactly(path):
         check_alignment_properties(attn, y_mask, y_lengths, inp["x_mask"])
 
 
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_kernel_index_arithmetic_reproduces_reference(path):
+    """The arithmetic of csrc/align.cu replayed in numpy float32, statement by statement (k_align_len: sequential un-fused
+    mul / add, truncation; k_align_expand: binary search for the first cum[i] > t, one-hot store, gather) -- checks the algorithm
+    the kernels implement against the reference fixtures on a box without a GPU.  The kernels themselves: tests/test_align_gpu.py."""
+    f32 = np.float32
+    g, inp, length_scale, attn_ref, y_max, Ty = load_case(path)
+    logw, xm, mu_x = inp["logw"].numpy()[:, 0], inp["x_mask"].numpy()[:, 0], inp["mu_x"].numpy()
+    B, Tx = logw.shape
+    cum, y_len = np.zeros((B, Tx), f32), np.zeros(B, np.int64)
+    for b in range(B):
+        c = f32(0)
+        for i in range(Tx):
+            w = f32(np.exp(logw[b, i])) * xm[b, i]
+            c = f32(c + f32(np.ceil(w) * f32(length_scale)))
+            cum[b, i] = c
+        y_len[b] = int(max(c, f32(1)))
+    assert np.array_equal(y_len, g["y_lengths"])
+    attn, mu_y, y_mask = np.zeros((B, Tx, Ty), f32), np.zeros((B, 80, Ty), f32), np.zeros((B, Ty), f32)
+    for b in range(B):
+        for t in range(Ty):
+            ym = f32(1) if t < y_len[b] else f32(0)
+            y_mask[b, t] = ym
+            lo = int(np.searchsorted(cum[b], f32(t), side="right"))         # first i with t < cum[i]
+            if lo < Tx:
+                a = xm[b, lo] * ym
+                attn[b, lo, t] = a
+                mu_y[b, :, t] = a * mu_x[b, :, lo]
+    assert np.array_equal(attn, attn_ref[:, 0]) and np.array_equal(mu_y, g["mu_y"]) and np.array_equal(y_mask, g["y_mask"][:, 0])
+
+
 def test_oracle_gather_equals_matmul_at_full_size():
     """BASELINE.json's long-form text length (C5: 512 phonemes): `attn^T mu_x` is a gather of mu_x columns."""
     inp = synth_align_inputs(4, 512, seed=9, ragged=True, mean_dur=4.0)
