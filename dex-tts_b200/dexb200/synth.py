@@ -277,9 +277,10 @@ def synth_align_inputs(B, Tx, n_feats=80, seed=61, ragged=False, mean_dur=4.0):
 
 
 def text_manifest(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8,
-                  kernel_size=3):
+                  kernel_size=3, adaln=True):
     """[(name relative to ``encoder.``, shape, kind)] -- the ``state_dict`` of the reference TextEncoder for n_spks <= 1
-    (DEX-TTS/model/text_encoder.py:97-142: Embedding, ConvReluNorm prenet, RetNetModel, proj_m, DurationPredictor), in its order."""
+    (DEX-TTS/model/text_encoder.py:97-142: Embedding, ConvReluNorm prenet, RetNetModel, proj_m, DurationPredictor), in its order.
+    adaln=False: GeDEX-TTS's encoder (no AdaptiveLayerNorm in the RetNet layers)."""
     C, Fc, Fd = n_channels, filter_channels, filter_channels_dp
     out = [("emb.weight", (n_vocab, C), "emb")]
     for i in range(3):                                                               # prenet: kernel 5, 3 layers (:116-117)
@@ -293,7 +294,7 @@ def text_manifest(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024,
         out.append((p + "retention_layer_norm.weight", (C,), "bn_w"))
         out.extend([(p + "ffn.fc1.weight", (Fc, C), "lin"), (p + "ffn.fc2.weight", (C, Fc), "lin"), (p + "ffn.gate.weight", (Fc, C), "lin"),
                     (p + "final_layer_norm.weight", (C,), "bn_w")])
-        for a in ("adaln_1", "adaln_2"):
+        for a in (("adaln_1", "adaln_2") if adaln else ()):
             out.extend([(p + a + ".W_scale.weight", (C, C), "ada"), (p + a + ".W_scale.bias", (C,), "bn_w"),
                         (p + a + ".W_bias.weight", (C, C), "ada"), (p + a + ".W_bias.bias", (C,), "bn_b")])
     out.extend([("encoder.layer_norm.weight", (C,), "bn_w"),

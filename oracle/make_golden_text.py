@@ -19,15 +19,16 @@ from dexb200.synth import synth_text, synth_text_weights              # noqa: E4
 ENC_CFG = dict(n_channels=192, filter_channels=1024, filter_channels_dp=256, n_layers=8, kernel_size=3, p_dropout=0.1, n_heads=2,
                window_size=4, use_softmax=True, use_decay=False)     # DEX-TTS/config/VCTK/base.yaml:51-61
 CASES = [
-    # name,        B, Tx,  ragged, seed
-    ("text_b1",    1, 19,  False,  81),
-    ("text_b2r",   2, 128, True,   82),      # the phoneme length of BASELINE.json's C2 / C3, one padded utterance
+    # name,            variant, B, Tx,  ragged, seed
+    ("text_b1",        "dex",   1, 19,  False,  81),
+    ("text_b2r",       "dex",   2, 128, True,   82),      # the phoneme length of BASELINE.json's C2 / C3, one padded utterance
+    ("text_gedex_b2r", "gedex", 2, 45,  True,   83),      # GeDEX-TTS: the same encoder without AdaLN / style (same yaml values)
 ]
 
 
-def run_case(name, B, Tx, ragged, seed):
-    enc, _ = ref_loader.build_reference_text_encoder(ENC_CFG)
-    sd = synth_text_weights(prefix="")
+def run_case(name, variant, B, Tx, ragged, seed):
+    enc, _ = ref_loader.build_reference_text_encoder(ENC_CFG, variant=variant)
+    sd = synth_text_weights(prefix="", adaln=variant == "dex")
     assert list(sd.keys()) == list(enc.state_dict().keys()), "manifest order differs from the reference state_dict"
     enc.load_state_dict(sd, strict=True)
     inp = synth_text(B, Tx, seed=seed, ragged=ragged)
@@ -37,10 +38,10 @@ def run_case(name, B, Tx, ragged, seed):
         hooks.append(enc.encoder.layers[l].register_forward_hook(
             lambda m, i, o, l=l: taps.__setitem__(f"layer{l}", o[0].detach().numpy().copy())))
     with torch.no_grad():
-        mu, logw, x_mask = enc(inp["x"], inp["x_lengths"], inp["sty"])
+        mu, logw, x_mask = enc(inp["x"], inp["x_lengths"], inp["sty"]) if variant == "dex" else enc(inp["x"], inp["x_lengths"])
     for h in hooks:
         h.remove()
-    arrs = dict(mu=mu.numpy(), logw=logw.numpy(), x_mask=x_mask.numpy(), meta=np.array([B, Tx, int(ragged), seed], dtype=np.int64),
+    arrs = dict(mu=mu.numpy(), logw=logw.numpy(), x_mask=x_mask.numpy(), meta=np.array([B, Tx, int(ragged), seed, int(variant == "dex")], dtype=np.int64),
                 keys=np.array(list(enc.state_dict().keys())), **taps)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **arrs)

@@ -97,8 +97,8 @@ def build_reference_decoder(variant, decoder_cfg, dit_cfg, n_feats=80, n_spks=No
     return dec.eval(), mod
 
 
-def load_reference_text_encoder():
-    """-> the reference's ``model.text_encoder`` module (DEX-TTS), imported unmodified.  Extra shims (none edits a
+def load_reference_text_encoder(variant="dex"):
+    """-> the reference's ``model.text_encoder`` module (DEX-TTS or GeDEX-TTS), imported unmodified.  Extra shims (none edits a
     reference file): ``transformers.top_k_top_p_filtering`` (imported by name at DEX-TTS/model/retention.py:12, removed from
     transformers after the pinned 4.35.2, never called on this path) and ``timm.models.layers.drop_path`` (retention.py:9; the
     identity in eval mode).  transformers is imported before the timm stub is installed: its lazy-module probe calls
@@ -106,7 +106,7 @@ def load_reference_text_encoder():
     import transformers
     if not hasattr(transformers, "top_k_top_p_filtering"):
         transformers.top_k_top_p_filtering = lambda *a, **k: None
-    load_reference("dex")
+    load_reference(variant)
     import timm
     layers = types.ModuleType("timm.models.layers")
     layers.drop_path = lambda x, drop_prob=0.0, training=False, scale_by_keep=True: x
@@ -115,10 +115,10 @@ def load_reference_text_encoder():
     return importlib.import_module("model.text_encoder")
 
 
-def build_reference_text_encoder(encoder_cfg, n_vocab=149, n_feats=80, n_spks=1, spk_emb_dim=64):
-    """Construct the reference ``TextEncoder`` as DEX-TTS/model/tts.py:29 does.  transformers 5.x ``PretrainedConfig`` no longer
+def build_reference_text_encoder(encoder_cfg, n_vocab=149, n_feats=80, n_spks=1, spk_emb_dim=64, variant="dex"):
+    """Construct the reference ``TextEncoder`` as DEX-TTS/model/tts.py:29 (GeDEX-TTS/model/tts.py:24) does.  transformers 5.x ``PretrainedConfig`` no longer
     defines ``use_cache`` (read at DEX-TTS/model/retnet.py:79): set it on the instance's config, as SURVEY.md §8c prescribes."""
-    mod = load_reference_text_encoder()
+    mod = load_reference_text_encoder(variant)
     enc = mod.TextEncoder(**encoder_cfg, n_vocab=n_vocab, n_feats=n_feats, n_spks=n_spks, spk_emb_dim=spk_emb_dim)
     if not hasattr(enc.encoder.config, "use_cache"):
         enc.encoder.config.use_cache = True

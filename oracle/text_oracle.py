@@ -21,7 +21,10 @@ use_glu, subln -> pre-norm with alpha = 1, layernorm_eps 1e-6, no final embeddin
 the identity.  With ``use_softmax=True, use_decay=False`` (DEX-TTS/config/VCTK/base.yaml:60-61) the "retention" is softmax
 attention with rotary q / k, a key-padding fill of -1e4 (not -inf), a per-head RMS norm and a swish gate.
 
-Parity pin: outputs of the unmodified reference TextEncoder, generated in the build container by oracle/make_golden_text.py and
+GeDEX-TTS ships the same encoder without the AdaptiveLayerNorm layers and without the ``sty`` argument (GeDEX-TTS/model/
+text_encoder.py, retention.py): ``sty=None`` here.
+
+Parity pin: outputs of the unmodified reference TextEncoder of both repositories, generated in the build container by oracle/make_golden_text.py and
 committed as tests/golden/text_*.npz; tests/test_text_oracle.py replays them.
 """
 import math
@@ -82,7 +85,8 @@ def _glu(w, p, x):
 
 
 def retnet(w, h, x_mask, sty, n_layers=8, n_heads=2, prefix="encoder.encoder", taps=None):
-    """RetNetModel.forward(inputs_embeds=h (B,T,C), attention_mask=x_mask (B,1,T), sty (B,C)) -> last_hidden_state (B,T,C)."""
+    """RetNetModel.forward(inputs_embeds=h (B,T,C), attention_mask=x_mask (B,1,T), sty (B,C)) -> last_hidden_state (B,T,C).
+    sty=None: the GeDEX-TTS flavour, whose decoder layers have no AdaptiveLayerNorm (GeDEX-TTS/model/retention.py:453-505)."""
     T = h.shape[1]
     index = torch.arange(T).to(h)
     angle = w[prefix + ".retnet_rel_pos.angle"]
@@ -91,9 +95,11 @@ def retnet(w, h, x_mask, sty, n_layers=8, n_heads=2, prefix="encoder.encoder", t
     for l in range(n_layers):
         p = f"{prefix}.layers.{l}"
         h = h + _retention(w, p + ".retention", _rms_norm(h, w[p + ".retention_layer_norm.weight"]), sin, cos, pair_mask, n_heads)
-        h = _ada_layer_norm(w, p + ".adaln_1", h, sty)                                                # :487
+        if sty is not None:
+            h = _ada_layer_norm(w, p + ".adaln_1", h, sty)                                            # :487 (DEX-TTS only)
         h = h + _glu(w, p + ".ffn", _rms_norm(h, w[p + ".final_layer_norm.weight"]))
-        h = _ada_layer_norm(w, p + ".adaln_2", h, sty)                                                # :505
+        if sty is not None:
+            h = _ada_layer_norm(w, p + ".adaln_2", h, sty)                                            # :505 (DEX-TTS only)
         if taps is not None:
             taps[f"layer{l}"] = h
     return _rms_norm(h, w[prefix + ".layer_norm.weight"])                                             # retnet.py:162-163
@@ -118,7 +124,8 @@ def duration_predictor(w, x, x_mask, prefix="encoder.proj_w"):
 
 
 def text_encoder(w, x_ids, x_lengths, sty, n_layers=8, n_heads=2, prefix="encoder", taps=None):
-    """TextEncoder.forward(x, x_lengths, sty, spk=None) for n_spks <= 1, text_encoder.py:129-142.
+    """TextEncoder.forward(x, x_lengths, sty, spk=None) for n_spks <= 1, text_encoder.py:129-142; with sty=None it is
+    GeDEX-TTS's TextEncoder.forward(x, x_lengths, spk=None) (GeDEX-TTS/model/text_encoder.py:132-146: the same code without the style).
     x_ids (B,Tx) long, x_lengths (B,), sty (B,C) -> (mu_x (B,n_feats,Tx), logw (B,1,Tx), x_mask (B,1,Tx))."""
     emb = w[prefix + ".emb.weight"]
     C = emb.shape[1]
