@@ -350,3 +350,38 @@ def synth_text(B, Tx, n_vocab=149, c_sty=192, seed=81, ragged=False):
         x_lengths[1:] = torch.randint(max(1, int(0.5 * Tx)), Tx + 1, (B - 1,), generator=g)
     x = x * (torch.arange(Tx)[None, :] < x_lengths[:, None])                       # the collate pads ids with 0
     return dict(x=x, x_lengths=x_lengths, sty=torch.randn(B, c_sty, generator=g))
+
+
+def synth_tts_weights(variant="dex", seed=100):
+    """Every tensor of the reference ``DeXTTS`` / ``GeDEXTTS`` (n_spks <= 1) as one flat dict: the encoders and ``conv_sty`` under
+    their ``state_dict`` names, the decoder under ``denoise_fn.*`` (upstream: ``decoder.denoise_fn.*`` and, aliased,
+    ``decoder.precond_model.model.*``)."""
+    from .manifest import DecoderCfg
+    w = dict(synth_decoder_weights(DecoderCfg.make(variant), seed=seed, live=True))
+    w.update(synth_text_weights(seed=seed, adaln=variant == "dex"))
+    if variant == "dex":
+        w.update(synth_tv_weights(seed=seed))
+        w.update(synth_lf0_weights(seed=seed))
+        w.update(synth_tiv_weights(seed=seed))
+        w.update(synth_conv_sty_weights(seed=seed))
+    return w
+
+
+def reference_state_dict(w):
+    """Flat dict of ``synth_tts_weights`` -> the key layout of the reference model's ``state_dict`` (decoder tensors twice)."""
+    sd = {}
+    for k, v in w.items():
+        if k.startswith("denoise_fn."):
+            sd["decoder." + k] = v
+            sd["decoder.precond_model.model." + k[len("denoise_fn."):]] = v
+        else:
+            sd[k] = v
+    return sd
+
+
+def seeded_noise(seed):
+    """noise(shape) -> N(0, 1) CPU tensor from a private generator: the injected Gaussian draw of Diffusion.forward."""
+    g = torch.Generator()
+    g.manual_seed(seed)
+    randn = torch.randn                     # bound now: the golden generators patch torch.randn while the reference runs
+    return lambda shape: randn(shape, generator=g)

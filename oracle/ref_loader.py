@@ -123,3 +123,41 @@ def build_reference_text_encoder(encoder_cfg, n_vocab=149, n_feats=80, n_spks=1,
     if not hasattr(enc.encoder.config, "use_cache"):
         enc.encoder.config.use_cache = True
     return enc.eval(), mod
+
+
+def load_reference_tts(variant="dex"):
+    """-> the reference's ``model.tts`` module (``DeXTTS`` / ``GeDEXTTS``), imported unmodified.  On top of the text-encoder shims:
+    ``model.monotonic_align`` (DEX-TTS/model/tts.py:7; a Cython extension whose shipped binary is stale, called only by
+    ``compute_loss`` at tts.py:108) is registered as a stub whose ``maximum_path`` raises."""
+    load_reference_text_encoder(variant)
+    mas = types.ModuleType("model.monotonic_align")
+
+    def maximum_path(*a, **k):
+        raise RuntimeError("monotonic_align is a training-only Cython extension; not available in the oracle harness")
+    mas.maximum_path = maximum_path
+    sys.modules["model.monotonic_align"] = mas
+    sys.modules["model"].monotonic_align = mas
+    return importlib.import_module("model.tts")
+
+
+def reference_model_cfg(variant="dex", n_vocab=149):
+    """``cfg.model`` as the entry scripts build it: the ``model:`` block of config/{VCTK,LJSpeech}/base.yaml with attribute access,
+    plus ``n_vocab`` = len(symbols) + 1 (add_blank), which main.py / synthesize.py fill in at run time."""
+    import yaml
+    sub, ds = {"dex": ("DEX-TTS", "VCTK"), "gedex": ("GeDEX-TTS", "LJSpeech")}[variant]
+    with open(os.path.join(REF_ROOT, sub, "config", ds, "base.yaml")) as f:
+        raw = yaml.safe_load(f)["model"]
+    wrap = lambda d: DotDict({k: wrap(v) if isinstance(v, dict) else v for k, v in d.items()})
+    cfg = wrap(raw)
+    cfg.n_vocab = n_vocab
+    return cfg
+
+
+def build_reference_tts(variant="dex", n_vocab=149):
+    """Construct ``DeXTTS(cfg.model)`` / ``GeDEXTTS(cfg.model)`` as synthesize.py:67 does (eval mode)."""
+    mod = load_reference_tts(variant)
+    cfg = reference_model_cfg(variant, n_vocab)
+    model = (mod.DeXTTS if variant == "dex" else mod.GeDEXTTS)(cfg)
+    if not hasattr(model.encoder.encoder.config, "use_cache"):
+        model.encoder.encoder.config.use_cache = True
+    return model.eval(), mod, cfg
