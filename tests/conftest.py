@@ -14,8 +14,6 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # modules that set RUN_LAST = True (GPU tests committed before they could be run on a B200) go to the end of the session
-    items.sort(key=lambda it: bool(getattr(it.module, "RUN_LAST", False)))
     try:
         import torch
         has_gpu = torch.cuda.is_available()

@@ -1,7 +1,6 @@
 """GPU parity of the duration / alignment glue (dexb_align_lengths / dexb_align_expand through the C ABI, drop-in
 ``model.align_durations``) against the reference fixtures (tests/golden/align_*.npz) and the CPU oracle: bit-exact, this is
-index / byte work.  Written in the session whose GPU budget was already spent -- NOT YET RUN on a B200 when committed, hence
-RUN_LAST (tests/conftest.py): a failure here cannot hide the rest of the suite behind `-x`."""
+index / byte work (run on a B200: profiles/r01_pytest_gpu_v31_align.log)."""
 import glob
 import os
 
@@ -14,7 +13,6 @@ from dexb200.synth import synth_align_inputs
 from test_align_oracle import check_alignment_properties, load_case
 
 pytestmark = pytest.mark.gpu
-RUN_LAST = True
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "align_*.npz")))
 
