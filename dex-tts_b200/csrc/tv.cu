@@ -917,3 +917,600 @@ int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const flo
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// Part 3: text encoder -- TextEncoder.forward, DEX-TTS/model/text_encoder.py:129-142
+// (GeDEX-TTS/model/text_encoder.py:132-146 is the same code without the style input), eval mode, n_spks <= 1:
+//
+//   x  = emb[ids] * sqrt(C)                                                              (:130)
+//   x  = (x + proj(3 x relu(cln(conv5(x * mask))))) * mask                               prenet, ConvReluNorm (:56-64)
+//   8x RetNetDecoderLayer (retention.py:458-514) with use_softmax, no decay -- softmax attention in RetNet clothing:
+//        h = h + out_proj(swish(g) * rms_head(softmax(rope(q) rope(k d^-0.5)^T | pair mask, fill -1e4) v)),  q/k/v/g = W rms(h) w
+//        h = adaln_1(h, sty)                                                             (DEX-TTS only; base.py:180-194)
+//        h = h + fc2(gelu(fc1 rms(h) w) * gate rms(h) w);  h = adaln_2(h, sty)           GLU (retention.py:371-381)
+//   x  = rms(h) w * mask                                                                 (retnet.py:162, text_encoder.py:137)
+//   mu = proj_m(x) * mask;  logw = proj(cln(relu(conv3(cln(relu(conv3(x*mask))) * mask))) * mask) * mask     (:138-141, :84-95)
+//
+// Rows [B*Tx][C] like the other encoders; every Linear / Conv1d is a 1 x k-tap implicit GEMM on the tcgen05 engine (split-bf16 x3,
+// the plans of part 1), with one fp32 row kernel between two GEMMs: k_txt_row (residual | channel LayerNorm + ReLU | AdaLN |
+// RMSNorm | mask | split-operand store, one warp per token).  Attention over <= a few hundred tokens with head dim 96 is 25 MFLOP
+// per utterance and layer: it stays in fp32 on the CUDA cores (k_txt_attn: one warp per (utterance, head, query), online softmax,
+// the per-head RMS norm and the swish gate fused behind it) -- the stage is bound by its ~120 launch latencies, not by a roofline.
+// =====================================================================================================================
+
+struct TxtLayer {
+  dexb::TvConv q, k, v, g, o, fc1, gate, fc2;
+  const float *rln = nullptr, *fln = nullptr;        // retention_layer_norm.weight, final_layer_norm.weight
+};
+
+struct dexb_text : dexb::EncBase {
+  int n_vocab = 0, n_feats = 0, C = 0, Fc = 0, Fd = 0, heads = 0, L = 0, ksz = 3, adaln = 1;
+  const float *emb = nullptr, *angle = nullptr, *out_ln = nullptr, *dpw = nullptr, *dpb = nullptr;
+  dexb::TvConv pre[3], pre_proj, proj_m, dp1, dp2;
+  std::vector<TxtLayer> layers;
+  float *adaW = nullptr, *adaB = nullptr;            // packed [L][4][C][C] / [L][4][C]: adaln_1.W_scale, .W_bias, adaln_2.W_scale, .W_bias
+  // (B, Tx) plan: residual stream, prenet input, q / k / v / g rows, the two GLU branches, AdaLN scale / bias [L][4][B][C]
+  float *hf = nullptr, *x0f = nullptr, *qf = nullptr, *kf = nullptr, *vf = nullptr, *gf = nullptr, *f1 = nullptr, *f2 = nullptr,
+        *ada = nullptr;
+  int layer_limit = -1;                              // unit-parity aid: >= 0 stops the forward after that many RetNet layers
+};
+
+namespace dexb {
+
+constexpr int kTxtMaxDpl = 4;                       // head dim / 32 the attention kernel keeps per lane (96 -> 3)
+
+struct TxtRow {
+  const float* in;           // [rows][C]
+  const float* resid;        // [rows][C] added first (RetNetDecoderLayer.residual_connection with alpha = 1), or null
+  const float *ln_g, *ln_b;  // channel LayerNorm of model.text_encoder.LayerNorm (eps 1e-4, rsqrt), or null
+  int relu;                  // ReLU after that LayerNorm (ConvReluNorm: conv -> norm -> relu)
+  const float *ada_scale, *ada_bias;   // [B][C]: AdaptiveLayerNorm (x - mean) / sqrt(var + 1e-5) * scale + bias, or null
+  float* out_f;              // fp32 rows of the value at this point (the residual stream), or null
+  const float* rms_w;        // then RMSNorm (eps 1e-6) * weight, or null
+  const float* mask;         // [rows] or null
+  bf16* os;                  // split rows [rows][hi(C)|lo(C)] or null
+  float* of2;                // fp32 rows of the final value or null
+  long rows;
+  int C, T;
+};
+
+// ids (B*Tx) -> x = emb[id] * sqrt(C) (text_encoder.py:130): fp32 rows (the prenet's residual input) and the split rows of x * mask.
+// Ids outside [0, n_vocab) are clamped (upstream raises an IndexError on the host; a device kernel cannot).
+__global__ void k_txt_embed(const long long* __restrict__ ids, const float* __restrict__ emb, const float* __restrict__ mask,
+                            float* __restrict__ x0, bf16* __restrict__ xs, long rows, int C, int n_vocab, float scale) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long r = i / C;
+  const int c = (int)(i % C);
+  long long id = ids[r];
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  const float v = emb[id * C + c] * scale;
+  x0[i] = v;
+  bf16 hi, lo;
+  split2(v * mask[r], hi, lo);
+  xs[r * 2 * C + c] = hi;
+  xs[r * 2 * C + C + c] = lo;
+}
+
+// one warp per token: everything between two GEMMs of the text encoder
+__global__ void __launch_bounds__(256) k_txt_row(const TxtRow p) {
+  const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  const int C = p.C;
+  float v[kTvMaxC / 32];
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    float x = 0.f;
+    if (c < C) {
+      x = p.in[r * C + c];
+      if (p.resid != nullptr) x += p.resid[r * C + c];
+    }
+    v[j] = x;                                                          // lanes beyond C hold zeros throughout
+  }
+  if (p.ln_g != nullptr || p.ada_scale != nullptr) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) s += v[j];
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const float d = (lane + 32 * j < C) ? v[j] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float var = warp_sum(q) / (float)C;                          // biased, both norms
+    if (p.ln_g != nullptr) {
+      const float rstd = rsqrtf(var + 1e-4f);
+#pragma unroll
+      for (int j = 0; j < kTvMaxC / 32; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const float y = (v[j] - mean) * rstd * p.ln_g[c] + p.ln_b[c];
+          v[j] = p.relu ? fmaxf(y, 0.f) : y;
+        }
+      }
+    } else {
+      const float sd = sqrtf(var + 1e-5f);
+      const long b = r / p.T;
+#pragma unroll
+      for (int j = 0; j < kTvMaxC / 32; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) v[j] = (v[j] - mean) / sd * p.ada_scale[b * C + c] + p.ada_bias[b * C + c];
+      }
+    }
+  }
+  if (p.out_f != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) p.out_f[r * C + c] = v[j];
+    }
+  }
+  if (p.rms_w != nullptr) {
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) q = fmaf(v[j], v[j], q);
+    const float rr = rsqrtf(warp_sum(q) / (float)C + 1e-6f);
+#pragma unroll
+    for (int j = 0; j < kTvMaxC / 32; ++j) {
+      const int c = lane + 32 * j;
+      if (c < C) v[j] = v[j] * rr * p.rms_w[c];
+    }
+  }
+  const float m = p.mask != nullptr ? p.mask[r] : 1.f;
+#pragma unroll
+  for (int j = 0; j < kTvMaxC / 32; ++j) {
+    const int c = lane + 32 * j;
+    if (c >= C) continue;
+    const float x = v[j] * m;
+    if (p.os != nullptr) {
+      bf16 hi, lo;
+      split2(x, hi, lo);
+      p.os[r * 2 * C + c] = hi;
+      p.os[r * 2 * C + C + c] = lo;
+    }
+    if (p.of2 != nullptr) p.of2[r * C + c] = x;
+  }
+}
+
+// AdaLN scale / bias of every layer for this batch: out[m][b][c] = W[m][c][:] . sty[b][:] + bias[m][c]  (base.py:189-190); one warp each
+__global__ void __launch_bounds__(256) k_txt_ada(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ sty,
+                                                 float* __restrict__ out, int M, int B, int C) {
+  const long wid = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (wid >= (long)M * B * C) return;
+  const int lane = threadIdx.x & 31;
+  const int c = (int)(wid % C), b = (int)((wid / C) % B);
+  const long m = wid / ((long)C * B);
+  const float* w = W + (m * C + c) * C;
+  const float* s = sty + (long)b * C;
+  float part = 0.f;
+  for (int k = lane; k < C; k += 32) part = fmaf(w[k], s[k], part);
+  part = warp_sum(part);
+  if (lane == 0) out[wid] = part + bias[m * C + c];
+}
+
+// q, k rows [rows][C] in place: k *= d^-0.5 (retention.py:281), then theta_shift on both (retention.py:28-37) with
+// sin / cos(t * angle[i]), angle repeated per pair (retention.py:75-76, 140-142).  One thread per (token, channel pair).
+__global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ angle, long rows, int C, int d, int T,
+                           float scaling) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int half = C / 2;
+  if (i >= rows * half) return;
+  const long r = i / half;
+  const int c0 = 2 * (int)(i % half);
+  const int t = (int)(r % T);
+  const float ph = __fmul_rn((float)t, angle[c0 % d]);
+  const float sn = sinf(ph), cs = cosf(ph);
+  float* qp = q + r * C + c0;
+  float* kp = k + r * C + c0;
+  const float q0 = qp[0], q1 = qp[1];
+  qp[0] = q0 * cs + (-q1) * sn;
+  qp[1] = q1 * cs + q0 * sn;
+  const float k0 = kp[0] * scaling, k1 = kp[1] * scaling;
+  kp[0] = k0 * cs + (-k1) * sn;
+  kp[1] = k1 * cs + k0 * sn;
+}
+
+// MultiScaleRetention.parallel_retention with use_softmax (retention.py:223-250) + group_norm + gate (:290-292).  One warp per
+// (utterance, head, query); lane l holds dims l, l + 32, ... of the head.  Scores of (query, key) pairs with a padded member are
+// -1e4 as upstream (a padded query therefore averages v over ALL keys).  Output: split rows of swish(g) * rms_head(softmax(s) v).
+__global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                                  const float* __restrict__ g, const float* __restrict__ mask, bf16* __restrict__ os,
+                                                  int B, int T, int C, int heads) {
+  const long wid = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (wid >= (long)B * heads * T) return;
+  const int lane = threadIdx.x & 31;
+  const int t = (int)(wid % T), hd = (int)((wid / T) % heads), b = (int)(wid / ((long)T * heads));
+  const int d = C / heads, dpl = d / 32;
+  const long r = (long)b * T + t;
+  const float qm = mask[r];
+  float qv[kTxtMaxDpl], acc[kTxtMaxDpl];
+#pragma unroll
+  for (int i = 0; i < kTxtMaxDpl; ++i) {
+    qv[i] = i < dpl ? q[r * C + hd * d + lane + 32 * i] : 0.f;
+    acc[i] = 0.f;
+  }
+  float mx = -INFINITY, l = 0.f;
+  const float* kb = k + (long)b * T * C + hd * d + lane;
+  const float* vb = v + (long)b * T * C + hd * d + lane;
+  const float* mb = mask + (long)b * T;
+  for (int j = 0; j < T; ++j) {
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < kTxtMaxDpl; ++i)
+      if (i < dpl) part = fmaf(qv[i], kb[(long)j * C + 32 * i], part);
+    float s = warp_sum(part);
+    if (qm == 0.f || mb[j] == 0.f) s = -1e4f;
+    const float mn = fmaxf(mx, s);
+    const float corr = expf(mx - mn);                                  // first key: exp(-inf) = 0
+    const float pj = expf(s - mn);
+    l = l * corr + pj;
+#pragma unroll
+    for (int i = 0; i < kTxtMaxDpl; ++i)
+      if (i < dpl) acc[i] = acc[i] * corr + pj * vb[(long)j * C + 32 * i];
+    mx = mn;
+  }
+  const float inv = 1.f / l;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kTxtMaxDpl; ++i) {
+    acc[i] *= inv;                                                     // slots beyond dpl stay zero
+    ss = fmaf(acc[i], acc[i], ss);
+  }
+  const float rr = rsqrtf(warp_sum(ss) / (float)d + 1e-6f);            // group_norm: RMSNorm(head_dim), no affine
+#pragma unroll
+  for (int i = 0; i < kTxtMaxDpl; ++i) {
+    if (i >= dpl) continue;
+    const int c = hd * d + lane + 32 * i;
+    const float gv = g[r * C + c];
+    const float o = gv / (1.f + expf(-gv)) * (acc[i] * rr);            // swish gate
+    bf16 hi, lo;
+    split2(o, hi, lo);
+    os[r * 2 * C + c] = hi;
+    os[r * 2 * C + C + c] = lo;
+  }
+}
+
+// GLU.forward (retention.py:371-381): gelu(fc1 x) * gate x (exact gelu) -> split rows [rows][hi(F)|lo(F)], the operand of fc2
+__global__ void k_txt_glu(const float* __restrict__ a, const float* __restrict__ gate, bf16* __restrict__ os, long rows, int F) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= rows * F) return;
+  const long r = i / F;
+  const int c = (int)(i % F);
+  const float x = a[i];
+  const float y = x * 0.5f * (1.f + erff(x * 0.70710678118654752f)) * gate[i];
+  bf16 hi, lo;
+  split2(y, hi, lo);
+  os[r * 2 * F + c] = hi;
+  os[r * 2 * F + F + c] = lo;
+}
+
+// DurationPredictor.proj (text_encoder.py:94-95): Conv1d(Fd, 1, 1) of the masked rows, * mask; one warp per token
+__global__ void __launch_bounds__(256) k_txt_dp_out(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                    const float* __restrict__ mask, float* __restrict__ logw, long rows, int C) {
+  const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float part = 0.f;
+  for (int c = lane; c < C; c += 32) part = fmaf(x[r * C + c], w[c], part);
+  part = warp_sum(part);
+  if (lane == 0) logw[r] = (part + bias[0]) * mask[r];
+}
+
+// Linear (co, ci) or Conv1d (co, ci, taps) weight -> packed split operand (same layout as tv_pack_conv)
+static int txt_pack(EncBase* h, const std::string& wname, const std::string& bname, int ci, int co, int taps, bool linear, TvConv* c,
+                    cudaStream_t st) {
+  c->ci = ci; c->co = co; c->K = tv_pad64(ci); c->taps = taps;
+  const float* w = nullptr;
+  if (linear) DEXB_TRY(tv_get(h, wname, {co, ci}, &w));
+  else DEXB_TRY(tv_get(h, wname, {co, ci, taps}, &w));
+  if (c->w == nullptr) DEXB_CUDA_OK(cudaMalloc(&c->w, (size_t)taps * co * 2 * c->K * sizeof(bf16)));
+  k_tv_pack_w<<<cdiv((long)taps * co * c->K, 256), 256, 0, st>>>(w, c->w, co, ci, c->K, taps);
+  c->bias = nullptr;
+  if (!bname.empty()) DEXB_TRY(tv_get(h, bname, {co}, &c->bias));
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static void txt_release_plan(dexb_text* h) {
+  enc_release_rows(h);
+  float** bufs[] = {&h->hf, &h->x0f, &h->qf, &h->kf, &h->vf, &h->gf, &h->f1, &h->f2, &h->ada};
+  for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
+}
+
+static int txt_plan(dexb_text* h, int B, int T) {
+  if (B == h->B && T == h->T) return 0;
+  txt_release_plan(h);
+  DEXB_TRY(gemm_global_init());
+  const int C = h->C;
+  int Kmax = C, Cmax = C;
+  if (h->Fc > Kmax) Kmax = h->Fc;
+  if (h->Fd > Kmax) Kmax = h->Fd;
+  if (h->Fd > Cmax) Cmax = h->Fd;
+  if (h->n_feats > Cmax) Cmax = h->n_feats;
+  const long rows = (long)B * T;
+  DEXB_CUDA_OK(cudaMalloc(&h->xs, rows * 2 * Kmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->hs, rows * 2 * Kmax * sizeof(bf16)));
+  DEXB_CUDA_OK(cudaMalloc(&h->acc, rows * Cmax * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->xf, rows * Cmax * sizeof(float)));
+  float** cbufs[] = {&h->hf, &h->x0f, &h->qf, &h->kf, &h->vf, &h->gf};
+  for (float** b : cbufs) DEXB_CUDA_OK(cudaMalloc(b, rows * C * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->f1, rows * h->Fc * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->f2, rows * h->Fc * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->ada, (size_t)h->L * 4 * B * C * sizeof(float)));
+  h->B = B; h->T = T;
+  for (int i = 0; i < 3; ++i) DEXB_TRY(tv_plan_conv(h, &h->pre[i], h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->pre_proj, h->xs, h->acc));
+  for (auto& ly : h->layers) {
+    DEXB_TRY(tv_plan_conv(h, &ly.q, h->xs, h->qf));
+    DEXB_TRY(tv_plan_conv(h, &ly.k, h->xs, h->kf));
+    DEXB_TRY(tv_plan_conv(h, &ly.v, h->xs, h->vf));
+    DEXB_TRY(tv_plan_conv(h, &ly.g, h->xs, h->gf));
+    DEXB_TRY(tv_plan_conv(h, &ly.o, h->hs, h->acc));
+    DEXB_TRY(tv_plan_conv(h, &ly.fc1, h->xs, h->f1));
+    DEXB_TRY(tv_plan_conv(h, &ly.gate, h->xs, h->f2));
+    DEXB_TRY(tv_plan_conv(h, &ly.fc2, h->hs, h->acc));
+  }
+  DEXB_TRY(tv_plan_conv(h, &h->proj_m, h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->dp1, h->xs, h->acc));
+  DEXB_TRY(tv_plan_conv(h, &h->dp2, h->hs, h->acc));
+  return 0;
+}
+
+static TxtRow txt_row(const dexb_text* h, const float* in) {
+  TxtRow p;
+  memset(&p, 0, sizeof(p));
+  p.in = in;
+  p.rows = (long)h->B * h->T;
+  p.C = h->C; p.T = h->T;
+  return p;
+}
+static void txt_launch_row(const TxtRow& p, cudaStream_t st) { k_txt_row<<<cdiv(p.rows, 8), 256, 0, st>>>(p); }
+
+}  // namespace dexb
+
+extern "C" {
+
+int dexb_text_create(int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp, int n_heads, int n_layers,
+                     int kernel_size, int adaln, dexb_text** out) {
+  DEXB_CHECK(out != nullptr, "dexb_text_create: null argument");
+  int dev = 0, major = 0;
+  DEXB_CUDA_OK(cudaGetDevice(&dev));
+  DEXB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  DEXB_CHECK(major == 10, "dexb200 is built for sm_100a only (device %d has compute capability major %d); there is no fallback",
+             dev, major);
+  DEXB_CHECK(n_vocab >= 1 && n_feats >= 1 && n_feats <= kTvMaxC && n_layers >= 1 && n_layers <= 64 && (kernel_size == 1 || kernel_size == 3 || kernel_size == 5),
+             "dexb_text_create: n_vocab %d / n_feats %d / n_layers %d / kernel_size %d out of range", n_vocab, n_feats, n_layers, kernel_size);
+  DEXB_CHECK(n_channels >= 64 && n_channels % 64 == 0 && n_channels <= kTvMaxC && filter_channels_dp >= 64 && filter_channels_dp % 64 == 0 &&
+                 filter_channels_dp <= kTvMaxC && filter_channels >= 64 && filter_channels % 64 == 0,
+             "dexb_text_create: n_channels %d / filter_channels_dp %d must be multiples of 64 (<= %d), filter_channels %d a multiple of 64",
+             n_channels, filter_channels_dp, kTvMaxC, filter_channels);
+  DEXB_CHECK(n_heads >= 1 && n_channels % n_heads == 0 && (n_channels / n_heads) % 32 == 0 && n_channels / n_heads <= 32 * kTxtMaxDpl,
+             "dexb_text_create: head dim %d / %d must be a multiple of 32 (<= %d)", n_channels, n_heads, 32 * kTxtMaxDpl);
+  dexb_text* h = new dexb_text();
+  h->n_vocab = n_vocab; h->n_feats = n_feats; h->C = n_channels; h->Fc = filter_channels; h->Fd = filter_channels_dp;
+  h->heads = n_heads; h->L = n_layers; h->ksz = kernel_size; h->adaln = adaln ? 1 : 0;
+  h->layers.resize(n_layers);
+  *out = h;
+  return 0;
+}
+
+void dexb_text_destroy(dexb_text* h) {
+  if (h == nullptr) return;
+  txt_release_plan(h);
+  TvConv* cs[7] = {&h->pre[0], &h->pre[1], &h->pre[2], &h->pre_proj, &h->proj_m, &h->dp1, &h->dp2};
+  for (TvConv* c : cs) tv_free_conv(c);
+  for (auto& ly : h->layers) {
+    TvConv* ls[8] = {&ly.q, &ly.k, &ly.v, &ly.g, &ly.o, &ly.fc1, &ly.gate, &ly.fc2};
+    for (TvConv* c : ls) tv_free_conv(c);
+  }
+  cudaFree(h->adaW); cudaFree(h->adaB);
+  for (auto& kv : h->w) cudaFree(kv.second.p);
+  delete h;
+}
+
+int dexb_text_load_weight(dexb_text* h, const char* name, const float* data_dev, const int64_t* shape, int ndim) {
+  DEXB_CHECK(h != nullptr && name != nullptr && data_dev != nullptr && shape != nullptr && ndim >= 1 && ndim <= 4,
+             "dexb_text_load_weight: bad argument");
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    DEXB_CHECK(shape[i] >= 1, "dexb_text_load_weight(%s): empty dimension", name);
+    n *= (size_t)shape[i];
+  }
+  TvTensor& t = h->w[name];
+  if (t.p != nullptr && t.n != n) { cudaFree(t.p); t.p = nullptr; }
+  if (t.p == nullptr) DEXB_CUDA_OK(cudaMalloc(&t.p, n * sizeof(float)));
+  t.n = n;
+  t.shape.assign(shape, shape + ndim);
+  DEXB_CUDA_OK(cudaMemcpy(t.p, data_dev, n * sizeof(float), cudaMemcpyDeviceToDevice));
+  h->finalized = false;
+  return 0;
+}
+
+int dexb_text_finalize_weights(dexb_text* h, void* stream) {
+  DEXB_CHECK(h != nullptr, "null handle");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->C;
+  DEXB_TRY(tv_get(h, "emb.weight", {h->n_vocab, C}, &h->emb));
+  for (int i = 0; i < 3; ++i) {
+    const std::string s = std::to_string(i);
+    DEXB_TRY(txt_pack(h, "prenet.conv_layers." + s + ".weight", "prenet.conv_layers." + s + ".bias", C, C, 5, false, &h->pre[i], st));
+    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".gamma", {C}, &h->pre[i].ln_g));
+    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".beta", {C}, &h->pre[i].ln_b));
+  }
+  DEXB_TRY(txt_pack(h, "prenet.proj.weight", "prenet.proj.bias", C, C, 1, false, &h->pre_proj, st));
+  if (h->adaln) {
+    if (h->adaW == nullptr) {
+      DEXB_CUDA_OK(cudaMalloc(&h->adaW, (size_t)h->L * 4 * C * C * sizeof(float)));
+      DEXB_CUDA_OK(cudaMalloc(&h->adaB, (size_t)h->L * 4 * C * sizeof(float)));
+    }
+  }
+  for (int l = 0; l < h->L; ++l) {
+    const std::string p = "encoder.layers." + std::to_string(l) + ".";
+    TxtLayer& ly = h->layers[l];
+    DEXB_TRY(txt_pack(h, p + "retention.q_proj.weight", "", C, C, 1, true, &ly.q, st));
+    DEXB_TRY(txt_pack(h, p + "retention.k_proj.weight", "", C, C, 1, true, &ly.k, st));
+    DEXB_TRY(txt_pack(h, p + "retention.v_proj.weight", "", C, C, 1, true, &ly.v, st));
+    DEXB_TRY(txt_pack(h, p + "retention.g_proj.weight", "", C, C, 1, true, &ly.g, st));
+    DEXB_TRY(txt_pack(h, p + "retention.out_proj.weight", "", C, C, 1, true, &ly.o, st));
+    DEXB_TRY(txt_pack(h, p + "ffn.fc1.weight", "", C, h->Fc, 1, true, &ly.fc1, st));
+    DEXB_TRY(txt_pack(h, p + "ffn.gate.weight", "", C, h->Fc, 1, true, &ly.gate, st));
+    DEXB_TRY(txt_pack(h, p + "ffn.fc2.weight", "", h->Fc, C, 1, true, &ly.fc2, st));
+    DEXB_TRY(tv_get(h, p + "retention_layer_norm.weight", {C}, &ly.rln));
+    DEXB_TRY(tv_get(h, p + "final_layer_norm.weight", {C}, &ly.fln));
+    if (h->adaln) {
+      const char* names[4] = {"adaln_1.W_scale", "adaln_1.W_bias", "adaln_2.W_scale", "adaln_2.W_bias"};
+      for (int m = 0; m < 4; ++m) {
+        const float *w = nullptr, *b = nullptr;
+        DEXB_TRY(tv_get(h, p + names[m] + ".weight", {C, C}, &w));
+        DEXB_TRY(tv_get(h, p + names[m] + ".bias", {C}, &b));
+        DEXB_CUDA_OK(cudaMemcpyAsync(h->adaW + ((size_t)l * 4 + m) * C * C, w, (size_t)C * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        DEXB_CUDA_OK(cudaMemcpyAsync(h->adaB + ((size_t)l * 4 + m) * C, b, (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      }
+    }
+  }
+  DEXB_TRY(tv_get(h, "encoder.layer_norm.weight", {C}, &h->out_ln));
+  DEXB_TRY(tv_get(h, "encoder.retnet_rel_pos.angle", {C / h->heads}, &h->angle));
+  DEXB_TRY(txt_pack(h, "proj_m.weight", "proj_m.bias", C, h->n_feats, 1, false, &h->proj_m, st));
+  DEXB_TRY(txt_pack(h, "proj_w.conv_1.weight", "proj_w.conv_1.bias", C, h->Fd, h->ksz, false, &h->dp1, st));
+  DEXB_TRY(tv_get(h, "proj_w.norm_1.gamma", {h->Fd}, &h->dp1.ln_g));
+  DEXB_TRY(tv_get(h, "proj_w.norm_1.beta", {h->Fd}, &h->dp1.ln_b));
+  DEXB_TRY(txt_pack(h, "proj_w.conv_2.weight", "proj_w.conv_2.bias", h->Fd, h->Fd, h->ksz, false, &h->dp2, st));
+  DEXB_TRY(tv_get(h, "proj_w.norm_2.gamma", {h->Fd}, &h->dp2.ln_g));
+  DEXB_TRY(tv_get(h, "proj_w.norm_2.beta", {h->Fd}, &h->dp2.ln_b));
+  DEXB_TRY(tv_get(h, "proj_w.proj.weight", {1, h->Fd, 1}, &h->dpw));
+  DEXB_TRY(tv_get(h, "proj_w.proj.bias", {1}, &h->dpb));
+  DEXB_CUDA_OK(cudaStreamSynchronize(st));
+  txt_release_plan(h);                      // plans hold the packed-weight pointers of the previous finalize
+  h->finalized = true;
+  return 0;
+}
+
+int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, int B, int Tx, float* mu_dev,
+                      float* logw_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && ids_dev != nullptr && mask_dev != nullptr && mu_dev != nullptr && logw_dev != nullptr,
+             "dexb_text_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_text_forward: call dexb_text_finalize_weights first");
+  DEXB_CHECK(B >= 1 && Tx >= 1, "dexb_text_forward: B = %d, Tx = %d", B, Tx);
+  DEXB_CHECK((sty_dev != nullptr) == (h->adaln != 0), "dexb_text_forward: the style vector is %s for this encoder",
+             h->adaln ? "required (DEX-TTS: AdaptiveLayerNorm)" : "not taken (GeDEX-TTS)");
+  cudaStream_t st = (cudaStream_t)stream;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+  DEXB_TRY(txt_plan(h, B, Tx));
+  const int C = h->C, T = Tx;
+  const long rows = (long)B * T;
+  h->launches = 0;
+  if (h->adaln) {
+    k_txt_ada<<<cdiv((long)h->L * 4 * B * C, 8), 256, 0, st>>>(h->adaW, h->adaB, sty_dev, h->ada, h->L * 4, B, C);
+    h->launches += 1;
+  }
+  k_txt_embed<<<cdiv(rows * C, 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), h->emb, mask_dev, h->x0f, h->xs, rows, C,
+                                                  h->n_vocab, (float)sqrt((double)C));
+  h->launches += 1;
+  // prenet: 3 x (conv5 -> channel LayerNorm -> ReLU), input masked before every conv; then (x + proj(.)) * mask
+  for (int i = 0; i < 3; ++i) {
+    DEXB_TRY(gemm_launch(h->pre[i].plan, h->pre[i].plan.p, 0, st));
+    TxtRow p = txt_row(h, h->acc);
+    p.ln_g = h->pre[i].ln_g; p.ln_b = h->pre[i].ln_b; p.relu = 1;
+    p.mask = mask_dev; p.os = h->xs;
+    txt_launch_row(p, st);
+    h->launches += 2;
+  }
+  DEXB_TRY(gemm_launch(h->pre_proj.plan, h->pre_proj.plan.p, 0, st));
+  {
+    TxtRow p = txt_row(h, h->acc);
+    p.resid = h->x0f; p.mask = mask_dev; p.of2 = h->hf;                // hf = (x + proj(x)) * mask: the residual stream
+    txt_launch_row(p, st);
+    TxtRow n = txt_row(h, h->hf);
+    n.rms_w = h->layers[0].rln; n.os = h->xs;                          // operand of layer 0's q / k / v / g projections
+    txt_launch_row(n, st);
+    h->launches += 3;
+  }
+  const int d = C / h->heads;
+  for (int l = 0; l < h->L; ++l) {
+    if (h->layer_limit >= 0 && l >= h->layer_limit) break;
+    TxtLayer& ly = h->layers[l];
+    DEXB_TRY(gemm_launch(ly.q.plan, ly.q.plan.p, 0, st));
+    DEXB_TRY(gemm_launch(ly.k.plan, ly.k.plan.p, 0, st));
+    DEXB_TRY(gemm_launch(ly.v.plan, ly.v.plan.p, 0, st));
+    DEXB_TRY(gemm_launch(ly.g.plan, ly.g.plan.p, 0, st));
+    k_txt_rope<<<cdiv(rows * (C / 2), 256), 256, 0, st>>>(h->qf, h->kf, h->angle, rows, C, d, T, 1.f / sqrtf((float)d));
+    k_txt_attn<<<cdiv((long)B * h->heads * T, 8), 256, 0, st>>>(h->qf, h->kf, h->vf, h->gf, mask_dev, h->hs, B, T, C, h->heads);
+    DEXB_TRY(gemm_launch(ly.o.plan, ly.o.plan.p, 0, st));
+    {
+      TxtRow p = txt_row(h, h->acc);                                   // h = adaln_1(h + out_proj(.)); operand = rms(h) * w
+      p.resid = h->hf;
+      if (h->adaln) {
+        p.ada_scale = h->ada + ((size_t)l * 4 + 0) * B * C;
+        p.ada_bias = h->ada + ((size_t)l * 4 + 1) * B * C;
+      }
+      p.out_f = h->hf; p.rms_w = ly.fln; p.os = h->xs;
+      txt_launch_row(p, st);
+    }
+    DEXB_TRY(gemm_launch(ly.fc1.plan, ly.fc1.plan.p, 0, st));
+    DEXB_TRY(gemm_launch(ly.gate.plan, ly.gate.plan.p, 0, st));
+    k_txt_glu<<<cdiv(rows * h->Fc, 256), 256, 0, st>>>(h->f1, h->f2, h->hs, rows, h->Fc);
+    DEXB_TRY(gemm_launch(ly.fc2.plan, ly.fc2.plan.p, 0, st));
+    {
+      const bool last = l == h->L - 1;
+      TxtRow p = txt_row(h, h->acc);                                   // h = adaln_2(h + ffn(.)); operand of the next layer / the heads
+      p.resid = h->hf;
+      if (h->adaln) {
+        p.ada_scale = h->ada + ((size_t)l * 4 + 2) * B * C;
+        p.ada_bias = h->ada + ((size_t)l * 4 + 3) * B * C;
+      }
+      p.out_f = h->hf;
+      p.rms_w = last ? h->out_ln : h->layers[l + 1].rln;
+      if (last) p.mask = mask_dev;                                     // x = layer_norm(h) * x_mask (text_encoder.py:137)
+      p.os = h->xs;
+      txt_launch_row(p, st);
+    }
+    h->launches += 13;             // 4 projections, rope, attention, out_proj, row, fc1, gate, glu, fc2, row
+  }
+  if (h->layer_limit >= 0) {                 // unit parity: the residual stream is read back with dexb_text_copy_stream
+    DEXB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  // mu = proj_m(x) * mask -> (B, n_feats, Tx)
+  DEXB_TRY(gemm_launch(h->proj_m.plan, h->proj_m.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->proj_m, 0, 0, 0.f);
+    p.mask = mask_dev; p.ocm = mu_dev;
+    tv_launch_post(p, st);
+  }
+  // logw = DurationPredictor(x, mask): conv -> relu -> norm -> (mask) conv -> relu -> norm -> (mask) proj -> mask
+  DEXB_TRY(gemm_launch(h->dp1.plan, h->dp1.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->dp1, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.os = h->hs;
+    tv_launch_post(p, st);
+  }
+  DEXB_TRY(gemm_launch(h->dp2.plan, h->dp2.plan.p, 0, st));
+  {
+    TvPost p = tv_post(h, h->dp2, 1, 2, 1e-4f);
+    p.mask = mask_dev; p.of = h->xf;
+    tv_launch_post(p, st);
+  }
+  k_txt_dp_out<<<cdiv(rows, 8), 256, 0, st>>>(h->xf, h->dpw, h->dpb, mask_dev, logw_dev, rows, h->Fd);
+  h->launches += 7;
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+long dexb_text_last_launch_count(const dexb_text* h) { return h != nullptr ? h->launches : 0; }
+
+int dexb_text_set_layer_limit(dexb_text* h, int n_layers) {
+  DEXB_CHECK(h != nullptr && n_layers >= -1 && n_layers <= h->L, "dexb_text_set_layer_limit: bad argument");
+  h->layer_limit = n_layers;
+  return 0;
+}
+
+int dexb_text_copy_stream(const dexb_text* h, float* rows_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && rows_dev != nullptr && h->hf != nullptr, "dexb_text_copy_stream: no forward has run on this handle");
+  DEXB_CUDA_OK(cudaMemcpyAsync(rows_dev, h->hf, (size_t)h->B * h->T * h->C * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -226,6 +226,31 @@ int dexb_align_lengths(const float* logw_dev, const float* x_mask_dev, int B, in
 int dexb_align_expand(const float* cum_dev, const float* x_mask_dev, const int64_t* y_lengths_dev, const float* mu_x_dev, int B,
                       int Tx, int n_feats, int Ty, float* attn_dev, float* y_mask_dev, float* mu_y_dev, void* stream);
 
+/* ---- text encoder ---------------------------------------------------------------------------------
+ * replaces: TextEncoder (DEX-TTS/model/text_encoder.py:97-142; attached as DeXTTS.encoder, DEX-TTS/model/tts.py:29,51; GeDEX-TTS/
+ * model/text_encoder.py:99-146 / tts.py:24,34 with adaln = 0) in eval mode for n_spks <= 1 and the shipped RetNet settings
+ * (use_softmax = True, use_decay = False, GLU feed-forward, pre-RMSNorm: DEX-TTS/config/VCTK/base.yaml:51-61, model/retnet_cfg.py).
+ * Tensor names are the module's own state_dict keys relative to `encoder.` ("emb.weight", "prenet.conv_layers.0.weight",
+ * "encoder.layers.3.retention.q_proj.weight", "proj_w.norm_1.gamma", ...).  Creation / weight loading / finalisation behave like
+ * the dexb_tiv_* calls. */
+typedef struct dexb_text dexb_text;
+int dexb_text_create(int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp, int n_heads, int n_layers,
+                     int kernel_size, int adaln, dexb_text** out);
+void dexb_text_destroy(dexb_text* h);
+int dexb_text_load_weight(dexb_text* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_text_finalize_weights(dexb_text* h, void* stream);
+/* replaces: TextEncoder.forward(x, x_lengths, sty, spk=None) (text_encoder.py:129-142).  ids_dev (B, Tx) int64 phoneme ids,
+ * mask_dev (B, Tx) = sequence_mask(x_lengths) in {0,1}, sty_dev (B, n_channels) style vector (NULL iff adaln = 0) ->
+ * mu_dev (B, n_feats, Tx), logw_dev (B, 1, Tx).  Allocation behaviour as dexb_tiv_forward. */
+int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, int B, int Tx, float* mu_dev,
+                      float* logw_dev, void* stream);
+long dexb_text_last_launch_count(const dexb_text* h);
+/* unit-parity aids (no reference counterpart): n_layers >= 0 makes dexb_text_forward stop after the prenet and that many RetNet
+ * layers (mu / logw are then not written), -1 restores the full forward; dexb_text_copy_stream copies the residual stream
+ * (B * Tx, n_channels) fp32 rows -- the prenet output for n_layers = 0, RetNetDecoderLayer n - 1's output otherwise. */
+int dexb_text_set_layer_limit(dexb_text* h, int n_layers);
+int dexb_text_copy_stream(const dexb_text* h, float* rows_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
