@@ -11,9 +11,12 @@ for p in (ROOT, os.path.join(ROOT, "dex-tts_b200"), os.path.join(ROOT, "oracle")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "run_last: GPU tests committed before they could be run on a B200 as pytest items; they are "
+                                       "ordered after every validated test so that -x cannot hide the validated suite behind them")
 
 
 def pytest_collection_modifyitems(config, items):
+    items.sort(key=lambda it: it.get_closest_marker("run_last") is not None)          # stable: everything else keeps its order
     try:
         import torch
         has_gpu = torch.cuda.is_available()

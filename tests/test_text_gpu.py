@@ -14,7 +14,7 @@ import text_oracle as TO
 from dexb200.synth import synth_text, synth_text_weights
 from parity import tensor_rel_err
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.run_last]
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "text_*.npz")))
 TOL = 1e-3             # the path tolerance (north_star), as max |a - b| / RMS(reference tensor)

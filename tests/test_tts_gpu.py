@@ -22,7 +22,7 @@ from test_tts_module_cpu import build
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 from make_golden_tts import synth_tts_inputs  # noqa: E402
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.run_last]
 
 GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "tts_*.npz")))
 
