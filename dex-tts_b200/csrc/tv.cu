@@ -1,5 +1,6 @@
 // TV encoder, LF0 encoder and style fusion of DEX-TTS: the once-per-utterance stage that builds the loop's `sty`
-// (DeXTTS.forward, DEX-TTS/model/tts.py:42-49).  Part 1: the TV encoder; part 2 (end of file): LF0 encoder + fusion.
+// (DeXTTS.forward, DEX-TTS/model/tts.py:42-49).  Part 1: the TV encoder; part 2: LF0 encoder + fusion; part 3 (end of file): the
+// text encoder (tts.py:51), which is built from the same row layout, GEMM plans and row-kernel pattern.
 //
 // TVEncoder.forward, DEX-TTS/model/ref_encoder.py:109-140, over BasicConv (model/base.py:33-63), Projection (:8-34),
 // VQEmbeddingEMA (:181-235, eval branch) and model.base.LayerNorm (base.py:139-159).

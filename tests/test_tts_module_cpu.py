@@ -104,3 +104,20 @@ def test_training_entry_point_raises():
     model, _ = build("gedex")
     with pytest.raises(NotImplementedError):
         model.compute_loss()
+
+
+def test_dropin_package_serves_the_reference_import_lines():
+    """`from model import DeXTTS` / `from model.utils import fix_len_compatibility` (DEX-TTS/synthesize.py:11, main.py:14) resolve to the
+    CUDA package when dex-tts_b200/dropin is first on the path -- in a fresh interpreter, so no other `model` is cached."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "dex-tts_b200", "dropin"), os.path.join(root, "dex-tts_b200")]))
+    code = ("from model import DeXTTS, GeDEXTTS\n"
+            "from model.utils import fix_len_compatibility, sequence_mask\n"
+            "from model.diffusion import Diffusion\n"
+            "import dexb200.model as M\n"
+            "assert DeXTTS is M.DeXTTS and GeDEXTTS is M.GeDEXTTS and Diffusion is M.Diffusion\n"
+            "assert fix_len_compatibility(61) == 64\n"
+            "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
