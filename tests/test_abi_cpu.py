@@ -86,3 +86,19 @@ def test_align_entry_points_validate_arguments_before_touching_the_gpu():
     assert L.dexb_align_expand(p, p, ip, None, 1, 4, 80, 8, None, p, p, None) == -1
     assert L.dexb_align_expand(p, p, ip, p, 1, 4, 80, 0, None, p, p, None) == -1
     assert b"Ty = 0" in L.dexb_last_error()
+
+
+def test_text_encoder_handle_fails_loudly_without_gpu():
+    """dexb_text_create touches the device first: on a box without one it returns an error code and a message, never a handle."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes
+    from dexb200 import lib
+    L = lib.load()
+    h = ctypes.c_void_p()
+    rc = L.dexb_text_create(149, 80, 192, 1024, 256, 2, 8, 3, 1, ctypes.byref(h))
+    assert rc != 0 and not h.value and len(L.dexb_last_error()) > 0
+    from dexb200.model import TextEncoder
+    with pytest.raises(RuntimeError):
+        TextEncoder(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8,
+                    kernel_size=3, p_dropout=0.1, use_softmax=True, use_decay=False).cuda_engine()

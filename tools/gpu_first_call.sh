@@ -13,6 +13,7 @@ python -m pytest tests -q -m gpu -s 2>&1 | tail -150 > "$OUT/${TAG}_pytest_gpu.l
 tail -3 "$OUT/${TAG}_pytest_gpu.log"
 python tools/text_check.py > "$OUT/${TAG}_text_check.log" 2>&1
 python tools/align_bench.py > "$OUT/${TAG}_align_bench.json" 2> "$OUT/${TAG}_align_bench.err"
+python tools/tts_bench.py > "$OUT/${TAG}_tts_bench.json" 2> "$OUT/${TAG}_tts_bench.err"
 python tools/enc_bench.py > "$OUT/${TAG}_enc_bench.json" 2> "$OUT/${TAG}_enc_bench.err"
 python bench.py --steps 5 --warmup 3 > "$OUT/${TAG}_bench_default.json" 2> "$OUT/${TAG}_bench_default.err"
 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/${TAG}_bench_reference.json" 2> "$OUT/${TAG}_bench_reference.err"
