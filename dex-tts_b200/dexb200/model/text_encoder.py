@@ -100,8 +100,10 @@ class TextEncoderEngine:
 
 
 def _register_text(root, manifest, n_channels):
-    """Parameters / buffers under the reference's names with the reference's initialisation (text_encoder.py:113-127,52-53;
-    retention.py:225-229,75-86; base.py:174-178)."""
+    """Parameters / buffers under the reference's names.  Initial values: the tensors upstream zero-initialises stay zero (prenet.proj,
+    text_encoder.py:52-53; the AdaLN W_scale / W_bias weights with biases 1 / 0, base.py:174-178), the embedding is N(0, C^-0.5)
+    (:113-114), the two RetNetRelPos buffers are upstream's closed forms (retention.py:75-86); every other weight gets a plain
+    U(-1, 1) / sqrt(fan_in) draw (upstream: xavier / nn.Linear defaults) -- real use loads a checkpoint over them."""
     n_heads = [shape[0] for _, shape, kind in manifest if kind == "decay"][0]
     for name, shape, kind in manifest:
         parts = name.split(".")
@@ -122,7 +124,7 @@ def _register_text(root, manifest, n_channels):
             t = torch.zeros(shape)
         elif kind == "bias":
             t = torch.zeros(shape)
-        elif kind == "bn_w":
+        elif kind == "bn_w":                                 # norm gains and the AdaLN W_scale bias: 1
             t = torch.ones(shape)
         elif kind == "bn_b":
             t = torch.zeros(shape)
