@@ -1221,9 +1221,7 @@ static void txt_release_plan(dexb_text* h) {
   for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
 }
 
-static int txt_plan(dexb_text* h, int B, int T) {
-  if (B == h->B && T == h->T) return 0;
-  txt_release_plan(h);
+static int txt_plan_build(dexb_text* h, int B, int T) {
   DEXB_TRY(gemm_global_init());
   const int C = h->C;
   int Kmax = C, Cmax = C;
@@ -1258,6 +1256,13 @@ static int txt_plan(dexb_text* h, int B, int T) {
   DEXB_TRY(tv_plan_conv(h, &h->dp1, h->xs, h->acc));
   DEXB_TRY(tv_plan_conv(h, &h->dp2, h->hs, h->acc));
   return 0;
+}
+static int txt_plan(dexb_text* h, int B, int T) {
+  if (B == h->B && T == h->T) return 0;
+  txt_release_plan(h);
+  const int rc = txt_plan_build(h, B, T);
+  if (rc != 0) txt_release_plan(h);          // never keep a half-built plan: the next call starts from scratch
+  return rc;
 }
 
 static TxtRow txt_row(const dexb_text* h, const float* in) {
