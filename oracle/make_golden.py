@@ -35,6 +35,9 @@ CASES = [
     ("dex_b1",     "dex",   1, 44, 23, 4, False, True, 21),
     ("dex_b2r",    "dex",   2, 48, 19, 3, True,  True, 22),
     ("gedex_spk_b2r", "gedex", 2, 44, 0, 3, True, True, 14, 4),    # multi-speaker GeDEX-TTS: n_spks = 4 (third input channel)
+    # DEX-TTS/config/LibriTTS/base.yaml:65,77: decoder dim 128, DiT hidden 384 (head dim 192).  Oracle-only fixture: the CUDA engine
+    # instantiates dim 64 / hidden 256 so far, so the name keeps it out of the GPU tests' dex_* / gedex_* globs.
+    ("libri_dex_b1", "dex", 1, 44, 23, 3, False, True, 31, None, dict(dim=128, hidden=384)),
 ]
 TEMPERATURE = 1.5
 TAP_STRIDE = 16
@@ -48,8 +51,8 @@ def ref_cfgs(cfg):
     return dec, dit
 
 
-def run_case(name, variant, B, T, Ts, steps, ragged, live, seed, n_spks=None):
-    cfg = DecoderCfg.make(variant, n_spks=n_spks)
+def run_case(name, variant, B, T, Ts, steps, ragged, live, seed, n_spks=None, dims=None):
+    cfg = DecoderCfg.make(variant, n_spks=n_spks, **(dims or {}))
     dec_cfg, dit_cfg = ref_cfgs(cfg)
     dec, mod = ref_loader.build_reference_decoder(variant, dec_cfg, dit_cfg, n_spks=n_spks)
     w = synth_decoder_weights(cfg, seed=100, live=live)
@@ -98,7 +101,8 @@ def run_case(name, variant, B, T, Ts, steps, ragged, live, seed, n_spks=None):
         for h in hooks:
             h.remove()
     out = dict(y=y.numpy(), meta=np.array([B, T, Ts, steps, int(ragged), int(live), seed] + ([int(n_spks)] if n_spks else []), dtype=np.int64),
-               variant=np.array(variant), temperature=np.array(TEMPERATURE, dtype=np.float32))
+               variant=np.array(variant), temperature=np.array(TEMPERATURE, dtype=np.float32),
+               dims=np.array([cfg.dim, cfg.hidden], dtype=np.int64))
     for k, v in taps.items():               # intermediates: channel-strided subsample keeps the fixtures small
         a = v.numpy().astype(np.float32)
         out["tap_" + k] = a if a.ndim == 3 else a[:, ::TAP_STRIDE]

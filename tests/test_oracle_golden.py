@@ -12,7 +12,8 @@ from dexb200.manifest import DecoderCfg
 from dexb200.synth import synth_decoder_weights, synth_inputs
 from parity import per_bin_violation, tensor_rel_err
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if os.path.basename(p).startswith(("dex_", "gedex_")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+              if os.path.basename(p).startswith(("dex_", "gedex_", "libri_dex_")))       # libri_*: LibriTTS decoder sizes (dim 128 / hidden 384)
 
 
 def load_case(path):
@@ -20,7 +21,8 @@ def load_case(path):
     meta = [int(v) for v in g["meta"]]
     B, T, Ts, steps, ragged, live, seed = meta[:7]
     variant = str(g["variant"])
-    cfg = DecoderCfg.make(variant, n_spks=meta[7] if len(meta) > 7 else None)     # 8th entry: multi-speaker GeDEX-TTS
+    dims = dict(dim=int(g["dims"][0]), hidden=int(g["dims"][1])) if "dims" in g.files else {}
+    cfg = DecoderCfg.make(variant, n_spks=meta[7] if len(meta) > 7 else None, **dims)     # 8th entry: multi-speaker GeDEX-TTS
     w = synth_decoder_weights(cfg, seed=100, live=bool(live))
     inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=seed, ragged=bool(ragged))
     cond = None
@@ -38,7 +40,7 @@ def test_golden_present():
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_matches_reference(path):
     g, cfg, w, inp, cond, steps = load_case(path)
-    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks)
+    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks, dim=cfg.dim, hidden=cfg.hidden)
     with torch.no_grad():
         y = O.reverse_diffusion(w, ocfg, inp["z"], inp["mask"], inp["mu"], steps,
                                 temperature=float(g["temperature"]), cond=cond)
@@ -51,7 +53,7 @@ def test_oracle_matches_reference(path):
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_intermediates(path):
     g, cfg, w, inp, cond, steps = load_case(path)
-    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks)
+    ocfg = O.make_cfg(cfg.variant, n_spks=cfg.n_spks, dim=cfg.dim, hidden=cfg.hidden)
     taps = {}
     ts = O.sigma_schedule(steps)
     x0 = (inp["z"] / float(g["temperature"]) + inp["mu"]) * ts[0]
