@@ -277,17 +277,20 @@ def synth_align_inputs(B, Tx, n_feats=80, seed=61, ragged=False, mean_dur=4.0):
 
 
 def text_manifest(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8,
-                  kernel_size=3, adaln=True):
+                  kernel_size=3, adaln=True, spk_emb_dim=0):
     """[(name relative to ``encoder.``, shape, kind)] -- the ``state_dict`` of the reference TextEncoder for n_spks <= 1
     (DEX-TTS/model/text_encoder.py:97-142: Embedding, ConvReluNorm prenet, RetNetModel, proj_m, DurationPredictor), in its order.
-    adaln=False: GeDEX-TTS's encoder (no AdaptiveLayerNorm in the RetNet layers)."""
-    C, Fc, Fd = n_channels, filter_channels, filter_channels_dp
-    out = [("emb.weight", (n_vocab, C), "emb")]
+    adaln=False: GeDEX-TTS's encoder (no AdaptiveLayerNorm in the RetNet layers).  spk_emb_dim > 0: the n_spks > 1 layout, where the
+    speaker embedding is concatenated to the prenet output and everything behind the prenet is n_channels + spk_emb_dim wide
+    (text_encoder.py:119-127,135-136) -- oracle / fixtures only, the CUDA text encoder takes spk_emb_dim = 0."""
+    P, Fc, Fd = n_channels, filter_channels, filter_channels_dp                      # P: embedding / prenet width
+    out = [("emb.weight", (n_vocab, P), "emb")]
     for i in range(3):                                                               # prenet: kernel 5, 3 layers (:116-117)
-        out.extend([(f"prenet.conv_layers.{i}.weight", (C, C, 5), "conv"), (f"prenet.conv_layers.{i}.bias", (C,), "bias")])
+        out.extend([(f"prenet.conv_layers.{i}.weight", (P, P, 5), "conv"), (f"prenet.conv_layers.{i}.bias", (P,), "bias")])
     for i in range(3):
-        out.extend([(f"prenet.norm_layers.{i}.gamma", (C,), "bn_w"), (f"prenet.norm_layers.{i}.beta", (C,), "bn_b")])
-    out.extend([("prenet.proj.weight", (C, C, 1), "conv"), ("prenet.proj.bias", (C,), "bias")])
+        out.extend([(f"prenet.norm_layers.{i}.gamma", (P,), "bn_w"), (f"prenet.norm_layers.{i}.beta", (P,), "bn_b")])
+    out.extend([("prenet.proj.weight", (P, P, 1), "conv"), ("prenet.proj.bias", (P,), "bias")])
+    C = P + spk_emb_dim                                                              # width of everything behind the prenet
     for l in range(n_layers):                                                        # RetNetDecoderLayer (retention.py:396-513)
         p = f"encoder.layers.{l}."
         out.extend([(p + f"retention.{n}_proj.weight", (C, C), "lin") for n in ("q", "k", "v", "g", "out")])

@@ -123,9 +123,11 @@ def duration_predictor(w, x, x_mask, prefix="encoder.proj_w"):
     return F.conv1d(x * x_mask, w[prefix + ".proj.weight"], w[prefix + ".proj.bias"]) * x_mask
 
 
-def text_encoder(w, x_ids, x_lengths, sty, n_layers=8, n_heads=2, prefix="encoder", taps=None):
+def text_encoder(w, x_ids, x_lengths, sty, n_layers=8, n_heads=2, prefix="encoder", taps=None, spk=None):
     """TextEncoder.forward(x, x_lengths, sty, spk=None) for n_spks <= 1, text_encoder.py:129-142; with sty=None it is
     GeDEX-TTS's TextEncoder.forward(x, x_lengths, spk=None) (GeDEX-TTS/model/text_encoder.py:132-146: the same code without the style).
+    spk (B, spk_emb_dim): the n_spks > 1 branch -- the speaker embedding is repeated over time and concatenated to the prenet output
+    (:135-136), everything behind it is C + spk_emb_dim wide.
     x_ids (B,Tx) long, x_lengths (B,), sty (B,C) -> (mu_x (B,n_feats,Tx), logw (B,1,Tx), x_mask (B,1,Tx))."""
     emb = w[prefix + ".emb.weight"]
     C = emb.shape[1]
@@ -134,6 +136,8 @@ def text_encoder(w, x_ids, x_lengths, sty, n_layers=8, n_heads=2, prefix="encode
     x = prenet(w, x, x_mask, prefix + ".prenet")                                                      # :134
     if taps is not None:
         taps["prenet"] = x
+    if spk is not None:
+        x = torch.cat([x, spk.unsqueeze(-1).repeat(1, 1, x.shape[-1])], dim=1)                        # :135-136
     x = retnet(w, x.transpose(1, 2), x_mask, sty, n_layers, n_heads, prefix + ".encoder", taps).transpose(1, 2) * x_mask   # :137
     mu = F.conv1d(x, w[prefix + ".proj_m.weight"], w[prefix + ".proj_m.bias"]) * x_mask               # :138
     return mu, duration_predictor(w, x, x_mask, prefix + ".proj_w"), x_mask                           # :140-142

@@ -20,23 +20,24 @@ TOL = 2e-5      # measured 0 (bit-exact) in the build container; the bound cover
 
 def oracle_case(path):
     g = np.load(path)
-    B, Tx, ragged, seed, dex = [int(v) for v in g["meta"]]
+    B, Tx, ragged, seed, dex, n_spks = [int(v) for v in g["meta"]]
     inp = synth_text(B, Tx, seed=seed, ragged=bool(ragged))
     taps = {}
+    spk = torch.randn(B, 64, generator=torch.Generator().manual_seed(seed + 7)) if n_spks > 1 else None
     with torch.no_grad():                                   # dex = 0: GeDEX-TTS's encoder (no AdaLN, no style argument)
-        mu, logw, x_mask = TO.text_encoder(synth_text_weights(adaln=bool(dex)), inp["x"], inp["x_lengths"],
-                                           inp["sty"] if dex else None, taps=taps)
+        mu, logw, x_mask = TO.text_encoder(synth_text_weights(adaln=bool(dex), spk_emb_dim=64 if n_spks > 1 else 0), inp["x"],
+                                           inp["x_lengths"], inp["sty"] if dex else None, taps=taps, spk=spk)
     return g, inp, mu, logw, x_mask, taps
 
 
 def test_golden_present():
-    assert len(GOLD) >= 3
+    assert len(GOLD) >= 4
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_manifest_is_the_reference_state_dict_layout(path):
     g = np.load(path)
-    assert [n for n, _, _ in text_manifest(adaln=bool(g["meta"][4]))] == [str(k) for k in g["keys"]]
+    assert [n for n, _, _ in text_manifest(adaln=bool(g["meta"][4]), spk_emb_dim=64 if g["meta"][5] > 1 else 0)] == [str(k) for k in g["keys"]]
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
