@@ -5,7 +5,8 @@ What is asserted and why: the text side (enc_out, the hard alignment) is held to
 away from rounding boundaries; the decoder is compared with the CPU oracle of the loop fed with the GPU's OWN conditioning (mu_y,
 sty, ref_skips captured at ``model.decoder``) -- on these random weights two sampler steps amplify a 1e-6 perturbation of ``sty`` a
 hundredfold (tests/test_tts_oracle.py), so dec_out against the fixture is printed, not bounded.  Written after this round's GPU budget was
-spent: NOT YET RUN on a B200 (every stage it chains has its own GPU tests that were)."""
+spent: NOT YET RUN on a B200 (every stage it chains was checked on one: the GPU suite, tools/text_check.py); its Python logic was
+dry-run on the CPU with oracle-backed stages."""
 import glob
 import os
 import sys
