@@ -90,6 +90,8 @@ SYMBOLS = {
     "dexb_text_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "dexb_text_set_layer_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dexb_text_copy_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_mas_maximum_path": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_align_lengths": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_align_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,

@@ -7,3 +7,4 @@ from .ref_encoder import LF0Encoder, TIVEncoder, TVEncoder, style_fusion  # noqa
 from .utils import align_durations, fix_len_compatibility, sequence_mask  # noqa: F401
 from .text_encoder import GeTextEncoder, TextEncoder  # noqa: F401
 from .tts import DeXTTS, GeDEXTTS  # noqa: F401
+from . import monotonic_align  # noqa: F401,E402

@@ -251,6 +251,13 @@ long dexb_text_last_launch_count(const dexb_text* h);
 int dexb_text_set_layer_limit(dexb_text* h, int n_layers);
 int dexb_text_copy_stream(const dexb_text* h, float* rows_dev, void* stream);
 
+/* replaces: monotonic_align.maximum_path(value, mask) (DEX-TTS/model/monotonic_align/__init__.py:8-25 over the Cython kernel
+ * core.pyx:9-47; call site DEX-TTS/model/tts.py:108, training).  value_dev, mask_dev (B, Tx, Ty) fp32 (mask in {0,1}, the outer product
+ * of the two sequence masks) -> path_dev (B, Tx, Ty) fp32 zeros / ones.  scratch_dev: B * Tx * Ty bytes.  One CTA per utterance;
+ * the per-utterance lengths are read from the mask's first column / row as upstream does.  Never allocates or synchronises. */
+int dexb_mas_maximum_path(const float* value_dev, const float* mask_dev, int B, int Tx, int Ty, uint8_t* scratch_dev, float* path_dev,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,13 @@ def test_text_encoder_handle_fails_loudly_without_gpu():
     with pytest.raises(RuntimeError):
         TextEncoder(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8,
                     kernel_size=3, p_dropout=0.1, use_softmax=True, use_decay=False).cuda_engine()
+
+
+def test_mas_entry_point_validates_arguments_before_touching_the_gpu():
+    import ctypes
+    from dexb200 import lib
+    L = lib.load()
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.dexb_mas_maximum_path(None, p, 1, 2, 2, p, p, None) == -1 and b"null" in L.dexb_last_error()
+    assert L.dexb_mas_maximum_path(p, p, 1, 5000, 2, p, p, None) == -1 and b"Tx = 5000" in L.dexb_last_error()

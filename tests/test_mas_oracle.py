@@ -58,3 +58,35 @@ def test_oracle_path_is_optimal_on_a_small_case():
     best = max(sum(value[0, x, y] for y, x in enumerate(np.cumsum((0,) + steps)))
                for steps in itertools.product((0, 1), repeat=6) if sum(steps) == 3)
     assert abs(float((out * value[0]).sum()) - float(best)) < 1e-5
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_kernel_arithmetic_reproduces_reference(path):
+    """csrc/mas.cu replayed in numpy float32, statement by statement: only the previous column is kept (two buffers), the backtrack
+    decision is taken in the forward pass and stored per (y, x), the walk back reads the stored decisions.  Checks the algorithm the
+    kernel implements against the reference kernel's output on a box without a GPU; the kernel itself: tests/test_mas_gpu.py."""
+    f32 = np.float32
+    value, mask, ref = load_case(path)
+    B, Tx, Ty = value.shape
+    out = np.zeros_like(ref)
+    for b in range(B):
+        t_x = int((mask[b, :, 0] != 0).sum())
+        t_y = int((mask[b, 0, :] != 0).sum())
+        dec = np.zeros((Ty, Tx), np.uint8)
+        prev, cur = np.full(Tx, np.nan, f32), np.full(Tx, np.nan, f32)          # NaN: a read outside the previous band would show
+        for y in range(t_y):
+            for x in range(max(0, t_x + y - t_y), min(t_x, y + 1)):
+                raw = f32(value[b, x, y] * mask[b, x, y])
+                v_cur = f32(-1e9) if x == y else prev[x]
+                v_prev = (f32(0) if y == 0 else f32(-1e9)) if x == 0 else prev[x - 1]
+                assert not (np.isnan(v_cur) or np.isnan(v_prev))
+                cur[x] = f32(max(v_cur, v_prev) + raw)
+                dec[y, x] = 1 if (x == y or v_cur < v_prev) else 0
+            prev, cur = cur, prev
+            cur[:] = np.nan
+        index = t_x - 1
+        for y in range(t_y - 1, -1, -1):
+            out[b, index, y] = 1
+            if index != 0 and y > 0 and dec[y, index]:
+                index -= 1
+    assert np.array_equal(out, ref)
