@@ -16,7 +16,10 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    items.sort(key=lambda it: it.get_closest_marker("run_last") is not None)          # stable: everything else keeps its order
+    def last_key(it):                        # (0, 0) for validated items; run_last(n) items after them, in increasing n
+        m = it.get_closest_marker("run_last")
+        return (0, 0) if m is None else (1, m.args[0] if m.args else 0)
+    items.sort(key=last_key)                 # stable: everything else keeps its order
     try:
         import torch
         has_gpu = torch.cuda.is_available()
