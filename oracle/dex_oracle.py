@@ -320,6 +320,17 @@ def edm_precond(w, cfg, x, sigma, mask, mu, cond=None, sigma_data=0.5, taps=None
     return c_skip * x + c_out * f_x
 
 
+def edm_loss(w, cfg, x0, mask, mu, rnd_normal, noise, cond=None, P_mean=-1.2, P_std=1.2, sigma_data=0.5, n_feats=80):
+    """EDMLoss.forward with loss_type 'base', DEX-TTS/model/edm.py:31-38,64-68 (the training branch of Diffusion.forward,
+    diffusion.py:252-254), with its two Gaussian draws injected: rnd_normal (B,1,1) -> the per-utterance noise
+    level, noise (B,80,T) -> the prior-shifted perturbation (noise + mu) * sigma.  Forward value only; no CUDA side."""
+    sigma = (rnd_normal * P_std + P_mean).exp()                                                       # :34
+    weight = (sigma ** 2 + sigma_data ** 2) / (sigma * sigma_data) ** 2                               # :38
+    n = (noise + mu) * sigma                                                                          # :64
+    d_yn = edm_precond(w, cfg, x0 + n, sigma.reshape(-1), mask, mu, cond=cond, sigma_data=sigma_data)  # :65
+    return torch.sum(weight * ((d_yn - x0) ** 2)) / torch.sum(mask * n_feats)                         # :66
+
+
 def sigma_schedule(num_steps, sigma_min=0.002, sigma_max=80.0, rho=7, dtype=torch.float32):
     """EDM discretisation in fp32 as the reference computes it, plus the trailing 0.  DEX-TTS/model/edm.py:135-152,179-180."""
     idx = torch.arange(num_steps)
