@@ -126,6 +126,11 @@ int dexb_reverse_diffusion_host(dexb_handle* h, float* x_inout_host, const float
   return 0;
 }
 
+int dexb_debug_tap(dexb_handle* h, const char* name, float* out_dev, int* C, int* H, int* W, void* stream) {
+  DEXB_CHECK(h != nullptr && name != nullptr, "null argument");
+  return engine_debug_tap(h, name, out_dev, C, H, W, (cudaStream_t)stream);
+}
+
 int dexb_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, void* stream) {
   DEXB_CHECK(h != nullptr, "null handle");
   return engine_profile_step(h, step, buf, buflen, (cudaStream_t)stream);

@@ -1086,6 +1086,38 @@ int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mas
   return 0;
 }
 
+// Test aid: copy one internal activation of the LAST un-graphed network call (dexb_denoise_once) as fp32 (B, C, H, W).
+// Only buffers that are not overwritten later in the step are offered.  Names follow the reference modules whose output they hold:
+//   d00 / d01 (downs.0.0 / downs.0.1), skip (downs.1.2, masked), tv_out (tv_adaptor), dit_out (vit), u00 / u01 (ups.0.0 / ups.0.1),
+//   up_out (ups.0.3).
+int engine_debug_tap(dexb_handle* h, const char* name, float* out, int* C_out, int* H_out, int* W_out, cudaStream_t st) {
+  DEXB_CHECK(h->planned, "dexb_debug_tap: call dexb_plan / dexb_denoise_once first");
+  const int d = h->cfg.dim, mid = 2 * d;
+  const std::string n = name;
+  const bf16* sp = nullptr; const float* fp = nullptr;
+  long stride = 0; int hi = 0, lo = 0, C = 0, H = 0, W = 0;
+  if (n == "d00") { sp = h->B0; stride = 2 * d; lo = d; C = d; H = h->H0; W = h->W0; }
+  else if (n == "d01") { sp = h->C0; stride = 2 * d; lo = d; C = d; H = h->H0; W = h->W0; }
+  else if (n == "skip") { sp = h->cat; stride = 4 * mid; hi = mid; lo = 3 * mid; C = mid; H = h->H1; W = h->W1; }
+  else if (n == "dit_out") { sp = h->cat; stride = 4 * mid; hi = 0; lo = 2 * mid; C = mid; H = h->H1; W = h->W1; }
+  else if (n == "tv_out") {
+    DEXB_CHECK(h->cfg.variant == 1, "tap 'tv_out' exists for DEX-TTS only");
+    fp = h->tvout; stride = mid; C = mid; H = h->H1; W = h->W1;
+  }
+  else if (n == "u00") { sp = h->B1; stride = 2 * d; lo = d; C = d; H = h->H1; W = h->W1; }
+  else if (n == "u01") { sp = h->C1; stride = 2 * d; lo = d; C = d; H = h->H1; W = h->W1; }
+  else if (n == "up_out") { sp = h->A0; stride = 2 * d; lo = d; C = d; H = h->H0; W = h->W0; }
+  else DEXB_CHECK(false, "dexb_debug_tap: unknown tap '%s'", name);
+  if (C_out != nullptr) *C_out = C;
+  if (H_out != nullptr) *H_out = H;
+  if (W_out != nullptr) *W_out = W;
+  if (out != nullptr) {
+    launch_tap_nchw(sp, stride, hi, lo, fp, stride, out, h->B, C, (long)H * W, st);
+    DEXB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 // One un-graphed network call with CUDA events around every launch; writes "tag\tms\tgflop" lines into buf.
 int engine_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, cudaStream_t st) {
   DEXB_CHECK(h->planned, "dexb_profile_step: call dexb_plan (and one dexb_reverse_diffusion) first");

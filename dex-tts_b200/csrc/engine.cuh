@@ -161,4 +161,5 @@ int engine_run(dexb_handle* h, float* x_inout, const float* mu, const float* mas
 void engine_release_plan(dexb_handle* h);
 int engine_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, cudaStream_t st);
 void engine_release_weights(dexb_handle* h);
+int engine_debug_tap(dexb_handle* h, const char* name, float* out, int* C, int* H, int* W, cudaStream_t st);
 }  // namespace dexb

@@ -135,5 +135,8 @@ int launch_stft_mel(const float* wav, int B, int S, const float* window, const f
                     int n_mels, float* mel, cudaStream_t st);
 void launch_unpack_rows(const bf16* in, float* out, long rows, int K, cudaStream_t st);
 void launch_pack_rows(const float* in, bf16* out, long rows, int K, cudaStream_t st);
+// debug tap: S view (sp != null) or F rows (fp) of B images x P pixels x C channels -> fp32 (B, C, P)
+void launch_tap_nchw(const bf16* sp, long s_stride, int hi, int lo, const float* fp, long f_stride, float* out, int B, int C, long P,
+                     cudaStream_t st);
 
 }  // namespace dexb

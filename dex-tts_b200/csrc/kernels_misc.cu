@@ -222,4 +222,23 @@ void launch_unpack_rows(const bf16* in, float* out, long rows, int K, cudaStream
   k_unpack_rows<<<cdiv(rows * K, 256), 256, 0, st>>>(in, out, rows, K);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Debug tap (test aid, dexb_debug_tap): an internal NHWC activation (S view or F rows) -> fp32 NCHW like the reference's tensors.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tap_nchw(const bf16* __restrict__ sp, long s_stride, int hi, int lo,
+                                                  const float* __restrict__ fp, long f_stride, float* __restrict__ out, int B,
+                                                  int C, long P) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)B * C * P) return;
+  const long p = i % P;
+  const int c = (int)((i / P) % C), b = (int)(i / (P * C));
+  const long row = (long)b * P + p;
+  out[i] = (sp != nullptr) ? join2(sp[row * s_stride + hi + c], sp[row * s_stride + lo + c]) : fp[row * f_stride + c];
+}
+void launch_tap_nchw(const bf16* sp, long s_stride, int hi, int lo, const float* fp, long f_stride, float* out, int B, int C, long P,
+                     cudaStream_t st) {
+  k_tap_nchw<<<cdiv((long)B * C * P, 256), 256, 0, st>>>(sp, s_stride, hi, lo, fp, f_stride, out, B, C, P);
+}
+
 }  // namespace dexb

@@ -181,6 +181,17 @@ class ReverseDiffusion:
         del keep
         return out
 
+    def debug_tap(self, name):
+        """fp32 (B, C, H, W) copy of an internal activation of the last ``denoise_once`` call (names: include/dexb200.h)."""
+        C, H, W = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        _lib.check(self.L.dexb_debug_tap(self.h, name.encode(), None, ctypes.byref(C), ctypes.byref(H), ctypes.byref(W), _stream()),
+                   "dexb_debug_tap")
+        out = torch.empty(self.plan_key[0], C.value, H.value, W.value, device="cuda", dtype=torch.float32)
+        _lib.check(self.L.dexb_debug_tap(self.h, name.encode(), _ptr(out), ctypes.byref(C), ctypes.byref(H), ctypes.byref(W), _stream()),
+                   "dexb_debug_tap")
+        torch.cuda.synchronize()
+        return out
+
     def profile_step(self, step=0):
         """[(tag, ms, gflop)] for every launch of one network call (un-graphed, events around each launch)."""
         buf = ctypes.create_string_buffer(1 << 16)

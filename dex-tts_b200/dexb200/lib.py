@@ -52,6 +52,8 @@ SYMBOLS = {
                                       ctypes.c_void_p]),
     "dexb_stft_mel": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_debug_tap": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
     "dexb_profile_step": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]),
     "dexb_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "dexb_simt_fallbacks": (ctypes.c_int, [ctypes.c_void_p]),

@@ -112,6 +112,12 @@ int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft,
                   int hop, int n_mels, float* mel_dev, void* stream);
 
+/* Test aid (failure localisation against the reference's forward hooks, oracle/make_golden.py): copies one internal activation of
+ * the LAST dexb_denoise_once call as fp32 (B, C, H, W) into out_dev and reports C, H, W (out_dev == NULL: sizes only).  Names are
+ * the reference modules whose output the buffer holds (DEX-TTS/model/diffusion.py:204-232): "d00", "d01" (downs.0.0/1),
+ * "skip" (downs.1.2, masked), "tv_out" (tv_adaptor), "dit_out" (vit), "u00", "u01" (ups.0.0/1), "up_out" (ups.0.3). */
+int dexb_debug_tap(dexb_handle* h, const char* name, float* out_dev, int* C, int* H, int* W, void* stream);
+
 /* Profiling aid: runs network call `step` once, un-graphed, with CUDA events around every launch, on the inputs staged
  * by the last dexb_reverse_diffusion; writes one "tag<TAB>ms<TAB>gflop" line per launch into buf.  Synchronises. */
 int dexb_profile_step(dexb_handle* h, int step, char* buf, size_t buflen, void* stream);

@@ -274,7 +274,11 @@ def denoiser(w, cfg, x, mask, mu, t, cond=None, prefix="denoise_fn", taps=None):
     m0 = mask.unsqueeze(1)                                                                     # (B,1,1,T)
     # level 0
     h = _resnet(w, p + ".downs.0.0", h, m0, t_unet)
+    if taps is not None:
+        taps["d00"] = h
     h = _resnet(w, p + ".downs.0.1", h, m0, t_unet)
+    if taps is not None:
+        taps["d01"] = h
     h = _linear_attention(w, p + ".downs.0.2", h)
     h = F.conv2d(h * m0, w[p + ".downs.0.3.conv.weight"], w[p + ".downs.0.3.conv.bias"], stride=2, padding=1)
     m1 = m0[:, :, :, ::2]
@@ -286,6 +290,7 @@ def denoiser(w, cfg, x, mask, mu, t, cond=None, prefix="denoise_fn", taps=None):
     h = h * m1
     if taps is not None:
         taps["down_out"] = h
+        taps["skip"] = h
     if dex:
         h = _tv_adaptor(w, p + ".tv_adaptor", h, m1, cond["sty"], sty_mask, t_sty)
         if taps is not None:
@@ -299,7 +304,11 @@ def denoiser(w, cfg, x, mask, mu, t, cond=None, prefix="denoise_fn", taps=None):
     # up
     h = torch.cat((h, skip), dim=1)
     h = _resnet(w, p + ".ups.0.0", h, m1, t_unet)
+    if taps is not None:
+        taps["u00"] = h
     h = _resnet(w, p + ".ups.0.1", h, m1, t_unet)
+    if taps is not None:
+        taps["u01"] = h
     h = _linear_attention(w, p + ".ups.0.2", h)
     h = F.conv_transpose2d(h * m1, w[p + ".ups.0.3.conv.weight"], w[p + ".ups.0.3.conv.bias"], stride=2, padding=1)
     if taps is not None:

@@ -38,9 +38,14 @@ CASES = [
     # DEX-TTS/config/LibriTTS/base.yaml:65,77: decoder dim 128, DiT hidden 384 (head dim 192).  Oracle-only fixture: the CUDA engine
     # instantiates dim 64 / hidden 256 so far, so the name keeps it out of the GPU tests' dex_* / gedex_* globs.
     ("libri_dex_b1", "dex", 1, 44, 23, 3, False, True, 31, None, dict(dim=128, hidden=384)),
+    # the benchmarked mel length (BASELINE.json configs 2-4: 80x512, style length 259): different code runs there -- four halo tiles
+    # per row, the attention tail split, split-KV linear-attention contexts.  Taps are additionally strided along time.
+    ("dex_t512_b1", "dex",  1, 512, 259, 3, False, True, 41),
+    ("gedex_t512_b1", "gedex", 1, 512, 0, 3, False, True, 42),
 ]
 TEMPERATURE = 1.5
 TAP_STRIDE = 16
+TAP_WSTRIDE = 8          # additional stride along time for the T >= 256 cases
 
 
 def ref_cfgs(cfg):
@@ -105,7 +110,9 @@ def run_case(name, variant, B, T, Ts, steps, ragged, live, seed, n_spks=None, di
                dims=np.array([cfg.dim, cfg.hidden], dtype=np.int64))
     for k, v in taps.items():               # intermediates: channel-strided subsample keeps the fixtures small
         a = v.numpy().astype(np.float32)
-        out["tap_" + k] = a if a.ndim == 3 else a[:, ::TAP_STRIDE]
+        wst = TAP_WSTRIDE if T >= 256 else 1
+        out["tap_" + k] = a if a.ndim == 3 else a[:, ::TAP_STRIDE, :, ::wst]
+    out["tap_wstride"] = np.array(TAP_WSTRIDE if T >= 256 else 1, dtype=np.int64)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: y {tuple(y.shape)} |y|max {float(y.abs().max()):.4f} -> {os.path.relpath(path, ROOT)} "
