@@ -175,8 +175,11 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
   if (gp.halo && BN <= 128) {                          // the plan encoded 136-row A boxes: halo mode is the only valid launch
     int nb = (kTcSmemMax - tc_halo_bytes(BN, 0)) / (2 * BN * kTcBlockK * 2);
     if (nb > kTcMaxStages) nb = kTcMaxStages;
+    static int grouped = -1;                             // DEXB_HALO_GROUP=0: one barrier round per tap (the round-1 scheme)
+    if (grouped < 0) { const char* e = getenv("DEXB_HALO_GROUP"); grouped = (e != nullptr) ? atoi(e) : 1; }
+    const int mode = (grouped != 0 && nb >= 6) ? -(nb + 16) : -nb;      // grouped rounds need two rounds of weight slots
     const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_halo_bytes(BN, nb), st, gp.tmA, gp.tmB, p, (int)total, ntn, -nb);
+    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_halo_bytes(BN, nb), st, gp.tmA, gp.tmB, p, (int)total, ntn, mode);
     return 0;
   }
   const int rb = rb_stages_for(p, BN, m_tiles, ntn);
@@ -191,7 +194,11 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
   return 0;
 }
 
-int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st) {
+int gemm_launch(const GemmPlan& gp, const GemmParams& p_in, int engine, cudaStream_t st) {
+  static int late_wait = -1;
+  if (late_wait < 0) { const char* e = getenv("DEXB_EARLY_WAIT"); late_wait = (e != nullptr && e[0] == '0') ? 1 : 0; }
+  GemmParams p = p_in;
+  p.late_wait = late_wait;
   if (engine == 0 && gp.tc_ok) {
     if (epi_fast_ok(p)) {
       switch (gp.block_n) {

@@ -354,7 +354,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const GemmParams p, const int total_tiles, const int ntn, const int rb) {
   using SM = TcSmem<BLOCK_N>;
   const bool halo = rb < 0;
-  const int STAGES = rb > 0 ? rb : (halo ? -rb : SM::kStages);
+  // rb <= -16: halo mode with GROUPED rounds (STAGES = -rb - 16 >= 6 weight slots): the slab of a (dy, k-chunk) and the three weight
+  // tiles of its dx taps land on ONE barrier (a_full), so the MMA-issuing thread waits once per 24 MMAs instead of four times.
+  // Measured (tools/issue_bench.cu, profiles/r02_issue_bench.txt): an mbarrier wait costs the issuing thread ~240 cycles that do
+  // not overlap with the tensor pipe; one round per 3 stages + waiting for the NEXT round before committing this one brings the
+  // BLOCK_N = 64 stage from 987 to 589 cycles (tensor time 473).
+  const bool hgrp = rb <= -16;
+  const int STAGES = rb > 0 ? rb : (halo ? (hgrp ? -rb - 16 : -rb) : SM::kStages);
   constexpr int BB2 = 2 * SM::kBBytes;                               // one resident weight chunk: [B_hi | B_lo]
   // Stacked-N split product (BLOCK_N <= 128): B_hi and B_lo tiles are adjacent in shared memory, so ONE MMA with
   // N = 2*BLOCK_N computes A_hi*B_hi (columns [0, BN)) and A_hi*B_lo (columns [BN, 2BN)); a second MMA adds A_lo*B_hi to
@@ -428,6 +434,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kc = 0; kc < kchunks; ++kc) {
               ptx::mbar_wait(&a_empty[sa], pa ^ 1);
               uint8_t* sl = smem + sa * (2 * kTcHaloSlab);
+              if (hgrp) {
+                // one barrier per round: slab + the three weight tiles.  a_full[sa] of round r is re-armed for round r + 3 only
+                // after slab slot sa was released, i.e. after the issuer has passed the wait of round r.
+                uint64_t* gb = &a_full[sa];
+                ptx::mbar_expect_tx(gb, 2 * kTcHaloSlab + 3 * BB2);
+                ptx::tma_load_4d(sl, &tmA, gb, p.a_hi + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
+                ptx::tma_load_4d(sl + kTcHaloSlab, &tmA, gb, p.a_lo + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
+                if (++sa == kTcHaloASlots) { sa = 0; pa ^= 1; }
+                for (int tx = 0; tx < 3; ++tx) {
+                  ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+                  uint8_t* st = ring + s * BB2;
+                  if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+                  const int br = brow + tx * p.b_rows_per_tap;
+                  ptx::tma_load_3d(st, &tmB, gb, p.b_hi + kc * kTcBlockK, br, 0);
+                  ptx::tma_load_3d(st + SM::kBBytes, &tmB, gb, p.b_lo + kc * kTcBlockK, br, 0);
+                }
+                continue;
+              }
               ptx::mbar_expect_tx(&a_full[sa], 2 * kTcHaloSlab);
               ptx::tma_load_4d(sl, &tmA, &a_full[sa], p.a_hi + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
               ptx::tma_load_4d(sl + kTcHaloSlab, &tmA, &a_full[sa], p.a_lo + kc * kTcBlockK, tl.cw0 - 1, tl.ch0 + ty - 1, tl.img_a);
@@ -492,10 +516,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t bres_u = ptx::smem_u32(smem) >> 4;
       uint32_t s = 0, ph = 0;
       int li = 0;                                            // local tile counter -> accumulator buffer li & 1
+      const bool early_wait = p.late_wait == 0;              // tuning aid: DEXB_EARLY_WAIT=0 restores wait-at-the-top
+      bool pre_g = false;
       if (rb > 0 && blockIdx.x < total_tiles) ptx::mbar_wait(b_full, 0);
       if constexpr (STACKED) {
         if (halo) {
           uint32_t sa = 0, pa = 0;
+          bool prewaited = false;
           const uint32_t slab_u = ptx::smem_u32(smem) >> 4;
           for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
             const int buf = li & 1;
@@ -503,11 +530,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
             const int na = 3 * kchunks;                      // (dy, k-chunk) slab steps of a tile
+            if (hgrp) {
+              for (int ia = 0; ia < na; ++ia) {
+                if (!prewaited) ptx::mbar_wait(&a_full[sa], pa);
+                prewaited = false;
+                ptx::tc_fence_after();
+                const uint32_t a_base = slab_u + sa * (uint32_t)(2 * kTcHaloSlab >> 4);
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx) {
+                  const uint32_t a_hi = a_base + (uint32_t)(tx * 8);
+                  const uint32_t a_lo = a_hi + (kTcHaloSlab >> 4);
+                  const uint32_t b_hi = ring_u + s * stage_u;
+#pragma unroll
+                  for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+                    const uint32_t ko = kk * 2;
+                    const uint64_t dbh = kDescBase + (b_hi + ko);
+                    ptx::mma_bf16_ss(tacc, kDescBase + (a_hi + ko), dbh, idesc2, (ia > 0 || tx > 0 || kk > 0) ? 1u : 0u);
+                    ptx::mma_bf16_ss(tacc, kDescBase + (a_lo + ko), dbh, idesc, 1u);
+                  }
+                  ptx::mma_commit(&empty_bar[s]);            // weight slot free once these MMAs have retired
+                  if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+                }
+                const uint32_t sa0 = sa;
+                if (++sa == kTcHaloASlots) { sa = 0; pa ^= 1; }
+                if (ia == na - 1) {
+                  ptx::mma_commit(&acc_full[buf]);           // never delay the epilogue behind the next tile's operands
+                } else {
+                  ptx::mbar_wait(&a_full[sa], pa);           // the next round's operands, BEFORE this round's slab commit
+                  prewaited = true;
+                }
+                ptx::mma_commit(&a_empty[sa0]);
+              }
+              continue;
+            }
+            // per-tap rounds (weight tiles too large for two grouped rounds): the wait for the NEXT stage is issued before this
+            // stage's commit (profiles/r02_issue_bench.txt: 1127 -> 924 cycles per BLOCK_N = 128 stage); never across a tile end
+            bool pre_b = false;
             for (int ia = 0; ia < na; ++ia) {
-              ptx::mbar_wait(&a_full[sa], pa);
+              if (!prewaited) ptx::mbar_wait(&a_full[sa], pa);
+              prewaited = false;
               const uint32_t a_base = slab_u + sa * (uint32_t)(2 * kTcHaloSlab >> 4);
+              uint32_t san = sa + 1, pan = pa;
+              if (san == kTcHaloASlots) { san = 0; pan ^= 1; }
               for (int tx = 0; tx < 3; ++tx) {
-                ptx::mbar_wait(&full_bar[s], ph);
+                if (!pre_b) ptx::mbar_wait(&full_bar[s], ph);
+                pre_b = false;
                 ptx::tc_fence_after();
                 const uint32_t a_hi = a_base + (uint32_t)(tx * 8);          // tap dx: the slab shifted by dx rows of 128 B
                 const uint32_t a_lo = a_hi + (kTcHaloSlab >> 4);
@@ -519,12 +586,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   ptx::mma_bf16_ss(tacc, kDescBase + (a_hi + ko), dbh, idesc2, (ia > 0 || tx > 0 || kk > 0) ? 1u : 0u);
                   ptx::mma_bf16_ss(tacc, kDescBase + (a_lo + ko), dbh, idesc, 1u);
                 }
-                ptx::mma_commit(&empty_bar[s]);
+                uint64_t* eb = &empty_bar[s];
                 if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+                const bool last = (ia == na - 1) && (tx == 2);
+                if (last) ptx::mma_commit(&acc_full[buf]);
+                else if (early_wait) {
+                  if (tx == 2) { ptx::mbar_wait(&a_full[san], pan); prewaited = true; }
+                  ptx::mbar_wait(&full_bar[s], ph);
+                  pre_b = true;
+                }
+                ptx::mma_commit(eb);
               }
               ptx::mma_commit(&a_empty[sa]);                 // slab free once the MMAs of its three taps have retired
-              if (ia == na - 1) ptx::mma_commit(&acc_full[buf]);
-              if (++sa == kTcHaloASlots) { sa = 0; pa ^= 1; }
+              sa = san; pa = pan;
             }
           }
         }
@@ -536,7 +610,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tacc = tmem_base + (uint32_t)(buf * ACC_COLS);
         uint32_t bres = bres_u;                              // resident weight chunk of this iteration
         for (int it = 0; it < nk; ++it, bres += (uint32_t)(BB2 >> 4)) {
-          ptx::mbar_wait(&full_bar[s], ph);
+          if (!pre_g) ptx::mbar_wait(&full_bar[s], ph);
+          pre_g = false;
           ptx::tc_fence_after();
           const uint32_t a_hi = ring_u + s * stage_u;
           const uint32_t a_lo = a_hi + (SM::kABytes >> 4);
@@ -565,9 +640,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
-          ptx::mma_commit(&empty_bar[s]);                    // frees the smem stage when these MMAs retire
-          if (it == nk - 1) ptx::mma_commit(&acc_full[buf]); // accumulator complete
+          uint64_t* eb = &empty_bar[s];
           if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+          if (it == nk - 1) ptx::mma_commit(&acc_full[buf]); // accumulator complete
+          else if (early_wait) { ptx::mbar_wait(&full_bar[s], ph); pre_g = true; }   // next stage of this tile, before the commit
+          ptx::mma_commit(eb);                               // frees the smem stage when these MMAs retire
         }
       }
     }
