@@ -292,9 +292,9 @@ int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float
 }
 
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft, int hop,
-                  int n_mels, float* mel_dev, void* stream) {
+                  int n_mels, float* mel_dev, float* energy_dev, void* stream) {
   DEXB_CHECK(wav_dev != nullptr && window_dev != nullptr && mel_basis_dev != nullptr && mel_dev != nullptr, "null argument");
-  return launch_stft_mel(wav_dev, B, S, window_dev, mel_basis_dev, n_fft, hop, n_mels, mel_dev, (cudaStream_t)stream);
+  return launch_stft_mel(wav_dev, B, S, window_dev, mel_basis_dev, n_fft, hop, n_mels, mel_dev, energy_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -132,7 +132,7 @@ void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D,
 void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, cudaStream_t st);
 void launch_pack_convT(const float* w, bf16* out, int Ci, int Co, cudaStream_t st);
 int launch_stft_mel(const float* wav, int B, int S, const float* window, const float* mel_basis, int n_fft, int hop,
-                    int n_mels, float* mel, cudaStream_t st);
+                    int n_mels, float* mel, float* energy /*(B, frames) or null*/, cudaStream_t st);
 void launch_unpack_rows(const bf16* in, float* out, long rows, int K, cudaStream_t st);
 void launch_pack_rows(const float* in, bf16* out, long rows, int K, cudaStream_t st);
 // debug tap: S view (sp != null) or F rows (fp) of B images x P pixels x C channels -> fp32 (B, C, P)

@@ -239,15 +239,17 @@ def attn_test(qkv, heads):
     return out
 
 
-def stft_mel(wav, window, mel_basis, n_fft=1024, hop=256):
-    """wav (B,S) in [-1,1] on CUDA -> log-mel (B, n_mels, 1 + S // hop).  Mirrors TacotronSTFT.mel_spectrogram."""
+def stft_mel(wav, window, mel_basis, n_fft=1024, hop=256, return_energy=False):
+    """wav (B,S) in [-1,1] on CUDA -> log-mel (B, n_mels, 1 + S // hop) [, energy (B, 1 + S // hop)].  Mirrors
+    TacotronSTFT.mel_spectrogram (DEX-TTS/audio/stft.py:159-178)."""
     L = _lib.load()
     wav = wav.float().contiguous()
     B, S = wav.shape
     n_mels = mel_basis.shape[0]
     out = torch.empty(B, n_mels, S // hop + 1, device=wav.device, dtype=torch.float32)
+    energy = torch.empty(B, S // hop + 1, device=wav.device, dtype=torch.float32) if return_energy else None
     window = window.float().contiguous()
     mel_basis = mel_basis.float().contiguous()
-    _lib.check(L.dexb_stft_mel(_ptr(wav), B, S, _ptr(window), _ptr(mel_basis), n_fft, hop, n_mels, _ptr(out), _stream()),
-               "dexb_stft_mel")
-    return out
+    _lib.check(L.dexb_stft_mel(_ptr(wav), B, S, _ptr(window), _ptr(mel_basis), n_fft, hop, n_mels, _ptr(out),
+                               _ptr(energy) if energy is not None else None, _stream()), "dexb_stft_mel")
+    return (out, energy) if return_energy else out

@@ -9,7 +9,8 @@ temperature + mu``, diffusion.py:256-257) and hands the trajectory to libdexb200
 DiffusionDenoiser, all steps in one CUDA graph).  Parameters stay ordinary ``nn.Parameter``s registered under the
 reference's names -- including the aliasing of every denoiser tensor under both ``denoise_fn.*`` and
 ``precond_model.model.*`` (diffusion.py:242-243) -- so upstream checkpoints load with ``strict=True`` and ``.to()``,
-EMA copies etc. keep working.  The training branch (``infer=False`` -> EDMLoss) is out of scope and raises.
+EMA copies etc. keep working.  The training branch (``infer=False`` -> EDMLoss, diffusion.py:252-254) is not a CUDA path: it
+delegates to the reference's own ``model.diffusion.Diffusion`` running on THIS module's parameters (``reference_twin.py``).
 """
 import math
 
@@ -77,6 +78,17 @@ class _DiffusionBase(nn.Module):
         self._gemm_engine, self._nsplit = gemm_engine, nsplit
         self._engine = None
         self._sig = None
+        self._twin = None
+        self._ctor = dict(n_feats=n_feats, dim=dim, dit_cfg=dit_cfg, loss_type=loss_type, precond=precond, model_type=model_type,
+                          dim_mults=tuple(dim_mults), n_spks=n_spks, spk_emb_dim=spk_emb_dim, pe_scale=pe_scale)
+
+    def _training_twin(self):
+        """The reference's own ``Diffusion`` on this module's parameters (training branch only, see reference_twin.py)."""
+        if self._twin is None:
+            from .reference_twin import diffusion_twin
+            object.__setattr__(self, "_twin", diffusion_twin(self, self._ctor))     # not a registered sub-module: no duplicate keys
+        self._twin.train(self.training)
+        return self._twin
 
     # ---- CUDA engine management ---------------------------------------------------------------------
     def _weights_signature(self):
@@ -106,23 +118,25 @@ class Diffusion(_DiffusionBase):
     """DEX-TTS decoder (TV / TIV adaptors).  DEX-TTS/model/diffusion.py:238-259."""
     variant = "dex"
 
-    @torch.no_grad()
     def forward(self, x, mask, mu, ref, ref_lengths, sty, sty_lengths, n_timesteps=1, spk=None, infer=False, temperature=1.0,
                 mask_ratio=0):
-        if not infer:
-            raise NotImplementedError("training loss (EDMLoss, edm.py:22-68) is outside the CUDA inference path")
-        cond = dict(sty=sty, sty_lengths=sty_lengths, ref_skips=list(ref))
-        return self._run(x, mask, mu, n_timesteps, temperature, cond)
+        if not infer:                                                       # EDMLoss: the reference's PyTorch, our parameters
+            return self._training_twin()(x, mask, mu, ref, ref_lengths, sty, sty_lengths, n_timesteps=n_timesteps, spk=spk,
+                                         infer=False, temperature=temperature, mask_ratio=mask_ratio)
+        with torch.no_grad():
+            cond = dict(sty=sty, sty_lengths=sty_lengths, ref_skips=list(ref))
+            return self._run(x, mask, mu, n_timesteps, temperature, cond)
 
 
 class GeDiffusion(_DiffusionBase):
     """GeDEX-TTS decoder (no reference speech).  GeDEX-TTS/model/diffusion.py:209-229."""
     variant = "gedex"
 
-    @torch.no_grad()
     def forward(self, x, mask, mu, n_timesteps=1, spk=None, infer=False, temperature=1.0, mask_ratio=0):
         if not infer:
-            raise NotImplementedError("training loss (EDMLoss) is outside the CUDA inference path")
-        # n_spks > 1: `spk` is the speaker embedding GeDEXTTS.forward looked up (tts.py:30-31); it becomes the third input channel
-        cond = dict(spk=spk) if self.cfg.n_spks > 1 else None
-        return self._run(x, mask, mu, n_timesteps, temperature, cond)
+            return self._training_twin()(x, mask, mu, n_timesteps=n_timesteps, spk=spk, infer=False, temperature=temperature,
+                                         mask_ratio=mask_ratio)
+        with torch.no_grad():
+            # n_spks > 1: `spk` is the speaker embedding GeDEXTTS.forward looked up (tts.py:30-31); it becomes the third input channel
+            cond = dict(spk=spk) if self.cfg.n_spks > 1 else None
+            return self._run(x, mask, mu, n_timesteps, temperature, cond)

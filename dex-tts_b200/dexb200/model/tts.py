@@ -8,7 +8,8 @@ return value, same ``state_dict`` keys -- ``load_state_dict(ckpt['state_dict'])`
 ``forward`` is the reference's own sequence of calls with each stage replaced by its C-ABI counterpart: LF0 / TV encoders and the style
 fusion (``dexb_lf0_*``, ``dexb_tv_*``, ``dexb_style_fuse``), TIV encoder (``dexb_tiv_*``), text encoder (``dexb_text_*``), duration /
 alignment glue (``dexb_align_*``) and the reverse-diffusion loop (``dexb_reverse_diffusion``).  PyTorch only allocates the tensors and
-builds the three sequence masks.  ``compute_loss`` (training: EDMLoss, monotonic alignment search) is out of scope and raises.
+builds the three sequence masks.  ``compute_loss`` keeps the reference signature and delegates to the reference's own PyTorch
+training code running on this model's parameters, with the Monotonic Alignment Search on the CUDA kernel (``reference_twin.py``).
 """
 import torch
 import torch.nn as nn
@@ -28,6 +29,7 @@ class DeXTTS(nn.Module):
 
     def __init__(self, cfg):
         super().__init__()
+        self._cfg = cfg
         self.n_spks = 0                                                       # tts.py:16 forces cfg.n_spks = 0
         self.n_feats = _get(cfg, "n_feats")
         tv, dec = _get(cfg, "tv_encoder"), _get(cfg, "decoder")
@@ -61,9 +63,19 @@ class DeXTTS(nn.Module):
         dec_out = dec_out[:, :, :y_max_length]
         return enc_out, dec_out, attn[:, :, :y_max_length]                    # :74 (upstream slices the 4-D attn along Tx here)
 
-    def compute_loss(self, *args, **kwargs):
-        raise NotImplementedError("training (duration / prior / EDM losses, monotonic alignment search: tts.py:76-153) is outside the "
-                                  "CUDA inference path")
+    def _training_twin(self):
+        if getattr(self, "_twin", None) is None:
+            from .reference_twin import tts_twin
+            object.__setattr__(self, "_twin", tts_twin(self, self._cfg, "dex"))     # not a registered sub-module: no duplicate keys
+        self._twin.train(self.training)
+        return self._twin
+
+    def compute_loss(self, x, x_lengths, y, y_lengths, ref, ref_lengths, sty, sty_lengths, lf0, lf0_lengths, spk=None, out_size=None,
+                     mask_ratio=0):
+        """-> (dur_loss, prior_loss, diff_loss, vq_loss), DEX-TTS/model/tts.py:76-153.  Training is not a CUDA path of this package:
+        the reference's own modules compute it on this model's parameters (see reference_twin.py)."""
+        return self._training_twin().compute_loss(x, x_lengths, y, y_lengths, ref, ref_lengths, sty, sty_lengths, lf0, lf0_lengths,
+                                                  spk=spk, out_size=out_size, mask_ratio=mask_ratio)
 
 
 class GeDEXTTS(nn.Module):
@@ -71,6 +83,7 @@ class GeDEXTTS(nn.Module):
 
     def __init__(self, cfg):
         super().__init__()
+        self._cfg = cfg
         self.n_spks = _get(cfg, "n_spks")
         self.n_feats = _get(cfg, "n_feats")
         if self.n_spks > 1:
@@ -91,5 +104,14 @@ class GeDEXTTS(nn.Module):
         dec_out = dec_out[:, :, :y_max_length]
         return enc_out, dec_out, attn[:, :, :y_max_length]
 
-    def compute_loss(self, *args, **kwargs):
-        raise NotImplementedError("training (tts.py:58-121) is outside the CUDA inference path")
+    def _training_twin(self):
+        if getattr(self, "_twin", None) is None:
+            from .reference_twin import tts_twin
+            object.__setattr__(self, "_twin", tts_twin(self, self._cfg, "gedex"))
+        self._twin.train(self.training)
+        return self._twin
+
+    def compute_loss(self, x, x_lengths, y, y_lengths, spk=None, out_size=None, mask_ratio=0):
+        """-> (dur_loss, prior_loss, diff_loss), GeDEX-TTS/model/tts.py:58-121, computed by the reference's own modules on this
+        model's parameters (see reference_twin.py)."""
+        return self._training_twin().compute_loss(x, x_lengths, y, y_lengths, spk=spk, out_size=out_size, mask_ratio=mask_ratio)

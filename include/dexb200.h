@@ -107,10 +107,11 @@ int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, in
  * concatenated (before the proj Linear).  Allocates scratch and synchronises (test entry). */
 int dexb_attn_test(const float* qkv_dev, int B, int N, int heads, int hid, float* out_dev, void* stream);
 
-/* replaces: TacotronSTFT.mel_spectrogram (DEX-TTS/audio/stft.py:159-178) for 22.05 kHz / n_fft 1024 / hop 256 / 80 mels.
- * wav_dev (B, S) in [-1, 1]; mel_dev (B, 80, 1 + S/256) log-mel; mel_basis_dev (80, 513), window_dev (1024). */
+/* replaces: TacotronSTFT.mel_spectrogram (DEX-TTS/audio/stft.py:159-178) for n_fft 1024 / hop 256 and up to 128 mel rows.
+ * wav_dev (B, S) in [-1, 1]; mel_dev (B, n_mels, 1 + S/256) log-mel; mel_basis_dev (n_mels, 513), window_dev (1024);
+ * energy_dev (B, 1 + S/256) = L2 norm of the magnitude spectrum of every frame (stft.py:176), or NULL (the callers discard it). */
 int dexb_stft_mel(const float* wav_dev, int B, int S, const float* window_dev, const float* mel_basis_dev, int n_fft,
-                  int hop, int n_mels, float* mel_dev, void* stream);
+                  int hop, int n_mels, float* mel_dev, float* energy_dev, void* stream);
 
 /* Test aid (failure localisation against the reference's forward hooks, oracle/make_golden.py): copies one internal activation of
  * the LAST dexb_denoise_once call as fp32 (B, C, H, W) into out_dev and reports C, H, W (out_dev == NULL: sizes only).  Names are

@@ -100,10 +100,66 @@ def test_forward_glue_matches_reference_forward(path, monkeypatch):
     assert per_bin_violation(dec_out, torch.from_numpy(g["dec_out"])) < REL_TOL        # see tests/test_tts_oracle.py for the bound
 
 
-def test_training_entry_point_raises():
+REF_ROOT = os.environ.get("DEX_REFERENCE_ROOT", "/root/reference")
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "DEX-TTS", "model")),
+                                     reason="the reference checkout is only present in the build container")
+
+
+def _train_batch(variant, B=2, Tx=17, Ty=44, Ts=23):
+    inp = synth_tts_inputs(variant, B, Tx, Ts, 5, True)
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(B, 80, Ty, generator=g)
+    y_lengths = torch.tensor([Ty, Ty - 8])
+    return inp, y, y_lengths
+
+
+@needs_reference
+@pytest.mark.parametrize("variant", ["dex", "gedex"])
+def test_compute_loss_delegates_to_the_reference_on_our_parameters(variant, monkeypatch):
+    """``compute_loss`` (tts.py:76-153 / GeDEX tts.py:58-121) keeps its signature and is computed by the reference's own modules running
+    on the drop-in's parameters: same value as the unmodified reference model with the same weights and RNG state, and gradients land
+    on the drop-in's ``nn.Parameter``s.  (MAS runs on the CUDA kernel in production; on this CPU box the oracle stands in.)"""
+    import ref_loader
+    import mas_oracle
+    import dexb200.model.monotonic_align as M
+    import dexb200.model.reference_twin as RT
+    ref_model, _, cfg = ref_loader.build_reference_tts(variant)                       # installs the timm / transformers shims as well
+    mas = lambda value, mask: torch.from_numpy(mas_oracle.maximum_path(value.detach().numpy(), mask.detach().numpy())).to(value.dtype)
+    monkeypatch.setattr(M, "maximum_path", mas)
+    sys.modules["model.monotonic_align"].maximum_path = mas                          # the stub ref_loader registered for the reference model
+    RT.set_reference_dir(os.path.join(REF_ROOT, "DEX-TTS" if variant == "dex" else "GeDEX-TTS"))
+    model, w = build(variant)
+    ref_model.load_state_dict(reference_state_dict(w), strict=True)
+    model.train(); ref_model.train()
+    model._training_twin()                       # build the twin now: constructing it draws from the global RNG (parameter init)
+    inp, y, y_lengths = _train_batch(variant)
+    if variant == "dex":
+        args = (inp["x"], inp["x_lengths"], y, y_lengths, inp["ref"], inp["ref_lengths"], inp["ref"], inp["ref_lengths"], inp["lf0"],
+                inp["lf0_lengths"])
+    else:
+        args = (inp["x"], inp["x_lengths"], y, y_lengths)
+    torch.manual_seed(3); np.random.seed(3)
+    ours = model.compute_loss(*args, out_size=None)
+    torch.manual_seed(3); np.random.seed(3)
+    theirs = ref_model.compute_loss(*args, out_size=None)
+    assert len(ours) == len(theirs) == (4 if variant == "dex" else 3)
+    for a, b in zip(ours, theirs):
+        assert torch.isfinite(a).all() and torch.allclose(a, b, rtol=1e-5, atol=1e-6), (float(a), float(b))
+    sum(ours[:3]).backward()
+    grads = [p.grad for p in model.decoder.parameters() if p.grad is not None]
+    assert len(grads) > 50 and all(torch.isfinite(g).all() for g in grads)
+    assert list(model.state_dict().keys()) == list(ref_model.state_dict().keys())     # the twin adds no keys
+    RT.set_reference_dir(None)
+
+
+def test_training_entry_point_without_a_reference_checkout_says_what_to_do(tmp_path, monkeypatch):
+    import dexb200.model.reference_twin as RT
+    RT.set_reference_dir(None)
+    monkeypatch.delenv("DEXB_REFERENCE_DIR", raising=False)
+    monkeypatch.chdir(tmp_path)
     model, _ = build("gedex")
-    with pytest.raises(NotImplementedError):
-        model.compute_loss()
+    with pytest.raises(RuntimeError, match="DEXB_REFERENCE_DIR"):
+        model.compute_loss(torch.zeros(1, 4, dtype=torch.long), torch.tensor([4]), torch.zeros(1, 80, 8), torch.tensor([8]))
 
 
 def test_dropin_package_serves_the_reference_import_lines():
