@@ -7,10 +7,16 @@ A bench "step" is ONE complete reverse diffusion (all sampler steps) of one batc
 Default workload = BASELINE.json configs[1] ("C2"): DEX-TTS, batch 8 per GPU, 50 sampler steps, 80x512 mel, style
 length 259, synthetic inputs and seeded random ("live") weights of the reference architecture.
   value : mel-frames/s with inputs resident in HBM (CUDA events around K trajectories, max over ranks)
-  e2e   : the same metric through the host-buffer entry point (pinned host inputs -> device -> mel back on the host)
+  e2e   : the same metric through the public Python API, ``dexb200.model.Diffusion.forward(..., infer=True)`` (the module the
+          reference attaches as ``model.decoder``), with HOST inputs: pinned host tensors -> device copies -> loop -> mel back on
+          the host, all inside the timed region (+ the NCCL gather of the mels at N > 1)
+  parity: before anything is timed, sample 0 of the workload runs 2 sampler steps on the CUDA path and on the CPU oracle; the
+          per-bin violation (tolerance 1e-3) is printed in the line
   roofline     : the dominant kernel class (tcgen05 implicit-GEMM), timed live with CUDA events around its launches
-  cpu_baseline : the CPU oracle (port of the reference path, oracle/dex_oracle.py) timed on this box's host cores on a
-                 bounded sample (a few sampler steps of the same batch), extrapolated to the full step count
+  cpu_baseline : the REFERENCE's own modules (``baseline/_ref``: unmodified copy of DEX-TTS|GeDEX-TTS/model, staged by
+                 ``__graft_entry__.build()``) on this box's host cores, ``Diffusion.forward(infer=True)`` for a bounded number of
+                 sampler steps of the same batch, extrapolated to the full step count (kind "reference"; falls back to the
+                 oracle port, kind "port", when the staged copy is absent)
 `--impl reference` times that CPU path as the main line (rank 0 only).
 """
 import argparse
@@ -94,8 +100,8 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(variant, B, T, Ts, n_steps, sample_steps, repeats):
-    """Time the CPU oracle on `sample_steps` sampler steps of the workload's batch; returns (sec per sampler step, cores)."""
+def port_run(variant, B, T, Ts, n_steps, sample_steps, repeats):
+    """Time the CPU oracle (port) on `sample_steps` sampler steps of the workload's batch; returns (sec per sampler step, cores)."""
     import dex_oracle as O
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
@@ -119,65 +125,125 @@ def cpu_reference_run(variant, B, T, Ts, n_steps, sample_steps, repeats):
     return best, cores
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="dexb200")
-    ap.add_argument("--workload", default="C2")
-    ap.add_argument("--cpu-sample-steps", type=int, default=2)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile", action="store_true", help="print the per-launch breakdown of one network call to stderr")
-    ap.add_argument("--gemm-engine", type=int, default=0)
-    ap.add_argument("--nsplit", type=int, default=3)
-    args = ap.parse_args()
+_REF = {}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    variant, B, T, Ts, n_steps = WORKLOADS[args.workload]
-    wl = f"{args.workload}: {'DEX-TTS' if variant == 'dex' else 'GeDEX-TTS'} B={B}/GPU T={T} (80x{T} mel) Ts={Ts} {n_steps} sampler steps"
+
+def reference_root():
+    """Where the unmodified reference sources are: the copy staged by __graft_entry__.build() (travels to the GPU box), else the
+    checkout itself (build container)."""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isfile(os.path.join(cand, "DEX-TTS", "model", "diffusion.py")):
+            return cand
+    return None
+
+
+def reference_decoder(variant):
+    """The reference's own ``Diffusion`` (DEX-TTS/model/diffusion.py:238 / GeDEX-TTS/model/diffusion.py:209) with the seeded synthetic
+    weights, built exactly like oracle/make_golden.py builds it for the fixtures (shims: a timm stub, nothing edited)."""
+    if variant in _REF:
+        return _REF[variant]
+    root = reference_root()
+    if root is None:
+        return None
+    os.environ["DEX_REFERENCE_ROOT"] = root
+    import ref_loader
+    ref_loader.REF_ROOT = root
+    import contextlib
+    import io
+    cfg = DecoderCfg.make(variant)
+    dec_cfg = dict(dim=cfg.dim, pe_scale=cfg.pe_scale, dim_mults=[1, 2], model_type="dit", precond="edm", loss_type="base")
+    dit_cfg = dict(in_channels=3, patch_size=cfg.patch, stride_size=cfg.stride, overlap=True, hidden_size=cfg.hidden, depth=cfg.depth,
+                   num_heads=cfg.heads, mlp_ratio=cfg.mlp_ratio, out_channels=1, conv_pos=cfg.conv_pos,
+                   conv_pos_groups=cfg.conv_pos_groups, use_decoder=False, mask_type="time_random")
+    with contextlib.redirect_stdout(io.StringIO()):                  # the constructor prints a banner; stdout carries the JSON line
+        dec, mod = ref_loader.build_reference_decoder(variant, dec_cfg, dit_cfg)
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    sd = dict(w)
+    sd.update({k.replace("denoise_fn.", "precond_model.model."): v for k, v in w.items()})
+    dec.load_state_dict(sd, strict=True)
+    orig = mod.EDMPrecond.forward
+
+    def fwd(self, x, sigma, *a, **k):        # reference bug at B > 1 (SURVEY.md 0.3): sigma arrives 0-dim; per-sample math unchanged
+        return orig(self, x, sigma.reshape(-1).expand(x.shape[0]), *a, **k)
+    mod.EDMPrecond.forward = fwd
+    _REF[variant] = dec
+    return dec
+
+
+def cpu_reference_run(variant, B, T, Ts, n_steps, sample_steps, repeats):
+    """Time the reference's own ``Diffusion.forward(infer=True)`` for `sample_steps` sampler steps of the workload's batch on all host
+    cores; returns (sec per sampler step, cores, kind).  Falls back to the oracle port when the reference copy is not staged."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(cores)
+    dec = reference_decoder(variant)
+    if dec is None:
+        dt, cores = port_run(variant, B, T, Ts, n_steps, sample_steps, repeats)
+        return dt, cores, "port"
+    cfg = DecoderCfg.make(variant)
+    inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=1234)
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            if variant == "dex":
+                dec(inp["mu"], inp["mask"], inp["mu"], inp["ref_skips"], inp["ref_lengths"], inp["sty"], inp["sty_lengths"],
+                    n_timesteps=sample_steps, infer=True, temperature=1.5)
+            else:
+                dec(inp["mu"], inp["mask"], inp["mu"], n_timesteps=sample_steps, infer=True, temperature=1.5)
+            dt = (time.perf_counter() - t0) / sample_steps
+            best = dt if best is None else min(best, dt)
+    return best, cores, "reference"
+
+
+def parity_check(eng, variant, B, T, Ts, seed):
+    """Sample 0 of the workload, 2 sampler steps: CUDA path vs the CPU oracle (test infrastructure used as the checker only)."""
+    import dex_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity import REL_TOL, per_bin_violation
+    cfg = DecoderCfg.make(variant)
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=seed)
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]) if variant == "dex" else None
+    cond_d = dict(sty=cond["sty"].cuda(), sty_lengths=cond["sty_lengths"].cuda(), ref_skips=[r.cuda() for r in cond["ref_skips"]]) if cond else None
+    x0 = inp["z"] / 1.5 + inp["mu"]
+    y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), 2, cond=cond_d)[:1].cpu()
+    c1 = dict(sty=cond["sty"][:1], sty_lengths=cond["sty_lengths"][:1], ref_skips=[r[:1] for r in cond["ref_skips"]]) if cond else None
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = O.reverse_diffusion(w, O.make_cfg(variant), inp["z"][:1], inp["mask"][:1], inp["mu"][:1], 2, temperature=1.5, cond=c1)
+    v = per_bin_violation(y, ref)
+    return {"per_bin_violation": v, "tol": REL_TOL, "ok": bool(v < REL_TOL),
+            "checked": f"sample 0 of the timed batch (B={B}, T={T}), 2 sampler steps, CUDA path vs oracle/dex_oracle.py on the host"}
+
+
+def build_decoder(variant, gemm_engine=0, nsplit=3):
+    """The drop-in decoder module (``model.decoder`` of DeXTTS / GeDEXTTS) with the seeded synthetic weights, on the current GPU."""
+    from dexb200.model import Diffusion, GeDiffusion
+    cfg = DecoderCfg.make(variant)
+    dit = dict(in_channels=3, patch_size=cfg.patch, stride_size=cfg.stride, overlap=True, hidden_size=cfg.hidden, depth=cfg.depth,
+               num_heads=cfg.heads, mlp_ratio=cfg.mlp_ratio, out_channels=1, conv_pos=cfg.conv_pos, conv_pos_groups=cfg.conv_pos_groups,
+               use_decoder=False, mask_type="time_random")
+    cls = Diffusion if variant == "dex" else GeDiffusion
+    dec = cls(n_feats=cfg.n_feats, dim=cfg.dim, dit_cfg=dit, model_type="dit", dim_mults=[1, 2], n_spks=cfg.n_spks,
+              spk_emb_dim=cfg.spk_emb_dim, pe_scale=cfg.pe_scale, gemm_engine=gemm_engine, nsplit=nsplit)
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    sd = dict(w)
+    sd.update({k.replace("denoise_fn.", "precond_model.model."): v for k, v in w.items()})
+    dec.load_state_dict(sd, strict=True)
+    return dec.cuda().eval(), cfg
+
+
+def run_workload(args, name, rank, world, local_rank, dist, full):
+    """One bench line for workload `name`.  full = roofline / cpu_baseline / parity legs as well (the headline workload)."""
+    variant, B, T, Ts, n_steps = WORKLOADS[name]
+    wl = f"{name}: {'DEX-TTS' if variant == 'dex' else 'GeDEX-TTS'} B={B}/GPU T={T} (80x{T} mel) Ts={Ts} {n_steps} sampler steps"
     config = {"workload": wl, "batch_per_gpu": B, "mel_frames": T, "sampler_steps": n_steps, "style_len": Ts,
               "parallelism": f"dp{world}", "l2": "per-step working set (hundreds of MB of activations) exceeds the 126 MB L2",
               "weights": "seeded random init of the reference architecture, zero-initialised tensors re-drawn (live)"}
-
-    # -------------------------------------------------------------------------------- reference arm (CPU oracle)
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        K = max(1, args.steps)
-        times = []
-        for i in range(args.warmup + K):
-            dt, cores = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
-            if i >= args.warmup:
-                times.append(dt)
-            if sum(times) * args.cpu_sample_steps > 120:        # keep the whole arm within a few minutes
-                break
-        sec_step = sum(times) / len(times)
-        sec_traj = sec_step * n_steps
-        val = B * T / sec_traj
-        sample = (f"{args.cpu_sample_steps} of {n_steps} sampler steps of the full batch (B={B}, T={T}) per bench step, "
-                  f"extrapolated x{n_steps}/{args.cpu_sample_steps}; torch CPU fp32, {cores} threads")
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": len(times),
-                "warmup": args.warmup, "ms_per_step": sec_traj * 1e3, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": "mel-frames/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": val, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return
-
-    # -------------------------------------------------------------------------------- CUDA arm
-    from dexb200.engine import ReverseDiffusion
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    cfg = DecoderCfg.make(variant)
-    eng = ReverseDiffusion(cfg, gemm_engine=args.gemm_engine, nsplit=args.nsplit)
-    eng.load_state_dict(synth_decoder_weights(cfg, seed=100, live=True))
+    steps, warmup = (args.steps, max(3, args.warmup)) if full else (2, 3)
+    dec, cfg = build_decoder(variant, args.gemm_engine, args.nsplit)
+    eng = dec.cuda_engine()
+    parity = parity_check(eng, variant, B, T, Ts, 1234) if (rank == 0 and not args.no_parity) else None
     inp = synth_inputs(cfg, B, T, Ts=max(Ts, 1), seed=1234 + rank)
     x0 = inp["z"] / 1.5 + inp["mu"]
     cond_h = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"]) if variant == "dex" else None
@@ -187,18 +253,14 @@ def main():
     x0_d, mask_d, mu_d = dev(x0), dev(inp["mask"]), dev(inp["mu"])
     gathered = torch.empty(world * B, 80, T, device="cuda") if world > 1 else None
     audio_d = win_d = fb_d = None
-    if args.workload == "C3":
+    if name == "C3":
         # config 3 also runs the reference-audio front-end (STFT -> mel -> log) on 3 s of synthetic audio per utterance
+        from dexb200.audio.stft import slaney_mel_basis
         from dexb200.engine import stft_mel
         g = torch.Generator().manual_seed(99 + rank)
         audio_d = dev(torch.rand(B, 66150, generator=g) - 0.5)
         win_d = dev(torch.hann_window(1024, periodic=True))
-        try:
-            import torchaudio
-            fb = torchaudio.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 22050, norm="slaney", mel_scale="slaney").T.contiguous()
-        except Exception:
-            fb = torch.rand(80, 513) * 0.01
-        fb_d = dev(fb)
+        fb_d = dev(torch.from_numpy(slaney_mel_basis(22050, 1024, 80, 0.0, 8000.0)))
         # ... and the whole style stage of DeXTTS.forward (tts.py:42-50) on that mel: TIV encoder -> the loop's `ref_skips`;
         # TV encoder + LF0 encoder (synthetic log-F0 contour: pitch extraction is CPU pre-processing upstream) -> style fusion +
         # conv_sty -> the loop's `sty`
@@ -242,7 +304,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warmup):
         y = one_pass()
     barrier()
     assert torch.isfinite(y).all(), "non-finite mel"
@@ -252,7 +314,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_pass()
     e1.record()
     barrier()
@@ -261,28 +323,45 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    ms_per = ms / args.steps
+    ms_per = ms / steps
     value = world * B * T / (ms_per * 1e-3)
-    launches = eng.launches * args.steps
+    launches = eng.launches * steps
     if audio_d is not None:                               # C3: + the STFT kernel, the three encoders and the fusion of every step
-        launches += (1 + tiv.cuda_engine().launches + tv.cuda_engine().launches + lf0e.cuda_engine().launches + 2) * args.steps
+        launches += (1 + tiv.cuda_engine().launches + tv.cuda_engine().launches + lf0e.cuda_engine().launches + 2) * steps
 
-    # ---- e2e: host buffers in, host mel out, through the host entry point (pinned memory)
+    # ---- e2e: the public Python API (Diffusion.forward, the module the reference calls as model.decoder) on HOST inputs:
+    #      pinned host tensors -> device, loop, (gather,) mel -> pinned host tensor, everything inside the timed region
     pin = lambda t: t.contiguous().pin_memory()
-    x0_p, mask_p, mu_p = pin(x0), pin(inp["mask"]), pin(inp["mu"])
-    cond_p = dict(sty=pin(cond_h["sty"]), sty_lengths=cond_h["sty_lengths"].to(torch.int32), ref_skips=[pin(r) for r in cond_h["ref_skips"]]) \
-        if cond_h else None
-    h2d = sum(t.numel() * 4 for t in (x0_p, mask_p, mu_p))
+    mask_p, mu_p = pin(inp["mask"]), pin(inp["mu"])
+    out_p = torch.empty(B, 80, T).pin_memory()
+    cond_p = dict(sty=pin(cond_h["sty"]), sty_lengths=pin(cond_h["sty_lengths"]), ref_lengths=pin(inp["ref_lengths"]),
+                  ref_skips=[pin(r) for r in cond_h["ref_skips"]]) if cond_h else None
+    h2d = sum(t.numel() * t.element_size() for t in (mask_p, mu_p))
     if cond_p:
-        h2d += cond_p["sty"].numel() * 4 + B * 4 + sum(r.numel() * 4 for r in cond_p["ref_skips"])
-    d2h = x0_p.numel() * 4
-    eng.sample_host(x0_p, mask_p, mu_p, n_steps, cond=cond_p)
+        h2d += sum(t.numel() * t.element_size() for t in [cond_p["sty"], cond_p["sty_lengths"], cond_p["ref_lengths"]] + cond_p["ref_skips"])
+    d2h = out_p.numel() * 4
+
+    def e2e_pass():
+        mu_ = mu_p.cuda(non_blocking=True)
+        mask_ = mask_p.cuda(non_blocking=True)
+        if variant == "dex":
+            y_ = dec(mu_, mask_, mu_, [r.cuda(non_blocking=True) for r in cond_p["ref_skips"]], cond_p["ref_lengths"].cuda(non_blocking=True),
+                     cond_p["sty"].cuda(non_blocking=True), cond_p["sty_lengths"].cuda(non_blocking=True), n_timesteps=n_steps, infer=True,
+                     temperature=1.5)
+        else:
+            y_ = dec(mu_, mask_, mu_, n_timesteps=n_steps, infer=True, temperature=1.5)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y_)
+        out_p.copy_(y_, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_p
+
+    e2e_pass()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.sample_host(x0_p, mask_p, mu_p, n_steps, cond=cond_p)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    for _ in range(steps):
+        e2e_pass()
+    e2e_s = (time.perf_counter() - t0) / steps
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,8 +369,24 @@ def main():
     e2e_val = world * B * T / e2e_s
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- dominant kernel class, timed live: CUDA events around every launch of un-graphed network calls
     pk = peaks()
+    flops_traj = algorithmic_flops(variant, T, Ts) * B * n_steps
+    whole = {"algorithmic_tflop_per_step": flops_traj * 1e-12, "achieved_tflops": flops_traj * 1e-12 / (ms_per * 1e-3),
+             "frac_of_sustained_bf16_peak": flops_traj * 1e-12 / (ms_per * 1e-3) / pk["tf_sust"]}
+    line = {"metric": METRIC, "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 x3 MMA)",
+            "data": "synthetic", "config": config, "rtf": (ms_per * 1e-3) / (world * B * T * 256 / 22050.0),
+            "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3, "api": "dexb200.model.Diffusion.forward(infer=True) on pinned host tensors"
+                                                       + (" + all_gather_into_tensor of the mels" if world > 1 else "")},
+            "parity": parity, "gpu_launches": launches, "simt_fallback_gemms_per_net_call": eng.simt_fallbacks, "clocks": clk,
+            "whole_step": whole, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+    if not full:
+        del dec
+        torch.cuda.empty_cache()
+        return line
+
+    # ---- dominant kernel class, timed live: CUDA events around every launch of un-graphed network calls
     roof = None
     if rank == 0:
         agg = {}
@@ -311,14 +406,16 @@ def main():
         at = [(t, a) for t, a in agg.items() if t.startswith("attn_fwd_kernel")]
         a_ms, a_gf, a_n = sum(a[1] for _, a in at), sum(a[2] for _, a in at), sum(a[0] for _, a in at)
         ncu = {}
-        try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        except Exception:
-            pass
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BLOCK_N> (tcgen05 implicit GEMM, all conv/linear/attention contractions)",
+        for cand in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+            try:
+                ncu = json.load(open(os.path.join(ROOT, "profiles", cand)))
+                break
+            except Exception:
+                pass
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BLOCK_N> / conv2 (tcgen05 implicit GEMM, all conv / linear contractions)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": ncu.get("gemm_tc_kernel", {}).get("avg_dram_bytes_per_launch") if args.workload == "C2" else None,
-                "traffic_source": ncu.get("source") if args.workload == "C2" else None,
+                "traffic": ncu.get("gemm_tc_kernel", {}).get("avg_dram_bytes_per_launch") if name == "C2" else None,
+                "traffic_source": ncu.get("source") if name == "C2" else None,
                 "ncu_tensor_pipe_active_pct": ncu.get("gemm_tc_kernel", {}).get("time_weighted_tensor_pipe_active_pct"),
                 "launches_per_net_call": g_n // reps, "avg_launch_ms": g_ms / max(g_n, 1), "share_of_step": g_ms / tot if tot else None,
                 "peak_source": f"{pk['src']} sustained dense bf16 (MEASURED_PEAKS.json)",
@@ -332,24 +429,105 @@ def main():
                                  "avg_launch_ms": a_ms / max(a_n, 1), "share_of_step": a_ms / tot if tot else None,
                                  "ncu_tensor_pipe_active_pct": ncu.get("attn_fwd_kernel(dit)", {}).get("tensor_pipe_active_pct"),
                                  "note": "algorithmic 4*N*Nk*d FLOPs per head; issued MMA work is ~3.5x that (split-bf16 + max pass)"}
-    flops_traj = algorithmic_flops(variant, T, Ts) * B * n_steps
-    whole = {"algorithmic_tflop_per_step": flops_traj * 1e-12, "achieved_tflops": flops_traj * 1e-12 / (ms_per * 1e-3),
-             "frac_of_sustained_bf16_peak": flops_traj * 1e-12 / (ms_per * 1e-3) / pk["tf_sust"]}
-
+        if audio_d is not None:                                # C3: the STFT kernel alone against the HBM roofline
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            ts_ = []
+            for _ in range(10):
+                flush.zero_()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); stft_mel(audio_d, win_d, fb_d); b_.record()
+                torch.cuda.synchronize()
+                ts_.append(a_.elapsed_time(b_))
+            ts_.sort()
+            nb = B * (4 * 66150 + 4 * 80 * (66150 // 256 + 1))
+            roof["stft"] = {"kernel": "k_stft_mel", "bound": "hbm", "achieved": nb / (ts_[len(ts_) // 2] * 1e-3) / 1e9, "peak": pk["hbm"],
+                            "unit": "GB/s", "frac": nb / (ts_[len(ts_) // 2] * 1e-3) / 1e9 / pk["hbm"], "ms": ts_[len(ts_) // 2],
+                            "algorithmic_bytes": nb, "note": "latency / FFT-compute bound at this size: 11 MB of algorithmic traffic is "
+                            "~2 us of HBM time; cold L2 (256 MB flush before every timed launch)"}
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        sec_step, cores = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
-        cpu = {"value": B * T / (sec_step * n_steps), "unit": "mel-frames/s", "cores": cores, "kind": "port",
+        sec_step, cores, kind = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
+        what = ("the reference's own Diffusion.forward(infer=True) (baseline/_ref, unmodified DEX-TTS/GeDEX-TTS model package; sigma broadcast "
+                "to (B,) for B > 1)") if kind == "reference" else "oracle/dex_oracle.py (port)"
+        cpu = {"value": B * T / (sec_step * n_steps), "unit": "mel-frames/s", "cores": cores, "kind": kind,
                "sample": f"{args.cpu_sample_steps} of {n_steps} sampler steps of one batch (B={B}, T={T}) on the host cores, extrapolated "
-                         f"x{n_steps}/{args.cpu_sample_steps}; oracle/dex_oracle.py (torch CPU fp32, {cores} threads)"}
+                         f"x{n_steps}/{args.cpu_sample_steps}; {what}; torch CPU fp32, {cores} threads"}
+    line["roofline"] = roof
+    line["cpu_baseline"] = cpu
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dexb200")
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--other-workloads", default=None, help="comma list of extra workloads attached under `other_workloads` "
+                                                            "(default: C4,C5 -- the north star's 8-GPU configs -- when N == 8)")
+    ap.add_argument("--profile", action="store_true", help="print the per-launch breakdown of one network call to stderr")
+    ap.add_argument("--gemm-engine", type=int, default=0)
+    ap.add_argument("--nsplit", type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    variant, B, T, Ts, n_steps = WORKLOADS[args.workload]
+
+    # -------------------------------------------------------------------------------- reference arm: the reference's own CPU path
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = f"{args.workload}: {'DEX-TTS' if variant == 'dex' else 'GeDEX-TTS'} B={B}/GPU T={T} (80x{T} mel) Ts={Ts} {n_steps} sampler steps"
+        config = {"workload": wl, "batch_per_gpu": B, "mel_frames": T, "sampler_steps": n_steps, "style_len": Ts,
+                  "parallelism": f"dp{world}", "l2": "n/a (host)", "weights": "seeded random init of the reference architecture, zero-initialised tensors re-drawn (live)"}
+        K = max(1, args.steps)
+        times, kind, cores = [], "port", 1
+        t_begin = time.perf_counter()
+        for i in range(args.warmup + K):
+            dt, cores, kind = cpu_reference_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1)
+            if i >= args.warmup:
+                times.append(dt)
+            if time.perf_counter() - t_begin > 150 and times:      # keep the whole arm within a few minutes
+                break
+        sec_step = sum(times) / len(times)
+        sec_traj = sec_step * n_steps
+        val = B * T / sec_traj
+        what = ("the reference's own Diffusion.forward(infer=True) from baseline/_ref (unmodified model package; timm stub; sigma broadcast to "
+                "(B,) for B > 1)") if kind == "reference" else "oracle/dex_oracle.py (port of the reference path)"
+        sample = (f"{args.cpu_sample_steps} of {n_steps} sampler steps of the full batch (B={B}, T={T}) per bench step, "
+                  f"extrapolated x{n_steps}/{args.cpu_sample_steps}; {what}; torch CPU fp32, {cores} threads")
+        port_dt, _ = port_run(variant, B, T, Ts, n_steps, args.cpu_sample_steps, 1) if kind == "reference" else (sec_step, cores)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "mel-frames/s", "n_gpus": args.gpus, "steps": len(times),
+                "warmup": args.warmup, "ms_per_step": sec_traj * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "mel-frames/s", "cores": cores, "kind": kind, "sample": sample},
+                "port_cross_check": {"value": B * T / (port_dt * n_steps), "unit": "mel-frames/s", "kind": "port",
+                                     "what": "oracle/dex_oracle.py on the same sample"},
+                "e2e": {"value": val, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # -------------------------------------------------------------------------------- CUDA arm
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_workload(args, args.workload, rank, world, local_rank, dist, full=True)
+    others = args.other_workloads if args.other_workloads is not None else ("C4,C5" if world == 8 and args.workload == "C2" else "")
+    extra = {}
+    for name in [n for n in others.split(",") if n]:
+        extra[name] = run_workload(args, name, rank, world, local_rank, dist, full=False)
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": ms_per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (split-bf16 x3 MMA)",
-                "data": "synthetic", "config": config, "rtf": (ms_per * 1e-3) / (world * B * T * 256 / 22050.0),
-                "e2e": {"value": e2e_val, "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": launches, "simt_fallback_gemms_per_net_call": eng.simt_fallbacks, "clocks": clk, "roofline": roof,
-                "whole_step": whole, "cpu_baseline": cpu, "workspace_gb": eng.workspace_bytes / 2 ** 30}
+        if extra:
+            line["other_workloads"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

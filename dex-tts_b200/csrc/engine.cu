@@ -543,7 +543,9 @@ static int build_plans(dexb_handle* h) {
   if (dex) {
     {
       const char* ea = getenv("DEXB_ATTN");
-      h->fused_tv = attn_supported(mid) && !(ea != nullptr && ea[0] == '0');
+      // the fused cross-attention keeps all keys in one 512-wide tile; longer style sequences (reference utterances beyond ~5.9 s at
+      // hop 256 / 22.05 kHz) take the GEMM -> softmax -> GEMM route on the same operands
+      h->fused_tv = attn_supported(mid) && h->NK <= 512 && !(ea != nullptr && ea[0] == '0');
       if (h->fused_tv)
         DEXB_TRY(attn_plan_init_tv(&h->attn_tv, h->cat, 4L * mid, mid, 3 * mid, h->kq, h->sbias, h->vlt, h->sty_len, h->tvout,
                                    h->mask1, W1, B, H1 * W1, h->NK, h->KP, mid));
@@ -770,7 +772,7 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const
   const dexb_config& c = h->cfg;
   DEXB_CHECK(B >= 1 && T >= 8 && T % 4 == 0, "dexb_plan: need B >= 1 and T a multiple of 4 (fix_len_compatibility), got B=%d T=%d", B, T);
   DEXB_CHECK(n_steps >= 1 && sigmas_host != nullptr, "dexb_plan: need n_steps >= 1 and the sigma schedule");
-  DEXB_CHECK(c.variant == 0 || (Ts >= 2 && Ts + 1 <= 512), "dexb_plan: style length must be in [2, 511], got %d", Ts);
+  DEXB_CHECK(c.variant == 0 || Ts >= 2, "dexb_plan: style length must be >= 2, got %d", Ts);
   engine_release_plan(h);
   DEXB_TRY(gemm_global_init());
   DEXB_TRY(kernels_global_init());

@@ -61,32 +61,19 @@ __global__ void __launch_bounds__(256) k_tv_softmax(const float* __restrict__ sc
   const int b = (int)(row / Ppix);
   const int vis = sty_len[b] + 1;
   const float* sp = scores + row * sstride;
-  float v[16];                                               // NK <= 512
+  // three passes over the (L2-resident) score row: any number of style tokens (the fused attention kernel takes NK <= 512; this
+  // path serves longer reference utterances -- synthesize.py:96-99 passes the whole reference mel as `sty`)
   float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int j = lane + i * 32;
-    float x = -INFINITY;
-    if (j < NK) x = (j < vis) ? sp[j] : -1e4f;
-    v[i] = x;
-    mx = fmaxf(mx, x);
-  }
+  for (int j = lane; j < NK; j += 32) mx = fmaxf(mx, (j < vis) ? sp[j] : -1e4f);
   mx = warp_max(mx);
   float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int j = lane + i * 32;
-    const float e = (j < NK) ? expf(v[i] - mx) : 0.f;
-    v[i] = e;
-    sum += e;
-  }
+  for (int j = lane; j < NK; j += 32) sum += expf(((j < vis) ? sp[j] : -1e4f) - mx);
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
   bf16* op = P_ + row * (2 * (long)KP);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int j = lane + i * 32;
-    if (j < KP) split2(v[i] * inv, op[j], op[KP + j]);
+  for (int j = lane; j < KP; j += 32) {
+    const float e = (j < NK) ? expf(((j < vis) ? sp[j] : -1e4f) - mx) * inv : 0.f;
+    split2(e, op[j], op[KP + j]);
   }
 }
 void launch_tv_softmax(const float* scores, long sstride, const int* sty_len, bf16* P_, int B, int Ppix, int NK, int KP,

@@ -60,16 +60,24 @@ __global__ void __launch_bounds__(256, 4) k_stft_mel(const float* __restrict__ w
     sincospif((float)(2 * k) / (float)kFftN, &s, &c);
     tw[k] = make_float2(c, -s);
   }
-  // ---- 3a. non-zero run of every mel row (independent of the audio: overlaps the staging loads)
+  // ---- 3a. non-zero run of every mel row (independent of the audio: overlaps the staging loads).  All 17 loads of a row are
+  // issued before the first ballot -- with one dependent load per ballot the scan alone took ~100 k cycles per CTA on a cold L2.
   for (int m = warp; m < n_mels; m += 8) {
     const float* row = mel_basis + (long)m * kBins;
+    constexpr int kChunks = (kBins + 31) / 32;                   // 17
+    float v[kChunks];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int k = c * 32 + lane;
+      v[c] = (k < kBins) ? __ldg(row + k) : 0.f;
+    }
     int lo = kBins, hi = 0;
-    for (int k0 = 0; k0 < kBins; k0 += 32) {
-      const int k = k0 + lane;
-      const unsigned nz = __ballot_sync(0xffffffffu, k < kBins && __ldg(row + k) != 0.f);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const unsigned nz = __ballot_sync(0xffffffffu, v[c] != 0.f);
       if (nz != 0u) {
-        lo = min(lo, k0 + __ffs(nz) - 1);
-        hi = max(hi, k0 + 32 - __clz(nz));
+        lo = min(lo, c * 32 + __ffs(nz) - 1);
+        hi = max(hi, c * 32 + 32 - __clz(nz));
       }
     }
     if (lane == 0) { run_lo[m] = (short)min(lo, hi); run_hi[m] = (short)hi; }
@@ -145,7 +153,13 @@ __global__ void __launch_bounds__(256, 4) k_stft_mel(const float* __restrict__ w
     const float* row = mel_basis + (long)m * kBins;
     const float* mg = mag + f * kMagLd;
     float acc = 0.f;
-    for (int k = run_lo[m]; k < run_hi[m]; ++k) acc = fmaf(__ldg(row + k), mg[k], acc);
+    const int k1 = run_hi[m];
+    int k = run_lo[m];
+    for (; k + 4 <= k1; k += 4) {                                // four independent loads in flight; same summation order
+      const float w0 = __ldg(row + k), w1 = __ldg(row + k + 1), w2 = __ldg(row + k + 2), w3 = __ldg(row + k + 3);
+      acc = fmaf(w0, mg[k], acc); acc = fmaf(w1, mg[k + 1], acc); acc = fmaf(w2, mg[k + 2], acc); acc = fmaf(w3, mg[k + 3], acc);
+    }
+    for (; k < k1; ++k) acc = fmaf(__ldg(row + k), mg[k], acc);
     mel[((long)b * n_mels + m) * n_frames + f0 + f] = logf(fmaxf(acc, 1e-5f));
   }
   if (energy != nullptr && warp < nf) {                          // torch.norm(magnitudes, dim=1), stft.py:176

@@ -37,6 +37,7 @@ class ReverseDiffusion:
             raise RuntimeError("dexb200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.cfg = cfg
         self.L = _lib.load()
+        self.device = torch.cuda.current_device()          # the handle's allocations, streams and launches belong to this device
         c = _lib.DexbConfig(variant=1 if cfg.variant == "dex" else 0, dim=cfg.dim, hidden=cfg.hidden, depth=cfg.depth,
                             heads=cfg.heads, mlp_hidden=int(cfg.hidden * cfg.mlp_ratio), patch=cfg.patch, stride=cfg.stride,
                             conv_pos=cfg.conv_pos, conv_pos_groups=cfg.conv_pos_groups, n_feats=cfg.n_feats,
@@ -64,19 +65,31 @@ class ReverseDiffusion:
     # ---- weights -----------------------------------------------------------------------------------
     def load_state_dict(self, sd, prefix="denoise_fn."):
         """Copy every manifest tensor (``prefix + name``) to the handle and pack it.  Tensors may live on any device."""
-        dev = torch.device("cuda", torch.cuda.current_device())
-        for e in decoder_manifest(self.cfg):
-            key = prefix + e.name
-            if key not in sd:
-                raise RuntimeError(f"state dict is missing '{key}'")
-            t = sd[key].detach().to(device=dev, dtype=torch.float32).contiguous()
-            if tuple(t.shape) != tuple(e.shape):
-                raise RuntimeError(f"'{key}' has shape {tuple(t.shape)}, expected {tuple(e.shape)}")
-            shape = (ctypes.c_int64 * t.dim())(*t.shape)
-            _lib.check(self.L.dexb_load_weight(self.h, e.name.encode(), _ptr(t), shape, t.dim()), f"dexb_load_weight({e.name})")
-        torch.cuda.synchronize()
-        _lib.check(self.L.dexb_finalize_weights(self.h, _stream()), "dexb_finalize_weights")
+        dev = torch.device("cuda", self.device)
+        with torch.cuda.device(self.device):
+            staged = []
+            for e in decoder_manifest(self.cfg):
+                key = prefix + e.name
+                if key not in sd:
+                    raise RuntimeError(f"state dict is missing '{key}'")
+                t = sd[key].detach().to(device=dev, dtype=torch.float32).contiguous()
+                if tuple(t.shape) != tuple(e.shape):
+                    raise RuntimeError(f"'{key}' has shape {tuple(t.shape)}, expected {tuple(e.shape)}")
+                staged.append((e, t))
+            # the casts / copies above were enqueued on torch's current stream; dexb_load_weight copies synchronously on the legacy
+            # stream, which does not order against a non-blocking torch stream: finish them first
+            torch.cuda.current_stream().synchronize()
+            for e, t in staged:
+                shape = (ctypes.c_int64 * t.dim())(*t.shape)
+                _lib.check(self.L.dexb_load_weight(self.h, e.name.encode(), _ptr(t), shape, t.dim()), f"dexb_load_weight({e.name})")
+            torch.cuda.synchronize()
+            _lib.check(self.L.dexb_finalize_weights(self.h, _stream()), "dexb_finalize_weights")
         self.plan_key = None
+
+    def _check_device(self, t):
+        if not t.is_cuda or t.device.index != self.device:
+            raise RuntimeError(f"this dexb200 handle lives on cuda:{self.device} but got a tensor on {t.device}; build one engine (model "
+                               "copy) per device")
 
     # ---- plan --------------------------------------------------------------------------------------
     def plan(self, B, T, Ts, n_steps, Tr=None):
@@ -87,8 +100,9 @@ class ReverseDiffusion:
         sig = edm_sigmas(n_steps).contiguous()
         self.sigmas = sig
         ws = ctypes.c_size_t(0)
-        _lib.check(self.L.dexb_plan(self.h, key[0], key[1], key[2], key[3], key[4],
-                                    sig.numpy().ctypes.data_as(_lib.c_float_p), ctypes.byref(ws)), "dexb_plan")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dexb_plan(self.h, key[0], key[1], key[2], key[3], key[4],
+                                        sig.numpy().ctypes.data_as(_lib.c_float_p), ctypes.byref(ws)), "dexb_plan")
         self.workspace_bytes = ws.value
         self.plan_key = key
 
@@ -119,15 +133,17 @@ class ReverseDiffusion:
     def sample(self, x0, mask, mu, n_steps, cond=None):
         """x0 = z / temperature + mu (B,80,T) -> generated mel (B,80,T).  mask (B,1,T) or (B,T).  All CUDA fp32."""
         B, F, T = x0.shape
+        self._check_device(x0)
         Ts = cond["sty"].shape[-1] if self.cfg.variant == "dex" else 0
         Tr = cond["ref_skips"][0].shape[-1] if self.cfg.variant == "dex" else 0
         self.plan(B, T, Ts, n_steps, Tr)
-        x = x0.detach().float().contiguous().clone()
-        mu = mu.detach().float().contiguous()
-        m = mask.detach().float().reshape(B, T).contiguous()
-        c, keep = self._cond(cond, B)
-        _lib.check(self.L.dexb_reverse_diffusion(self.h, _ptr(x), _ptr(mu), _ptr(m), ctypes.byref(c) if c is not None else None,
-                                                 _stream()), "dexb_reverse_diffusion")
+        with torch.cuda.device(self.device):
+            x = x0.detach().float().contiguous().clone()
+            mu = mu.detach().float().contiguous()
+            m = mask.detach().float().reshape(B, T).contiguous()
+            c, keep = self._cond(cond, B)
+            _lib.check(self.L.dexb_reverse_diffusion(self.h, _ptr(x), _ptr(mu), _ptr(m), ctypes.byref(c) if c is not None else None,
+                                                     _stream()), "dexb_reverse_diffusion")
         self._keep = keep + [mu, m]
         return x
 

@@ -385,6 +385,12 @@ def style_fusion(conv_sty, sty_enc, sty_dec, sty_mask, lf0_enc, lf0_dec, lf0_mas
     if tuple(w.shape) != (N, C, 1):
         raise RuntimeError(f"conv_sty.weight has shape {tuple(w.shape)}, expected ({N}, {C}, 1)")
     z_before, z_dec, le, ld = f(sty_enc), f(sty_dec), f(lf0_enc), f(lf0_dec)
+    # dexb_style_fuse takes ONE channel count for the four tensors (every shipped config has tv_encoder.c_out == c_out_g == the LF0
+    # encoder's widths); anything else would read out of bounds inside the kernel
+    for name, t, T_ in (("sty_enc", z_before, Ts), ("lf0_enc", le, Tl), ("lf0_dec", ld, Tl)):
+        if tuple(t.shape) != (B, C, T_):
+            raise RuntimeError(f"style_fusion: {name} has shape {tuple(t.shape)}, expected ({B}, {C}, {T_}) -- the TV / LF0 encoder widths "
+                               f"(c_out, c_out_g) must all equal {C} for dexb_style_fuse")
     sm, lm = f(sty_mask).reshape(B, Ts), f(lf0_mask).reshape(B, Tl)
     scratch = torch.empty(B, C, device=z_dec.device, dtype=torch.float32)
     out_enc = torch.empty(B, C, device=z_dec.device, dtype=torch.float32) if want_sty_enc else None

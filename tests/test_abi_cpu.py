@@ -61,11 +61,20 @@ def test_module_state_dict_matches_manifest(variant):
     # zero-initialised tensors of the reference (adaLN-Zero, Rezero gates) are zero here too
     assert float(sd["denoise_fn.vit.blocks.0.adaLN_modulation.1.weight"].abs().max()) == 0.0
     assert float(sd["denoise_fn.downs.0.2.fn.g"]) == 0.0
-    with pytest.raises(NotImplementedError):
-        if variant == "dex":
-            m(None, None, None, None, None, None, None, infer=False)
-        else:
-            m(None, None, None, infer=False)
+    # the training branch delegates to the reference's own modules (reference_twin.py); without a checkout it says what to do
+    import dexb200.model.reference_twin as RT
+    RT.set_reference_dir(None)
+    os.environ.pop("DEXB_REFERENCE_DIR", None)
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        with pytest.raises(RuntimeError, match="DEXB_REFERENCE_DIR"):
+            if variant == "dex":
+                m(None, None, None, None, None, None, None, infer=False)
+            else:
+                m(None, None, None, infer=False)
+    finally:
+        os.chdir(cwd)
 
 
 def test_align_entry_points_validate_arguments_before_touching_the_gpu():

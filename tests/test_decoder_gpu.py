@@ -136,3 +136,19 @@ def test_fifty_step_trajectory_matches_oracle(variant, T):
     v = per_bin_violation(y, y_ref)
     print(f"50-step {variant} T={T}: per-bin violation {v:.3e} (tol {REL_TOL:g})")
     assert v < REL_TOL
+
+
+def test_style_reference_longer_than_the_fused_key_tile():
+    """Reference utterances beyond 511 frames (~5.9 s at hop 256): the TV adaptor leaves the fused cross-attention kernel (one 512-key
+    tile) for the GEMM -> softmax -> GEMM route; synthesize.py:96-99 passes the whole reference mel as `sty` with no cap."""
+    cfg = DecoderCfg.make("dex")
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    inp = synth_inputs(cfg, 2, 64, Ts=700, seed=19, ragged=True)
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"])
+    with torch.no_grad():
+        y_ref = O.reverse_diffusion(w, O.make_cfg("dex"), inp["z"], inp["mask"], inp["mu"], 3, temperature=1.5, cond=cond)
+    eng = get_engine("dex", True, 0)
+    x0 = inp["z"] / 1.5 + inp["mu"]
+    y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), 3, cond=to_cuda(cond)).cpu()
+    assert per_bin_violation(y, y_ref) < REL_TOL
+    assert eng.simt_fallbacks == 0
