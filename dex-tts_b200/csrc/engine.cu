@@ -56,6 +56,25 @@ static int debug_sync_check(const char* tag, cudaStream_t st) {
     }                                                                 \
   } while (0)
 
+// convolution + GroupNorm-apply of its output: ONE launch when the apply can ride in the convolution kernel (gemm.cuh, GNF),
+// otherwise the convolution followed by the stand-alone k_gn_apply pass
+#define GEMM_GN(plan, params, gnargs, slot)                                             \
+  do {                                                                                  \
+    if (gemm_can_fuse_gn((plan), (params), h->cfg.gemm_engine)) {                       \
+      GnFuse gf_;                                                                       \
+      gf_.a = (gnargs); gf_.done = h->gn_done + (long)(slot) * h->B; gf_.enabled = 1;   \
+      gf_.lag = h->gn_lag; gf_.mode = h->gn_mode;                                       \
+      if (h->prof) prof_begin(h, "gemm+gn:" #plan, gemm_flop(params), st);              \
+      DEXB_TRY(gemm_launch((plan), (params), h->cfg.gemm_engine, st, &gf_));            \
+      if (h->prof) prof_end(h, st);                                                     \
+      ++h->launches;                                                                    \
+      DEXB_TRY(debug_sync_check("gemm+gn:" #plan, st));                                 \
+    } else {                                                                            \
+      GEMM(plan, params);                                                               \
+      LAUNCH(launch_gn_apply((gnargs), st));                                            \
+    }                                                                                   \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------------
 // weights
 // ------------------------------------------------------------------------------------------------
@@ -409,6 +428,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   // per-step zeroed region
   const size_t z0 = (ar.off + 1023) & ~(size_t)1023;
   h->gn_stats = ar.get<double>((long)h->n_slots * B * 16);
+  h->gn_done = ar.get<unsigned>((long)h->n_slots * B);
   h->cstats = ar.get<double>(2L * B * mid * 2);
   LinAttW* las[3] = {&h->la0, &h->la1, &h->la2};
   for (LinAttW* la : las) {
@@ -820,6 +840,9 @@ int engine_plan(dexb_handle* h, int B, int T, int Ts, int Tr, int n_steps, const
   DEXB_TRY(build_tables(h, 0));
   DEXB_CUDA_OK(cudaDeviceSynchronize());
   if (ws_bytes != nullptr) *ws_bytes = h->ws_bytes;
+  { const char* e1 = getenv("DEXB_GN_LAG"); h->gn_lag = (e1 != nullptr && atoi(e1) >= 1) ? atoi(e1) : 2; }
+  { const char* e1 = getenv("DEXB_GN_REVERSE"); h->gn_reverse = (e1 != nullptr) ? atoi(e1) : 1; }
+  { const char* e1 = getenv("DEXB_GN_MODE"); h->gn_mode = (e1 != nullptr) ? atoi(e1) : 0; }
   const char* ng = getenv("DEXB_NO_GRAPH");
   h->use_graph = !(ng != nullptr && ng[0] == '1');
   h->planned = true;
@@ -839,6 +862,7 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
   a.B = h->B; a.P = P; a.W = W;
   a.mask = mask; a.mask_stride = W;
   a.out.p = out; a.out.stride = out_stride; a.out.hi = out_hi; a.out.lo = out_lo;
+  a.reverse = h->gn_reverse;
   return a;
 }
 
@@ -864,19 +888,18 @@ static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const 
                       long tmp_stride, bf16* out, long out_stride, const bf16* in, long in_stride, int in_hi, int in_lo,
                       bool first, cudaStream_t st) {
   const int P = H * W;
-  if (first) {
-    LAUNCH(launch_conv_in(h->x, h->mu, h->cin == 3 ? h->spk_s : nullptr, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
-                          h->gn_stats + (long)r.b1.slot * h->B * 16, h->B, H, W, r.co, st));
-  } else {
-    GEMM(r.b1.conv, r.b1.conv.p);
-  }
   {
     GnApplyArgs a = gn_args(h, r.b1, raw, P, W, mask, tmp, tmp_stride, 0, (int)(tmp_stride / 2));
     a.tbias = r.tbias + (long)step * r.co;
-    LAUNCH(launch_gn_apply(a, st));
+    if (first) {
+      LAUNCH(launch_conv_in(h->x, h->mu, h->cin == 3 ? h->spk_s : nullptr, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
+                            h->gn_stats + (long)r.b1.slot * h->B * 16, h->B, H, W, r.co, st));
+      LAUNCH(launch_gn_apply(a, st));
+    } else {
+      GEMM_GN(r.b1.conv, r.b1.conv.p, a, r.b1.slot);
+    }
   }
-  GEMM(r.b2.conv, r.b2.conv.p);
-  if (r.res_w != nullptr) GEMM(r.res, r.res.p);
+  if (r.res_w != nullptr) GEMM(r.res, r.res.p);          // before block2: its fused GroupNorm-apply adds this residual
   {
     GnApplyArgs a = gn_args(h, r.b2, raw, P, W, mask, out, out_stride, 0, (int)(out_stride / 2));
     if (first) {
@@ -887,7 +910,7 @@ static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const 
     } else {
       a.resid_s.p = const_cast<bf16*>(in); a.resid_s.stride = in_stride; a.resid_s.hi = in_hi; a.resid_s.lo = in_lo;
     }
-    LAUNCH(launch_gn_apply(a, st));
+    GEMM_GN(r.b2.conv, r.b2.conv.p, a, r.b2.slot);
   }
   return 0;
 }

@@ -133,6 +133,9 @@ struct dexb_handle {
   char* zero_base = nullptr;
   size_t zero_bytes = 0;
   double* gn_stats = nullptr;          // [slots][B][8][2]
+  int gn_reverse = 1;                  // stand-alone GroupNorm-apply walks the images backwards (DEXB_GN_REVERSE)
+  int gn_lag = 2, gn_mode = 0;         // tuning aids of the fused GroupNorm-apply (DEXB_GN_LAG / DEXB_GN_MODE)
+  unsigned* gn_done = nullptr;         // [slots][B] tiles of an image whose raw rows + sums are published (fused GroupNorm-apply)
   double* cstats = nullptr;            // [2][B][C1][2]
   int n_slots = 0;
   // plans of the non-block GEMMs

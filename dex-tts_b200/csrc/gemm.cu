@@ -120,6 +120,8 @@ int gemm_global_init() {
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   return resolve_encode();
 }
 
@@ -167,8 +169,8 @@ static bool epi_fast_ok(const GemmParams& p) {
   return true;
 }
 
-template <int BN, bool FAST>
-static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
+template <int BN, bool FAST, bool GNF = false>
+static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st, const typename GnFuseArg<GNF>::type& gf = {}) {
   const int ntn = cdiv(p.N, BN);
   const long m_tiles = (long)p.nz * p.TH * p.TW;
   const long total = m_tiles * ntn;
@@ -179,26 +181,45 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st) {
     if (grouped < 0) { const char* e = getenv("DEXB_HALO_GROUP"); grouped = (e != nullptr) ? atoi(e) : 1; }
     const int mode = (grouped != 0 && nb >= 6) ? -(nb + 16) : -nb;      // grouped rounds need two rounds of weight slots
     const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_halo_bytes(BN, nb), st, gp.tmA, gp.tmB, p, (int)total, ntn, mode);
+    launch_pdl(gemm_tc_kernel<BN, FAST, GNF>, dim3(grid), dim3(TcEpi<GNF>::kBlock), tc_halo_bytes(BN, nb), st, gp.tmA, gp.tmB, p, (int)total, ntn, mode, gf);
     return 0;
   }
   const int rb = rb_stages_for(p, BN, m_tiles, ntn);
   if (rb > 0) {
     const int nk = p.KH * p.KW * (p.K / kTcBlockK);
     const int grid = (g_num_sms / ntn) * ntn;            // multiple of ntn: a CTA never changes its n-tile
-    launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), tc_rb_bytes(BN, nk, rb), st, gp.tmA, gp.tmB, p, (int)total, ntn, rb);
+    launch_pdl(gemm_tc_kernel<BN, FAST, GNF>, dim3(grid), dim3(TcEpi<GNF>::kBlock), tc_rb_bytes(BN, nk, rb), st, gp.tmA, gp.tmB, p, (int)total, ntn, rb, gf);
     return 0;
   }
   const int grid = (int)(total < g_num_sms ? total : g_num_sms);
-  launch_pdl(gemm_tc_kernel<BN, FAST>, dim3(grid), dim3(kTcThreads), TcSmem<BN>::kBytes, st, gp.tmA, gp.tmB, p, (int)total, ntn, 0);
+  launch_pdl(gemm_tc_kernel<BN, FAST, GNF>, dim3(grid), dim3(TcEpi<GNF>::kBlock), TcSmem<BN>::kBytes, st, gp.tmA, gp.tmB, p, (int)total, ntn, 0, gf);
   return 0;
 }
 
-int gemm_launch(const GemmPlan& gp, const GemmParams& p_in, int engine, cudaStream_t st) {
+// GroupNorm-apply can ride in the convolution kernel (gemm.cuh, GNF) when the tcgen05 engine runs the FAST epilogue with deferred
+// GroupNorm sums (one n-tile of 64 or 128 channels, no heads) and a thread of the 512 epilogue threads keeps one channel octet.
+bool gemm_can_fuse_gn(const GemmPlan& gp, const GemmParams& p, int engine) {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("DEXB_GN_FUSE"); mode = (e != nullptr) ? atoi(e) : 0; }
+  if (mode == 0 || engine != 0 || !gp.tc_ok || !epi_fast_ok(p)) return false;
+  if (gp.block_n != 64 && gp.block_n != 128) return false;
+  return p.epi.gn_stats != nullptr && p.N <= gp.block_n && p.nheads == 1 && (p.N == 64 || p.N == 128) && p.epi.out_f32 != nullptr;
+}
+
+int gemm_launch(const GemmPlan& gp, const GemmParams& p_in, int engine, cudaStream_t st, const GnFuse* gf) {
   static int late_wait = -1;
   if (late_wait < 0) { const char* e = getenv("DEXB_EARLY_WAIT"); late_wait = (e != nullptr && e[0] == '0') ? 1 : 0; }
   GemmParams p = p_in;
   p.late_wait = late_wait;
+  if (gf != nullptr) {
+    DEXB_CHECK(gemm_can_fuse_gn(gp, p, engine) && gf->a.raw == p.epi.out_f32 && gf->a.C == p.N && gf->a.B == p.nz &&
+                   gf->a.P == p.OH * p.OW && gf->done != nullptr,
+               "gemm_launch: this convolution cannot carry a fused GroupNorm-apply");
+    if (gp.block_n == 64) DEXB_TRY((launch_tc<64, true, true>(gp, p, st, *gf)));
+    else DEXB_TRY((launch_tc<128, true, true>(gp, p, st, *gf)));
+    DEXB_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (engine == 0 && gp.tc_ok) {
     if (epi_fast_ok(p)) {
       switch (gp.block_n) {

@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "gemm_host.cuh"
+#include "gn_apply.cuh"
 #include "ptx.cuh"
 
 namespace dexb {
@@ -346,12 +347,71 @@ __device__ __forceinline__ TcTile tc_decode_tile(const GemmParams& p, int t, int
   return r;
 }
 
+// GroupNorm-apply fused into the producing convolution (GNF = true; convolutions whose epilogue defers the GroupNorm sums, i.e. one
+// n-tile).  Tiles are walked image-major, so all CTAs finish image i at about the same time.  When the epilogue warps of a CTA move
+// on to a new image they (1) flush their GroupNorm partial sums of the image they leave and publish its tile count
+// (__threadfence, named barrier of the 16 epilogue warps, ONE atomicAdd on done[img]), and (2) apply their share (1 / gridDim.x) of
+// every image that lies at least two images back: its counter is long complete and its raw fp32 rows are still in the 126 MB L2
+// (10.5 MB per level-0 image), so the stand-alone k_gn_apply pass -- an 84 MB HBM read + one launch per convolution, 10.6 % of a
+// network call -- is replaced by L2 reads issued in the idle time of the epilogue warps (a convolution tile is 9 x K/64 stages of
+// MMAs but only one 16-column chunk per epilogue warp).  The last images are applied after the CTA's last tile, waiting for the
+// other CTAs' counters.  No deadlock: the grid is <= #SMs with one CTA per SM (all co-resident), a CTA only waits for images it
+// has left behind, and the CTAs still holding tiles of the smallest unfinished image never wait for it.
+struct GnFuseNone {};
+template <bool GNF> struct GnFuseArg { using type = GnFuseNone; };
+template <> struct GnFuseArg<true> { using type = GnFuse; };
+
+// A fused kernel runs 2 epilogue warps per TMEM lane group instead of 4 (320 threads): a convolution tile is 9 x K/64 stages of MMAs
+// against ONE 16-column chunk per warp, so half the warps drain it just as well, and the block may then use ~200 registers per
+// thread -- the apply code (24 affine coefficients + four items in flight) lives beside the epilogue without a single spill.
+// That matters more than usual here: the kernel takes the whole 227 KB shared-memory carve-out, which leaves no L1 -- every spill
+// or stack access is an L2 round trip (a first version that called the apply as a __noinline__ function, and one that kept it
+// inline at 96 registers, made the convolution itself 25-35 % slower and the apply 2-3x slower than the stand-alone pass).
+constexpr int kTcEpiPerLGFused = 2;
+template <bool GNF> struct TcEpi {
+  static constexpr int kPerLG = GNF ? kTcEpiPerLGFused : kTcEpiPerLG;
+  static constexpr int kThreads = 128 * kPerLG;
+  static constexpr int kBlock = 64 + kThreads;
+};
+
+template <int NT>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+// warp-uniform: has image `img` been published by every CTA that holds tiles of it?  (acquire load by lane 0, broadcast)
+__device__ __forceinline__ bool gnf_image_ready(const unsigned* done, int img, unsigned target, bool block) {
+  unsigned ok = 0;
+  if ((threadIdx.x & 31) == 0) {
+    unsigned spins = 0, v;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(done + img) : "memory");
+      if (v >= target) { ok = 1; break; }
+      if (!block) break;
+      __nanosleep(200);
+      if (++spins > (1u << 23)) __trap();
+    }
+  }
+  return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+// Publish `cnt` completed tiles of image `img`: the epilogue warps' raw rows and GroupNorm sums become visible at GPU scope through
+// ONE fence (cumulative over the CTA barrier) and one relaxed atomic -- not one sequentially-consistent fence per thread.
+template <int NT>
+__device__ __forceinline__ void gnf_publish(unsigned* done, int img, int cnt, int epi_tid, int mode) {
+  if (mode == 3) return;
+  epi_bar_sync<NT>();
+  if (epi_tid == 0) {
+    // (__threadfence() is fence.sc.gpu = MEMBAR.SC.GPU + CCTL.IVALL; the release pattern only needs acq_rel)
+    if (mode == 4) __threadfence();
+    else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(done + img), "r"((unsigned)cnt) : "memory");
+  }
+}
+
 // 576 threads: registers are allocated per 4-warp group, so the block counts as 20 warps and gets 96 registers per thread
 // (112 fails to launch); the epilogue spills ~150 B per thread, which the extra warps more than pay for
-template <int BLOCK_N, bool FAST>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int BLOCK_N, bool FAST, bool GNF = false>
+__global__ void __launch_bounds__(TcEpi<GNF>::kBlock, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p, const int total_tiles, const int ntn, const int rb) {
+               const GemmParams p, const int total_tiles, const int ntn, const int rb, const __grid_constant__ typename GnFuseArg<GNF>::type gf) {
   using SM = TcSmem<BLOCK_N>;
   const bool halo = rb < 0;
   // rb <= -16: halo mode with GROUPED rounds (STAGES = -rb - 16 >= 6 weight slots): the slab of a (dy, k-chunk) and the three weight
@@ -392,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], kTcEpiThreads); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], TcEpi<GNF>::kThreads); }
     ptx::mbar_init(b_full, 1);
     for (int s = 0; s < kTcHaloASlots; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     ptx::fence_barrier_init();
@@ -657,7 +717,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;                            // row of the tile
     constexpr int CW = (BLOCK_N > 0) ? kTcEpiCW : 0;          // value-dependent, so `if constexpr (CW == 16)` discards the other branch
-    constexpr int MAXCH = (BLOCK_N / CW + kTcEpiPerLG - 1) / kTcEpiPerLG;   // chunks one warp owns per tile
+    constexpr int PLG = TcEpi<GNF>::kPerLG;                  // epilogue warps per TMEM lane group
+    constexpr int MAXCH = (BLOCK_N / CW + PLG - 1) / PLG;    // chunks one warp owns per tile
     const bool defer_gn = p.epi.gn_stats != nullptr && ntn == 1 && p.nheads == 1;
     float gacc[MAXCH][8];
 #pragma unroll
@@ -666,12 +727,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int g = 0; g < 8; ++g) gacc[k][g] = 0.f;
     int gn_img = -1;                                         // image the deferred sums belong to
     int li = 0;
+    [[maybe_unused]] int gn_cnt = 0;                         // GNF: tiles of image gn_img this CTA has completed
+    [[maybe_unused]] const int epi_tid = (int)threadIdx.x - 64;
+    // GNF apply state: image ap_img, item round ap_j of ap_J (items gi = ap_first + epi_tid + j * NT, gi < ap_last)
+    constexpr int NT = TcEpi<GNF>::kThreads;
+    [[maybe_unused]] int ap_img = 0, ap_j = 0, ap_J = 0, ap_ipt = 0;
+    [[maybe_unused]] unsigned ap_first = 0, ap_last = 0, gn_target = 0;
+    if constexpr (GNF) {
+      gn_target = (unsigned)(p.TH * p.TW);                   // tiles per image (one n-tile)
+      const unsigned ngroups = (unsigned)gf.a.P * (unsigned)(gf.a.C >> 3);
+      unsigned per = (ngroups + gridDim.x - 1) / gridDim.x;
+      per = (per + NT - 1) / NT * NT;
+      ap_first = blockIdx.x * per;
+      ap_last = (ap_first + per < ngroups) ? ap_first + per : ngroups;
+      ap_J = (ap_first < ngroups) ? (int)(per / NT) : 0;
+      if (ap_J == 0) ap_img = p.nz;                          // this CTA has no share
+      const int tiles_cta = total_tiles / (int)gridDim.x;    // >= 1: every CTA of a fused launch has at least one tile
+      ap_ipt = (p.nz * ap_J + tiles_cta - 1) / (tiles_cta > 0 ? tiles_cta : 1) + 1;      // item rounds per tile: keeps up with margin
+      ap_ipt = (ap_ipt + 3) & ~3;                            // whole groups of four (one L2 round trip each)
+      if (ap_ipt > 8) ap_ipt = 8;
+    }
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++li) {
       const TcTile tl = tc_decode_tile(p, t, ntn, BLOCK_N);
       const int buf = li & 1;
       if (defer_gn && tl.z != gn_img) {
-        if (gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, kTcEpiPerLG, gacc);
+        if (gn_img >= 0) {
+          epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, PLG, gacc);
+          if constexpr (GNF) { gnf_publish<NT>(gf.done, gn_img, gn_cnt, epi_tid, gf.mode); gn_cnt = 0; }
+        }
         gn_img = tl.z;
+      }
+      if constexpr (GNF) {
+        ++gn_cnt;
+        // a slice of the GroupNorm-apply of an image `lag` behind the tile front: its raw rows are in L2, and the loads' round trip is
+        // hidden behind the MMAs of this tile (the accumulator of the previous tile has been handed back already)
+        int budget = (gf.mode == 0) ? ap_ipt : 0;
+        while (budget > 0 && ap_img <= gn_img - gf.lag) {
+          if (!gnf_image_ready(gf.done, ap_img, gn_target, false)) break;
+          const int n = (budget < ap_J - ap_j) ? budget : ap_J - ap_j;
+          gn_apply_items(gf.a, ap_img, ap_first + (unsigned)epi_tid + (unsigned)ap_j * NT, ap_last, NT, n);
+          ap_j += n; budget -= n;
+          if (ap_j >= ap_J) { ++ap_img; ap_j = 0; }
+        }
       }
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
       const bool valid = (ch < p.CH) && (cw < p.CW);
@@ -680,7 +777,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr int NCH = BLOCK_N / CW;
       // chunks this warp owns: c = half, half + kTcEpiPerLG, ... while n0 + 32 c < N
       int nmine = 0;
-      for (int c = half; c < NCH && tl.n0 + c * CW < p.N; c += kTcEpiPerLG) ++nmine;
+      for (int c = half; c < NCH && tl.n0 + c * CW < p.N; c += PLG) ++nmine;
       if (nmine == 0) {
         ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);       // never hand a buffer back before its MMAs have completed
         ptx::tc_fence_before();
@@ -688,7 +785,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll 1
       for (int k = 0; k < nmine; ++k) {
-        const int c = half + kTcEpiPerLG * k;
+        const int c = half + PLG * k;
         const int n0c = tl.n0 + c * CW;
         const bool use_vt = !FAST && p.epi.out_vt != nullptr && n0c >= p.epi.out_s_ncols;
         // residual rows first: their L2 round trip overlaps the wait for the accumulator and the tensor-memory load
@@ -742,7 +839,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, kTcEpiPerLG, gacc);
+    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, PLG, gacc);
+    if constexpr (GNF) {
+      if (gn_img >= 0) gnf_publish<NT>(gf.done, gn_img, gn_cnt, epi_tid, gf.mode);
+      // the images still open (at least the last `lag`): wait for the other CTAs' tiles
+      for (; gf.mode != 2 && gf.mode != 3 && ap_img < p.nz; ++ap_img, ap_j = 0) {
+        gnf_image_ready(gf.done, ap_img, gn_target, true);
+        gn_apply_items(gf.a, ap_img, ap_first + (unsigned)epi_tid + (unsigned)ap_j * NT, ap_last, NT, ap_J - ap_j);
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -97,7 +97,10 @@ int gemm_global_init();
 int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, int n_bmat);
 // Enqueue on `st`.  `p` is normally gp.p, possibly with per-step pointers (bias / gate / stats) patched.
 // engine 0 = tcgen05 (falls back to the CUDA-core kernel only for shapes the plan marked ineligible), 1 = CUDA cores.
-int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st);
+// `gf` != null: the GroupNorm-apply of the convolution's output runs inside the kernel (only if gemm_can_fuse_gn says so).
+struct GnFuse;
+bool gemm_can_fuse_gn(const GemmPlan& gp, const GemmParams& p, int engine);
+int gemm_launch(const GemmPlan& gp, const GemmParams& p, int engine, cudaStream_t st, const GnFuse* gf = nullptr);
 // number of tcgen05 launches so far that had to take the generic (scalar-fallback) epilogue instantiation
 long gemm_generic_epilogue_launches();
 

@@ -1,0 +1,187 @@
+// GroupNorm-apply + Mish + mask (+ time bias | + residual) -> split-bf16 operand of the next convolution
+// (Block / ResnetBlock, DEX-TTS/model/diffusion.py:44-74).  The item code is shared by two callers:
+//   * k_gn_apply (kernels_unet.cu): a stand-alone pass, used behind the CUDA-core first convolution and as the fallback;
+//   * the epilogue warps of the persistent tcgen05 convolution kernel (gemm.cuh, GNF = true): every CTA applies its share of
+//     image i while the tensor pipe works on image i + 2 -- the raw fp32 image is read back from L2 (it was written one or two
+//     images ago), so the stand-alone pass and its HBM read disappear.
+#pragma once
+#include "common.cuh"
+
+namespace dexb {
+
+// per-step scalars of the EDM sampler / preconditioner (DEX-TTS/model/edm.py:88-98,185-203)
+struct StepScalars {
+  float sigma, sigma_next, c_skip, c_out, c_in, c_noise;
+};
+
+struct SView {            // a split-bf16 tensor view: element (row, c) hi at p[row*stride + hi + c], lo at ... + lo
+  bf16* p;
+  long stride;
+  int hi, lo;
+};
+
+struct GnApplyArgs {
+  const float* raw; int C; int G;          // F[M][C]
+  const double* stats;                      // [B][G][2]
+  const float* gamma; const float* beta;
+  int B, P, W;                              // P pixels per image, W image width (mask column = pixel % W)
+  const float* mask; long mask_stride;      // [B][W]
+  const float* tbias;                       // [C] added after Mish*mask (then masked again), or null
+  SView resid_s;                            // identity residual (already masked) or p == null
+  const float* resid_f; long resid_f_stride;   // fp32 residual (res_conv output incl. bias), masked on the fly
+  // residual computed from the network input (first ResnetBlock, res_conv 1x1 on 2 channels)
+  const float* rin_w; const float* rin_b;   // [C][2], [C] or null
+  const float* x; const float* mu; const StepScalars* tab; int step;
+  const float* spk_s; int H;                // third input channel spk_s[b][h] of the multi-speaker GeDEX-TTS (rin_w is [C][3] then)
+  SView out;
+  int reverse;                              // stand-alone pass: walk the images / chunks backwards (L2 reuse, see k_gn_apply)
+};
+
+// GroupNorm-apply fused into the convolution that produces `a.raw` (gemm.cuh, GNF kernels)
+struct GnFuse {
+  GnApplyArgs a;
+  unsigned* done;                           // [B] tiles of image b whose raw rows and statistics are globally visible (zeroed per step)
+  int enabled;
+  int lag;                                  // images between the tile front and the in-loop apply (tuning: DEXB_GN_LAG, default 2)
+  int mode;                                 // tuning aid (DEXB_GN_MODE): 0 = normal, 1 = apply everything after the last tile, 2 = never apply (wrong results)
+};
+
+#ifdef __CUDACC__
+// Mish with fast intrinsics (ex2.approx / approximate divide: ~1e-6 relative, far inside the split-bf16 noise floor)
+__device__ __forceinline__ float mish_fast(float x) {
+  if (x > 20.f) return x;
+  const float w = __expf(x);
+  const float n = w * (w + 2.f);
+  return x * __fdividef(n, n + 2.f);
+}
+
+// mean / rstd of one (image, group) straight from the double sums, per thread: two broadcast loads and a handful of DP
+// instructions -- no shared memory, no block barrier (a per-block prologue with __syncthreads was the top stall reason of the
+// GroupNorm-apply kernels: 2-2.8 stalled warps per issue slot, profiles/r01_ncu_small_kernels.md).
+// L2 = true: the sums were accumulated by other CTAs of the SAME kernel -> read them from L2 (ld.global.cg), never from L1.
+template <bool L2 = false>
+__device__ __forceinline__ void gn_thread_stats(const double* __restrict__ stats, int G, double inv_n, int b, int g, float& mean,
+                                                float& rstd) {
+  const double2* sp = reinterpret_cast<const double2*>(stats + ((long)b * G + g) * 2);
+  const double2 s = L2 ? __ldcg(sp) : *sp;
+  const double mean_d = s.x * inv_n;
+  double var_d = s.y * inv_n - mean_d * mean_d;
+  if (var_d < 0.) var_d = 0.;
+  mean = (float)mean_d;
+  rstd = 1.f / sqrtf((float)(var_d + 1e-5));                // sums and the variance in double, only the root in fp32
+}
+
+struct GnItem {
+  float4 r0, r1;                                             // 8 raw channels
+  uint4 q0, q1;                                              // residual: (hi, lo) of an S row or two float4 of an F row
+};
+
+// all global loads of one item (pixel `pix` of the whole batch, channels c0 .. c0 + 7); L2: see gn_thread_stats
+template <bool L2>
+__device__ __forceinline__ void gn_item_load(const GnApplyArgs& a, long pix, int c0, GnItem& it) {
+  const float4* rp = reinterpret_cast<const float4*>(a.raw + pix * a.C + c0);
+  if (L2) { it.r0 = __ldcg(rp); it.r1 = __ldcg(rp + 1); }
+  else { it.r0 = rp[0]; it.r1 = rp[1]; }
+  it.q0 = make_uint4(0, 0, 0, 0); it.q1 = make_uint4(0, 0, 0, 0);
+  if (a.resid_s.p != nullptr) {
+    const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
+    it.q0 = *reinterpret_cast<const uint4*>(q + a.resid_s.hi);
+    it.q1 = *reinterpret_cast<const uint4*>(q + a.resid_s.lo);
+  } else if (a.resid_f != nullptr) {
+    const float* q = a.resid_f + pix * a.resid_f_stride + c0;
+    it.q0 = *reinterpret_cast<const uint4*>(q);
+    it.q1 = *reinterpret_cast<const uint4*>(q + 4);
+  }
+}
+
+// normalise, Mish, mask, (+ time bias), + residual, split store.  p = pixel inside image b.
+__device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsigned p, int c0, const GnItem& it, float mean, float rstd,
+                                               const float (&ga)[8], const float (&be)[8], const float (&tb)[8]) {
+  const long pix = (long)b * a.P + p;
+  const int w = (int)(p % (unsigned)a.W);
+  const float m = a.mask[(long)b * a.mask_stride + w];
+  float v[8] = {it.r0.x, it.r0.y, it.r0.z, it.r0.w, it.r1.x, it.r1.y, it.r1.z, it.r1.w};
+  float res[8];
+  if (a.resid_s.p != nullptr) {
+    const bf16* hh = reinterpret_cast<const bf16*>(&it.q0);
+    const bf16* ll = reinterpret_cast<const bf16*>(&it.q1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = join2(hh[i], ll[i]);
+  } else if (a.resid_f != nullptr) {
+    const float* f0 = reinterpret_cast<const float*>(&it.q0);
+    const float* f1 = reinterpret_cast<const float*>(&it.q1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { res[i] = f0[i] * m; res[4 + i] = f1[i] * m; }
+  } else if (a.rin_w != nullptr) {
+    // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
+    const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
+    if (a.spk_s == nullptr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
+    } else {
+      const float in2 = a.spk_s[b * a.H + (int)(p / (unsigned)a.W)] * m;      // speaker channel: constant along time
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 3] * in0 + a.rin_w[(c0 + i) * 3 + 1] * in1 + a.rin_w[(c0 + i) * 3 + 2] * in2) * m;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) res[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float y = (v[i] - mean) * rstd * ga[i] + be[i];
+    y = mish_fast(y) * m;
+    y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
+    v[i] = y + res[i];
+  }
+  bf16* op = a.out.p + pix * a.out.stride + c0;
+  store_split8(op + a.out.hi, op + a.out.lo, v);
+}
+
+// gamma / beta / time bias of the 8 channels a thread keeps for all its items
+__device__ __forceinline__ void gn_thread_affine(const GnApplyArgs& a, int c0, float (&ga)[8], float (&be)[8], float (&tb)[8]) {
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
+  const float4 b0v = __ldg(reinterpret_cast<const float4*>(a.beta + c0)), b1v = __ldg(reinterpret_cast<const float4*>(a.beta + c0 + 4));
+  ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+  be[0] = b0v.x; be[1] = b0v.y; be[2] = b0v.z; be[3] = b0v.w; be[4] = b1v.x; be[5] = b1v.y; be[6] = b1v.z; be[7] = b1v.w;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tb[i] = 0.f;
+  if (a.tbias != nullptr) {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0)), t1 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0 + 4));
+    tb[0] = t0.x; tb[1] = t0.y; tb[2] = t0.z; tb[3] = t0.w; tb[4] = t1.x; tb[5] = t1.y; tb[6] = t1.z; tb[7] = t1.w;
+  }
+}
+
+// Fused path (gemm.cuh, GNF): a thread of the convolution's epilogue warps owns the items gi = first + tid + j * nthr (j = 0 .. J-1,
+// gi < last) of every image, where [first, last) is its CTA's share; nthr % (C / 8) == 0, so a thread keeps one channel octet.
+// gn_apply_items processes n item rounds starting at gi, four at a time: all four items' loads are in flight together (one L2 round
+// trip per group of four).
+__device__ __forceinline__ void gn_apply_items(const GnApplyArgs& a, int b, unsigned gi, unsigned last, unsigned nthr, int n) {
+  const int cpt = a.C >> 3;                                  // threads per pixel: 8 or 16
+  const int cshift = 31 - __clz(cpt);
+  const int gs = a.C / a.G;
+  const int c0 = (int)(gi & (unsigned)(cpt - 1)) * 8;
+  float ga[8], be[8], tb[8];
+  gn_thread_affine(a, c0, ga, be, tb);
+  float mean, rstd;
+  gn_thread_stats<true>(a.stats, a.G, 1.0 / ((double)a.P * gs), b, c0 / gs, mean, rstd);
+  const long img_row0 = (long)b * a.P;
+#pragma unroll 1
+  for (int j = 0; j < n; j += 4, gi += 4u * nthr) {
+    GnItem it[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned g = gi + (unsigned)k * nthr;
+      if (j + k < n && g < last) gn_item_load<true>(a, img_row0 + (g >> cshift), c0, it[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned g = gi + (unsigned)k * nthr;
+      if (j + k < n && g < last) gn_item_finish(a, b, g >> cshift, c0, it[k], mean, rstd, ga, be, tb);
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace dexb

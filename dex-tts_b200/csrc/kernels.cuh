@@ -3,19 +3,9 @@
 // work on `st` (no allocation, no host sync) so the whole trajectory can be captured in a CUDA graph.
 #pragma once
 #include "common.cuh"
+#include "gn_apply.cuh"
 
 namespace dexb {
-
-// per-step scalars of the EDM sampler / preconditioner (DEX-TTS/model/edm.py:88-98,185-203)
-struct StepScalars {
-  float sigma, sigma_next, c_skip, c_out, c_in, c_noise;
-};
-
-struct SView {            // a split-bf16 tensor view: element (row, c) hi at p[row*stride + hi + c], lo at ... + lo
-  bf16* p;
-  long stride;
-  int hi, lo;
-};
 
 // one-off cudaFuncSetAttribute calls (must run outside stream capture)
 int kernels_global_init();
@@ -33,21 +23,6 @@ void launch_conv_in(const float* x, const float* mu, const float* spk_s, const f
                     const float* w /*[C][2][3][3]*/, const float* bias, float* raw /*F[M][C]*/, double* stats, int B,
                     int H, int W, int C, cudaStream_t st);
 
-struct GnApplyArgs {
-  const float* raw; int C; int G;          // F[M][C]
-  const double* stats;                      // [B][G][2]
-  const float* gamma; const float* beta;
-  int B, P, W;                              // P pixels per image, W image width (mask column = pixel % W)
-  const float* mask; long mask_stride;      // [B][W]
-  const float* tbias;                       // [C] added after Mish*mask (then masked again), or null
-  SView resid_s;                            // identity residual (already masked) or p == null
-  const float* resid_f; long resid_f_stride;   // fp32 residual (res_conv output incl. bias), masked on the fly
-  // residual computed from the network input (first ResnetBlock, res_conv 1x1 on 2 channels)
-  const float* rin_w; const float* rin_b;   // [C][2], [C] or null
-  const float* x; const float* mu; const StepScalars* tab; int step;
-  const float* spk_s; int H;                // third input channel spk_s[b][h] of the multi-speaker GeDEX-TTS (rin_w is [C][3] then)
-  SView out;
-};
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st);
 
 // final_block GroupNorm+Mish -> final_conv 1x1 (C->1) -> EDM preconditioning -> Euler update of x (in place);

@@ -141,125 +141,41 @@ void launch_conv_in(const float* x, const float* mu, const float* spk_s, const f
 // ------------------------------------------------------------------------------------------------
 // GroupNorm-apply + Mish + mask (+ time bias | + residual) -> split-bf16.  8 channels per thread.
 // ------------------------------------------------------------------------------------------------
-// mean / rstd of one (image, group) straight from the double sums, per thread: two broadcast loads and a handful of DP
-// instructions -- no shared memory, no block barrier (a per-block prologue with __syncthreads was the top stall reason of the
-// GroupNorm-apply kernels: 2-2.8 stalled warps per issue slot, profiles/r01_ncu_small_kernels.md).
-__device__ __forceinline__ void gn_thread_stats(const double* __restrict__ stats, int G, double inv_n, int b, int g, float& mean,
-                                                float& rstd) {
-  const double2 s = *reinterpret_cast<const double2*>(stats + ((long)b * G + g) * 2);
-  const double mean_d = s.x * inv_n;
-  double var_d = s.y * inv_n - mean_d * mean_d;
-  if (var_d < 0.) var_d = 0.;
-  mean = (float)mean_d;
-  rstd = 1.f / sqrtf((float)(var_d + 1e-5));                // sums and the variance in double, only the root in fp32
-}
-// Mish with fast intrinsics (ex2.approx / approximate divide: ~1e-6 relative, far inside the split-bf16 noise floor)
-__device__ __forceinline__ float mish_fast(float x) {
-  if (x > 20.f) return x;
-  const float w = __expf(x);
-  const float n = w * (w + 2.f);
-  return x * __fdividef(n, n + 2.f);
-}
-
+// The item code (loads, statistics, Mish, residual variants, split store) lives in gn_apply.cuh: it is shared with the epilogue
+// warps of the tcgen05 convolution kernel, which apply an image in-kernel (gemm.cuh, GNF).
+//
 // grid = (chunks of ITEMS * 256 eight-channel groups, image): all index math is 32-bit with shifts (C/8 is a power of two) --
 // the first version derived (image, pixel, column) from a flat 64-bit index with four 64-bit divisions per item and was bound
-// by that integer code (2.7 TB/s), not by memory.  The double-precision statistics prologue is paid once per block and every
-// thread has ITEMS independent 32 B loads (+ residual) in flight; 256 % (C/8) == 0, so a thread keeps the same channel group
-// c0 for all its items (gamma / beta / time bias live in registers).
+// by that integer code (2.7 TB/s), not by memory.  Every thread has ITEMS independent 32 B loads (+ residual) in flight;
+// 256 % (C/8) == 0, so a thread keeps the same channel group c0 for all its items (gamma / beta / time bias live in registers).
 template <int ITEMS>
 __global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
   pdl_wait();
-  const int b = blockIdx.y;
+  // Images and chunks are walked BACKWARDS: the convolution that produced `raw` wrote image B-1 last, so the tail of the tensor is
+  // what the 126 MB L2 still holds; and this pass then leaves image 0 hottest for the next convolution, which starts there.
+  const int b = a.reverse ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
   const int cpt = a.C >> 3;                                  // threads per pixel: 8 or 16
   const int cshift = 31 - __clz(cpt);
   const unsigned ngroups = (unsigned)a.P << cshift;          // eight-channel groups per image
-  const unsigned base = blockIdx.x * (unsigned)(256 * ITEMS);
+  const unsigned base = (a.reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * (unsigned)(256 * ITEMS);
   const int gs = a.C / a.G;
   const int c0 = (int)(threadIdx.x & (cpt - 1)) * 8;
-  const int g = c0 / gs;
   float ga[8], be[8], tb[8];
-  {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0 + 4));
-    const float4 b0v = __ldg(reinterpret_cast<const float4*>(a.beta + c0)), b1v = __ldg(reinterpret_cast<const float4*>(a.beta + c0 + 4));
-    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
-    be[0] = b0v.x; be[1] = b0v.y; be[2] = b0v.z; be[3] = b0v.w; be[4] = b1v.x; be[5] = b1v.y; be[6] = b1v.z; be[7] = b1v.w;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tb[i] = 0.f;
-    if (a.tbias != nullptr) {
-      const float4 t0 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0)), t1 = __ldg(reinterpret_cast<const float4*>(a.tbias + c0 + 4));
-      tb[0] = t0.x; tb[1] = t0.y; tb[2] = t0.z; tb[3] = t0.w; tb[4] = t1.x; tb[5] = t1.y; tb[6] = t1.z; tb[7] = t1.w;
-    }
-  }
+  gn_thread_affine(a, c0, ga, be, tb);
   const long img_row0 = (long)b * a.P;                       // first pixel row of this image
-  // ---- phase 1: all loads
-  float4 r0[ITEMS], r1[ITEMS];
-  uint4 q0[ITEMS], q1[ITEMS];                                // residual: (hi, lo) of an S row or two float4 of an F row
+  GnItem it[ITEMS];
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
-    const long pix = img_row0 + ((gi < ngroups) ? (gi >> cshift) : 0u);
-    const float* rp = a.raw + pix * a.C + c0;
-    r0[j] = *reinterpret_cast<const float4*>(rp);
-    r1[j] = *reinterpret_cast<const float4*>(rp + 4);
-    q0[j] = make_uint4(0, 0, 0, 0); q1[j] = make_uint4(0, 0, 0, 0);
-    if (a.resid_s.p != nullptr) {
-      const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
-      q0[j] = *reinterpret_cast<const uint4*>(q + a.resid_s.hi);
-      q1[j] = *reinterpret_cast<const uint4*>(q + a.resid_s.lo);
-    } else if (a.resid_f != nullptr) {
-      const float* q = a.resid_f + pix * a.resid_f_stride + c0;
-      q0[j] = *reinterpret_cast<const uint4*>(q);
-      q1[j] = *reinterpret_cast<const uint4*>(q + 4);
-    }
+    gn_item_load<false>(a, img_row0 + ((gi < ngroups) ? (gi >> cshift) : 0u), c0, it[j]);
   }
   float mean, rstd;
-  gn_thread_stats(a.stats, a.G, 1.0 / ((double)a.P * gs), b, g, mean, rstd);
-  // ---- phase 2: normalise, Mish, mask, (+ time bias), + residual, split store
+  gn_thread_stats(a.stats, a.G, 1.0 / ((double)a.P * gs), b, c0 / gs, mean, rstd);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
     if (gi >= ngroups) continue;
-    const unsigned p = gi >> cshift;                          // pixel inside the image
-    const long pix = img_row0 + p;
-    const int w = (int)(p % (unsigned)a.W);
-    const float m = a.mask[(long)b * a.mask_stride + w];
-    float v[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
-    float res[8];
-    if (a.resid_s.p != nullptr) {
-      const bf16* hh = reinterpret_cast<const bf16*>(&q0[j]);
-      const bf16* ll = reinterpret_cast<const bf16*>(&q1[j]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = join2(hh[i], ll[i]);
-    } else if (a.resid_f != nullptr) {
-      const float* f0 = reinterpret_cast<const float*>(&q0[j]);
-      const float* f1 = reinterpret_cast<const float*>(&q1[j]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { res[i] = f0[i] * m; res[4 + i] = f1[i] * m; }
-    } else if (a.rin_w != nullptr) {
-      // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
-      const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
-      if (a.spk_s == nullptr) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 2] * in0 + a.rin_w[(c0 + i) * 2 + 1] * in1) * m;
-      } else {
-        const float in2 = a.spk_s[b * a.H + (int)(p / (unsigned)a.W)] * m;      // speaker channel: constant along time
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          res[i] = (a.rin_b[c0 + i] + a.rin_w[(c0 + i) * 3] * in0 + a.rin_w[(c0 + i) * 3 + 1] * in1 + a.rin_w[(c0 + i) * 3 + 2] * in2) * m;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) res[i] = 0.f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float y = (v[i] - mean) * rstd * ga[i] + be[i];
-      y = mish_fast(y) * m;
-      y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
-      v[i] = y + res[i];
-    }
-    bf16* op = a.out.p + pix * a.out.stride + c0;
-    store_split8(op + a.out.hi, op + a.out.lo, v);
+    gn_item_finish(a, b, gi >> cshift, c0, it[j], mean, rstd, ga, be, tb);
   }
 }
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
