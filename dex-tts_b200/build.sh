@@ -8,7 +8,7 @@ OBJ="$HERE/build"
 mkdir -p "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall ${DEXB_NVCC_EXTRA:-}"
 pids=()
-for f in api engine gemm attn posconv kernels_unet kernels_dit kernels_misc kernels_stft tiv tv align mas; do
+for f in api engine gemm attn posconv kernels_unet kernels_dit kernels_misc kernels_stft tiv tv align mas vocoder; do
   if [ ! -f "$OBJ/$f.o" ] || [ -n "$(find "$SRC" -newer "$OBJ/$f.o" \( -name '*.cu' -o -name '*.cuh' \) -print -quit)" ] || [ "$HERE/../include/dexb200.h" -nt "$OBJ/$f.o" ]; then
     nvcc $FLAGS -c "$SRC/$f.cu" -o "$OBJ/$f.o" &
     pids+=($!)

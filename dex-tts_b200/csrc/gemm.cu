@@ -166,6 +166,7 @@ static bool epi_fast_ok(const GemmParams& p) {
   if (e.out_s != nullptr && !(al(e.out_s, 32) && e.out_s_stride % 16 == 0 && e.out_s_hi % 16 == 0 && e.out_s_lo % 16 == 0 &&
                               e.out_s_ncols >= p.N))
     return false;
+  if (e.out_s_gshift > 0 && !(e.out_s_gshift >= 4 && e.out_s_gpitch % 16 == 0)) return false;   // a 16-column chunk stays in one group
   return true;
 }
 

@@ -192,8 +192,13 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
     }
   }
   if (e.out_s != nullptr && n0 < e.out_s_ncols) {
-    bf16* hp = e.out_s + row * e.out_s_stride + e.out_s_hi + nc0;
-    bf16* lp = e.out_s + row * e.out_s_stride + e.out_s_lo + nc0;
+    if (e.s_lrelu != 0.f) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * e.s_lrelu;
+    }
+    const int cs = (e.out_s_gshift > 0) ? (nc0 >> e.out_s_gshift) * e.out_s_gpitch + (nc0 & ((1 << e.out_s_gshift) - 1)) : nc0;
+    bf16* hp = e.out_s + row * e.out_s_stride + e.out_s_hi + cs;
+    bf16* lp = e.out_s + row * e.out_s_stride + e.out_s_lo + cs;
     if (FAST || (NV % 16 == 0 && n0 + NV <= N && n0 + NV <= e.out_s_ncols && ((reinterpret_cast<uintptr_t>(hp) & 31) == 0) &&
                  ((reinterpret_cast<uintptr_t>(lp) & 31) == 0))) {
 #pragma unroll

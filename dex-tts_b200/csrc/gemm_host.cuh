@@ -27,6 +27,10 @@ struct EpiParams {
   long out_s_stride;
   int out_s_hi, out_s_lo;
   int out_s_ncols;             // only columns n < out_s_ncols go to out_s (rest may go to out_vt)
+  float s_lrelu;               // != 0: the split store holds leaky_relu(v, s_lrelu) -- the operand of the next convolution -- while
+                               //       out_f32 keeps v itself (the residual stream of a HiFi-GAN ResBlock)
+  int out_s_gshift, out_s_gpitch;   // gshift > 0: columns are grouped by 2^gshift and group g goes to column g * gpitch + (n mod 2^gshift)
+                               //       (phase-stacked ConvTranspose1d: N = phases x channels, one split row per output time step)
   bf16* out_vt;                // transposed split store for columns n >= out_s_ncols:  vT[z'][d][token]
   long out_vt_zstride;         // elements between (img, head) matrices
   long out_vt_rstride;         // elements between d rows (= 2 * padded token count)

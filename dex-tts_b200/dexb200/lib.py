@@ -98,6 +98,13 @@ SYMBOLS = {
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_align_expand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_voc_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_int32_p, ctypes.c_int, c_int32_p, ctypes.c_int, c_int32_p, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_void_p)]),
+    "dexb_voc_destroy": (None, [ctypes.c_void_p]),
+    "dexb_voc_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, c_int64_p, ctypes.c_int]),
+    "dexb_voc_finalize_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_voc_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_voc_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
 }
 
 _lib = None

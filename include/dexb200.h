@@ -258,6 +258,25 @@ long dexb_text_last_launch_count(const dexb_text* h);
 int dexb_text_set_layer_limit(dexb_text* h, int n_layers);
 int dexb_text_copy_stream(const dexb_text* h, float* rows_dev, void* stream);
 
+/* ---- vocoder: HiFi-GAN v1 generator (the stage behind the loop, mel -> waveform) ---------------------------
+ * replaces: hifigan.Generator (DEX-TTS/hifigan/models.py:112-173 over ResBlock :24-109) in the state get_vocoder leaves it in --
+ * eval + remove_weight_norm (DEX-TTS/src/utils.py:251-281) -- called as `vocoder(y_dec)` at DEX-TTS/synthesize.py:106.
+ * Every Conv1d / ConvTranspose1d runs on the tcgen05 implicit-GEMM engine of the loop; the forward of a (B, T) shape is one CUDA graph. */
+typedef struct dexb_voc dexb_voc;
+/* replaces: Generator.__init__(h) with h = hifigan/config.json: n_mels 80, upsample_initial_channel 512, upsample_rates (8,8,2,2)
+ * (kernel = 2 x rate, as config.json pairs them), resblock_kernel_sizes (3,7,11), resblock_dilation_sizes (1,3,5) shared by the blocks. */
+int dexb_voc_create(int n_mels, int initial_channels, const int* upsample_rates, int n_up, const int* resblock_kernels, int n_rk,
+                    const int* resblock_dilations, int n_rd, dexb_voc** out);
+void dexb_voc_destroy(dexb_voc* h);
+/* replaces: load_state_dict + remove_weight_norm.  `name` = the generator's state_dict key after remove_weight_norm
+ * ("conv_pre.weight", "ups.2.bias", "resblocks.7.convs2.1.weight", "conv_post.weight", ...); the tensor is copied. */
+int dexb_voc_load_weight(dexb_voc* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
+int dexb_voc_finalize_weights(dexb_voc* h, void* stream);
+/* replaces: Generator.forward(x) (models.py:157-173): mel_dev (B, n_mels, T) fp32 -> wav_dev (B, 1, T * prod(upsample_rates)) fp32 in
+ * [-1, 1].  The first call for a new (B, T) allocates the workspace and captures the graph; later calls only launch it on `stream`. */
+int dexb_voc_forward(dexb_voc* h, const float* mel_dev, int B, int T, float* wav_dev, void* stream);
+long dexb_voc_last_launch_count(const dexb_voc* h);
+
 /* replaces: monotonic_align.maximum_path(value, mask) (DEX-TTS/model/monotonic_align/__init__.py:8-25 over the Cython kernel
  * core.pyx:9-47; call site DEX-TTS/model/tts.py:108, training).  value_dev, mask_dev (B, Tx, Ty) fp32 (mask in {0,1}, the outer product
  * of the two sequence masks) -> path_dev (B, Tx, Ty) fp32 zeros / ones.  scratch_dev: B * Tx * Ty bytes.  One CTA per utterance;
