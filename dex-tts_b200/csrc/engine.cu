@@ -9,6 +9,10 @@
 
 namespace dexb {
 
+// Taps fused per K chunk of the grouped positional convolution (generic GEMM path): K = PF * (channels per group) must be a multiple
+// of the 64-element swizzle span -- 2 for 32 channels per group (hidden 256 / 8 groups), 4 for 48 (hidden 384 / 8: LibriTTS config)
+static int posconv_pf(int cg) { return (2 * cg) % 64 == 0 ? 2 : 4; }
+
 static void prof_begin(dexb_handle* h, const char* tag, double flop, cudaStream_t st) {
   dexb_handle::ProfRec r;
   r.tag = tag; r.flop = flop;
@@ -200,7 +204,7 @@ static int layout_weights(dexb_handle* h, Arena& ar) {
     NEED_W(cw, "vit.pos_conv.0.weight", hid, cg, c.conv_pos, c.conv_pos);
     NEED_W(cb, "vit.pos_conv.0.bias", hid);
     (void)cw; h->posconv_b = cb->p;
-    h->posconv_w = ar.get<bf16>((long)c.conv_pos * (c.conv_pos / 2) * hid * 4 * cg);
+    h->posconv_w = ar.get<bf16>((long)c.conv_pos * c.conv_pos * hid * 2 * cg);        // [ky][kx / PF][co][hi(PF cg) | lo(PF cg)]
     if (posconv_supported(hid, c.conv_pos_groups, c.conv_pos)) h->pc_w = ar.get<bf16>((long)hid * cg * c.conv_pos * c.conv_pos * 2);
     NEED_W(t0, "vit.t_embedder.mlp.0.weight", hid, 256);
     NEED_W(t2, "vit.t_embedder.mlp.2.weight", hid, hid);
@@ -252,7 +256,10 @@ static void pack_la(dexb_handle* h, LinAttW& la, const std::string& p, cudaStrea
 
 int engine_finalize(dexb_handle* h, cudaStream_t st) {
   const dexb_config& c = h->cfg;
-  DEXB_CHECK(c.dim == 64, "only decoder.dim == 64 is instantiated (got %d)", c.dim);
+  DEXB_CHECK(c.dim == 64 || c.dim == 128, "decoder.dim must be 64 or 128 (got %d)", c.dim);
+  DEXB_CHECK((posconv_pf(c.hidden / c.conv_pos_groups) * (c.hidden / c.conv_pos_groups)) % 64 == 0 &&
+                 c.conv_pos % posconv_pf(c.hidden / c.conv_pos_groups) == 0,
+             "pos-conv: %d channels per group cannot be packed into 64-element K chunks", c.hidden / c.conv_pos_groups);
   DEXB_CHECK(c.hidden % 128 == 0 && c.hidden <= 384, "dit.hidden_size must be 128, 256 or 384 (got %d)", c.hidden);
   DEXB_CHECK(c.hidden % c.heads == 0 && (c.hidden / c.heads) % 64 == 0, "head dim must be a multiple of 64");
   DEXB_CHECK(c.conv_pos % 2 == 0 && c.hidden % c.conv_pos_groups == 0, "conv_pos must be even");
@@ -285,7 +292,8 @@ int engine_finalize(dexb_handle* h, cudaStream_t st) {
   const int fq = (c.n_feats / 2) / c.stride;
   launch_transpose_scale(find_w(h, "vit.freq_new_pos_embed")->p, h->fpos, hid, fq, 1.f, st);
   launch_pack_split(find_w(h, "vit.x_embedder.proj.2.weight")->p, mid, h->pe_w, 2L * mid, mid, hid, mid, st);
-  launch_pack_posconv(find_w(h, "vit.pos_conv.0.weight")->p, h->posconv_w, hid, hid / c.conv_pos_groups, c.conv_pos, st);
+  launch_pack_posconv(find_w(h, "vit.pos_conv.0.weight")->p, h->posconv_w, hid, hid / c.conv_pos_groups, c.conv_pos,
+                      posconv_pf(hid / c.conv_pos_groups), st);
   if (h->pc_w != nullptr) launch_posconv_pack_w(find_w(h, "vit.pos_conv.0.weight")->p, h->pc_w, c.conv_pos_groups, c.conv_pos, st);
   for (int i = 0; i < c.depth; ++i) {
     const std::string b = "vit.blocks." + std::to_string(i);
@@ -392,7 +400,8 @@ static int plan_la(dexb_handle* h, LinAttW& la, const bf16* in, long in_stride, 
     gp_out_f(p, h->kv, 256);
     DEXB_TRY(plan_shared(&la.kv, p));
   }
-  if (h->fused_la)                                    // G = softmax(k)^T x on the tensor cores; W_v is applied by the merge kernel
+  la.fused = h->fused_la && la.C <= 128;              // the context kernel keeps a 128 x C accumulator in tensor memory: C <= 128
+  if (la.fused)                                       // G = softmax(k)^T x on the tensor cores; W_v is applied by the merge kernel
     DEXB_TRY(attn_plan_init_la(&la.ctx_plan, la.kv_w, in, in_stride, in_hi, in_lo, la.part_o, la.part_l, la.part_m, h->B, H * W,
                                la.PP, la.C, la.splits));
   {
@@ -496,7 +505,10 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   h->pg = ar.get<float>(M * hid);                       // GELU(pos_conv) per grid position
   h->pe = ar.get<float>((long)B * h->Wq * hid);         // its mean over the frequency axis
   h->tiv_a = ar.get<float>((long)B * mid); h->tiv_d = ar.get<float>((long)B * mid);
-  h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + 1) * 4 * hid);
+  {
+    const int pf = posconv_pf(hid / c.conv_pos_groups);
+    h->pairs = ar.get<bf16>((long)B * h->Fq * (h->Wq + pf - 1) * 2 * pf * hid);
+  }
   h->pc_in = ar.get<bf16>(M * 2 * hid);
   h->xtok = ar.get<float>(M * hid);
   h->hS = ar.get<bf16>(M * 2 * hid);
@@ -607,17 +619,17 @@ static int build_plans(dexb_handle* h) {
     DEXB_TRY(plan_shared(&h->g_pe, p));
   }
   {
-    const int G = c.conv_pos_groups, cg = hid / G;
+    const int G = c.conv_pos_groups, cg = hid / G, pf = posconv_pf(cg);
     GemmParams p = gp_base(c);
-    gp_geom(p, B * G, Fq, Wq + 1);
+    gp_geom(p, B * G, Fq, Wq + pf - 1);
     p.nheads = G;
     p.CH = Fq; p.CW = Wq; p.OH = Fq; p.OW = Wq;
-    gp_a(p, h->pairs, 4L * hid, 0, 2 * hid, 2 * cg);
-    p.a_head_stride = 2 * cg;
-    gp_b(p, h->posconv_w, 2 * cg, cg);
+    gp_a(p, h->pairs, 2L * pf * hid, 0, pf * hid, pf * cg);
+    p.a_head_stride = pf * cg;
+    gp_b(p, h->posconv_w, pf * cg, cg);
     p.b_rows_per_tap = hid; p.b_head_rows = cg;
-    gp_taps(p, c.conv_pos, c.conv_pos / 2, -(c.conv_pos / 2), -(c.conv_pos / 2) + 1);
-    p.tap_sw = 2;
+    gp_taps(p, c.conv_pos, c.conv_pos / pf, -(c.conv_pos / 2), -(c.conv_pos / 2) + pf - 1);
+    p.tap_sw = pf;
     p.epi.bias = h->posconv_b; p.epi.bias_head_stride = cg;
     p.epi.act = 1;
     gp_out_f(p, h->pg, hid);                       // the mean over the frequency axis is taken by k_freq_mean (fixed order)
@@ -867,7 +879,7 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
 }
 
 static int run_la(dexb_handle* h, LinAttW& la, int P, cudaStream_t st) {
-  if (h->fused_la) {
+  if (la.fused) {
     if (h->prof) prof_begin(h, "attn_fwd_kernel(la ctx)", attn_flop(la.ctx_plan), st);
     DEXB_TRY(attn_launch(la.ctx_plan, st));
     if (h->prof) prof_end(h, st);
@@ -969,7 +981,7 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
     if (h->prof) prof_end(h, st);
     ++h->launches;
   } else {
-    LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, st));
+    LAUNCH(launch_pair_pack(h->xe, h->pairs, B, h->Fq, h->Wq, hid, hid / c.conv_pos_groups, posconv_pf(hid / c.conv_pos_groups), st));
     GEMM(h->g_posconv, h->g_posconv.p);
   }
   LAUNCH(launch_freq_mean(h->pg, h->pe, B, h->Fq, h->Wq, hid, st));

@@ -54,6 +54,7 @@ struct LinAttW {
   bf16* kv_w = nullptr;               // [256][hi(C)|lo(C)]  (rows 128..383 of to_qkv)
   const float *wq = nullptr, *wv = nullptr, *wout = nullptr, *bout = nullptr, *g = nullptr;
   int C = 0;
+  bool fused = false;                 // context on the tensor-core kernel (C <= 128) or the colmax / ctx CUDA-core kernels
   GemmPlan kv, apply;
   AttnPlan ctx_plan;
   int splits = 1, PP = 0;

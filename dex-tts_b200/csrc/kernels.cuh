@@ -103,8 +103,8 @@ void launch_tiv_sap(const float* t_tok, const float* rows, const float* W, const
 void launch_transpose_scale(const float* in, float* out, int R, int Cc, float scale, cudaStream_t st);
 void launch_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t st);
 void launch_tv_vlt_pack(const float* vl, bf16* vlt, int B, int Ts, int C, int KP, cudaStream_t st);
-void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D, int Cg, cudaStream_t st);
-void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, cudaStream_t st);
+void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D, int Cg, int PF, cudaStream_t st);
+void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, int PF, cudaStream_t st);
 void launch_pack_convT(const float* w, bf16* out, int Ci, int Co, cudaStream_t st);
 int launch_stft_mel(const float* wav, int B, int S, const float* window, const float* mel_basis, int n_fft, int hop,
                     int n_mels, float* mel, float* energy /*(B, frames) or null*/, cudaStream_t st);

@@ -124,24 +124,25 @@ void launch_tv_vlt_pack(const float* vl, bf16* vlt, int B, int Ts, int C, int KP
 }
 
 // ------------------------------------------------------------------------------------------------
-// pair packing for the grouped 16x16 positional conv (K = 32 per group and tap is too short for a 128 B swizzle
-// span, so two x-adjacent taps are fused into one K = 64 chunk):
-//   pairs[b][y][xx][g][half*Cg + ci] = e[b][y][xx - 1 + half][g*Cg + ci],  xx in [0, Wq], zero outside the image.
-// Row layout: [hi(G*2Cg) | lo(G*2Cg)].  One thread per (pixel xx, 8 channels).
+// pair packing for the grouped 16x16 positional conv (K = 32 or 48 per group and tap is too short for a 128 B swizzle
+// span, so PF x-adjacent taps are fused into one K = PF * Cg chunk: PF = 2 for Cg = 32 (K = 64), 4 for Cg = 48 (K = 192)):
+//   pairs[b][y][xx][g][f*Cg + ci] = e[b][y][xx - (PF - 1) + f][g*Cg + ci],  xx in [0, Wq + PF - 1), zero outside the image.
+// Row layout: [hi(G*PF*Cg) | lo(G*PF*Cg)].  One thread per (pixel xx, fused tap f, 8 channels).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pair_pack(const float* __restrict__ e, bf16* __restrict__ pairs, int B, int Fq,
-                                                   int Wq, int D, int Cg) {
+                                                   int Wq, int D, int Cg, int PF) {
   const int cpt = D / 8;
+  const int Wp = Wq + PF - 1;
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const long total = (long)B * Fq * (Wq + 1) * 2 * cpt;
+  const long total = (long)B * Fq * Wp * PF * cpt;
   if (gid >= total) return;
   const int c0 = (int)(gid % cpt) * 8;
   long t = gid / cpt;
-  const int half = (int)(t % 2); t /= 2;
-  const int xx = (int)(t % (Wq + 1)); t /= (Wq + 1);
+  const int half = (int)(t % PF); t /= PF;
+  const int xx = (int)(t % Wp); t /= Wp;
   const int y = (int)(t % Fq);
   const int b = (int)(t / Fq);
-  const int x = xx - 1 + half;
+  const int x = xx - (PF - 1) + half;
   float v[8];
   if (x >= 0 && x < Wq) {
     const float* q = e + ((((long)b * Fq + y) * Wq) + x) * D + c0;
@@ -153,17 +154,17 @@ __global__ void __launch_bounds__(256) k_pair_pack(const float* __restrict__ e, 
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
   }
   const int g = c0 / Cg, ci = c0 % Cg;
-  bf16* row = pairs + ((((long)b * Fq + y) * (Wq + 1)) + xx) * (4L * D);
-  const int col = g * 2 * Cg + half * Cg + ci;
-  store_split8(row + col, row + 2 * D + col, v);
+  bf16* row = pairs + ((((long)b * Fq + y) * Wp) + xx) * (2L * PF * D);
+  const int col = g * PF * Cg + half * Cg + ci;
+  store_split8(row + col, row + PF * D + col, v);
 }
-void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D, int Cg, cudaStream_t st) {
-  const long total = (long)B * Fq * (Wq + 1) * 2 * (D / 8);
-  k_pair_pack<<<cdiv(total, 256), 256, 0, st>>>(e, pairs, B, Fq, Wq, D, Cg);
+void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D, int Cg, int PF, cudaStream_t st) {
+  const long total = (long)B * Fq * (Wq + PF - 1) * PF * (D / 8);
+  k_pair_pack<<<cdiv(total, 256), 256, 0, st>>>(e, pairs, B, Fq, Wq, D, Cg, PF);
 }
 
-// pos-conv weight [Co][Cg][KP][KP] -> [tap = ky*(KP/2) + kxp][Co][hi(2Cg)|lo(2Cg)], k = (kx & 1)*Cg + ci
-__global__ void k_pack_posconv(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Cg, int KP) {
+// pos-conv weight [Co][Cg][KP][KP] -> [tap = ky*(KP/PF) + kx/PF][Co][hi(PF Cg)|lo(PF Cg)], k = (kx % PF)*Cg + ci
+__global__ void k_pack_posconv(const float* __restrict__ w, bf16* __restrict__ out, int Co, int Cg, int KP, int PF) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)Co * Cg * KP * KP;
   if (i >= total) return;
@@ -172,13 +173,13 @@ __global__ void k_pack_posconv(const float* __restrict__ w, bf16* __restrict__ o
   const int ky = (int)(t % KP); t /= KP;
   const int ci = (int)(t % Cg);
   const int co = (int)(t / Cg);
-  const int tap = ky * (KP / 2) + kx / 2;
-  const int k = (kx & 1) * Cg + ci;
-  bf16* row = out + ((long)tap * Co + co) * (4L * Cg);
-  split2(w[i], row[k], row[2 * Cg + k]);
+  const int tap = ky * (KP / PF) + kx / PF;
+  const int k = (kx % PF) * Cg + ci;
+  bf16* row = out + ((long)tap * Co + co) * (2L * PF * Cg);
+  split2(w[i], row[k], row[PF * Cg + k]);
 }
-void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, cudaStream_t st) {
-  k_pack_posconv<<<cdiv((long)Co * Cg * KP * KP, 256), 256, 0, st>>>(w, out, Co, Cg, KP);
+void launch_pack_posconv(const float* w, bf16* out, int Co, int Cg, int KP, int PF, cudaStream_t st) {
+  k_pack_posconv<<<cdiv((long)Co * Cg * KP * KP, 256), 256, 0, st>>>(w, out, Co, Cg, KP, PF);
 }
 
 // ConvTranspose2d(4x4, stride 2, pad 1) weight [Ci][Co][4][4] -> per output-parity phase (ry, rx) a 2x2-tap conv:

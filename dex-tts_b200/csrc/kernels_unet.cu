@@ -46,17 +46,18 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
                                                  int step, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ raw, double* __restrict__ stats, int B, int H,
                                                  int W) {
-  static_assert(C == 64, "one GroupNorm group per channel octet");
+  static_assert(C == 64 || C == 128, "GroupNorm(8, C): one or two channel octets per group");
   pdl_wait();
   constexpr int KT = 9 * CIN;                                // taps x input channels: [mu | c_in x | speaker channel]
+  constexpr int OCTS = C / 8, QUADS = 256 / OCTS;            // a block covers QUADS * 4 pixels of one row: 128 (C = 64) or 64 (C = 128)
   __shared__ __align__(16) float wsT[KT][C];                 // [k][co]
-  __shared__ float red[8][C / 8][2];
+  __shared__ float red[8][OCTS][2];
   for (int i = threadIdx.x; i < C * KT; i += 256) wsT[i % KT][i / KT] = w[i];
   __syncthreads();
   const int h = blockIdx.y, b = blockIdx.z;
-  const int oct = threadIdx.x & 7, quad = threadIdx.x >> 3;
+  const int oct = threadIdx.x % OCTS, quad = threadIdx.x / OCTS;
   const int c0 = oct * 8;
-  const int x0 = blockIdx.x * 128 + quad * 4;
+  const int x0 = blockIdx.x * (QUADS * 4) + quad * 4;
   const float c_in = tab[step].c_in;
   float va[3][6], vc[3][6], vs[3][6];                        // mu*mask, c_in*x*mask (and spk*mask) at rows h-1..h+1, columns x0-1..x0+4
 #pragma unroll
@@ -113,29 +114,34 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
       for (int i = 0; i < 8; ++i) { s += acc[p][i]; ss += acc[p][i] * acc[p][i]; }
     }
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  if (OCTS == 8) { s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8); }   // lanes of one octet
   s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane < 8) { red[warp][lane][0] = s; red[warp][lane][1] = ss; }
+  if (lane < OCTS) { red[warp][lane][0] = s; red[warp][lane][1] = ss; }
   __syncthreads();
-  if (threadIdx.x < C / 8) {
-    const int g = threadIdx.x;               // channels-per-group == 8 when C == 64 (GroupNorm(8, 64))
+  if (threadIdx.x < 8) {
+    const int g = threadIdx.x;               // GroupNorm(8, C): group g = OCTS / 8 consecutive channel octets
     double ds = 0., dss = 0.;
-    for (int wq = 0; wq < 8; ++wq) { ds += red[wq][g][0]; dss += red[wq][g][1]; }
-    atomicAdd(&stats[((long)b * (C / 8) + g) * 2], ds);
-    atomicAdd(&stats[((long)b * (C / 8) + g) * 2 + 1], dss);
+    for (int wq = 0; wq < 8; ++wq)
+      for (int o = 0; o < OCTS / 8; ++o) { ds += red[wq][g * (OCTS / 8) + o][0]; dss += red[wq][g * (OCTS / 8) + o][1]; }
+    atomicAdd(&stats[((long)b * 8 + g) * 2], ds);
+    atomicAdd(&stats[((long)b * 8 + g) * 2 + 1], dss);
   }
 }
 
 void launch_conv_in(const float* x, const float* mu, const float* spk_s, const float* mask, const StepScalars* tab, int step,
                     const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
                     cudaStream_t st) {
-  dim3 grid(cdiv(W, 128), H, B);
-  // stats layout is [B][8 groups][2]; only C == 64 (decoder.dim 64, GroupNorm(8, 64): one group per channel octet) is
-  // instantiated -- engine_finalize rejects other widths.
-  if (C != 64) return;
-  if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
-  else launch_pdl(k_conv_in<64, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+  // stats layout is [B][8 groups][2]; C = decoder.dim in {64, 128} (engine_finalize rejects other widths)
+  if (C == 64) {
+    dim3 grid(cdiv(W, 128), H, B);
+    if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
+    else launch_pdl(k_conv_in<64, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+  } else if (C == 128) {
+    dim3 grid(cdiv(W, 64), H, B);
+    if (spk_s == nullptr) launch_pdl(k_conv_in<128, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
+    else launch_pdl(k_conv_in<128, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -201,12 +207,14 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
                                                   const float* __restrict__ fc_b, const float* __restrict__ mask,
                                                   float* __restrict__ x, float* __restrict__ den_out,
                                                   const StepScalars* __restrict__ tab, int step, int B, int P, int W) {
-  // grid = (chunks of ITEMS * 256 eight-channel groups, image); C == 64: 8 lanes per pixel (32-bit index math, see k_gn_apply)
+  // grid = (chunks of ITEMS * 256 eight-channel groups, image); C / 8 = 8 or 16 lanes per pixel (32-bit index math, see k_gn_apply)
   pdl_wait();
   const int b = blockIdx.y;
-  const unsigned ngroups = (unsigned)P << 3;
+  const int cpt = C >> 3;
+  const int cshift = 31 - __clz(cpt);
+  const unsigned ngroups = (unsigned)P << cshift;
   const unsigned base = blockIdx.x * (unsigned)(256 * ITEMS);
-  const int c0 = (int)(threadIdx.x & 7) * 8;
+  const int c0 = (int)(threadIdx.x & (cpt - 1)) * 8;
   const int g = c0 / (C / G);
   float ga[8], be[8], fw[8];
 #pragma unroll
@@ -217,10 +225,10 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
-    const float* rp = raw + (img_row0 + ((gi < ngroups) ? (gi >> 3) : 0u)) * C + c0;
+    const float* rp = raw + (img_row0 + ((gi < ngroups) ? (gi >> cshift) : 0u)) * C + c0;
     r0[j] = *reinterpret_cast<const float4*>(rp);
     r1[j] = *reinterpret_cast<const float4*>(rp + 4);
-    xin[j] = (gi < ngroups && c0 == 0) ? x[img_row0 + (gi >> 3)] : 0.f;
+    xin[j] = (gi < ngroups && c0 == 0) ? x[img_row0 + (gi >> cshift)] : 0.f;
   }
   const StepScalars sc = tab[step];
   const float fcb = fc_b[0];
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
     const bool active = gi < ngroups;
-    const unsigned p = active ? (gi >> 3) : 0u;
+    const unsigned p = active ? (gi >> cshift) : 0u;
     const long pix = img_row0 + p;
     float part = 0.f;
     float m = 0.f;
@@ -243,10 +251,11 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
         part = fmaf(fw[i], y * m, part);
       }
     }
-    // reduce over the 8 lanes of a pixel (aligned groups of lanes)
+    // reduce over the 8 / 16 lanes of a pixel (aligned groups of lanes)
     part += __shfl_xor_sync(0xffffffffu, part, 1);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
     part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (cpt == 16) part += __shfl_xor_sync(0xffffffffu, part, 8);
     if (active && c0 == 0) {
       const float fx = (part + fcb) * m;
       const float xv = xin[j];
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
 void launch_gn_final(const float* raw, int C, int G, const double* stats, const float* gamma, const float* beta,
                      const float* fc_w, const float* fc_b, const float* mask, float* x, float* den_out,
                      const StepScalars* tab, int step, int B, int H, int W, cudaStream_t st) {
-  const long ngroups = (long)H * W * 8;                     // C == 64 (engine_finalize)
+  const long ngroups = (long)H * W * (C / 8);               // C in {64, 128} (engine_finalize)
   if (ngroups >= 8 * 256) {
     dim3 grid(cdiv(ngroups, 2 * 256), B);
     launch_pdl(k_gn_final<2>, grid, dim3(256), 0, st, raw, C, G, stats, gamma, beta, fc_w, fc_b, mask, x, den_out, tab, step, B, H * W, W);
@@ -487,15 +496,15 @@ __global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, 
   // thread = input channel ci and rows r0, r0 + 256/C, ...: one W_q column serves all its outputs; 32 independent loads in flight
   const float gg = g[0];
   const int ci = tid % C, r0 = tid / C, rstep = 256 / C;     // C == 64: rows r0, r0+4;  C == 128: rows r0, r0+2, r0+4, r0+6
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int nr = 8 / rstep;                                  // 2 or 4
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int nr = 8 / rstep;                                  // 2, 4 or 8 (C = 256: every thread owns one input channel and all 8 rows)
 #pragma unroll 4
   for (int h0 = 0; h0 < 128; h0 += 32) {
     float wv[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) wv[k] = __ldg(wq + (long)(h0 + k) * C + ci);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       if (i < nr) {
 #pragma unroll
         for (int k = 0; k < 32; ++k) acc[i] = fmaf(Ts[r0 + i * rstep][h0 + k], wv[k], acc[i]);
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, 
     }
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     if (i >= nr) break;
     const int co = co0 + r0 + i * rstep;
     const float v = gg * acc[i] + (co == ci ? 1.f : 0.f);

@@ -753,7 +753,8 @@ int dexb_lf0_create(int c_h, int c_out, int c_out_g, int num_layer, dexb_lf0** o
   DEXB_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   DEXB_CHECK(major == 10, "dexb200 is built for sm_100a only (device %d has compute capability major %d); there is no fallback",
              dev, major);
-  DEXB_CHECK(c_h == 192, "dexb_lf0_create: the GRU recurrence kernel is instantiated for c_h = 192 (hidden 96 per direction), got %d", c_h);
+  DEXB_CHECK(c_h == 192 || c_h == 256, "dexb_lf0_create: the GRU recurrence kernel is instantiated for c_h = 192 / 256 (hidden 96 / 128 per "
+             "direction: the VCTK and LibriTTS configs), got %d", c_h);
   DEXB_CHECK(c_out >= 64 && c_out % 64 == 0 && c_out <= kTvMaxC && c_out_g >= 64 && c_out_g % 64 == 0 && c_out_g <= kTvMaxC,
              "dexb_lf0_create: c_out = %d / c_out_g = %d must be multiples of 64 (<= %d)", c_out, c_out_g, kTvMaxC);
   DEXB_CHECK(num_layer >= 1 && num_layer <= 8, "dexb_lf0_create: num_layer = %d", num_layer);
@@ -858,7 +859,9 @@ int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, i
   for (int l = 0; l < h->L; ++l) {
     bf16* dst = (l & 1) ? h->xs : h->hs;
     DEXB_TRY(gemm_launch(h->ih[l].plan, h->ih[l].plan.p, 0, st));
-    k_gru_rec<96><<<dim3(B, 2), 3 * 96, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
+    if (h->c_h == 192) k_gru_rec<96><<<dim3(B, 2), 3 * 96, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
+                                                 l == h->L - 1 ? mask_dev : nullptr, dst, T);
+    else k_gru_rec<128><<<dim3(B, 2), 3 * 128, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
                                                  l == h->L - 1 ? mask_dev : nullptr, dst, T);
     h->launches += 2;
   }
@@ -946,6 +949,7 @@ struct TxtLayer {
 
 struct dexb_text : dexb::EncBase {
   int n_vocab = 0, n_feats = 0, C = 0, Fc = 0, Fd = 0, heads = 0, L = 0, ksz = 3, adaln = 1;
+  int C0 = 0, spk_dim = 0;                           // C0 = embedding / prenet width; C = C0 + spk_dim behind the prenet (n_spks > 1)
   const float *emb = nullptr, *angle = nullptr, *out_ln = nullptr, *dpw = nullptr, *dpb = nullptr;
   dexb::TvConv pre[3], pre_proj, proj_m, dp1, dp2;
   std::vector<TxtLayer> layers;
@@ -991,6 +995,18 @@ __global__ void k_txt_embed(const long long* __restrict__ ids, const float* __re
   split2(v * mask[r], hi, lo);
   xs[r * 2 * C + c] = hi;
   xs[r * 2 * C + C + c] = lo;
+}
+
+// n_spks > 1 (text_encoder.py:135-136): rows [C0] of the prenet output + the utterance's speaker embedding (NOT masked: upstream
+// repeats it over all Tx positions) -> the residual stream rows [C0 + S]
+__global__ void k_txt_cat_spk(const float* __restrict__ x, const float* __restrict__ spk, float* __restrict__ out, long rows, int C0, int S,
+                              int T) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const int C = C0 + S;
+  if (i >= rows * C) return;
+  const long r = i / C;
+  const int c = (int)(i % C);
+  out[i] = c < C0 ? x[r * C0 + c] : spk[(r / T) * S + (c - C0)];
 }
 
 // one warp per token: everything between two GEMMs of the text encoder
@@ -1265,12 +1281,12 @@ static int txt_plan(dexb_text* h, int B, int T) {
   return rc;
 }
 
-static TxtRow txt_row(const dexb_text* h, const float* in) {
+static TxtRow txt_row(const dexb_text* h, const float* in, int C = 0) {
   TxtRow p;
   memset(&p, 0, sizeof(p));
   p.in = in;
   p.rows = (long)h->B * h->T;
-  p.C = h->C; p.T = h->T;
+  p.C = C > 0 ? C : h->C; p.T = h->T;
   return p;
 }
 static void txt_launch_row(const TxtRow& p, cudaStream_t st) { k_txt_row<<<cdiv(p.rows, 8), 256, 0, st>>>(p); }
@@ -1280,7 +1296,7 @@ static void txt_launch_row(const TxtRow& p, cudaStream_t st) { k_txt_row<<<cdiv(
 extern "C" {
 
 int dexb_text_create(int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp, int n_heads, int n_layers,
-                     int kernel_size, int adaln, dexb_text** out) {
+                     int kernel_size, int adaln, int spk_emb_dim, dexb_text** out) {
   DEXB_CHECK(out != nullptr, "dexb_text_create: null argument");
   int dev = 0, major = 0;
   DEXB_CUDA_OK(cudaGetDevice(&dev));
@@ -1293,10 +1309,16 @@ int dexb_text_create(int n_vocab, int n_feats, int n_channels, int filter_channe
                  filter_channels_dp <= kTvMaxC && filter_channels >= 64 && filter_channels % 64 == 0,
              "dexb_text_create: n_channels %d / filter_channels_dp %d must be multiples of 64 (<= %d), filter_channels %d a multiple of 64",
              n_channels, filter_channels_dp, kTvMaxC, filter_channels);
-  DEXB_CHECK(n_heads >= 1 && n_channels % n_heads == 0 && (n_channels / n_heads) % 32 == 0 && n_channels / n_heads <= 32 * kTxtMaxDpl,
-             "dexb_text_create: head dim %d / %d must be a multiple of 32 (<= %d)", n_channels, n_heads, 32 * kTxtMaxDpl);
+  DEXB_CHECK(spk_emb_dim >= 0 && spk_emb_dim % 64 == 0 && n_channels + spk_emb_dim <= kTvMaxC,
+             "dexb_text_create: spk_emb_dim %d must be a multiple of 64 with n_channels + spk_emb_dim <= %d", spk_emb_dim, kTvMaxC);
+  DEXB_CHECK(spk_emb_dim == 0 || !adaln, "dexb_text_create: the speaker channel exists for GeDEX-TTS only (DeXTTS.forward passes spk=None "
+             "to its encoder, DEX-TTS/model/tts.py:52)");
+  const int Cw = n_channels + spk_emb_dim;
+  DEXB_CHECK(n_heads >= 1 && Cw % n_heads == 0 && (Cw / n_heads) % 32 == 0 && Cw / n_heads <= 32 * kTxtMaxDpl,
+             "dexb_text_create: head dim %d / %d must be a multiple of 32 (<= %d)", Cw, n_heads, 32 * kTxtMaxDpl);
   dexb_text* h = new dexb_text();
-  h->n_vocab = n_vocab; h->n_feats = n_feats; h->C = n_channels; h->Fc = filter_channels; h->Fd = filter_channels_dp;
+  h->n_vocab = n_vocab; h->n_feats = n_feats; h->C = Cw; h->C0 = n_channels; h->spk_dim = spk_emb_dim;
+  h->Fc = filter_channels; h->Fd = filter_channels_dp;
   h->heads = n_heads; h->L = n_layers; h->ksz = kernel_size; h->adaln = adaln ? 1 : 0;
   h->layers.resize(n_layers);
   *out = h;
@@ -1338,15 +1360,15 @@ int dexb_text_load_weight(dexb_text* h, const char* name, const float* data_dev,
 int dexb_text_finalize_weights(dexb_text* h, void* stream) {
   DEXB_CHECK(h != nullptr, "null handle");
   cudaStream_t st = (cudaStream_t)stream;
-  const int C = h->C;
-  DEXB_TRY(tv_get(h, "emb.weight", {h->n_vocab, C}, &h->emb));
+  const int C = h->C, C0 = h->C0;
+  DEXB_TRY(tv_get(h, "emb.weight", {h->n_vocab, C0}, &h->emb));
   for (int i = 0; i < 3; ++i) {
     const std::string s = std::to_string(i);
-    DEXB_TRY(txt_pack(h, "prenet.conv_layers." + s + ".weight", "prenet.conv_layers." + s + ".bias", C, C, 5, false, &h->pre[i], st));
-    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".gamma", {C}, &h->pre[i].ln_g));
-    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".beta", {C}, &h->pre[i].ln_b));
+    DEXB_TRY(txt_pack(h, "prenet.conv_layers." + s + ".weight", "prenet.conv_layers." + s + ".bias", C0, C0, 5, false, &h->pre[i], st));
+    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".gamma", {C0}, &h->pre[i].ln_g));
+    DEXB_TRY(tv_get(h, "prenet.norm_layers." + s + ".beta", {C0}, &h->pre[i].ln_b));
   }
-  DEXB_TRY(txt_pack(h, "prenet.proj.weight", "prenet.proj.bias", C, C, 1, false, &h->pre_proj, st));
+  DEXB_TRY(txt_pack(h, "prenet.proj.weight", "prenet.proj.bias", C0, C0, 1, false, &h->pre_proj, st));
   if (h->adaln) {
     if (h->adaW == nullptr) {
       DEXB_CUDA_OK(cudaMalloc(&h->adaW, (size_t)h->L * 4 * C * C * sizeof(float)));
@@ -1394,31 +1416,33 @@ int dexb_text_finalize_weights(dexb_text* h, void* stream) {
   return 0;
 }
 
-int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, int B, int Tx, float* mu_dev,
-                      float* logw_dev, void* stream) {
+int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, const float* spk_dev, int B, int Tx,
+                      float* mu_dev, float* logw_dev, void* stream) {
   DEXB_CHECK(h != nullptr && ids_dev != nullptr && mask_dev != nullptr && mu_dev != nullptr && logw_dev != nullptr,
              "dexb_text_forward: null argument");
   DEXB_CHECK(h->finalized, "dexb_text_forward: call dexb_text_finalize_weights first");
   DEXB_CHECK(B >= 1 && Tx >= 1, "dexb_text_forward: B = %d, Tx = %d", B, Tx);
   DEXB_CHECK((sty_dev != nullptr) == (h->adaln != 0), "dexb_text_forward: the style vector is %s for this encoder",
              h->adaln ? "required (DEX-TTS: AdaptiveLayerNorm)" : "not taken (GeDEX-TTS)");
+  DEXB_CHECK((spk_dev != nullptr) == (h->spk_dim > 0), "dexb_text_forward: the speaker embedding is %s for this encoder",
+             h->spk_dim > 0 ? "required (n_spks > 1)" : "not taken (n_spks <= 1)");
   cudaStream_t st = (cudaStream_t)stream;
   static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
   DEXB_TRY(txt_plan(h, B, Tx));
-  const int C = h->C, T = Tx;
+  const int C = h->C, C0 = h->C0, T = Tx;
   const long rows = (long)B * T;
   h->launches = 0;
   if (h->adaln) {
     k_txt_ada<<<cdiv((long)h->L * 4 * B * C, 8), 256, 0, st>>>(h->adaW, h->adaB, sty_dev, h->ada, h->L * 4, B, C);
     h->launches += 1;
   }
-  k_txt_embed<<<cdiv(rows * C, 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), h->emb, mask_dev, h->x0f, h->xs, rows, C,
-                                                  h->n_vocab, (float)sqrt((double)C));
+  k_txt_embed<<<cdiv(rows * C0, 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), h->emb, mask_dev, h->x0f, h->xs, rows, C0,
+                                                   h->n_vocab, (float)sqrt((double)C0));
   h->launches += 1;
   // prenet: 3 x (conv5 -> channel LayerNorm -> ReLU), input masked before every conv; then (x + proj(.)) * mask
   for (int i = 0; i < 3; ++i) {
     DEXB_TRY(gemm_launch(h->pre[i].plan, h->pre[i].plan.p, 0, st));
-    TxtRow p = txt_row(h, h->acc);
+    TxtRow p = txt_row(h, h->acc, C0);
     p.ln_g = h->pre[i].ln_g; p.ln_b = h->pre[i].ln_b; p.relu = 1;
     p.mask = mask_dev; p.os = h->xs;
     txt_launch_row(p, st);
@@ -1426,9 +1450,14 @@ int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_de
   }
   DEXB_TRY(gemm_launch(h->pre_proj.plan, h->pre_proj.plan.p, 0, st));
   {
-    TxtRow p = txt_row(h, h->acc);
-    p.resid = h->x0f; p.mask = mask_dev; p.of2 = h->hf;                // hf = (x + proj(x)) * mask: the residual stream
+    TxtRow p = txt_row(h, h->acc, C0);
+    p.resid = h->x0f; p.mask = mask_dev;
+    p.of2 = h->spk_dim > 0 ? h->qf : h->hf;                            // (x + proj(x)) * mask: the residual stream (its first C0 channels)
     txt_launch_row(p, st);
+    if (h->spk_dim > 0) {
+      k_txt_cat_spk<<<cdiv(rows * C, 256), 256, 0, st>>>(h->qf, spk_dev, h->hf, rows, C0, h->spk_dim, T);
+      h->launches += 1;
+    }
     TxtRow n = txt_row(h, h->hf);
     n.rms_w = h->layers[0].rln; n.os = h->xs;                          // operand of layer 0's q / k / v / g projections
     txt_launch_row(n, st);

@@ -83,12 +83,12 @@ SYMBOLS = {
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
-    "dexb_text_create": (ctypes.c_int, [ctypes.c_int] * 9 + [ctypes.POINTER(ctypes.c_void_p)]),
+    "dexb_text_create": (ctypes.c_int, [ctypes.c_int] * 10 + [ctypes.POINTER(ctypes.c_void_p)]),
     "dexb_text_destroy": (None, [ctypes.c_void_p]),
     "dexb_text_load_weight": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, c_int64_p, ctypes.c_int]),
     "dexb_text_finalize_weights": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
-    "dexb_text_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "dexb_text_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "dexb_text_last_launch_count": (ctypes.c_long, [ctypes.c_void_p]),
     "dexb_text_set_layer_limit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "dexb_text_copy_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -4,7 +4,7 @@ Replaces (same constructor arguments, same ``forward`` signature and return valu
     DEX-TTS/model/text_encoder.py:97-142     class TextEncoder  (attached as ``DeXTTS.encoder``, DEX-TTS/model/tts.py:29,51)
     GeDEX-TTS/model/text_encoder.py:99-146   class TextEncoder  (``GeDEXTTS.encoder``, GeDEX-TTS/model/tts.py:24,34) -> ``GeTextEncoder``
 
-SURVEY.md §8f rank 2.  Eval mode, ``n_spks <= 1`` and the RetNet settings of the shipped configs (``use_softmax=True``,
+SURVEY.md §8f rank 2.  Eval mode (``n_spks > 1``: GeDEX-TTS only, as upstream) and the RetNet settings of the shipped configs (``use_softmax=True``,
 ``use_decay=False``; GLU feed-forward, pre-RMSNorm -- the defaults of model/retnet_cfg.py the reference never overrides).  Parameters
 and the two RetNetRelPos buffers are registered under the reference's names (``emb.weight``, ``prenet.conv_layers.0.weight``,
 ``encoder.layers.3.retention.q_proj.weight``, ``encoder.retnet_rel_pos.angle``, ``proj_w.norm_1.gamma`` ...), so upstream checkpoints
@@ -25,17 +25,18 @@ from .utils import sequence_mask
 class TextEncoderEngine:
     """ctypes driver of the ``dexb_text_*`` entry points (include/dexb200.h).  One handle = one (device, weights) pair."""
 
-    def __init__(self, n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size, adaln=True):
+    def __init__(self, n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size, adaln=True,
+                 spk_emb_dim=0):
         if not torch.cuda.is_available():
             raise RuntimeError("dexb200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.dims = dict(n_vocab=int(n_vocab), n_feats=int(n_feats), n_channels=int(n_channels), filter_channels=int(filter_channels),
                          filter_channels_dp=int(filter_channels_dp), n_heads=int(n_heads), n_layers=int(n_layers),
-                         kernel_size=int(kernel_size), adaln=bool(adaln))
+                         kernel_size=int(kernel_size), adaln=bool(adaln), spk_emb_dim=int(spk_emb_dim))
         d = self.dims
         self.L = _lib.load()
         h = ctypes.c_void_p()
         _lib.check(self.L.dexb_text_create(d["n_vocab"], d["n_feats"], d["n_channels"], d["filter_channels"], d["filter_channels_dp"],
-                                           d["n_heads"], d["n_layers"], d["kernel_size"], int(d["adaln"]), ctypes.byref(h)),
+                                           d["n_heads"], d["n_layers"], d["kernel_size"], int(d["adaln"]), d["spk_emb_dim"], ctypes.byref(h)),
                    "dexb_text_create")
         self.h = h
 
@@ -68,26 +69,32 @@ class TextEncoderEngine:
         _lib.check(self.L.dexb_text_finalize_weights(self.h, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
                    "dexb_text_finalize_weights")
 
-    def forward(self, x, x_mask, sty=None):
-        """x (B, Tx) int64 CUDA, x_mask (B, 1, Tx) or (B, Tx), sty (B, C) or None -> (mu (B, n_feats, Tx), logw (B, 1, Tx))."""
+    def forward(self, x, x_mask, sty=None, spk=None):
+        """x (B, Tx) int64 CUDA, x_mask (B, 1, Tx) or (B, Tx), sty (B, C) or None, spk (B, spk_emb_dim) or None (n_spks > 1) ->
+        (mu (B, n_feats, Tx), logw (B, 1, Tx))."""
         B, Tx = x.shape
         ids = x.detach().to(torch.int64).contiguous()
         m = x_mask.detach().float().reshape(B, Tx).contiguous()
         s = sty.detach().float().reshape(B, self.dims["n_channels"]).contiguous() if sty is not None else None
+        if (spk is not None) != (self.dims["spk_emb_dim"] > 0):
+            raise RuntimeError("the speaker embedding is " + ("required: this encoder was built for n_spks > 1" if spk is None
+                                                              else "not taken by an encoder built for n_spks <= 1"))
+        k = spk.detach().float().reshape(B, self.dims["spk_emb_dim"]).contiguous() if spk is not None else None
         mu = torch.empty(B, self.dims["n_feats"], Tx, device=x.device, dtype=torch.float32)
         logw = torch.empty(B, 1, Tx, device=x.device, dtype=torch.float32)
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-        _lib.check(self.L.dexb_text_forward(self.h, p(ids), p(m), p(s), B, Tx, p(mu), p(logw),
+        _lib.check(self.L.dexb_text_forward(self.h, p(ids), p(m), p(s), p(k), B, Tx, p(mu), p(logw),
                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dexb_text_forward")
-        self._keep = (ids, m, s)
+        self._keep = (ids, m, s, k)
         return mu, logw
 
-    def forward_stream(self, x, x_mask, sty=None, n_layers=0):
+    def forward_stream(self, x, x_mask, sty=None, n_layers=0, spk=None):
         """Unit-parity aid: run the prenet and the first ``n_layers`` RetNet layers only -> the residual stream (B, Tx, C)."""
         _lib.check(self.L.dexb_text_set_layer_limit(self.h, int(n_layers)), "dexb_text_set_layer_limit")
         try:
-            self.forward(x, x_mask, sty)
-            out = torch.empty(x.shape[0], x.shape[1], self.dims["n_channels"], device=x.device, dtype=torch.float32)
+            self.forward(x, x_mask, sty, spk)
+            out = torch.empty(x.shape[0], x.shape[1], self.dims["n_channels"] + self.dims["spk_emb_dim"], device=x.device,
+                              dtype=torch.float32)
             _lib.check(self.L.dexb_text_copy_stream(self.h, ctypes.c_void_p(out.data_ptr()),
                                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dexb_text_copy_stream")
         finally:
@@ -146,14 +153,15 @@ class _TextEncoderBase(nn.Module):
     def __init__(self, n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size, p_dropout,
                  use_softmax, use_decay, window_size=None, spk_emb_dim=64, n_spks=1):
         super().__init__()
-        if n_spks > 1:
-            raise NotImplementedError("the CUDA text encoder implements n_spks <= 1 (no speaker channel concatenated to the prenet output)")
+        if n_spks > 1 and self.adaln:
+            raise NotImplementedError("n_spks > 1 exists for GeDEX-TTS only: DeXTTS forces n_spks = 0 (DEX-TTS/model/tts.py:18) and passes "
+                                      "spk=None to its encoder (:52)")
         if not use_softmax or use_decay:
             raise NotImplementedError("the CUDA text encoder implements the shipped RetNet settings: use_softmax=True, use_decay=False")
         self.n_vocab, self.n_feats, self.n_channels, self.n_spks = n_vocab, n_feats, n_channels, n_spks
         self.dims = dict(n_vocab=int(n_vocab), n_feats=int(n_feats), n_channels=int(n_channels), filter_channels=int(filter_channels),
                          filter_channels_dp=int(filter_channels_dp), n_heads=int(n_heads), n_layers=int(n_layers),
-                         kernel_size=int(kernel_size), adaln=self.adaln)
+                         kernel_size=int(kernel_size), adaln=self.adaln, spk_emb_dim=int(spk_emb_dim) if n_spks > 1 else 0)
         _register_text(self, text_manifest(**self.dims), n_channels)
         self._engine = None
         self._sig = None
@@ -171,11 +179,11 @@ class _TextEncoderBase(nn.Module):
             self._sig = sig
         return self._engine
 
-    def _run(self, x, x_lengths, sty):
+    def _run(self, x, x_lengths, sty, spk=None):
         if not x.is_cuda:
             raise RuntimeError("dexb200.TextEncoder runs on CUDA (sm_100a) only; move the model and inputs to the GPU")
         x_mask = torch.unsqueeze(sequence_mask(x_lengths, x.size(1)), 1).to(torch.float32)          # text_encoder.py:132
-        mu, logw = self.cuda_engine().forward(x, x_mask, sty)
+        mu, logw = self.cuda_engine().forward(x, x_mask, sty, spk if self.n_spks > 1 else None)
         return mu, logw, x_mask
 
 
@@ -194,4 +202,4 @@ class GeTextEncoder(_TextEncoderBase):
 
     @torch.no_grad()
     def forward(self, x, x_lengths, spk=None):
-        return self._run(x, x_lengths, None)
+        return self._run(x, x_lengths, None, spk)                 # n_spks > 1: spk (B, spk_emb_dim) joins behind the prenet (:141-142)

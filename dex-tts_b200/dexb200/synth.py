@@ -355,11 +355,40 @@ def synth_text(B, Tx, n_vocab=149, c_sty=192, seed=81, ragged=False):
     return dict(x=x, x_lengths=x_lengths, sty=torch.randn(B, c_sty, generator=g))
 
 
-def synth_tts_weights(variant="dex", seed=100):
+LIBRITTS_MODEL_CFG = dict(                    # the `model:` block of DEX-TTS/config/LibriTTS/base.yaml:23-83 (+ n_vocab, set by the scripts)
+    sil_token=True, add_blank=True, n_feats=80, n_spks=0, spk_emb_dim=64, n_vocab=149,
+    tv_encoder=dict(c_in=80, num_layer=6, c_h=256, c_out=256, c_out_g=256, commit_w=0.25, n_emb=512),
+    lf0_encoder=dict(c_in=1, c_h=256, c_out=256, c_out_g=256, num_layer=2),
+    tiv_encoder=dict(c_in=80, num_layer=6, c_h=256, c_out=64),
+    encoder=dict(n_channels=256, filter_channels=1024, filter_channels_dp=256, n_layers=8, kernel_size=3, p_dropout=0.1, n_heads=2,
+                 window_size=4, use_softmax=True, use_decay=False),
+    decoder=dict(dim=128, pe_scale=1000, dim_mults=[1, 2], model_type="dit", precond="edm", loss_type="base"),
+    dit=dict(in_channels=3, patch_size=3, stride_size=2, overlap=True, hidden_size=384, depth=4, num_heads=2, mlp_ratio=2, out_channels=1,
+             conv_pos=16, conv_pos_groups=8, use_decoder=False, mask_type="time_random"))
+
+
+def synth_tts_weights(variant="dex", seed=100, dataset="VCTK"):
     """Every tensor of the reference ``DeXTTS`` / ``GeDEXTTS`` (n_spks <= 1) as one flat dict: the encoders and ``conv_sty`` under
     their ``state_dict`` names, the decoder under ``denoise_fn.*`` (upstream: ``decoder.denoise_fn.*`` and, aliased,
-    ``decoder.precond_model.model.*``)."""
+    ``decoder.precond_model.model.*``).  dataset="LibriTTS": the sizes of DEX-TTS/config/LibriTTS/base.yaml (decoder dim 128 / DiT
+    hidden 384, 256-wide encoders)."""
     from .manifest import DecoderCfg
+    if dataset == "LibriTTS":
+        assert variant == "dex"
+        m = LIBRITTS_MODEL_CFG
+        w = dict(synth_decoder_weights(DecoderCfg.make("dex", dim=m["decoder"]["dim"], hidden=m["dit"]["hidden_size"]), seed=seed, live=True))
+        e = m["encoder"]
+        w.update(synth_text_weights(seed=seed, adaln=True, n_channels=e["n_channels"], filter_channels=e["filter_channels"],
+                                    filter_channels_dp=e["filter_channels_dp"], n_heads=e["n_heads"], n_layers=e["n_layers"],
+                                    kernel_size=e["kernel_size"]))
+        tv, lf, ti = m["tv_encoder"], m["lf0_encoder"], m["tiv_encoder"]
+        w.update(synth_tv_weights(c_in=tv["c_in"], c_out=tv["c_out"], c_out_g=tv["c_out_g"], num_layer=tv["num_layer"], c_h=tv["c_h"],
+                                  n_emb=tv["n_emb"], seed=seed))
+        w.update(synth_lf0_weights(c_h=lf["c_h"], c_out=lf["c_out"], c_out_g=lf["c_out_g"], num_layer=lf["num_layer"], c_in=lf["c_in"],
+                                   seed=seed))
+        w.update(synth_tiv_weights(c_in=ti["c_in"], c_out=ti["c_out"], num_layer=ti["num_layer"], c_h=ti["c_h"], seed=seed))
+        w.update(synth_conv_sty_weights(c_in=tv["c_out_g"], c_out=2 * m["decoder"]["dim"], seed=seed))
+        return w
     w = dict(synth_decoder_weights(DecoderCfg.make(variant), seed=seed, live=True))
     w.update(synth_text_weights(seed=seed, adaln=variant == "dex"))
     if variant == "dex":

@@ -242,15 +242,17 @@ int dexb_align_expand(const float* cum_dev, const float* x_mask_dev, const int64
  * the dexb_tiv_* calls. */
 typedef struct dexb_text dexb_text;
 int dexb_text_create(int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp, int n_heads, int n_layers,
-                     int kernel_size, int adaln, dexb_text** out);
+                     int kernel_size, int adaln, int spk_emb_dim, dexb_text** out);
 void dexb_text_destroy(dexb_text* h);
 int dexb_text_load_weight(dexb_text* h, const char* name, const float* data_dev, const int64_t* shape, int ndim);
 int dexb_text_finalize_weights(dexb_text* h, void* stream);
 /* replaces: TextEncoder.forward(x, x_lengths, sty, spk=None) (text_encoder.py:129-142).  ids_dev (B, Tx) int64 phoneme ids,
- * mask_dev (B, Tx) = sequence_mask(x_lengths) in {0,1}, sty_dev (B, n_channels) style vector (NULL iff adaln = 0) ->
+ * mask_dev (B, Tx) = sequence_mask(x_lengths) in {0,1}, sty_dev (B, n_channels) style vector (NULL iff adaln = 0), spk_dev (B, spk_emb_dim)
+ * speaker embedding (NULL iff spk_emb_dim = 0; n_spks > 1 of GeDEX-TTS/model/text_encoder.py:119-127,141-142: concatenated behind the
+ * prenet, everything after it is n_channels + spk_emb_dim wide) ->
  * mu_dev (B, n_feats, Tx), logw_dev (B, 1, Tx).  Allocation behaviour as dexb_tiv_forward. */
-int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, int B, int Tx, float* mu_dev,
-                      float* logw_dev, void* stream);
+int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, const float* spk_dev, int B, int Tx,
+                      float* mu_dev, float* logw_dev, void* stream);
 long dexb_text_last_launch_count(const dexb_text* h);
 /* unit-parity aids (no reference counterpart): n_layers >= 0 makes dexb_text_forward stop after the prenet and that many RetNet
  * layers (mu / logw are then not written), -1 restores the full forward; dexb_text_copy_stream copies the residual stream

@@ -25,11 +25,15 @@ CASES = [
     ("tts_dex_b1",   "dex",   1, 22, 37, 3,     False,  91,   1.5,         1.0),
     ("tts_dex_b2r",  "dex",   2, 24, 29, 2,     True,   92,   1.5,         1.0),
     ("tts_gedex_b2r", "gedex", 2, 38, 0, 3,     True,   93,   1.5,         1.0),
+    # DEX-TTS/config/LibriTTS/base.yaml (decoder dim 128, DiT hidden 384, 256-wide encoders); the name does not match tts_*.npz on
+    # purpose: the VCTK-size tests glob that pattern
+    ("libritts_dex_b1", "dex", 1, 20, 31, 2,    False,  94,   1.5,         1.0, "LibriTTS"),
+    ("libritts_dex_b2r", "dex", 2, 21, 27, 2,   True,   95,   1.5,         1.0, "LibriTTS"),
 ]
 
 
-def synth_tts_inputs(variant, B, Tx, Ts, seed, ragged):
-    inp = synth_text(B, Tx, seed=seed, ragged=ragged)
+def synth_tts_inputs(variant, B, Tx, Ts, seed, ragged, c_sty=192):
+    inp = synth_text(B, Tx, c_sty=c_sty, seed=seed, ragged=ragged)
     if variant == "dex":
         mel = synth_ref_mel(B, Ts, seed=seed + 1, ragged=ragged)             # synthesize.py:94-97: ref = sty = the reference mel
         lf0 = synth_lf0(B, Ts, seed=seed + 2, ragged=ragged)
@@ -37,9 +41,9 @@ def synth_tts_inputs(variant, B, Tx, Ts, seed, ragged):
     return inp
 
 
-def run_case(name, variant, B, Tx, Ts, steps, ragged, seed, temperature, length_scale):
-    model, mod, _ = ref_loader.build_reference_tts(variant)
-    model.load_state_dict(reference_state_dict(synth_tts_weights(variant)), strict=True)
+def run_case(name, variant, B, Tx, Ts, steps, ragged, seed, temperature, length_scale, dataset="VCTK"):
+    model, mod, _ = ref_loader.build_reference_tts(variant, dataset=dataset if dataset != "VCTK" else None)
+    model.load_state_dict(reference_state_dict(synth_tts_weights(variant, dataset=dataset)), strict=True)
     inp = synth_tts_inputs(variant, B, Tx, Ts, seed, ragged)
     if B > 1 and variant == "dex":
         edm = sys.modules["model.edm"]
@@ -66,7 +70,7 @@ def run_case(name, variant, B, Tx, Ts, steps, ragged, seed, temperature, length_
     cap["keys"] = np.array(list(sd.keys()))
     cap["shapes"] = np.array([",".join(str(n) for n in v.shape) for v in sd.values()])
     arrs = dict(enc_out=enc_out.numpy(), dec_out=dec_out.numpy(), attn=np.packbits(attn.numpy().astype(np.uint8), axis=-1),
-                attn_shape=np.array(attn.shape, dtype=np.int64), variant=np.array(variant),
+                attn_shape=np.array(attn.shape, dtype=np.int64), variant=np.array(variant), dataset=np.array(dataset),
                 meta=np.array([B, Tx, Ts, steps, int(ragged), seed], dtype=np.int64), scale=np.array([temperature, length_scale]), **cap)
     path = os.path.join(ROOT, "tests", "golden", name + ".npz")
     np.savez_compressed(path, **arrs)

@@ -140,11 +140,13 @@ def load_reference_tts(variant="dex"):
     return importlib.import_module("model.tts")
 
 
-def reference_model_cfg(variant="dex", n_vocab=149):
+def reference_model_cfg(variant="dex", n_vocab=149, dataset=None):
     """``cfg.model`` as the entry scripts build it: the ``model:`` block of config/{VCTK,LJSpeech}/base.yaml with attribute access,
     plus ``n_vocab`` = len(symbols) + 1 (add_blank), which main.py / synthesize.py fill in at run time."""
     import yaml
     sub, ds = {"dex": ("DEX-TTS", "VCTK"), "gedex": ("GeDEX-TTS", "LJSpeech")}[variant]
+    if dataset is not None:
+        ds = dataset                                             # e.g. DEX-TTS/config/LibriTTS/base.yaml
     with open(os.path.join(REF_ROOT, sub, "config", ds, "base.yaml")) as f:
         raw = yaml.safe_load(f)["model"]
     wrap = lambda d: DotDict({k: wrap(v) if isinstance(v, dict) else v for k, v in d.items()})
@@ -153,10 +155,10 @@ def reference_model_cfg(variant="dex", n_vocab=149):
     return cfg
 
 
-def build_reference_tts(variant="dex", n_vocab=149):
+def build_reference_tts(variant="dex", n_vocab=149, dataset=None):
     """Construct ``DeXTTS(cfg.model)`` / ``GeDEXTTS(cfg.model)`` as synthesize.py:67 does (eval mode)."""
     mod = load_reference_tts(variant)
-    cfg = reference_model_cfg(variant, n_vocab)
+    cfg = reference_model_cfg(variant, n_vocab, dataset)
     model = (mod.DeXTTS if variant == "dex" else mod.GeDEXTTS)(cfg)
     if not hasattr(model.encoder.encoder.config, "use_cache"):
         model.encoder.encoder.config.use_cache = True

@@ -105,7 +105,7 @@ def test_text_encoder_handle_fails_loudly_without_gpu():
     from dexb200 import lib
     L = lib.load()
     h = ctypes.c_void_p()
-    rc = L.dexb_text_create(149, 80, 192, 1024, 256, 2, 8, 3, 1, ctypes.byref(h))
+    rc = L.dexb_text_create(149, 80, 192, 1024, 256, 2, 8, 3, 1, 0, ctypes.byref(h))
     assert rc != 0 and not h.value and len(L.dexb_last_error()) > 0
     from dexb200.model import TextEncoder
     with pytest.raises(RuntimeError):

@@ -152,3 +152,51 @@ def test_style_reference_longer_than_the_fused_key_tile():
     y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), 3, cond=to_cuda(cond)).cpu()
     assert per_bin_violation(y, y_ref) < REL_TOL
     assert eng.simt_fallbacks == 0
+
+
+# ---- LibriTTS decoder sizes (DEX-TTS/config/LibriTTS/base.yaml:65,77: decoder.dim 128, dit.hidden_size 384 -> head dim 192) -------
+# Different code runs there: conv_in / final kernels at 128 channels, 256-channel GroupNorm (4 chunks per group, two n-tiles: per-tile
+# statistics), the CUDA-core LinearAttention context at C = 256, the GEMM -> softmax -> GEMM routes of the TV adaptor (256 channels)
+# and of the DiT attention (head dim 192), and the positional convolution with 48 channels per group (four taps per K chunk).
+LIBRI = dict(dim=128, hidden=384)
+
+
+def _libri_engine(gemm_engine=0):
+    from dexb200.engine import ReverseDiffusion
+    cfg = DecoderCfg.make("dex", **LIBRI)
+    eng = ReverseDiffusion(cfg, gemm_engine=gemm_engine)
+    eng.load_state_dict(synth_decoder_weights(cfg, seed=100, live=True))
+    return cfg, eng
+
+
+def test_libritts_sizes_match_reference_fixture():
+    path = os.path.join(os.path.dirname(__file__), "golden", "libri_dex_b1.npz")
+    g = np.load(path)
+    B, T, Ts, steps, ragged, live, seed = [int(v) for v in g["meta"][:7]]
+    assert [int(v) for v in g["dims"]] == [128, 384]
+    cfg, eng = _libri_engine()
+    inp = synth_inputs(cfg, B, T, Ts=Ts, seed=seed, ragged=bool(ragged))
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"])
+    x0 = inp["z"] / float(g["temperature"]) + inp["mu"]
+    y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
+    v = per_bin_violation(y, torch.from_numpy(g["y"]))
+    print(f"libri_dex_b1 (dim 128 / hidden 384): per-bin violation {v:.2e} vs the unmodified reference, launches {eng.launches}")
+    assert v < REL_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("B,T,Ts", [(2, 128, 259), (1, 512, 100)])
+def test_libritts_sizes_match_oracle(B, T, Ts):
+    cfg, eng = _libri_engine()
+    inp = synth_inputs(cfg, B, T, Ts=Ts, seed=900 + T, ragged=B > 1)
+    cond = dict(sty=inp["sty"], sty_lengths=inp["sty_lengths"], ref_skips=inp["ref_skips"])
+    w = synth_decoder_weights(cfg, seed=100, live=True)
+    steps = 3
+    with torch.no_grad():
+        ref = O.reverse_diffusion(w, O.make_cfg("dex", **LIBRI), inp["z"], inp["mask"], inp["mu"], steps, temperature=1.5, cond=cond)
+    x0 = inp["z"] / 1.5 + inp["mu"]
+    y = eng.sample(x0.cuda(), inp["mask"].cuda(), inp["mu"].cuda(), steps, cond=to_cuda(cond)).cpu()
+    v = per_bin_violation(y, ref)
+    print(f"LibriTTS sizes B={B} T={T} Ts={Ts}: per-bin violation {v:.2e}")
+    assert v < REL_TOL
+    eng.close()

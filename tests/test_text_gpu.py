@@ -17,7 +17,8 @@ from parity import tensor_rel_err
 pytestmark = [pytest.mark.gpu, pytest.mark.run_last]
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "text_*.npz"))
-              if "_spk_" not in os.path.basename(p))       # the n_spks > 1 fixture is oracle-only (the CUDA encoder takes n_spks <= 1)
+              if "_spk_" not in os.path.basename(p))       # the n_spks > 1 fixture has its own test below (speaker input)
+GOLD_SPK = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "text_*_spk_*.npz")))
 TOL = 1e-3             # the path tolerance (north_star), as max |a - b| / RMS(reference tensor)
 KW = dict(n_vocab=149, n_feats=80, n_channels=192, filter_channels=1024, filter_channels_dp=256, n_heads=2, n_layers=8, kernel_size=3,
           p_dropout=0.1, use_softmax=True, use_decay=False, window_size=4)        # DEX-TTS/config/VCTK/base.yaml:51-61
@@ -52,6 +53,37 @@ def test_text_encoder_matches_reference_fixture(path):
     assert float((mu.cpu() * pad).abs().max()) == 0.0 and float((logw.cpu() * pad).abs().max()) == 0.0
     mu2, logw2, _ = enc(x, xl, sty) if dex else enc(x, xl)          # the layer limit of forward_stream is restored; reproducible
     assert torch.equal(mu, mu2) and torch.equal(logw, logw2)
+
+
+@pytest.mark.parametrize("path", GOLD_SPK, ids=[os.path.basename(p)[:-4] for p in GOLD_SPK])
+def test_multi_speaker_text_encoder_matches_reference_fixture(path):
+    """n_spks > 1 (GeDEX-TTS/config/VCTK: 108 speakers): the speaker embedding joins behind the prenet, the RetNet / proj_m / duration
+    predictor run 256 wide with head dim 128 (GeDEX-TTS/model/text_encoder.py:119-127,141-142).  Fixture = the unmodified reference."""
+    from dexb200.model import GeTextEncoder
+    g = np.load(path)
+    B, Tx, ragged, seed, dex, n_spks = [int(v) for v in g["meta"][:6]]
+    assert not dex and n_spks > 1
+    inp = synth_text(B, Tx, seed=seed, ragged=bool(ragged))
+    enc = GeTextEncoder(**KW, spk_emb_dim=64, n_spks=n_spks)
+    sd = synth_text_weights(prefix="", adaln=False, spk_emb_dim=64)
+    assert list(sd.keys()) == list(g["keys"]) == list(enc.state_dict().keys())
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.cuda().eval()
+    spk = torch.randn(B, 64, generator=torch.Generator().manual_seed(seed + 7))          # oracle/make_golden_text.py
+    x, xl = inp["x"].cuda(), inp["x_lengths"].cuda()
+    mu, logw, x_mask = enc(x, xl, spk=spk.cuda())
+    eng = enc.cuda_engine()
+    assert eng.launches == 1 + 6 + 3 + 1 + 8 * 13 + 7
+    errs = {"mu": tensor_rel_err(mu.cpu(), torch.from_numpy(g["mu"])), "logw": tensor_rel_err(logw.cpu(), torch.from_numpy(g["logw"])),
+            "layer0": tensor_rel_err(eng.forward_stream(x, x_mask, None, 1, spk=spk.cuda()).cpu(), torch.from_numpy(g["layer0"])),
+            "layer7": tensor_rel_err(eng.forward_stream(x, x_mask, None, 8, spk=spk.cuda()).cpu(), torch.from_numpy(g["layer7"]))}
+    pre = eng.forward_stream(x, x_mask, None, 0, spk=spk.cuda()).cpu()                      # (B, Tx, 192 + 64)
+    errs["prenet"] = tensor_rel_err(pre[:, :, :192], torch.from_numpy(g["prenet"]).transpose(1, 2))
+    assert torch.equal(pre[:, :, 192:], spk[:, None, :].expand(B, Tx, 64))                  # repeated over ALL positions, unmasked
+    print(f"text fixture {os.path.basename(path)}: " + " ".join(f"{k} {e:.2e}" for k, e in errs.items()))
+    assert max(errs.values()) < TOL, errs
+    with pytest.raises(RuntimeError):
+        enc(x, xl)                                           # the speaker embedding is required for n_spks > 1
 
 
 @pytest.mark.parametrize("B,Tx,ragged", [(8, 128, True), (2, 512, True), (1, 1, False)])
