@@ -1,7 +1,7 @@
 """The reference's entry scripts import unchanged under the drop-in packages (BASELINE.json north_star: "drops in under synthesize.py
 and main.py unchanged").
 
-A fresh interpreter gets ``dex-tts_b200/dropin`` (packages literally named ``model`` and ``audio``) and ``dex-tts_b200`` in front of a
+A fresh interpreter gets ``dex-tts_b200/dropin`` (packages literally named ``model``, ``audio`` and ``hifigan``) and ``dex-tts_b200`` in front of a
 COPY of the reference checkout on ``sys.path``, plus empty stand-ins for the third-party modules this image does not have (matplotlib,
 neptune, soundfile, ... -- none of them is on the accelerated path), and executes ``import main`` / ``import synthesize``: every
 ``from model ...`` / ``import audio`` line of the scripts and of ``src/{dataset,train,evaluation,utils}.py`` must resolve to dexb200.
@@ -63,6 +63,8 @@ def test_main_and_synthesize_import_under_the_dropin(tmp_path, variant, cls):
                 setattr(transformers, name, None)
         import main, synthesize
         import model, audio, dexb200.model as M, dexb200.audio as A
+        import hifigan, dexb200.hifigan as H, src.utils              # get_vocoder builds hifigan.Generator (src/utils.py:251-281)
+        assert hifigan.Generator is H.Generator and src.utils.hifigan.Generator is H.Generator and hifigan.AttrDict is H.AttrDict
         assert model.{cls} is M.{cls}, model.__file__
         assert main.fix_len_compatibility is M.fix_len_compatibility
         assert synthesize.{cls} is M.{cls}
