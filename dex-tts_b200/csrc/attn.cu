@@ -1,10 +1,14 @@
 // Fused DiT self-attention (timm Attention inside DiTBlock, DEX-TTS/model/dit.py:270,282): softmax(q k^T / sqrt(hd)) v
 // for one (sample, head) and 128 queries per CTA, no key mask (the reference has none), split-bf16 x3 precision.
 //
-// Exact two-pass softmax without accumulator rescaling:
-//   pass 1: S = Qhi Khi^T (bf16 only -- the row maximum only has to be approximately right) -> running row max m
-//   pass 2: S = Q K^T (3 MMAs per product) -> P = exp2((S - m) * scale * log2e) -> split P to shared memory
-//           -> O += P V (3 MMAs per product), row sums l in registers;  out = O / l.
+// One pass over the keys with LAZY rescaling (r02; AttnParams::one_pass, DEXB_ATTN_ONEPASS=0 restores the two-pass kernel):
+//   S = Q K^T (3 MMAs per product) -> tile row maximum (the two column halves of a row exchange it through shared memory) ->
+//   the reference maximum m of a row only moves when a tile exceeds it by more than 2^8 in the exponent (then l and the row of
+//   the O accumulator in tensor memory are multiplied by exp2(m_old - m_new): between the wait for P(j-1) V(j-1) and the hand-over
+//   of P(j), when O is stable; after the first tile that is rare) -> P = exp2((S - m) * scale * log2e) <= 256 -> O += P V.
+//   softmax is shift-invariant, so any m gives the same result; the split-bf16 P keeps its relative precision up to 2^8.
+// The two-pass variant it replaces (exact maximum first, from S = Qhi Khi^T only, then the pass above without rescaling) issued
+// 1/7 more MMA work and streamed K twice.
 // S (2 x 64 columns) and O (128 columns) live in TMEM; K / V^T tiles of 64 keys stream through a 2-stage TMA ring;
 // warp 0 = TMA, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax (one query row per thread) + epilogue.
 // S(j+1) is issued before P(j) V(j) so the tensor pipe works while the softmax warps exponentiate.
@@ -27,7 +31,8 @@ constexpr int kKBytes = 4 * 8192;                         // [hi kc0][hi kc1][lo
 constexpr int kVBytes = 2 * 16384;                        // [hi][lo], 128 d-rows x 128 B (64 keys) each
 constexpr int kStage = kKBytes + kVBytes;                 // 64 KiB
 constexpr int kBarOff = kAtStages * kStage;               // 192 KiB
-constexpr int kAtSmem = kBarOff + 128 + 1024 + 1024;      // barriers (128 B) + max/sum exchange (1 KiB) + alignment slack
+constexpr int kAtSmem = kBarOff + 128 + 2048 + 1024;      // barriers (128 B) + max/sum exchange (2 x 1 KiB) + alignment slack
+constexpr float kAtTau = 8.f;       // one-pass softmax: the reference maximum moves when a tile exceeds it by 2^kAtTau
 // tensor-memory columns (512 allocated): both MMA A operands (Q and P) live here, so shared memory only carries the
 // streamed K / V^T tiles -- with split-bf16 every A tile would otherwise be re-read from shared memory three times per
 // k-step and the kernel is shared-memory-bandwidth bound (profiles/r01_ncu_v4.md)
@@ -109,16 +114,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       const int kcol = p.k_hi + head * kAtHD, lo = p.k_lo - p.k_hi;
-      for (int it = 0; it < 2 * nt; ++it) {
+      const int npre = p.one_pass ? 0 : nt;             // two-pass: nt max-pass stages (K hi only) first
+      for (int it = 0; it < npre + nt; ++it) {
         const int s = it % kAtStages;
         const uint32_t ph = (it / kAtStages) & 1;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
         uint8_t* st = smem + s * kStage;
-        if (it < nt) {
+        if (it < npre) {
           ptx::mbar_expect_tx(&k_full[s], kch * 8192);
           for (int kc = 0; kc < kch; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, (t0 + it) * kAtBN, b);
         } else {
-          const int j = t0 + it - nt;
+          const int j = t0 + it - npre;
           ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192 + 2 * p.vchunks * 8192);
           for (int part = 0; part < 2; ++part)
             for (int kc = 0; kc < kch; ++kc)
@@ -170,10 +176,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       }
       __syncwarp();
     };
-    for (int it = 0; it < nt; ++it) issue_s(it, false);
-    if (nt > 0) issue_s(nt, true);
+    const int npre = p.one_pass ? 0 : nt;
+    for (int it = 0; it < npre; ++it) issue_s(it, false);
+    if (nt > 0) issue_s(npre, true);
     for (int j = 0; j < nt; ++j) {
-      const int it = nt + j;
+      const int it = npre + j;
       if (j + 1 < nt) issue_s(it + 1, true);
       ptx::mbar_wait(p_full, j & 1);
       ptx::tc_fence_after();
@@ -234,7 +241,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     const float* kb = (p.kbias != nullptr) ? p.kbias + (long)b * p.kbias_stride : nullptr;
     float v[32];
     float m = -INFINITY;
-    for (int it = 0; it < nt; ++it) {
+    const bool onep = p.one_pass != 0;
+    const int npre = onep ? 0 : nt;
+    for (int it = 0; it < npre; ++it) {
       const int s = it & 1;
       ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
       ptx::tc_fence_after();
@@ -253,14 +262,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       }
     }
     // combine the two column halves of every row (named barrier over the 256 softmax threads only)
-    xch[hf * 128 + r] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(m, xch[(hf ^ 1) * 128 + r]);
     const float sl2 = p.scale_log2e;
-    const float msl = m * sl2;
+    if (!onep) {
+      xch[hf * 128 + r] = m;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m = fmaxf(m, xch[(hf ^ 1) * 128 + r]);
+    }
+    float msl = m * sl2;
     float l = 0.f;
     for (int j = 0; j < nt; ++j) {
-      const int it = nt + j, s = it & 1;
+      const int it = npre + j, s = it & 1;
       ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
       ptx::tc_fence_after();
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
@@ -270,6 +281,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       if (kb != nullptr) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + (t0 + j) * kAtBN + hf * 32 + c);
+      }
+      float resc = 1.f;                                      // one pass: factor the O row has to be multiplied with (1 = none)
+      if (onep) {
+        float mt = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < nvalid) mt = fmaxf(mt, v[c]);
+        float* xb = xch + (j & 1) * 256;                     // double-buffered: one barrier per tile is enough
+        xb[hf * 128 + r] = mt;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mt = fmaxf(mt, xb[(hf ^ 1) * 128 + r]);
+        if (mt * sl2 > msl + kAtTau) {                       // also the first tile (m = -inf); both halves of a row decide alike
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(resc) : "f"(msl - mt * sl2));       // exp2(-inf) = 0 on the first tile
+          l *= resc;
+          m = mt;
+          msl = m * sl2;
+          if (j == 0) resc = 1.f;                            // O is empty: the first P V overwrites it
+        }
       }
       uint32_t hi2[16], lo2[16];
 #pragma unroll
@@ -288,6 +317,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       }
       ptx::mbar_wait(p_empty, (j & 1) ^ 1);               // P(j-1) V(j-1) has consumed the previous P
       ptx::tc_fence_after();
+      if (onep && __any_sync(0xffffffffu, resc != 1.f)) {  // O is stable here: P(j-1) V(j-1) has retired, P(j) V(j) waits for p_full
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          if (hf >= p.vchunks) break;
+          float o[32];
+          ptx::tmem_ld32(tl + kTmO + hf * 64 + c * 32, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= resc;
+          ptx::tmem_st32(tl + kTmO + hf * 64 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(o));
+        }
+      }
       ptx::tmem_st16(tl + kTmPh + hf * 16, hi2);
       ptx::tmem_st16(tl + kTmPl + hf * 16, lo2);
       ptx::tmem_wait_st();
@@ -295,7 +335,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::mbar_arrive(p_full);
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the max exchange
-    xch[hf * 128 + r] = l;
+    xch[hf * 128 + r] = l;                                  // (the two halves of a row hold the same m in both variants)
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += xch[(hf ^ 1) * 128 + r];
     const int row = m0 + r;
@@ -393,6 +433,11 @@ int attn_global_init() {
 }
 
 bool attn_supported(int hd) { return hd == kAtHD; }
+static int attn_one_pass() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DEXB_ATTN_ONEPASS"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v;
+}
 
 int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int B, int N, int NP, int heads, int hid) {
   DEXB_CHECK(hid / heads == kAtHD, "fused attention is instantiated for head dim %d", kAtHD);
@@ -400,6 +445,7 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = N; p.NK = N; p.KP = NP; p.nheads = heads;
+  p.one_pass = attn_one_pass();
   p.nt = (N + kAtBN - 1) / kAtBN;
   p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid; p.q_img_rows = N;
   p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
@@ -429,6 +475,7 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = P; p.NK = NK; p.KP = KP; p.nheads = 1;
+  p.one_pass = attn_one_pass();
   p.nt = (NK + kAtBN - 1) / kAtBN;
   p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo; p.q_img_rows = P;
   p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
@@ -452,6 +499,7 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = 128; p.NK = P; p.KP = PP; p.nheads = 1;
+  p.one_pass = attn_one_pass();
   p.nt = (P + kAtBN - 1) / kAtBN;
   p.kv_splits = splits;
   p.tiles_per_split = (p.nt + splits - 1) / splits;

@@ -59,3 +59,21 @@ def test_fused_attention_large_logits():
     out = attn_test(qkv.cuda(), 2).cpu().double()
     err = (out - ref).abs().max().item() / ref.pow(2).mean().sqrt().item()
     assert torch.isfinite(out).all() and err < 1.5e-3, err      # CPU emulation of the same split arithmetic: 5.9e-4
+
+
+@pytest.mark.parametrize("B,N", [(1, 650), (3, 1000)])
+def test_fused_attention_rising_logits(B, N):
+    """Keys whose norm grows with the key index: the row maximum keeps rising from tile to tile, so the one-pass kernel has to move its
+    reference maximum and rescale the O accumulator in tensor memory several times per row (the lazy-rescale path; N = 1000 with B = 3
+    also takes the tail split, whose partials carry the reference maximum of their key range)."""
+    from dexb200.engine import attn_test
+    g = torch.Generator().manual_seed(7 * N + B)
+    qkv = torch.randn(B, N, 768, generator=g)
+    ramp = torch.linspace(0.3, 8.0, N).reshape(1, N, 1)
+    qkv[..., 256:512] *= ramp                  # k of both heads
+    qkv[..., :256] *= 1.5
+    ref = reference(qkv, 2)
+    out = attn_test(qkv.cuda(), 2).cpu().double()
+    err = (out - ref).abs().max().item() / ref.pow(2).mean().sqrt().item()
+    print(f"attn rising logits B={B} N={N}: max err / rms = {err:.3e}")
+    assert torch.isfinite(out).all() and err < 1.5e-3, err
