@@ -43,6 +43,16 @@ constexpr uint32_t kTmQl = 320;     // 64      Q lo
 constexpr uint32_t kTmPh = 384;     // 32      P hi: 64 bf16 per row
 constexpr uint32_t kTmPl = 416;     // 32      P lo
 
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2) and the three-input maximum (FMNMX3): the softmax warps -- not the tensor pipe -- set the
+// tile time of this kernel (profiles/r02_attn.md: 395 instructions per warp and 64-key tile, 75 % of their time busy), so the inner
+// loop is written for instruction count.
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t f2_sub(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float f_max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -151,7 +161,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     auto issue_s = [&](int it, bool full) {
       const int st = it % kAtStages, sb = it & 1;
       ptx::mbar_wait(&k_full[st], (it / kAtStages) & 1);
-      ptx::mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
+      // One pass: S buffer `sb` was last used by tile it - 2, whose P the issuer has already waited for (p_full(it - 2) is only complete
+      // once all 256 softmax threads have read that S tile) -- no second wait: every mbarrier wait costs this thread ~240 cycles that
+      // the tensor pipe does not hide (profiles/r02_issue_bench.md).  The two-pass variant's max pass has no P hand-over: it waits.
+      if (!p.one_pass) ptx::mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
         const uint32_t k_base = ptx::smem_u32(smem + st * kStage);
@@ -282,12 +295,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + (t0 + j) * kAtBN + hf * 32 + c);
       }
+      const bool fast = nvalid >= 32;                        // every column of this thread's half is a real key (all but the last tile)
       float resc = 1.f;                                      // one pass: factor the O row has to be multiplied with (1 = none)
       if (onep) {
         float mt = -INFINITY;
+        if (fast) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < nvalid) mt = fmaxf(mt, v[c]);
+          for (int c = 0; c < 32; c += 2) mt = f_max3(mt, v[c], v[c + 1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < nvalid) mt = fmaxf(mt, v[c]);
+        }
         float* xb = xch + (j & 1) * 256;                     // double-buffered: one barrier per tile is enough
         xb[hf * 128 + r] = mt;
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -301,6 +320,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         }
       }
       uint32_t hi2[16], lo2[16];
+      if (fast) {
+        // two columns per instruction: P = exp2(S * scale*log2e - m * scale*log2e), row sum, hi / lo split (same roundings as below)
+        const uint64_t sc2 = f2_pack(sl2, sl2), nm2 = f2_pack(-msl, -msl);
+        uint64_t ls2 = f2_pack(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float a0, a1, e0, e1;
+          f2_unpack(f2_fma(f2_pack(v[c], v[c + 1]), sc2, nm2), a0, a1);
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+          const uint64_t e2 = f2_pack(e0, e1);
+          ls2 = f2_add(ls2, e2);
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+          float d0, d1;
+          f2_unpack(f2_sub(e2, f2_pack(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u))), d0, d1);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(d0, d1);
+          hi2[c >> 1] = hb;
+          lo2[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        float s0, s1;
+        f2_unpack(ls2, s0, s1);
+        l += s0 + s1;
+      } else {
 #pragma unroll
       for (int c = 0; c < 32; c += 2) {
         float e0, e1;
@@ -314,6 +357,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         const __nv_bfloat162 l2 = __floats2bfloat162_rn(e0 - __uint_as_float(hb << 16), e1 - __uint_as_float(hb & 0xffff0000u));
         hi2[c >> 1] = hb;
         lo2[c >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
       }
       ptx::mbar_wait(p_empty, (j & 1) ^ 1);               // P(j-1) V(j-1) has consumed the previous P
       ptx::tc_fence_after();
