@@ -1,16 +1,21 @@
 // Fused DiT self-attention (timm Attention inside DiTBlock, DEX-TTS/model/dit.py:270,282): softmax(q k^T / sqrt(hd)) v
 // for one (sample, head) and 128 queries per CTA, no key mask (the reference has none), split-bf16 x3 precision.
 //
-// One pass over the keys with LAZY rescaling (r02; AttnParams::one_pass, DEXB_ATTN_ONEPASS=0 restores the two-pass kernel):
+// One pass over the keys with LAZY rescaling (r02):
 //   S = Q K^T (3 MMAs per product) -> tile row maximum (the two column halves of a row exchange it through shared memory) ->
 //   the reference maximum m of a row only moves when a tile exceeds it by more than 2^8 in the exponent (then l and the row of
 //   the O accumulator in tensor memory are multiplied by exp2(m_old - m_new): between the wait for P(j-1) V(j-1) and the hand-over
 //   of P(j), when O is stable; after the first tile that is rare) -> P = exp2((S - m) * scale * log2e) <= 256 -> O += P V.
 //   softmax is shift-invariant, so any m gives the same result; the split-bf16 P keeps its relative precision up to 2^8.
-// The two-pass variant it replaces (exact maximum first, from S = Qhi Khi^T only, then the pass above without rescaling) issued
-// 1/7 more MMA work and streamed K twice.
-// S (2 x 64 columns) and O (128 columns) live in TMEM; K / V^T tiles of 64 keys stream through a 2-stage TMA ring;
-// warp 0 = TMA, warp 1 = tcgen05.mma issuer, warps 2..5 = softmax (one query row per thread) + epilogue.
+//   (r01 ran an exact two-pass softmax -- row maximum first, from S = Qhi Khi^T only: 1/7 more MMA work and K streamed twice.)
+// S (2 x 64 columns) and O (128 columns) live in TMEM; K and V^T tiles of 64 keys stream through two separate 3-slot TMA rings:
+// a K slot is released when S(j) has retired, a V slot when P(j) V(j) has (one tile later), which gives both streams ~2.5 tiles of
+// lead over the TMA round trip (one ring of (K, V) stages had one tile; measured neutral -- see below).
+// What bounds it (profiles/r02_attn.md): after these changes the issuing thread hardly ever waits (1.4 polls of p_full per tile, its
+// UTCHMMA slots stall on a full MMA queue) and the softmax warps idle 40 % of the time waiting for S: the tile time is the tensor
+// pipe's own occupancy -- 36 TS-mode MMAs per 64-key tile (24 of N = 64 at 75 % efficiency, 12 of N = 128 at 86 %), 57-60 % math
+// active.  Wider instructions would need a 128-key S tile, which does not fit tensor memory next to O, Q and P (640 > 512 columns).
+// warp 0 = TMA, warp 1 = tcgen05.mma issuer, warps 2..9 = softmax (one query row x half of the columns per thread) + epilogue.
 // S(j+1) is issued before P(j) V(j) so the tensor pipe works while the softmax warps exponentiate.
 #include "attn.cuh"
 
@@ -26,12 +31,12 @@ constexpr int kAtBM = 128;          // queries per CTA
 constexpr int kAtBN = 64;           // keys per iteration
 constexpr int kAtHD = 128;          // head dim
 constexpr int kAtThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two column halves x four lane groups)
-constexpr int kAtStages = 3;
+constexpr int kAtStages = 3;                              // slots of the K ring and of the V ring
 constexpr int kKBytes = 4 * 8192;                         // [hi kc0][hi kc1][lo kc0][lo kc1], 64 rows x 128 B each
 constexpr int kVBytes = 2 * 16384;                        // [hi][lo], 128 d-rows x 128 B (64 keys) each
-constexpr int kStage = kKBytes + kVBytes;                 // 64 KiB
-constexpr int kBarOff = kAtStages * kStage;               // 192 KiB
-constexpr int kAtSmem = kBarOff + 128 + 2048 + 1024;      // barriers (128 B) + max/sum exchange (2 x 1 KiB) + alignment slack
+constexpr int kVOff = kAtStages * kKBytes;                // V ring behind the K ring
+constexpr int kBarOff = kAtStages * (kKBytes + kVBytes);  // 192 KiB
+constexpr int kAtSmem = kBarOff + 256 + 2048 + 1024;      // barriers (256 B) + max/sum exchange (2 x 1 KiB) + alignment slack
 constexpr float kAtTau = 8.f;       // one-pass softmax: the reference maximum moves when a tile exceeds it by 2^kAtTau
 // tensor-memory columns (512 allocated): both MMA A operands (Q and P) live here, so shared memory only carries the
 // streamed K / V^T tiles -- with split-bf16 every A tile would otherwise be re-read from shared memory three times per
@@ -66,7 +71,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   uint64_t* p_full = bars + 11;       // 1
   uint64_t* p_empty = bars + 12;      // 1
   uint64_t* o_full = bars + 13;       // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* v_full = bars + 14;       // 3
+  uint64_t* v_empty = bars + 17;      // 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // DiT / TV: blockIdx.x = query tile, all key tiles.  Split-KV mode (linear-attention context, one 128-row query tile):
@@ -108,7 +115,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 8);
     }
-    for (int s = 0; s < kAtStages; ++s) { ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < kAtStages; ++s) {
+      ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
+    }
     ptx::mbar_init(p_full, 8); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
@@ -124,31 +134,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       const int kcol = p.k_hi + head * kAtHD, lo = p.k_lo - p.k_hi;
-      const int npre = p.one_pass ? 0 : nt;             // two-pass: nt max-pass stages (K hi only) first
-      for (int it = 0; it < npre + nt; ++it) {
-        const int s = it % kAtStages;
-        const uint32_t ph = (it / kAtStages) & 1;
-        ptx::mbar_wait(&k_empty[s], ph ^ 1);
-        uint8_t* st = smem + s * kStage;
-        if (it < npre) {
-          ptx::mbar_expect_tx(&k_full[s], kch * 8192);
-          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_3d(st + kc * 8192, &tmK, &k_full[s], kcol + kc * 64, (t0 + it) * kAtBN, b);
-        } else {
-          const int j = t0 + it - npre;
-          ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192 + 2 * p.vchunks * 8192);
+      auto load_k = [&](int i) {                           // K tile i of this CTA's key range -> K ring
+        const int s = i % kAtStages, j = t0 + i;
+        ptx::mbar_wait(&k_empty[s], ((i / kAtStages) & 1) ^ 1);
+        uint8_t* st = smem + s * kKBytes;
+        ptx::mbar_expect_tx(&k_full[s], 2 * kch * 8192);
+        for (int part = 0; part < 2; ++part)
+          for (int kc = 0; kc < kch; ++kc)
+            ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
+      };
+      auto load_v = [&](int i) {                           // V tile i -> V ring
+        const int s = i % kAtStages, j = t0 + i;
+        ptx::mbar_wait(&v_empty[s], ((i / kAtStages) & 1) ^ 1);
+        uint8_t* st = smem + kVOff + s * kVBytes;
+        ptx::mbar_expect_tx(&v_full[s], 2 * p.vchunks * 8192);
+        if (p.v_mn) {                                      // row-major V: [part][d chunk of 64] boxes of 64 keys x 128 B
           for (int part = 0; part < 2; ++part)
-            for (int kc = 0; kc < kch; ++kc)
-              ptx::tma_load_3d(st + (part * 2 + kc) * 8192, &tmK, &k_full[s], part * lo + kcol + kc * 64, j * kAtBN, b);
-          if (p.v_mn) {                                    // row-major V: [part][d chunk of 64] boxes of 64 keys x 128 B
-            for (int part = 0; part < 2; ++part)
-              for (int c = 0; c < p.vchunks; ++c)
-                ptx::tma_load_3d(st + kKBytes + part * 16384 + c * 8192, &tmV, &k_full[s],
-                                 (part ? p.v_lo : p.v_hi) + head * kAtHD + c * 64, j * kAtBN, b);
-          } else {
-            for (int part = 0; part < 2; ++part)
-              ptx::tma_load_3d(st + kKBytes + part * 16384, &tmV, &k_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
-          }
+            for (int c = 0; c < p.vchunks; ++c)
+              ptx::tma_load_3d(st + part * 16384 + c * 8192, &tmV, &v_full[s], (part ? p.v_lo : p.v_hi) + head * kAtHD + c * 64,
+                               j * kAtBN, b);
+        } else {
+          for (int part = 0; part < 2; ++part)
+            ptx::tma_load_3d(st + part * 16384, &tmV, &v_full[s], part * p.KP + j * kAtBN, head * kAtHD, b);
         }
+      };
+      // issue order = the order in which the tensor pipe frees the slots: S(0) S(1) PV(0) S(2) PV(1) S(3) PV(2) ...
+      for (int i = 0; i < kAtStages && i < nt; ++i) load_k(i);
+      for (int i = 0; i < kAtStages && i < nt; ++i) load_v(i);
+      if (kAtStages < nt) load_k(kAtStages);
+      for (int i = 0; kAtStages + i < nt; ++i) {
+        if (kAtStages + 1 + i < nt) load_k(kAtStages + 1 + i);
+        load_v(kAtStages + i);
       }
     }
   } else if (warp == 1) {
@@ -157,17 +173,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     const uint32_t idesc_o = ptx::make_idesc_bf16(128, 64 * p.vchunks, p.v_mn);
     ptx::mbar_wait(q_full, 0);
     ptx::tc_fence_after();
-    // S[it & 1] = Q K^T for iteration `it` (Q from tensor memory); frees the stage itself only in pass 1
-    auto issue_s = [&](int it, bool full) {
+    // S[it & 1] = Q K^T for key tile `it` (Q from tensor memory); the K slot is free again once these MMAs have retired
+    auto issue_s = [&](int it) {
       const int st = it % kAtStages, sb = it & 1;
       ptx::mbar_wait(&k_full[st], (it / kAtStages) & 1);
-      // One pass: S buffer `sb` was last used by tile it - 2, whose P the issuer has already waited for (p_full(it - 2) is only complete
-      // once all 256 softmax threads have read that S tile) -- no second wait: every mbarrier wait costs this thread ~240 cycles that
-      // the tensor pipe does not hide (profiles/r02_issue_bench.md).  The two-pass variant's max pass has no P hand-over: it waits.
-      if (!p.one_pass) ptx::mbar_wait(&s_empty[sb], ((it >> 1) & 1) ^ 1);
+      // S buffer `sb` was last used by tile it - 2, whose P the issuer has already waited for (p_full(it - 2) is only complete once
+      // all softmax warps have read that S tile) -- no wait on s_empty: every mbarrier wait costs this thread ~240 cycles that the
+      // tensor pipe does not hide (profiles/r02_issue_bench.md)
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t k_base = ptx::smem_u32(smem + st * kStage);
+        const uint32_t k_base = ptx::smem_u32(smem + st * kKBytes);
         const uint32_t d = tmem + kTmS + (uint32_t)(sb * kAtBN);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
@@ -177,28 +192,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
             const uint32_t qh = tmem + kTmQh + (uint32_t)(kc * 32 + kk * 8);
             const uint32_t ql = tmem + kTmQl + (uint32_t)(kc * 32 + kk * 8);
             const uint64_t kh = ptx::make_desc_k128(k_base + kc * 8192 + kk * 32);
+            const uint64_t kl = ptx::make_desc_k128(k_base + (2 + kc) * 8192 + kk * 32);
             ptx::mma_bf16_ts(d, qh, kh, idesc_s, (kc | kk) ? 1u : 0u);
-            if (full) {
-              const uint64_t kl = ptx::make_desc_k128(k_base + (2 + kc) * 8192 + kk * 32);
-              ptx::mma_bf16_ts(d, qh, kl, idesc_s, 1u);
-              ptx::mma_bf16_ts(d, ql, kh, idesc_s, 1u);
-            }
+            ptx::mma_bf16_ts(d, qh, kl, idesc_s, 1u);
+            ptx::mma_bf16_ts(d, ql, kh, idesc_s, 1u);
           }
-        if (!full) ptx::mma_commit(&k_empty[st]);
+        ptx::mma_commit(&k_empty[st]);
         ptx::mma_commit(&s_full[sb]);
       }
       __syncwarp();
     };
-    const int npre = p.one_pass ? 0 : nt;
-    for (int it = 0; it < npre; ++it) issue_s(it, false);
-    if (nt > 0) issue_s(npre, true);
+    if (nt > 0) issue_s(0);
     for (int j = 0; j < nt; ++j) {
-      const int it = npre + j;
-      if (j + 1 < nt) issue_s(it + 1, true);
+      if (j + 1 < nt) issue_s(j + 1);
+      ptx::mbar_wait(&v_full[j % kAtStages], (j / kAtStages) & 1);        // landed ~2 tiles ago: before the (long) wait for P
       ptx::mbar_wait(p_full, j & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        const uint32_t v_base = ptx::smem_u32(smem + (it % kAtStages) * kStage + kKBytes);
+        const uint32_t v_base = ptx::smem_u32(smem + kVOff + (j % kAtStages) * kVBytes);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint32_t ph_ = tmem + kTmPh + (uint32_t)(kk * 8);
@@ -212,7 +223,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
           ptx::mma_bf16_ts(tm_o, pl_, vh, idesc_o, 1u);
         }
         ptx::mma_commit(p_empty);
-        ptx::mma_commit(&k_empty[it % kAtStages]);
+        ptx::mma_commit(&v_empty[j % kAtStages]);
         if (j == nt - 1) ptx::mma_commit(o_full);
       }
       __syncwarp();
@@ -225,7 +236,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     const int hf = (warp - 2) >> 2;
     const int r = lg * 32 + lane;
     const uint32_t tl = tmem + ((uint32_t)(lg * 32) << 16);
-    float* xch = reinterpret_cast<float*>(smem + kBarOff + 128);        // [2][128] exchange of row max / row sum halves
+    float* xch = reinterpret_cast<float*>(smem + kBarOff + 256);        // [2][2][128] exchange of row max / row sum halves
     {
       // stage this thread's half of the query row (64 of the 128 head dims, hi and lo) into tensor memory
       uint32_t qh[32], ql[32];
@@ -253,39 +264,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     const int nkv = (p.vis_len != nullptr) ? min(p.NK, p.vis_len[b] + 1) : p.NK;
     const float* kb = (p.kbias != nullptr) ? p.kbias + (long)b * p.kbias_stride : nullptr;
     float v[32];
-    float m = -INFINITY;
-    const bool onep = p.one_pass != 0;
-    const int npre = onep ? 0 : nt;
-    for (int it = 0; it < npre; ++it) {
-      const int s = it & 1;
-      ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
-      ptx::tc_fence_after();
-      ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive_warp(&s_empty[s]);
-      const int nvalid = nkv - (t0 + it) * kAtBN - hf * 32;
-      if (kb != nullptr) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < nvalid) m = fmaxf(m, v[c] + __ldg(kb + (t0 + it) * kAtBN + hf * 32 + c));
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < nvalid) m = fmaxf(m, v[c]);
-      }
-    }
-    // combine the two column halves of every row (named barrier over the 256 softmax threads only)
+    float m = -INFINITY;                                     // reference maximum of this row (shared by its two column halves)
     const float sl2 = p.scale_log2e;
-    if (!onep) {
-      xch[hf * 128 + r] = m;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      m = fmaxf(m, xch[(hf ^ 1) * 128 + r]);
-    }
     float msl = m * sl2;
     float l = 0.f;
     for (int j = 0; j < nt; ++j) {
-      const int it = npre + j, s = it & 1;
-      ptx::mbar_wait(&s_full[s], (it >> 1) & 1);
+      const int s = j & 1;
+      ptx::mbar_wait(&s_full[s], (j >> 1) & 1);
       ptx::tc_fence_after();
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
@@ -296,8 +281,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         for (int c = 0; c < 32; ++c) v[c] += __ldg(kb + (t0 + j) * kAtBN + hf * 32 + c);
       }
       const bool fast = nvalid >= 32;                        // every column of this thread's half is a real key (all but the last tile)
-      float resc = 1.f;                                      // one pass: factor the O row has to be multiplied with (1 = none)
-      if (onep) {
+      float resc = 1.f;                                      // factor the O row has to be multiplied with (1 = none)
+      {
         float mt = -INFINITY;
         if (fast) {
 #pragma unroll
@@ -361,7 +346,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       }
       ptx::mbar_wait(p_empty, (j & 1) ^ 1);               // P(j-1) V(j-1) has consumed the previous P
       ptx::tc_fence_after();
-      if (onep && __any_sync(0xffffffffu, resc != 1.f)) {  // O is stable here: P(j-1) V(j-1) has retired, P(j) V(j) waits for p_full
+      if (__any_sync(0xffffffffu, resc != 1.f)) {  // O is stable here: P(j-1) V(j-1) has retired, P(j) V(j) waits for p_full
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           if (hf >= p.vchunks) break;
@@ -379,7 +364,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::mbar_arrive_warp(p_full);
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the max exchange
-    xch[hf * 128 + r] = l;                                  // (the two halves of a row hold the same m in both variants)
+    xch[hf * 128 + r] = l;                                  // (the two halves of a row hold the same m)
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += xch[(hf ^ 1) * 128 + r];
     const int row = m0 + r;
@@ -477,11 +462,7 @@ int attn_global_init() {
 }
 
 bool attn_supported(int hd) { return hd == kAtHD; }
-static int attn_one_pass() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DEXB_ATTN_ONEPASS"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
-  return v;
-}
+
 
 int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int B, int N, int NP, int heads, int hid) {
   DEXB_CHECK(hid / heads == kAtHD, "fused attention is instantiated for head dim %d", kAtHD);
@@ -489,7 +470,6 @@ int attn_plan_init(AttnPlan* ap, const bf16* qkv, const bf16* vT, bf16* out, int
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = N; p.NK = N; p.KP = NP; p.nheads = heads;
-  p.one_pass = attn_one_pass();
   p.nt = (N + kAtBN - 1) / kAtBN;
   p.q = qkv; p.q_stride = 6L * hid; p.q_hi = 0; p.q_lo = 3 * hid; p.q_img_rows = N;
   p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
@@ -519,7 +499,6 @@ int attn_plan_init_tv(AttnPlan* ap, const bf16* x, long x_stride, int x_hi, int 
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = P; p.NK = NK; p.KP = KP; p.nheads = 1;
-  p.one_pass = attn_one_pass();
   p.nt = (NK + kAtBN - 1) / kAtBN;
   p.q = x; p.q_stride = x_stride; p.q_hi = x_hi; p.q_lo = x_lo; p.q_img_rows = P;
   p.kchunks = 2; p.vchunks = 2; p.kv_splits = 1; p.tiles_per_split = p.nt;
@@ -543,7 +522,6 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
   AttnParams& p = ap->p;
   memset(&p, 0, sizeof(p));
   p.NQ = 128; p.NK = P; p.KP = PP; p.nheads = 1;
-  p.one_pass = attn_one_pass();
   p.nt = (P + kAtBN - 1) / kAtBN;
   p.kv_splits = splits;
   p.tiles_per_split = (p.nt + splits - 1) / splits;

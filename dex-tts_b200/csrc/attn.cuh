@@ -32,7 +32,6 @@ struct AttnParams {
   const int* vis_len;
   // epilogue: mode 0 = split rows (head h at column h*128); mode 1 = fp32 rows (O/l + the Q row as residual) * rowmask;
   // mode 2 = split-KV partials: part_o [b][split][128][128] un-normalised, part_l / part_m [b][split][128]
-  int one_pass;              // 1: single pass over the keys with lazy rescaling (default); 0: exact two-pass softmax (DEXB_ATTN_ONEPASS=0)
   int out_mode;
   bf16* out;
   long out_stride;
