@@ -111,15 +111,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    ptx::mbar_init(q_full, 8);                        // one arrival per softmax warp (ptx::mbar_arrive_warp)
+    ptx::mbar_init(q_full, 256);
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 8);
+      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 256);
     }
     for (int s = 0; s < kAtStages; ++s) {
       ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
       ptx::mbar_init(&v_full[s], 1); ptx::mbar_init(&v_empty[s], 1);
     }
-    ptx::mbar_init(p_full, 8); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(p_full, 256); ptx::mbar_init(p_empty, 1); ptx::mbar_init(o_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -258,7 +258,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::tmem_st32(tl + kTmQl + hf * 32, ql);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::mbar_arrive_warp(q_full);
+      ptx::mbar_arrive(q_full);
     }
     // keys that take part: all NK, or only the visible ones of this image (TV adaptor)
     const int nkv = (p.vis_len != nullptr) ? min(p.NK, p.vis_len[b] + 1) : p.NK;
@@ -274,7 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::tc_fence_after();
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
       ptx::tc_fence_before();
-      ptx::mbar_arrive_warp(&s_empty[s]);
+      ptx::mbar_arrive(&s_empty[s]);
       const int nvalid = nkv - (t0 + j) * kAtBN - hf * 32;
       if (kb != nullptr) {
 #pragma unroll
@@ -361,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::tmem_st16(tl + kTmPl + hf * 16, lo2);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::mbar_arrive_warp(p_full);
+      ptx::mbar_arrive(p_full);
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the max exchange
     xch[hf * 128 + r] = l;                                  // (the two halves of a row hold the same m)

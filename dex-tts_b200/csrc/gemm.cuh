@@ -457,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], TcEpi<GNF>::kThreads / 32); }      // one arrival per epilogue warp
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&acc_full[b], 1); ptx::mbar_init(&acc_empty[b], TcEpi<GNF>::kThreads); }
     ptx::mbar_init(b_full, 1);
     for (int s = 0; s < kTcHaloASlots; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     ptx::fence_barrier_init();
@@ -786,7 +786,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (nmine == 0) {
         ptx::mbar_wait(&acc_full[buf], (li >> 1) & 1);       // never hand a buffer back before its MMAs have completed
         ptx::tc_fence_before();
-        ptx::mbar_arrive_warp(&acc_empty[buf]);
+        ptx::mbar_arrive(&acc_empty[buf]);
       }
 #pragma unroll 1
       for (int k = 0; k < nmine; ++k) {
@@ -831,7 +831,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (k == nmine - 1) {                                // last chunk read: hand the buffer back to the MMA warp
           ptx::tc_fence_before();
-          ptx::mbar_arrive_warp(&acc_empty[buf]);
+          ptx::mbar_arrive(&acc_empty[buf]);
         }
         if (!(p.dbg & 1)) {
           if constexpr (!FAST) {

@@ -74,8 +74,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     ptx::prefetch_tmap(&tmW);
     for (int s = 0; s < kPcStages; ++s) { ptx::mbar_init(&in_full[s], 1); ptx::mbar_init(&in_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&w_full[s], 4); ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 4);     // per-warp arrivals
-      ptx::mbar_init(&ws_full[s], 1); ptx::mbar_init(&ws_empty[s], 4);
+      ptx::mbar_init(&w_full[s], 128); ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 128);
+      ptx::mbar_init(&ws_full[s], 1); ptx::mbar_init(&ws_empty[s], 128);
     }
     ptx::fence_barrier_init();
   }
@@ -121,8 +121,11 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         for (int kg = 0; kg < KG; ++kg, ++s) {
           const int bf = s & 1;
           const uint32_t ph = (s >> 1) & 1;
+          // ONE wait per step: w_full(s) is only complete once all four accumulation warps have staged the weights of step s, and each
+          // of them arrived on d_empty(s - 2) one loop iteration earlier (it reads D(s - 2), then stages W(s)) -- so the accumulator
+          // buffer of this step is free as well.  A second wait would cost the issuing thread ~240 cycles per step against ~350
+          // cycles of MMAs (six N = 96 TS-mode instructions): r01 waited on both and ran 61 % tensor-pipe active.
           ptx::mbar_wait(&w_full[bf], ph);
-          ptx::mbar_wait(&d_empty[bf], ph ^ 1);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t in_base = ptx::smem_u32(smem + st * kPcRowBytes);
@@ -161,12 +164,12 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
         h[i * 4] = a.x; h[i * 4 + 1] = a.y; h[i * 4 + 2] = a.z; h[i * 4 + 3] = a.w;
         l[i * 4] = c.x; l[i * 4 + 1] = c.y; l[i * 4 + 2] = c.z; l[i * 4 + 3] = c.w;
       }
-      ptx::mbar_arrive_warp(&ws_empty[bf]);
+      ptx::mbar_arrive(&ws_empty[bf]);
       ptx::tmem_st16(tl_lane + kTmW + bf * 32, h);
       ptx::tmem_st16(tl_lane + kTmW + bf * 32 + 16, l);
       ptx::tmem_wait_st();
       ptx::tc_fence_before();
-      ptx::mbar_arrive_warp(&w_full[bf]);
+      ptx::mbar_arrive(&w_full[bf]);
     };
     uint32_t s = 0;
     int t = blockIdx.x;
@@ -207,7 +210,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
           ptx::tc_fence_before();
-          ptx::mbar_arrive_warp(&d_empty[bf]);
+          ptx::mbar_arrive(&d_empty[bf]);
 #pragma unroll
           for (int i = 0; i < 32; ++i) { acc[i] += v0[i]; acc[32 + i] += v1[i]; }
 #pragma unroll

@@ -53,13 +53,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// One arrival per WARP (barrier count = number of warps): 32 lanes arriving on the same mbarrier are 32 serialised shared-memory
-// atomics -- ~1 000 cycles for the 256 / 512 threads of a consumer group, on the critical path of every hand-over.  All lanes must
-// reach the call (warp-convergent code); __syncwarp orders the lanes' prior writes before lane 0's release.
-__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
-}
+// (Arrivals stay per thread: a warp-wide mbarrier.arrive on one address is aggregated by the hardware; electing one lane behind a
+//  __syncwarp was measured neutral in the attention / GEMM kernels and 6 % slower in the pos-conv kernel, profiles/r02_attn.md.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
