@@ -423,12 +423,13 @@ def run_workload(args, name, rank, world, local_rank, dist, full):
                         f"bound), so the attainable fraction is <= 1/{args.nsplit}"}
         if a_ms > 0:
             a_ach = a_gf / a_ms
-            roof["attention"] = {"kernel": "attn_fwd_kernel (fused two-pass attention, Q/P in tensor memory; DiT blocks + TV adaptor)",
+            roof["attention"] = {"kernel": "attn_fwd_kernel (fused one-pass attention with lazy rescaling, Q/P in tensor memory; DiT blocks + TV adaptor "
+                                           "+ linear-attention contexts)",
                                  "bound": "tensor", "achieved": a_ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                                  "frac": a_ach / pk["tf_sust"], "launches_per_net_call": a_n // reps,
                                  "avg_launch_ms": a_ms / max(a_n, 1), "share_of_step": a_ms / tot if tot else None,
                                  "ncu_tensor_pipe_active_pct": ncu.get("attn_fwd_kernel(dit)", {}).get("tensor_pipe_active_pct"),
-                                 "note": "algorithmic 4*N*Nk*d FLOPs per head; issued MMA work is ~3.5x that (split-bf16 + max pass)"}
+                                 "note": "algorithmic 4*N*Nk*d FLOPs per head; issued MMA work is 3x that (split-bf16)"}
         if audio_d is not None:                                # C3: the STFT kernel alone against the HBM roofline
             flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
             ts_ = []
@@ -454,7 +455,38 @@ def run_workload(args, name, rank, world, local_rank, dist, full):
                          f"x{n_steps}/{args.cpu_sample_steps}; {what}; torch CPU fp32, {cores} threads"}
     line["roofline"] = roof
     line["cpu_baseline"] = cpu
+    if rank == 0 and world == 1 and name == "C2" and not args.no_pipeline:
+        line["pipeline"] = pipeline_stages(B, T)
     return line
+
+
+def pipeline_stages(B, T):
+    """Not part of the metric: device time of the stage BEHIND the loop for the same batch -- the HiFi-GAN v1 vocoder on the tcgen05 GEMM
+    engine (dexb_voc_forward, one CUDA graph) turning the B x T mel frames into B x 256 T samples -- so the line shows what the loop's
+    share of mel -> waveform is.  Never fails the bench: errors are reported in the key."""
+    try:
+        from dexb200.hifigan.models import VocoderEngine
+        from dexb200.synth import HIFIGAN_V1_CFG, synth_vocoder_weights
+        eng = VocoderEngine(HIFIGAN_V1_CFG)
+        eng.load_state_dict(synth_vocoder_weights())
+        mel = (torch.randn(B, 80, T, generator=torch.Generator().manual_seed(3)) * 1.5 - 4.0).cuda()
+        for _ in range(3):
+            wav = eng.forward(mel)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            wav = eng.forward(mel)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 5
+        out = {"vocoder_ms": ms, "vocoder_launches": eng.launches, "audio_seconds": B * T * 256 / 22050.0,
+               "vocoder_rtf": ms * 1e-3 / (B * T * 256 / 22050.0), "finite": bool(torch.isfinite(wav).all()),
+               "what": f"hifigan.Generator (HiFi-GAN v1) on the mel of the same batch (B={B}, T={T}), seeded random weights"}
+        eng.close()
+        return out
+    except Exception as e:                                   # pragma: no cover
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -467,6 +499,7 @@ def main():
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the `pipeline` key (vocoder device time for the same batch)")
     ap.add_argument("--other-workloads", default=None, help="comma list of extra workloads attached under `other_workloads` "
                                                             "(default: C4,C5 -- the north star's 8-GPU configs -- when N == 8)")
     ap.add_argument("--profile", action="store_true", help="print the per-launch breakdown of one network call to stderr")

@@ -417,3 +417,22 @@ def seeded_noise(seed):
     g.manual_seed(seed)
     randn = torch.randn                     # bound now: the golden generators patch torch.randn while the reference runs
     return lambda shape: randn(shape, generator=g)
+
+
+HIFIGAN_V1_CFG = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+                      resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])    # DEX-TTS/hifigan/config.json
+
+
+def synth_vocoder_weights(seed=100, cfg=None):
+    """Seeded HiFi-GAN v1 generator tensors (state after remove_weight_norm) at a scale that keeps the activations O(1) through the four
+    stages -- benchmark input for ``dexb200.hifigan`` (the parity fixtures use oracle/vocoder_oracle.py's own draw)."""
+    from .hifigan.models import vocoder_manifest
+    w = {}
+    for name, shape in vocoder_manifest(cfg or HIFIGAN_V1_CFG):
+        g = _gen(seed, "vocoder." + name)
+        if name.endswith("bias"):
+            w[name] = 0.05 * torch.randn(shape, generator=g)
+        else:
+            fan = (shape[0] * shape[2] / 8.0) if name.startswith("ups.") else shape[1] * shape[2]
+            w[name] = torch.randn(shape, generator=g) * (0.7 / fan ** 0.5)
+    return w
