@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/dexb200.h"
+#include "enc_graph.cuh"
 #include "gemm_host.cuh"
 
 namespace dexb {
@@ -47,6 +48,7 @@ struct dexb_tiv {
   dexb::bf16 *xs = nullptr, *hs = nullptr;     // split rows [B*T][hi(Kmax)|lo(Kmax)]: block input / hidden activation
   float *acc = nullptr, *xf = nullptr;         // fp32 rows [B*T][c_h]: raw conv output / block input (residual)
   long launches = 0;
+  dexb::EncGraph g;                            // CUDA-graph replay of the forward of this plan (enc_graph.cuh)
 };
 
 namespace dexb {
@@ -196,6 +198,7 @@ static void tiv_free_conv(TivConv* c) {
 }
 
 static void tiv_release_plan(dexb_tiv* h) {
+  enc_graph_release(&h->g);
   cudaFree(h->xs); cudaFree(h->hs); cudaFree(h->acc); cudaFree(h->xf);
   h->xs = h->hs = nullptr;
   h->acc = h->xf = nullptr;
@@ -314,14 +317,10 @@ int dexb_tiv_finalize_weights(dexb_tiv* h, void* stream) {
   return 0;
 }
 
-int dexb_tiv_forward(dexb_tiv* h, const float* ref_dev, const float* mask_dev, int B, int T, float* out_dev,
-                     float* const* skips_dev, void* stream) {
-  DEXB_CHECK(h != nullptr && ref_dev != nullptr && mask_dev != nullptr && skips_dev != nullptr, "dexb_tiv_forward: null argument");
-  DEXB_CHECK(h->finalized, "dexb_tiv_forward: call dexb_tiv_finalize_weights first");
-  DEXB_CHECK(B >= 1 && T >= 2, "dexb_tiv_forward: B = %d, T = %d (InstanceNorm1D needs at least two frames)", B, T);
-  for (int l = 0; l < h->L; ++l) DEXB_CHECK(skips_dev[l] != nullptr, "dexb_tiv_forward: skips_dev[%d] is null", l);
-  cudaStream_t st = (cudaStream_t)stream;
-  DEXB_TRY(tiv_plan(h, B, T));
+}  // extern "C"
+
+static int tiv_enqueue(dexb_tiv* h, const float* ref_dev, const float* mask_dev, int B, int T, float* out_dev, float* const* skips_dev,
+                       cudaStream_t st) {
   const long rows = (long)B * T;
   const int C = h->c_h;
   h->launches = 0;
@@ -347,6 +346,40 @@ int dexb_tiv_forward(dexb_tiv* h, const float* ref_dev, const float* mask_dev, i
     h->launches += 2;
   }
   DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" {
+
+int dexb_tiv_forward(dexb_tiv* h, const float* ref_dev, const float* mask_dev, int B, int T, float* out_dev,
+                     float* const* skips_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && ref_dev != nullptr && mask_dev != nullptr && skips_dev != nullptr, "dexb_tiv_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_tiv_forward: call dexb_tiv_finalize_weights first");
+  DEXB_CHECK(B >= 1 && T >= 2, "dexb_tiv_forward: B = %d, T = %d (InstanceNorm1D needs at least two frames)", B, T);
+  for (int l = 0; l < h->L; ++l) DEXB_CHECK(skips_dev[l] != nullptr, "dexb_tiv_forward: skips_dev[%d] is null", l);
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(tiv_plan(h, B, T));
+  if (!enc_graphs_on()) return tiv_enqueue(h, ref_dev, mask_dev, B, T, out_dev, skips_dev, st);
+  const size_t rows = (size_t)B * T;
+  for (int pass = 0; pass < 2; ++pass) {                      // pass 0 sizes the staging buffer, pass 1 uses it
+    EncStage a{pass == 0 ? nullptr : h->g.stage};
+    float* g_ref = a.get<float>(rows * h->c_in);
+    float* g_mask = a.get<float>(rows);
+    float* g_out = a.get<float>(rows * h->c_out);
+    float* g_skips[DEXB_TIV_MAX_LAYERS];
+    for (int l = 0; l < h->L; ++l) g_skips[l] = a.get<float>(rows * h->c_h);
+    if (pass == 0) {
+      if (h->g.stage == nullptr) DEXB_CUDA_OK(cudaMalloc(&h->g.stage, a.off + 256));
+      continue;
+    }
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_ref, ref_dev, rows * h->c_in * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_mask, mask_dev, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // out_conv is always part of the graph (one graph per plan, whatever the caller asks for)
+    DEXB_TRY(enc_graph_run(&h->g, &h->launches, st, [&](cudaStream_t cs) { return tiv_enqueue(h, g_ref, g_mask, B, T, g_out, g_skips, cs); }));
+    for (int l = 0; l < h->L; ++l)
+      DEXB_CUDA_OK(cudaMemcpyAsync(skips_dev[l], g_skips[l], rows * h->c_h * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (out_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(out_dev, g_out, rows * h->c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 

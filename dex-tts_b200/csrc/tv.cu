@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "../../include/dexb200.h"
+#include "enc_graph.cuh"
 #include "gemm_host.cuh"
 
 namespace dexb {
@@ -68,6 +69,7 @@ struct EncBase {
   bf16 *xs = nullptr, *hs = nullptr;           // split rows, up to 2 * max(K) columns
   float *acc = nullptr, *xf = nullptr;         // fp32 rows, up to max(C) columns
   long launches = 0;
+  EncGraph g;                                  // CUDA-graph replay of the forward of this plan (enc_graph.cuh)
 };
 
 }  // namespace dexb
@@ -306,6 +308,7 @@ static void tv_free_conv(TvConv* c) {
 }
 
 static void enc_release_rows(EncBase* h) {
+  enc_graph_release(&h->g);
   cudaFree(h->xs); cudaFree(h->hs); cudaFree(h->acc); cudaFree(h->xf);
   h->xs = h->hs = nullptr;
   h->acc = h->xf = nullptr;
@@ -463,13 +466,8 @@ int dexb_tv_finalize_weights(dexb_tv* h, void* stream) {
   return 0;
 }
 
-int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int B, int T, float* z_before_dev, float* z_dec_dev,
-                    float* vq_loss_dev, int32_t* idx_dev, void* stream) {
-  DEXB_CHECK(h != nullptr && sty_dev != nullptr && mask_dev != nullptr && z_dec_dev != nullptr, "dexb_tv_forward: null argument");
-  DEXB_CHECK(h->finalized, "dexb_tv_forward: call dexb_tv_finalize_weights first");
-  DEXB_CHECK(B >= 1 && T >= 1, "dexb_tv_forward: B = %d, T = %d", B, T);
-  cudaStream_t st = (cudaStream_t)stream;
-  DEXB_TRY(tv_plan(h, B, T));
+static int tv_enqueue(dexb_tv* h, const float* sty_dev, const float* mask_dev, int B, int T, float* z_before_dev, float* z_dec_dev,
+                      float* vq_loss_dev, int32_t* idx_dev, cudaStream_t st) {
   const long rows = (long)B * T;
   h->launches = 0;
   // in_conv(sty * mask) * mask
@@ -537,6 +535,39 @@ int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int
   }
   h->launches += 8;
   DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dexb_tv_forward(dexb_tv* h, const float* sty_dev, const float* mask_dev, int B, int T, float* z_before_dev, float* z_dec_dev,
+                    float* vq_loss_dev, int32_t* idx_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && sty_dev != nullptr && mask_dev != nullptr && z_dec_dev != nullptr, "dexb_tv_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_tv_forward: call dexb_tv_finalize_weights first");
+  DEXB_CHECK(B >= 1 && T >= 1, "dexb_tv_forward: B = %d, T = %d", B, T);
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(tv_plan(h, B, T));
+  if (!enc_graphs_on()) return tv_enqueue(h, sty_dev, mask_dev, B, T, z_before_dev, z_dec_dev, vq_loss_dev, idx_dev, st);
+  const size_t rows = (size_t)B * T;
+  for (int pass = 0; pass < 2; ++pass) {                      // pass 0 sizes the staging buffer, pass 1 uses it
+    EncStage a{pass == 0 ? nullptr : h->g.stage};
+    float* g_sty = a.get<float>(rows * h->c_in);
+    float* g_mask = a.get<float>(rows);
+    float* g_zb = a.get<float>(rows * h->c_out);
+    float* g_zd = a.get<float>(rows * h->c_g);
+    float* g_loss = a.get<float>(1);
+    int32_t* g_idx = a.get<int32_t>(rows);
+    if (pass == 0) {
+      if (h->g.stage == nullptr) DEXB_CUDA_OK(cudaMalloc(&h->g.stage, a.off + 256));
+      continue;
+    }
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_sty, sty_dev, rows * h->c_in * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_mask, mask_dev, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // every optional output is always produced into the staging buffers (one graph per plan, whatever the caller asks for)
+    DEXB_TRY(enc_graph_run(&h->g, &h->launches, st, [&](cudaStream_t cs) { return tv_enqueue(h, g_sty, g_mask, B, T, g_zb, g_zd, g_loss, g_idx, cs); }));
+    if (z_before_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(z_before_dev, g_zb, rows * h->c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(z_dec_dev, g_zd, rows * h->c_g * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (vq_loss_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(vq_loss_dev, g_loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (idx_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(idx_dev, g_idx, rows * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
@@ -843,15 +874,8 @@ int dexb_lf0_finalize_weights(dexb_lf0* h, void* stream) {
   return 0;
 }
 
-int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, int B, int T, float* lf0_enc_dev, float* lf0_dec_dev,
-                     void* stream) {
-  DEXB_CHECK(h != nullptr && lf0_dev != nullptr && mask_dev != nullptr && lf0_enc_dev != nullptr && lf0_dec_dev != nullptr,
-             "dexb_lf0_forward: null argument");
-  DEXB_CHECK(h->finalized, "dexb_lf0_forward: call dexb_lf0_finalize_weights first");
-  DEXB_CHECK(B >= 1 && T >= 1, "dexb_lf0_forward: B = %d, T = %d", B, T);
-  DEXB_CHECK(h->c_out == h->c_h, "dexb_lf0_forward: out_conv must keep the channel count of the GRU (c_out == c_h)");
-  cudaStream_t st = (cudaStream_t)stream;
-  DEXB_TRY(lf0_plan(h, B, T));
+static int lf0_enqueue(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, int B, int T, float* lf0_enc_dev, float* lf0_dec_dev,
+                       cudaStream_t st) {
   const long rows = (long)B * T;
   h->launches = 0;
   k_lf0_in<<<cdiv(rows, 8), 256, 0, st>>>(lf0_dev, mask_dev, h->in_w, h->in_g, h->in_b, h->xs, rows, h->c_h, T);
@@ -895,6 +919,36 @@ int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, i
   }
   h->launches += 8;
   DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dexb_lf0_forward(dexb_lf0* h, const float* lf0_dev, const float* mask_dev, int B, int T, float* lf0_enc_dev, float* lf0_dec_dev,
+                     void* stream) {
+  DEXB_CHECK(h != nullptr && lf0_dev != nullptr && mask_dev != nullptr && lf0_enc_dev != nullptr && lf0_dec_dev != nullptr,
+             "dexb_lf0_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_lf0_forward: call dexb_lf0_finalize_weights first");
+  DEXB_CHECK(B >= 1 && T >= 1, "dexb_lf0_forward: B = %d, T = %d", B, T);
+  DEXB_CHECK(h->c_out == h->c_h, "dexb_lf0_forward: out_conv must keep the channel count of the GRU (c_out == c_h)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(lf0_plan(h, B, T));
+  if (!enc_graphs_on()) return lf0_enqueue(h, lf0_dev, mask_dev, B, T, lf0_enc_dev, lf0_dec_dev, st);
+  const size_t rows = (size_t)B * T;
+  for (int pass = 0; pass < 2; ++pass) {
+    EncStage a{pass == 0 ? nullptr : h->g.stage};
+    float* g_lf0 = a.get<float>(rows);
+    float* g_mask = a.get<float>(rows);
+    float* g_enc = a.get<float>(rows * h->c_out);
+    float* g_dec = a.get<float>(rows * h->c_g);
+    if (pass == 0) {
+      if (h->g.stage == nullptr) DEXB_CUDA_OK(cudaMalloc(&h->g.stage, a.off + 256));
+      continue;
+    }
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_lf0, lf0_dev, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_mask, mask_dev, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_TRY(enc_graph_run(&h->g, &h->launches, st, [&](cudaStream_t cs) { return lf0_enqueue(h, g_lf0, g_mask, B, T, g_enc, g_dec, cs); }));
+    DEXB_CUDA_OK(cudaMemcpyAsync(lf0_enc_dev, g_enc, rows * h->c_out * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(lf0_dec_dev, g_dec, rows * h->c_g * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
@@ -1416,19 +1470,10 @@ int dexb_text_finalize_weights(dexb_text* h, void* stream) {
   return 0;
 }
 
-int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, const float* spk_dev, int B, int Tx,
-                      float* mu_dev, float* logw_dev, void* stream) {
-  DEXB_CHECK(h != nullptr && ids_dev != nullptr && mask_dev != nullptr && mu_dev != nullptr && logw_dev != nullptr,
-             "dexb_text_forward: null argument");
-  DEXB_CHECK(h->finalized, "dexb_text_forward: call dexb_text_finalize_weights first");
-  DEXB_CHECK(B >= 1 && Tx >= 1, "dexb_text_forward: B = %d, Tx = %d", B, Tx);
-  DEXB_CHECK((sty_dev != nullptr) == (h->adaln != 0), "dexb_text_forward: the style vector is %s for this encoder",
-             h->adaln ? "required (DEX-TTS: AdaptiveLayerNorm)" : "not taken (GeDEX-TTS)");
-  DEXB_CHECK((spk_dev != nullptr) == (h->spk_dim > 0), "dexb_text_forward: the speaker embedding is %s for this encoder",
-             h->spk_dim > 0 ? "required (n_spks > 1)" : "not taken (n_spks <= 1)");
-  cudaStream_t st = (cudaStream_t)stream;
+// every launch of one forward on `st`; all pointers are device pointers that stay valid until the work has run
+static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, const float* spk_dev, int B, int Tx,
+                        float* mu_dev, float* logw_dev, cudaStream_t st) {
   static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
-  DEXB_TRY(txt_plan(h, B, Tx));
   const int C = h->C, C0 = h->C0, T = Tx;
   const long rows = (long)B * T;
   h->launches = 0;
@@ -1531,6 +1576,47 @@ int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_de
   k_txt_dp_out<<<cdiv(rows, 8), 256, 0, st>>>(h->xf, h->dpw, h->dpb, mask_dev, logw_dev, rows, h->Fd);
   h->launches += 7;
   DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int dexb_text_forward(dexb_text* h, const int64_t* ids_dev, const float* mask_dev, const float* sty_dev, const float* spk_dev, int B, int Tx,
+                      float* mu_dev, float* logw_dev, void* stream) {
+  DEXB_CHECK(h != nullptr && ids_dev != nullptr && mask_dev != nullptr && mu_dev != nullptr && logw_dev != nullptr,
+             "dexb_text_forward: null argument");
+  DEXB_CHECK(h->finalized, "dexb_text_forward: call dexb_text_finalize_weights first");
+  DEXB_CHECK(B >= 1 && Tx >= 1, "dexb_text_forward: B = %d, Tx = %d", B, Tx);
+  DEXB_CHECK((sty_dev != nullptr) == (h->adaln != 0), "dexb_text_forward: the style vector is %s for this encoder",
+             h->adaln ? "required (DEX-TTS: AdaptiveLayerNorm)" : "not taken (GeDEX-TTS)");
+  DEXB_CHECK((spk_dev != nullptr) == (h->spk_dim > 0), "dexb_text_forward: the speaker embedding is %s for this encoder",
+             h->spk_dim > 0 ? "required (n_spks > 1)" : "not taken (n_spks <= 1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DEXB_TRY(txt_plan(h, B, Tx));
+  if (!enc_graphs_on() || h->layer_limit >= 0)
+    return text_enqueue(h, ids_dev, mask_dev, sty_dev, spk_dev, B, Tx, mu_dev, logw_dev, st);
+  // graph replay: inputs / outputs go through fixed staging buffers of the plan
+  const size_t rows = (size_t)B * Tx;
+  for (int pass = 0; pass < 2; ++pass) {
+    EncStage a{pass == 0 ? nullptr : h->g.stage};
+    int64_t* g_ids = a.get<int64_t>(rows);
+    float* g_mask = a.get<float>(rows);
+    float* g_sty = a.get<float>((size_t)B * h->C0);
+    float* g_spk = a.get<float>((size_t)B * (h->spk_dim > 0 ? h->spk_dim : 1));
+    float* g_mu = a.get<float>(rows * h->n_feats);
+    float* g_logw = a.get<float>(rows);
+    if (pass == 0) {
+      if (h->g.stage == nullptr) DEXB_CUDA_OK(cudaMalloc(&h->g.stage, a.off + 256));
+      continue;
+    }
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_ids, ids_dev, rows * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(g_mask, mask_dev, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (sty_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(g_sty, sty_dev, (size_t)B * h->C0 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (spk_dev != nullptr) DEXB_CUDA_OK(cudaMemcpyAsync(g_spk, spk_dev, (size_t)B * h->spk_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_TRY(enc_graph_run(&h->g, &h->launches, st, [&](cudaStream_t cs) {
+      return text_enqueue(h, g_ids, g_mask, sty_dev != nullptr ? g_sty : nullptr, spk_dev != nullptr ? g_spk : nullptr, B, Tx, g_mu, g_logw, cs);
+    }));
+    DEXB_CUDA_OK(cudaMemcpyAsync(mu_dev, g_mu, rows * h->n_feats * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DEXB_CUDA_OK(cudaMemcpyAsync(logw_dev, g_logw, rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 
