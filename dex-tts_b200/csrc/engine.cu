@@ -371,6 +371,20 @@ static void gp_out_s(GemmParams& p, bf16* out, long stride, int hi, int lo) {
 static void gp_out_f(GemmParams& p, float* out, long stride) { p.epi.out_f32 = out; p.epi.out_f32_stride = stride; }
 static void gp_rowmask(GemmParams& p, const float* m, long stride) { p.epi.rowmask = m; p.epi.rowmask_stride = stride; }
 
+// Wave quantisation of the token GEMMs: with one persistent CTA per SM the launch takes ceil(tiles / #SMs) rounds.  At C2 the
+// 256-wide DiT linears (proj, fc2: 162 m-tiles x 2 n-tiles of 128 = 324 tiles) run 3 rounds, the last one 19 % full; with 64-wide
+// n-tiles it is 5 rounds of half the work (2.5 instead of 3 units).  Take the narrower tile when it saves >= 12 %.
+static int pick_bn_for_waves(long m_tiles, int N) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("DEXB_BN_WAVES"); on = (e != nullptr) ? atoi(e) : 1; }
+  if (!on || N < 128 || N % 64 != 0) return 0;
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long r128 = (m_tiles * ((N + 127) / 128) + sms - 1) / sms * 128;
+  const long r64 = (m_tiles * (N / 64) + sms - 1) / sms * 64;
+  return (r64 * 100 <= r128 * 88) ? 64 : 0;
+}
+
 static int plan_shared(GemmPlan* gp, GemmParams& p) {
   gp_tile(p);
   return gemm_plan_init(gp, p, p.a_by_z ? p.nz : p.nz / p.nheads, (long)p.KH * p.KW * p.b_rows_per_tap, 1);
@@ -699,6 +713,7 @@ static int build_plans(dexb_handle* h) {
       p.epi.bias = k.proj_b;
       p.epi.resid_f32 = h->xtok; p.epi.resid_f32_stride = hid;
       gp_out_f(p, h->xtok, hid);
+      p.block_n_hint = pick_bn_for_waves((M + 127) / 128, hid);
       DEXB_TRY(plan_shared(&k.proj, p));
     }
     {
@@ -708,6 +723,7 @@ static int build_plans(dexb_handle* h) {
       gp_b(p, k.fc1_w, hid, c.mlp_hidden);
       p.epi.bias = k.fc1_b; p.epi.act = 1;
       gp_out_s(p, h->h2S, 2 * c.mlp_hidden, 0, c.mlp_hidden);
+      p.block_n_hint = pick_bn_for_waves((M + 127) / 128, c.mlp_hidden);
       DEXB_TRY(plan_shared(&k.fc1, p));
     }
     {
@@ -718,6 +734,7 @@ static int build_plans(dexb_handle* h) {
       p.epi.bias = k.fc2_b;
       p.epi.resid_f32 = h->xtok; p.epi.resid_f32_stride = hid;
       gp_out_f(p, h->xtok, hid);
+      p.block_n_hint = pick_bn_for_waves((M + 127) / 128, hid);
       DEXB_TRY(plan_shared(&k.fc2, p));
     }
   }

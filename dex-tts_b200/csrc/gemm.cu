@@ -64,7 +64,7 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
   DEXB_CHECK(q.nheads >= 1 && q.nz >= 1 && q.nz % q.nheads == 0, "gemm: nz %d / nheads %d", q.nz, q.nheads);
   q.TH = cdiv(q.CH, q.BH);
   q.TW = cdiv(q.CW, q.BW);
-  gp->block_n = pick_block_n(q.N);
+  gp->block_n = (q.block_n_hint == 64 || q.block_n_hint == 128) ? q.block_n_hint : pick_block_n(q.N);
   gp->n_img_a = n_img_a;
   gp->tc_ok = (q.K % kTcBlockK == 0) && (q.a_row_stride % 8 == 0) && (q.b_row_stride % 8 == 0) &&
               (q.in_stride == 1 || q.in_stride == 2) && (q.BW * q.in_stride <= 256) && (q.BH * q.in_stride <= 256) &&

@@ -71,6 +71,7 @@ struct GemmParams {
   int b_head_stride;           // extra B column offset per head
   int b_head_rows;             // extra B row offset per head
   int b_mode;                  // 0: shared weights, 1: per image (z / nheads), 2: per z
+  int block_n_hint;            // 0 = pick the n-tile width from N; 64 / 128 = the caller's choice (wave quantisation, see engine.cu)
   int nsplit;                  // 3 = bf16x3 (default), 1 = hi*hi only
   int late_wait;               // tuning aid (DEXB_EARLY_WAIT=0): the MMA issuer waits for a stage at its top instead of one stage ahead
   int dbg;                     // tuning aid (dexb_gemm_bench): bit 0 = skip the epilogue, bit 1 = skip the MMAs, bit 2 = skip TMA of A
