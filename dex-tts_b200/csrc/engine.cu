@@ -500,7 +500,9 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
       const int Pl = (la == &h->la0) ? h->H0 * h->W0 : h->H1 * h->W1;
       const int ntl = (Pl + 63) / 64;
       la->PP = ntl * 64;
-      int sp = (2 * 148 + B - 1) / B;
+      static int la_waves = -1;                          // key ranges per image so that B * splits CTAs fill this many waves of 148 SMs
+      if (la_waves < 0) { const char* e = getenv("DEXB_LA_WAVES"); la_waves = (e != nullptr && atoi(e) >= 1) ? atoi(e) : 1; }   // 1: 0.048 vs 0.057 ms for the three merges (fewer partials), context kernel unchanged
+      int sp = (la_waves * 148 + B - 1) / B;
       if (sp > ntl) sp = ntl;
       if (sp < 1) sp = 1;
       const int tps = (ntl + sp - 1) / sp;
