@@ -199,6 +199,16 @@ int dexb_gemm_test(int engine, int nsplit, const float* a_dev, int nimg, int H, 
   return 0;
 }
 
+// operand fill for the micro-benchmark: pseudo-random bf16 in [-1, 1) (DEXB_BENCH_RANDOM=1; tensor-core power, and with it the SM clock
+// under the board's power cap, depends on how many operand bits toggle -- constant operands flatter the kernel)
+__global__ void k_bench_fill(bf16* p, long n, unsigned seed) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    unsigned x = (unsigned)i * 2654435761u + seed;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    p[i] = __float2bfloat16((float)(x & 0xffff) * (1.f / 32768.f) - 1.f);
+  }
+}
+
 int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, int KW, int offH, int offW, int in_stride,
                     int out_mode, int dbg, int iters, float* ms_out) {
   DEXB_CHECK(ms_out != nullptr && iters >= 1, "gemm_bench: bad argument");
@@ -217,6 +227,13 @@ int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, in
   DEXB_CUDA_OK(cudaMemset(as, 0x3c, rows * 2 * K * sizeof(bf16)));
   DEXB_CUDA_OK(cudaMemset(ws, 0x3c, (long)taps * N * 2 * K * sizeof(bf16)));
   DEXB_CUDA_OK(cudaMemset(bias, 0, N * sizeof(float)));
+  {
+    const char* e = getenv("DEXB_BENCH_RANDOM");
+    if (e != nullptr && atoi(e) != 0) {
+      k_bench_fill<<<1024, 256>>>(as, rows * 2 * K, 1u);
+      k_bench_fill<<<256, 256>>>(ws, (long)taps * N * 2 * K, 2u);
+    }
+  }
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.nz = nimg; p.nheads = 1; p.H = H; p.W = W; p.in_stride = in_stride;

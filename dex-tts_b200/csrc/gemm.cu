@@ -1,6 +1,7 @@
 // Host side of the implicit-GEMM engine: tensor-map construction (driver entry point resolved at run time, so the
 // library does not link libcuda), tile-shape selection and launch of either engine.
 #include "gemm.cuh"
+#include "conv_pair.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -97,6 +98,10 @@ int gemm_plan_init(GemmPlan* gp, const GemmParams& p, int n_img_a, long b_rows, 
     const cuuint32_t box[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)gp->block_n, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     DEXB_TRY(encode_bf16(&gp->tmB, q.Bw, 3, dims, str, box, es, "B"));
+    if (gp->halo) {
+      const cuuint32_t boxh[3] = {(cuuint32_t)kTcBlockK, (cuuint32_t)(gp->block_n / 2), 1};
+      DEXB_TRY(encode_bf16(&gp->tmBh, q.Bw, 3, dims, str, boxh, es, "B half"));
+    }
   }
   return 0;
 }
@@ -122,6 +127,8 @@ int gemm_global_init() {
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, cp_smem_bytes(64)));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cp_smem_bytes(128)));
   return resolve_encode();
 }
 
@@ -175,6 +182,17 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st, c
   const int ntn = cdiv(p.N, BN);
   const long m_tiles = (long)p.nz * p.TH * p.TW;
   const long total = m_tiles * ntn;
+  if constexpr (FAST && !GNF && (BN == 64 || BN == 128)) {
+    // CTA pairs (conv_pair.cuh): two m-tiles of one n-tile per cluster, half of the weight tile per CTA.  DEXB_PAIR=0: single CTAs.
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* e = getenv("DEXB_PAIR"); pair_mode = (e != nullptr) ? atoi(e) : 1; }
+    if (gp.halo && pair_mode != 0 && m_tiles % 2 == 0 && g_num_sms >= 2) {
+      const long pairs = (m_tiles / 2) * ntn;
+      const int grid = 2 * (int)(pairs < g_num_sms / 2 ? pairs : g_num_sms / 2);
+      launch_pdl(conv_pair_kernel<BN>, dim3(grid), dim3(kTcThreads), cp_smem_bytes(BN), st, gp.tmA, gp.tmBh, p, (int)pairs, ntn);
+      return 0;
+    }
+  }
   if (gp.halo && BN <= 128) {                          // the plan encoded 136-row A boxes: halo mode is the only valid launch
     int nb = (kTcSmemMax - tc_halo_bytes(BN, 0)) / (2 * BN * kTcBlockK * 2);
     if (nb > kTcMaxStages) nb = kTcMaxStages;

@@ -88,6 +88,7 @@ constexpr int kTcBlockK = 64;                  // 64 bf16 = 128 B = one swizzle 
 
 struct GemmPlan {
   CUtensorMap tmA, tmB;        // 64 B aligned by the type's own alignment
+  CUtensorMap tmBh;            // halo mode: weight boxes of block_n / 2 rows (CTA-pair kernel, conv_pair.cuh)
   GemmParams p;
   int block_n;
   int n_img_a;

@@ -11,6 +11,7 @@
 #include "ptx.cuh"
 
 using namespace dexb;
+using bf16 = __nv_bfloat16;
 
 namespace p2 {
 __device__ __forceinline__ uint32_t cta_rank() {
@@ -51,7 +52,8 @@ __host__ __device__ inline int sw128(int row, int k) { return row * 128 + (((k >
 // smem per CTA and slot (64 KB): A_hi 16 KB | A_lo 16 KB | B 32 KB (up to 256 rows)
 // mode 0: cta_group::1, every CTA on its own.  mode 1: cta_group::2, the even CTA of a pair issues M = 256 MMAs.
 // check: one stage (K = 64) on operands from global memory, D written back (fp32 [cta][128][2 BN]).
-__global__ void __launch_bounds__(128, 1) k_cta2(int bn, int stages, int mode, const bf16* __restrict__ a_g, const bf16* __restrict__ b_g,
+template <int mode>
+__global__ void __launch_bounds__(128, 1) k_cta2(int bn, int stages, const bf16* __restrict__ a_g, const bf16* __restrict__ b_g,
                                                  float* __restrict__ d_g, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -122,7 +124,6 @@ __global__ void __launch_bounds__(128, 1) k_cta2(int bn, int stages, int mode, c
     for (int c0 = 0; c0 < 2 * bn; c0 += 32) {
       float v[32];
       ptx::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
-      ptx::tmem_ld_wait();
       for (int i = 0; i < 32; ++i) d[(long)threadIdx.x * 256 + c0 + i] = v[i];
     }
   }
@@ -145,15 +146,16 @@ static void launch(int ctas, int bn, int stages, int mode, const bf16* a, const 
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_cta2, bn, stages, mode, a, b, d, out);
-  if (e != cudaSuccess) { printf("launch error %s\n", cudaGetErrorString(e)); exit(1); }
+  cfg.numAttrs = mode ? 1 : 0;
+  cudaError_t e = mode ? cudaLaunchKernelEx(&cfg, k_cta2<1>, bn, stages, a, b, d, out) : cudaLaunchKernelEx(&cfg, k_cta2<0>, bn, stages, a, b, d, out);
+  if (e != cudaSuccess) { printf("launch error %s (ctas %d mode %d)\n", cudaGetErrorString(e), ctas, mode); exit(1); }
 }
 
 int main() {
   long long* dcyc;
   cudaMalloc(&dcyc, 8);
-  cudaFuncSetAttribute(k_cta2, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
+  cudaFuncSetAttribute(k_cta2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
+  cudaFuncSetAttribute(k_cta2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024);
   // ---- semantics: one pair, one stage, small integers
   for (int bn : {64, 128}) {
     const int N2 = 2 * bn;
@@ -205,6 +207,17 @@ int main() {
     cudaFree(da); cudaFree(db); cudaFree(dd);
   }
   // ---- timing
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 194 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nclusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, k_cta2<1>, &cfg);
+    printf("cudaOccupancyMaxActiveClusters(cluster 2, 194 KB): %d (%s)\n", nclusters, cudaGetErrorString(e));
+  }
   for (int bn : {64, 128}) {
     for (int mode = 0; mode < 2; ++mode) {
       const int stages = 9 * 32;
