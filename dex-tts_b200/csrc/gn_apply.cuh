@@ -47,12 +47,16 @@ struct GnFuse {
 };
 
 #ifdef __CUDACC__
-// Mish with fast intrinsics (ex2.approx / approximate divide: ~1e-6 relative, far inside the split-bf16 noise floor)
+// Mish, branch-free on the raw MUFU approximations: w = 2^(min(x, 20) log2 e), n = w (w + 2), mish = x n / (n + 2) -- 9 instructions.
+// (__expf / __fdividef carry denormal range checks and the x > 20 early-out was a divergent branch: 19 instructions and two
+//  BSSY / BSYNC pairs per element; the stand-alone pass issued 49 instructions per element and was issue-bound, not HBM-bound.)
+// Above 20 the clamp gives n / (n + 2) == 1 in fp32, i.e. x itself, which is what torch's softplus threshold does.
 __device__ __forceinline__ float mish_fast(float x) {
-  if (x > 20.f) return x;
-  const float w = __expf(x);
+  float w, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(fminf(x, 20.f) * 1.4426950408889634f));
   const float n = w * (w + 2.f);
-  return x * __fdividef(n, n + 2.f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+  return x * (n * r);
 }
 
 // mean / rstd of one (image, group) straight from the double sums, per thread: two broadcast loads and a handful of DP
@@ -94,8 +98,8 @@ __device__ __forceinline__ void gn_item_load(const GnApplyArgs& a, long pix, int
   }
 }
 
-// normalise, Mish, mask, (+ time bias), + residual, split store.  p = pixel inside image b.
-__device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsigned p, int c0, const GnItem& it, float mean, float rstd,
+// normalise, Mish, mask, (+ time bias), + residual, split store.  p = pixel inside image b; ga[] = rstd * gamma.
+__device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsigned p, int c0, const GnItem& it, float mean,
                                                const float (&ga)[8], const float (&be)[8], const float (&tb)[8]) {
   const long pix = (long)b * a.P + p;
   const int w = (int)(p % (unsigned)a.W);
@@ -103,10 +107,13 @@ __device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsi
   float v[8] = {it.r0.x, it.r0.y, it.r0.z, it.r0.w, it.r1.x, it.r1.y, it.r1.z, it.r1.w};
   float res[8];
   if (a.resid_s.p != nullptr) {
-    const bf16* hh = reinterpret_cast<const bf16*>(&it.q0);
-    const bf16* ll = reinterpret_cast<const bf16*>(&it.q1);
+    // (hi, lo) pairs of bf16 -> fp32: a bf16 is the upper half of a float
+    const uint32_t hq[4] = {it.q0.x, it.q0.y, it.q0.z, it.q0.w}, lq[4] = {it.q1.x, it.q1.y, it.q1.z, it.q1.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) res[i] = join2(hh[i], ll[i]);
+    for (int i = 0; i < 4; ++i) {
+      res[2 * i] = __uint_as_float(hq[i] << 16) + __uint_as_float(lq[i] << 16);
+      res[2 * i + 1] = __uint_as_float(hq[i] & 0xffff0000u) + __uint_as_float(lq[i] & 0xffff0000u);
+    }
   } else if (a.resid_f != nullptr) {
     const float* f0 = reinterpret_cast<const float*>(&it.q0);
     const float* f1 = reinterpret_cast<const float*>(&it.q1);
@@ -130,13 +137,29 @@ __device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsi
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float y = (v[i] - mean) * rstd * ga[i] + be[i];
-    y = mish_fast(y) * m;
-    y = (y + tb[i]) * m;                                     // tb == 0 without a time bias: (y*m)*m == y*m for m in {0,1}
-    v[i] = y + res[i];
+    // ga[] holds rstd * gamma (gn_thread_scale).  m is 0 or 1, so both products below are exact and the two fused multiply-adds
+    // round exactly like (mish * m + tb) * m + res.
+    const float y = mish_fast(fmaf(v[i] - mean, ga[i], be[i]));
+    v[i] = fmaf(fmaf(y, m, tb[i]), m, res[i]);
   }
   bf16* op = a.out.p + pix * a.out.stride + c0;
-  store_split8(op + a.out.hi, op + a.out.lo, v);
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {                              // packed conversions: one F2FP per pair (store_split16's scheme)
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * i] - __uint_as_float(hb << 16), v[2 * i + 1] - __uint_as_float(hb & 0xffff0000u));
+    h[i] = hb;
+    l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  *reinterpret_cast<uint4*>(op + a.out.hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(op + a.out.lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// rstd folded into gamma once per thread: the per-element normalisation is one subtraction and one fused multiply-add
+__device__ __forceinline__ void gn_thread_scale(float rstd, float (&ga)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ga[i] *= rstd;
 }
 
 // gamma / beta / time bias of the 8 channels a thread keeps for all its items
@@ -166,6 +189,7 @@ __device__ __forceinline__ void gn_apply_items(const GnApplyArgs& a, int b, unsi
   gn_thread_affine(a, c0, ga, be, tb);
   float mean, rstd;
   gn_thread_stats<true>(a.stats, a.G, 1.0 / ((double)a.P * gs), b, c0 / gs, mean, rstd);
+  gn_thread_scale(rstd, ga);
   const long img_row0 = (long)b * a.P;
 #pragma unroll 1
   for (int j = 0; j < n; j += 4, gi += 4u * nthr) {
@@ -178,7 +202,7 @@ __device__ __forceinline__ void gn_apply_items(const GnApplyArgs& a, int b, unsi
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned g = gi + (unsigned)k * nthr;
-      if (j + k < n && g < last) gn_item_finish(a, b, g >> cshift, c0, it[k], mean, rstd, ga, be, tb);
+      if (j + k < n && g < last) gn_item_finish(a, b, g >> cshift, c0, it[k], mean, ga, be, tb);
     }
   }
 }

@@ -177,11 +177,12 @@ __global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
   }
   float mean, rstd;
   gn_thread_stats(a.stats, a.G, 1.0 / ((double)a.P * gs), b, c0 / gs, mean, rstd);
+  gn_thread_scale(rstd, ga);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
     if (gi >= ngroups) continue;
-    gn_item_finish(a, b, gi >> cshift, c0, it[j], mean, rstd, ga, be, tb);
+    gn_item_finish(a, b, gi >> cshift, c0, it[j], mean, ga, be, tb);
   }
 }
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
   const float fcb = fc_b[0];
   float mean, rstd;
   gn_thread_stats(stats, G, 1.0 / ((double)P * (C / G)), b, g, mean, rstd);
+  gn_thread_scale(rstd, ga);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
       const float v[8] = {r0[j].x, r0[j].y, r0[j].z, r0[j].w, r1[j].x, r1[j].y, r1[j].z, r1[j].w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float y = mish_fast((v[i] - mean) * rstd * ga[i] + be[i]) * m;
+        const float y = mish_fast(fmaf(v[i] - mean, ga[i], be[i])) * m;
         part = fmaf(fw[i], y * m, part);
       }
     }
