@@ -212,7 +212,8 @@ def parity_check(eng, variant, B, T, Ts, seed):
     with torch.no_grad():
         ref = O.reverse_diffusion(w, O.make_cfg(variant), inp["z"][:1], inp["mask"][:1], inp["mu"][:1], 2, temperature=1.5, cond=c1)
     v = per_bin_violation(y, ref)
-    return {"per_bin_violation": v, "tol": REL_TOL, "ok": bool(v < REL_TOL),
+    rms_err = float((y.double() - ref.double()).pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt())
+    return {"per_bin_violation": v, "rms_rel_err": rms_err, "tol": REL_TOL, "ok": bool(v < REL_TOL),
             "checked": f"sample 0 of the timed batch (B={B}, T={T}), 2 sampler steps, CUDA path vs oracle/dex_oracle.py on the host"}
 
 

@@ -80,18 +80,24 @@ struct GnItem {
   uint4 q0, q1;                                              // residual: (hi, lo) of an S row or two float4 of an F row
 };
 
+// Residual variant of a launch, compiled in (KIND >= 0) or looked up per item (KIND = kGnAny: the fused path, one kernel for all):
+constexpr int kGnAny = -1, kGnPlain = 0, kGnResS = 1, kGnResF = 2, kGnRin = 3;
+__host__ __device__ inline int gn_kind_of(const GnApplyArgs& a) {
+  return a.resid_s.p != nullptr ? kGnResS : (a.resid_f != nullptr ? kGnResF : (a.rin_w != nullptr ? kGnRin : kGnPlain));
+}
+
 // all global loads of one item (pixel `pix` of the whole batch, channels c0 .. c0 + 7); L2: see gn_thread_stats
-template <bool L2>
+template <bool L2, int KIND = kGnAny>
 __device__ __forceinline__ void gn_item_load(const GnApplyArgs& a, long pix, int c0, GnItem& it) {
   const float4* rp = reinterpret_cast<const float4*>(a.raw + pix * a.C + c0);
   if (L2) { it.r0 = __ldcg(rp); it.r1 = __ldcg(rp + 1); }
   else { it.r0 = rp[0]; it.r1 = rp[1]; }
   it.q0 = make_uint4(0, 0, 0, 0); it.q1 = make_uint4(0, 0, 0, 0);
-  if (a.resid_s.p != nullptr) {
+  if (KIND == kGnResS || (KIND == kGnAny && a.resid_s.p != nullptr)) {
     const bf16* q = a.resid_s.p + pix * a.resid_s.stride + c0;
     it.q0 = *reinterpret_cast<const uint4*>(q + a.resid_s.hi);
     it.q1 = *reinterpret_cast<const uint4*>(q + a.resid_s.lo);
-  } else if (a.resid_f != nullptr) {
+  } else if (KIND == kGnResF || (KIND == kGnAny && a.resid_f != nullptr)) {
     const float* q = a.resid_f + pix * a.resid_f_stride + c0;
     it.q0 = *reinterpret_cast<const uint4*>(q);
     it.q1 = *reinterpret_cast<const uint4*>(q + 4);
@@ -99,14 +105,15 @@ __device__ __forceinline__ void gn_item_load(const GnApplyArgs& a, long pix, int
 }
 
 // normalise, Mish, mask, (+ time bias), + residual, split store.  p = pixel inside image b; ga[] = rstd * gamma.
-__device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsigned p, int c0, const GnItem& it, float mean,
+// w = image column of the pixel (p % W), which the caller tracks incrementally.
+template <int KIND = kGnAny>
+__device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsigned p, int w, int c0, const GnItem& it, float mean,
                                                const float (&ga)[8], const float (&be)[8], const float (&tb)[8]) {
   const long pix = (long)b * a.P + p;
-  const int w = (int)(p % (unsigned)a.W);
   const float m = a.mask[(long)b * a.mask_stride + w];
   float v[8] = {it.r0.x, it.r0.y, it.r0.z, it.r0.w, it.r1.x, it.r1.y, it.r1.z, it.r1.w};
   float res[8];
-  if (a.resid_s.p != nullptr) {
+  if (KIND == kGnResS || (KIND == kGnAny && a.resid_s.p != nullptr)) {
     // (hi, lo) pairs of bf16 -> fp32: a bf16 is the upper half of a float
     const uint32_t hq[4] = {it.q0.x, it.q0.y, it.q0.z, it.q0.w}, lq[4] = {it.q1.x, it.q1.y, it.q1.z, it.q1.w};
 #pragma unroll
@@ -114,12 +121,12 @@ __device__ __forceinline__ void gn_item_finish(const GnApplyArgs& a, int b, unsi
       res[2 * i] = __uint_as_float(hq[i] << 16) + __uint_as_float(lq[i] << 16);
       res[2 * i + 1] = __uint_as_float(hq[i] & 0xffff0000u) + __uint_as_float(lq[i] & 0xffff0000u);
     }
-  } else if (a.resid_f != nullptr) {
+  } else if (KIND == kGnResF || (KIND == kGnAny && a.resid_f != nullptr)) {
     const float* f0 = reinterpret_cast<const float*>(&it.q0);
     const float* f1 = reinterpret_cast<const float*>(&it.q1);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { res[i] = f0[i] * m; res[4 + i] = f1[i] * m; }
-  } else if (a.rin_w != nullptr) {
+  } else if (KIND == kGnRin || (KIND == kGnAny && a.rin_w != nullptr)) {
     // res_conv(x * mask) of the first ResnetBlock: 1x1 conv on stack[mu, c_in*x]
     const float in0 = a.mu[pix] * m, in1 = (a.tab[a.step].c_in * a.x[pix]) * m;
     if (a.spk_s == nullptr) {
@@ -202,7 +209,7 @@ __device__ __forceinline__ void gn_apply_items(const GnApplyArgs& a, int b, unsi
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned g = gi + (unsigned)k * nthr;
-      if (j + k < n && g < last) gn_item_finish(a, b, g >> cshift, c0, it[k], mean, ga, be, tb);
+      if (j + k < n && g < last) gn_item_finish(a, b, g >> cshift, (int)((g >> cshift) % (unsigned)a.W), c0, it[k], mean, ga, be, tb);
     }
   }
 }

@@ -154,8 +154,12 @@ void launch_conv_in(const float* x, const float* mu, const float* spk_s, const f
 // the first version derived (image, pixel, column) from a flat 64-bit index with four 64-bit divisions per item and was bound
 // by that integer code (2.7 TB/s), not by memory.  Every thread has ITEMS independent 32 B loads (+ residual) in flight;
 // 256 % (C/8) == 0, so a thread keeps the same channel group c0 for all its items (gamma / beta / time bias live in registers).
-template <int ITEMS>
-__global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
+// A block covers ROUNDS x ITEMS x 256 consecutive groups: the per-thread prologue (affine coefficients, statistics in double) was a
+// third of the instructions of a two-item thread, and the kernel is issue-bound (ncu: 25.4 M warp instructions, 61 % SM busy at
+// 40 % of the HBM peak), so it is amortised over up to eight items; the residual variant is a template parameter and the image column
+// of a pixel (mask index) is advanced by the fixed pixel step of a round instead of a modulo per item.
+template <int ITEMS, int KIND>
+__global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a, const int rounds) {
   pdl_wait();
   // Images and chunks are walked BACKWARDS: the convolution that produced `raw` wrote image B-1 last, so the tail of the tensor is
   // what the 126 MB L2 still holds; and this pass then leaves image 0 hottest for the next convolution, which starts there.
@@ -163,37 +167,56 @@ __global__ void __launch_bounds__(256, 3) k_gn_apply(const GnApplyArgs a) {
   const int cpt = a.C >> 3;                                  // threads per pixel: 8 or 16
   const int cshift = 31 - __clz(cpt);
   const unsigned ngroups = (unsigned)a.P << cshift;          // eight-channel groups per image
-  const unsigned base = (a.reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * (unsigned)(256 * ITEMS);
+  const unsigned base = (a.reverse ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * (unsigned)(256 * ITEMS) * (unsigned)rounds;
   const int gs = a.C / a.G;
   const int c0 = (int)(threadIdx.x & (cpt - 1)) * 8;
   float ga[8], be[8], tb[8];
   gn_thread_affine(a, c0, ga, be, tb);
   const long img_row0 = (long)b * a.P;                       // first pixel row of this image
-  GnItem it[ITEMS];
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const unsigned gi = base + j * 256 + threadIdx.x;
-    gn_item_load<false>(a, img_row0 + ((gi < ngroups) ? (gi >> cshift) : 0u), c0, it[j]);
-  }
   float mean, rstd;
   gn_thread_stats(a.stats, a.G, 1.0 / ((double)a.P * gs), b, c0 / gs, mean, rstd);
   gn_thread_scale(rstd, ga);
+  const int pstep = 256 >> cshift;                           // pixels between consecutive items of a thread
+  unsigned gi = base + threadIdx.x;
+  int w = (int)((gi >> cshift) % (unsigned)a.W);             // column of the thread's first pixel; then += pstep (mod W) per item
+#pragma unroll 1
+  for (int r = 0; r < rounds; ++r) {
+    GnItem it[ITEMS];
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    const unsigned gi = base + j * 256 + threadIdx.x;
-    if (gi >= ngroups) continue;
-    gn_item_finish(a, b, gi >> cshift, c0, it[j], mean, ga, be, tb);
+    for (int j = 0; j < ITEMS; ++j) {
+      const unsigned g = gi + j * 256;
+      gn_item_load<false, KIND>(a, img_row0 + ((g < ngroups) ? (g >> cshift) : 0u), c0, it[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j, gi += 256) {
+      if (gi < ngroups) gn_item_finish<KIND>(a, b, gi >> cshift, w, c0, it[j], mean, ga, be, tb);
+      w += pstep;
+      while (w >= a.W) w -= a.W;
+    }
+  }
+}
+template <int ITEMS, int KIND>
+static void launch_gn_apply_k(const GnApplyArgs& a, long ngroups, cudaStream_t st) {
+  // rounds: as many as keep >= ~3 full waves of blocks (148 SMs x 3 resident blocks), at most 4
+  const long blocks1 = cdiv(ngroups, ITEMS * 256) * a.B;
+  int rounds = (int)(blocks1 / 1280);
+  rounds = rounds < 1 ? 1 : (rounds > 4 ? 4 : rounds);
+  dim3 grid(cdiv(ngroups, (long)ITEMS * 256 * rounds), a.B);
+  launch_pdl(k_gn_apply<ITEMS, KIND>, grid, dim3(256), 0, st, a, rounds);
+}
+template <int ITEMS>
+static void launch_gn_apply_i(const GnApplyArgs& a, long ngroups, cudaStream_t st) {
+  switch (gn_kind_of(a)) {
+    case kGnResS: launch_gn_apply_k<ITEMS, kGnResS>(a, ngroups, st); break;
+    case kGnResF: launch_gn_apply_k<ITEMS, kGnResF>(a, ngroups, st); break;
+    case kGnRin: launch_gn_apply_k<ITEMS, kGnRin>(a, ngroups, st); break;
+    default: launch_gn_apply_k<ITEMS, kGnPlain>(a, ngroups, st); break;
   }
 }
 void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
   const long ngroups = (long)a.P * (a.C / 8);
-  if (ngroups >= 8 * 256) {
-    dim3 grid(cdiv(ngroups, 2 * 256), a.B);
-    launch_pdl(k_gn_apply<2>, grid, dim3(256), 0, st, a);
-  } else {
-    dim3 grid(cdiv(ngroups, 256), a.B);
-    launch_pdl(k_gn_apply<1>, grid, dim3(256), 0, st, a);
-  }
+  if (ngroups >= 8 * 256) launch_gn_apply_i<2>(a, ngroups, st);
+  else launch_gn_apply_i<1>(a, ngroups, st);
 }
 
 // ------------------------------------------------------------------------------------------------
