@@ -543,6 +543,7 @@ int attn_plan_init_la(AttnPlan* ap, const bf16* wk, const bf16* x, long x_stride
 // Merge of the tail-split partials: out = sum_s f_s O_s / sum_s f_s l_s,  f_s = exp2((m_s - max_s m_s) * scale*log2e)  -> split rows.
 // One block per split tile, thread = (row, half of the 128 output columns).
 __global__ void __launch_bounds__(256) k_attn_tail_merge(const AttnParams p) {
+  pdl_wait();
   const int k = blockIdx.x, tile = p.tail_first + k;
   const int z = tile / p.q_tiles, m0 = (tile % p.q_tiles) * kAtBM;
   const int b = z / p.nheads, head = z % p.nheads;
@@ -620,7 +621,7 @@ int attn_launch(const AttnPlan& ap, cudaStream_t st) {
   if (p.tail_splits > 1) {
     const int total = ap.B * p.nheads * p.q_tiles, rem = total - p.tail_first;
     launch_pdl(attn_fwd_kernel, dim3(p.tail_first + rem * p.tail_splits), dim3(kAtThreads), kAtSmem, st, ap.tmK, ap.tmV, p);
-    k_attn_tail_merge<<<rem, 256, 0, st>>>(p);
+    launch_pdl(k_attn_tail_merge, dim3((unsigned)(rem)), dim3(256), 0, st, p);
     DEXB_CUDA_OK(cudaGetLastError());
     return 0;
   }

@@ -14,6 +14,7 @@ namespace dexb {
 __global__ void __launch_bounds__(256) k_tv_fold(const float* __restrict__ kw, const float* __restrict__ kw0,
                                                  const double* __restrict__ stats, int P, bf16* __restrict__ kq,
                                                  float* __restrict__ sbias, int B, int NK, int NKR, int C) {
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * NK) return;
   const int b = warp / NK, j = warp % NK;
@@ -35,11 +36,12 @@ __global__ void __launch_bounds__(256) k_tv_fold(const float* __restrict__ kw, c
 }
 void launch_tv_fold(const float* kw, const float* kw0, const double* stats, int P, bf16* kq, float* sbias, int B,
                     int NK, int NKR, int C, cudaStream_t st) {
-  k_tv_fold<<<cdiv((long)B * NK * 32, 256), 256, 0, st>>>(kw, kw0, stats, P, kq, sbias, B, NK, NKR, C);
+  launch_pdl(k_tv_fold, dim3((unsigned)(cdiv((long)B * NK * 32, 256))), dim3(256), 0, st, kw, kw0, stats, P, kq, sbias, B, NK, NKR, C);
 }
 
 // column 0 (the time token) of VL^T changes every step:  vlt[b][c][0] = vl0[c]
 __global__ void k_tv_vl0(const float* __restrict__ vl0, bf16* __restrict__ vlt, int B, int C, int KP) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C;
@@ -47,7 +49,7 @@ __global__ void k_tv_vl0(const float* __restrict__ vl0, bf16* __restrict__ vlt, 
   split2(vl0[c], row[0], row[KP]);
 }
 void launch_tv_vl0(const float* vl0, bf16* vlt, int B, int C, int KP, cudaStream_t st) {
-  k_tv_vl0<<<cdiv((long)B * C, 128), 128, 0, st>>>(vl0, vlt, B, C, KP);
+  launch_pdl(k_tv_vl0, dim3((unsigned)(cdiv((long)B * C, 128))), dim3(128), 0, st, vl0, vlt, B, C, KP);
 }
 
 // masked softmax over the NK = Ts+1 style tokens (key 0 = time token, always visible; masked keys get -1e4,
@@ -55,6 +57,7 @@ void launch_tv_vl0(const float* vl0, bf16* vlt, int B, int C, int KP, cudaStream
 __global__ void __launch_bounds__(256) k_tv_softmax(const float* __restrict__ scores, long sstride,
                                                     const int* __restrict__ sty_len, bf16* __restrict__ P_, long rows,
                                                     int Ppix, int NK, int KP) {
+  pdl_wait();
   const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256) k_tv_softmax(const float* __restrict__ sc
 void launch_tv_softmax(const float* scores, long sstride, const int* sty_len, bf16* P_, int B, int Ppix, int NK, int KP,
                        cudaStream_t st) {
   const long rows = (long)B * Ppix;
-  k_tv_softmax<<<cdiv(rows * 32, 256), 256, 0, st>>>(scores, sstride, sty_len, P_, rows, Ppix, NK, KP);
+  launch_pdl(k_tv_softmax, dim3((unsigned)(cdiv(rows * 32, 256))), dim3(256), 0, st, scores, sstride, sty_len, P_, rows, Ppix, NK, KP);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -90,6 +93,7 @@ void launch_tv_softmax(const float* scores, long sstride, const int* sty_len, bf
 // (InstanceNorm2D: unbiased variance over all pixels, eps 1e-5; base.py:95-109, ref_encoder.py:264-273)
 __global__ void k_tiv_affine(const double* __restrict__ stats, const float* __restrict__ sc, const float* __restrict__ sh,
                              float* __restrict__ a_out, float* __restrict__ d_out, int n, int P) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double sm = stats[(long)i * 2], ss = stats[(long)i * 2 + 1];
@@ -103,7 +107,7 @@ __global__ void k_tiv_affine(const double* __restrict__ stats, const float* __re
 }
 void launch_tiv_affine(const double* stats, const float* sc, const float* sh, float* a_out, float* d_out, int B, int C, int P,
                        cudaStream_t st) {
-  k_tiv_affine<<<cdiv((long)B * C, 128), 128, 0, st>>>(stats, sc, sh, a_out, d_out, B * C, P);
+  launch_pdl(k_tiv_affine, dim3((unsigned)(cdiv((long)B * C, 128))), dim3(128), 0, st, stats, sc, sh, a_out, d_out, B * C, P);
 }
 
 template <bool SPLIT_IN>
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin,
                                                   const float* __restrict__ tiv_shift, int use_tiv,
                                                   const float* __restrict__ dw_w, const float* __restrict__ dw_b,
                                                   SView out, int B, int H, int W, int C, int p, int s, int Fq, int Wq) {
+  pdl_wait();
   const int cpt = C / 8;
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)B * Fq * Wq * cpt;
@@ -163,13 +168,13 @@ void launch_dw_patch(const float* tv, const double* stats, const float* tiv_scal
                      int Wq, cudaStream_t st) {
   const long total = (long)B * Fq * Wq * (C / 8);
   SView none = {nullptr, 0, 0, 0};
-  k_dw_patch<false><<<cdiv(total, 256), 256, 0, st>>>(tv, none, stats, tiv_scale, tiv_shift, use_tiv, dw_w, dw_b, out, B,
+  launch_pdl(k_dw_patch<false>, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, tv, none, stats, tiv_scale, tiv_shift, use_tiv, dw_w, dw_b, out, B,
                                                        H, W, C, p, s, Fq, Wq);
 }
 void launch_dw_patch_s(SView in, const float* dw_w, const float* dw_b, SView out, int B, int H, int W, int C, int p,
                        int s, int Fq, int Wq, cudaStream_t st) {
   const long total = (long)B * Fq * Wq * (C / 8);
-  k_dw_patch<true><<<cdiv(total, 256), 256, 0, st>>>(nullptr, in, nullptr, nullptr, nullptr, 0, dw_w, dw_b, out, B, H, W,
+  launch_pdl(k_dw_patch<true>, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, nullptr, in, nullptr, nullptr, nullptr, 0, dw_w, dw_b, out, B, H, W,
                                                       C, p, s, Fq, Wq);
 }
 
@@ -226,6 +231,7 @@ void launch_ln_mod(const float* x, const float* shift, const float* scale, SView
 // pe[b][w][c] = mean over the frequency rows of pg[b][h][w][c] (dit.py:445), summed in a fixed order.  One thread = 4 channels.
 __global__ void __launch_bounds__(256) k_freq_mean(const float* __restrict__ pg, float* __restrict__ pe, int B, int Fq, int Wq,
                                                    int D) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)B * Wq * (D / 4);
   if (i >= total) return;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(256) k_freq_mean(const float* __restrict__ pg,
   *reinterpret_cast<float4*>(pe + ((long)b * Wq + w) * D + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
 }
 void launch_freq_mean(const float* pg, float* pe, int B, int Fq, int Wq, int D, cudaStream_t st) {
-  k_freq_mean<<<cdiv((long)B * Wq * (D / 4), 256), 256, 0, st>>>(pg, pe, B, Fq, Wq, D);
+  launch_pdl(k_freq_mean, dim3((unsigned)(cdiv((long)B * Wq * (D / 4), 256))), dim3(256), 0, st, pg, pe, B, Fq, Wq, D);
 }
 
 // x = xe + pe[b][w] + fpos[h]  (dit.py:444-447), stored fp32 (residual stream) and LN+modulated for block 0
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(256) k_tok_assemble(const float* __restrict__ 
                                                       const float* __restrict__ fpos, float* __restrict__ x,
                                                       const float* __restrict__ shift, const float* __restrict__ scale,
                                                       SView out, int B, int Fq, int Wq, int D) {
+  pdl_wait();
   const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long M = (long)B * Fq * Wq;
@@ -270,8 +277,8 @@ __global__ void __launch_bounds__(256) k_tok_assemble(const float* __restrict__ 
 void launch_tok_assemble(const float* xe, const float* pe, const float* fpos, float* x, const float* shift,
                          const float* scale, SView out, int B, int Fq, int Wq, int D, cudaStream_t st) {
   const long M = (long)B * Fq * Wq;
-  if (D == 256) k_tok_assemble<8><<<cdiv(M * 32, 256), 256, 0, st>>>(xe, pe, fpos, x, shift, scale, out, B, Fq, Wq, D);
-  else if (D == 384) k_tok_assemble<12><<<cdiv(M * 32, 256), 256, 0, st>>>(xe, pe, fpos, x, shift, scale, out, B, Fq, Wq, D);
+  if (D == 256) launch_pdl(k_tok_assemble<8>, dim3((unsigned)(cdiv(M * 32, 256))), dim3(256), 0, st, xe, pe, fpos, x, shift, scale, out, B, Fq, Wq, D);
+  else if (D == 384) launch_pdl(k_tok_assemble<12>, dim3((unsigned)(cdiv(M * 32, 256))), dim3(256), 0, st, xe, pe, fpos, x, shift, scale, out, B, Fq, Wq, D);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -279,6 +286,7 @@ void launch_tok_assemble(const float* xe, const float* pe, const float* fpos, fl
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_attn_softmax(const float* __restrict__ scores, long NS, bf16* __restrict__ P_,
                                                       long NP, int N) {
+  pdl_wait();
   extern __shared__ float rowbuf[];
   __shared__ float red[8];
   const long row = blockIdx.x;
@@ -309,7 +317,7 @@ __global__ void __launch_bounds__(256) k_attn_softmax(const float* __restrict__ 
   }
 }
 void launch_attn_softmax(const float* scores, long NS, bf16* P_, long NP, long rows, int N, cudaStream_t st) {
-  k_attn_softmax<<<(unsigned)rows, 256, (size_t)N * sizeof(float), st>>>(scores, NS, P_, NP, N);
+  launch_pdl(k_attn_softmax, dim3((unsigned)((unsigned)rows)), dim3(256), (size_t)N * sizeof(float), st, scores, NS, P_, NP, N);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -319,6 +327,7 @@ void launch_attn_softmax(const float* scores, long NS, bf16* P_, long NP, long r
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_transpose_v(const bf16* __restrict__ qkv, long row_stride, int v_hi, int v_lo,
                                                      bf16* __restrict__ vT, int N, long NP, int D, int hd) {
+  pdl_wait();
   __shared__ bf16 tile[32][34];
   const int b = blockIdx.z >> 1, part = blockIdx.z & 1;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(256) k_transpose_v(const bf16* __restrict__ qk
 void launch_transpose_v(const bf16* qkv, long row_stride, int v_hi, int v_lo, bf16* vT, int B, int N, long NP, int D, int hd,
                         cudaStream_t st) {
   dim3 grid(cdiv(N, 32), D / 32, B * 2), block(32, 8);
-  k_transpose_v<<<grid, block, 0, st>>>(qkv, row_stride, v_hi, v_lo, vT, N, NP, D, hd);
+  launch_pdl(k_transpose_v, grid, block, 0, st, qkv, row_stride, v_hi, v_lo, vT, N, NP, D, hd);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -346,6 +355,7 @@ void launch_transpose_v(const bf16* qkv, long row_stride, int v_hi, int v_lo, bf
 __global__ void __launch_bounds__(256) k_unpatchify(const float* __restrict__ y, SView out,
                                                     const float* __restrict__ mask1, int B, int Fq, int Wq, int s,
                                                     int C, int H, int W) {
+  pdl_wait();
   const int cpt = C / 8;
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)B * H * W * cpt;
@@ -372,7 +382,7 @@ __global__ void __launch_bounds__(256) k_unpatchify(const float* __restrict__ y,
 void launch_unpatchify(const float* y, SView out, const float* mask1, int B, int Fq, int Wq, int s, int C, int H, int W,
                        cudaStream_t st) {
   const long total = (long)B * H * W * (C / 8);
-  k_unpatchify<<<cdiv(total, 256), 256, 0, st>>>(y, out, mask1, B, Fq, Wq, s, C, H, W);
+  launch_pdl(k_unpatchify, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, y, out, mask1, B, Fq, Wq, s, C, H, W);
 }
 
 // ------------------------------------------------------------------------------------------------

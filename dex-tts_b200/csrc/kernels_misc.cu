@@ -131,6 +131,7 @@ void launch_tv_vlt_pack(const float* vl, bf16* vlt, int B, int Ts, int C, int KP
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pair_pack(const float* __restrict__ e, bf16* __restrict__ pairs, int B, int Fq,
                                                    int Wq, int D, int Cg, int PF) {
+  pdl_wait();
   const int cpt = D / 8;
   const int Wp = Wq + PF - 1;
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(256) k_pair_pack(const float* __restrict__ e, 
 }
 void launch_pair_pack(const float* e, bf16* pairs, int B, int Fq, int Wq, int D, int Cg, int PF, cudaStream_t st) {
   const long total = (long)B * Fq * (Wq + PF - 1) * PF * (D / 8);
-  k_pair_pack<<<cdiv(total, 256), 256, 0, st>>>(e, pairs, B, Fq, Wq, D, Cg, PF);
+  launch_pdl(k_pair_pack, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, e, pairs, B, Fq, Wq, D, Cg, PF);
 }
 
 // pos-conv weight [Co][Cg][KP][KP] -> [tap = ky*(KP/PF) + kx/PF][Co][hi(PF Cg)|lo(PF Cg)], k = (kx % PF)*Cg + ci

@@ -319,6 +319,7 @@ __device__ __forceinline__ float dec_ord(unsigned u) {
 // column max of k: kv rows are [k(128) | v(128)]; block = 128 threads (one per k column) over a chunk of pixels
 __global__ void __launch_bounds__(128) k_la_colmax(const float* __restrict__ kv, unsigned* __restrict__ kmax, int P,
                                                    int chunk) {
+  pdl_wait();
   const int b = blockIdx.y;
   const long p0 = (long)blockIdx.x * chunk;
   long p1 = p0 + chunk;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) k_la_colmax(const float* __restrict__ kv,
 void launch_la_colmax(const float* kv, unsigned* kmax_enc, int B, int P, cudaStream_t st) {
   const int chunk = 256;
   dim3 grid(cdiv(P, chunk), B);
-  k_la_colmax<<<grid, 128, 0, st>>>(kv, kmax_enc, P, chunk);
+  launch_pdl(k_la_colmax, grid, dim3(128), 0, st, kv, kmax_enc, P, chunk);
 }
 
 // ctx[b][h][d][e] += sum_n exp(k[n][h*32+d] - max) * v[n][h*32+e];  ssum[b][h*32+d] += sum_n exp(..)
@@ -341,6 +342,7 @@ constexpr int kLaTile = 32;
 constexpr int kLaPartial = 4096 + 128;       // one block's partial: ctx[4][32][32] | ssum[128]
 __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, const unsigned* __restrict__ kmax,
                                                 float* __restrict__ part, int P, int chunk) {
+  pdl_wait();
   __shared__ __align__(16) float ps[kLaTile][128];
   __shared__ __align__(16) float vs[kLaTile][128];
   const int b = blockIdx.y;
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(256) k_la_ctx(const float* __restrict__ kv, co
 // ctx[b][4096] | ssum[b][128]  =  sum over the blocks of an image, in block order
 __global__ void __launch_bounds__(256) k_la_reduce(const float* __restrict__ part, float* __restrict__ ctx,
                                                    float* __restrict__ ssum, int B, int nblk) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * kLaPartial) return;
   const int b = i / kLaPartial, k = i % kLaPartial;
@@ -431,8 +434,8 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float
   const int nblk = la_ctx_blocks(B, P);
   const int chunk = cdiv(cdiv(P, nblk), kLaTile) * kLaTile;
   dim3 grid(nblk, B);
-  k_la_ctx<<<grid, 256, 0, st>>>(kv, kmax_enc, part, P, chunk);
-  k_la_reduce<<<cdiv((long)B * kLaPartial, 256), 256, 0, st>>>(part, ctx, ssum, B, nblk);
+  launch_pdl(k_la_ctx, grid, dim3(256), 0, st, kv, kmax_enc, part, P, chunk);
+  launch_pdl(k_la_reduce, dim3((unsigned)(cdiv((long)B * kLaPartial, 256))), dim3(256), 0, st, part, ctx, ssum, B, nblk);
 }
 
 // Merge the split-KV partials of the tensor-core context kernel (attn.cu, out_mode 2) in split order, then finish the
@@ -444,6 +447,7 @@ template <int C>
 __global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
                                                     const float* __restrict__ part_m, const float* __restrict__ wv,
                                                     float* __restrict__ ctx, float* __restrict__ ssum, int S) {
+  pdl_wait();
   __shared__ float Gh[8][C + 1];
   __shared__ float Wvs[32][C + 1];
   const int h = blockIdx.x >> 2, rg = blockIdx.x & 3, b = blockIdx.y, tid = threadIdx.x;
@@ -487,8 +491,8 @@ __global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ par
 void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, const float* wv, float* ctx, float* ssum,
                        int B, int S, int C, cudaStream_t st) {
   dim3 grid(16, B);
-  if (C == 64) k_la_combine<64><<<grid, 64, 0, st>>>(part_o, part_l, part_m, wv, ctx, ssum, S);
-  else k_la_combine<128><<<grid, 64, 0, st>>>(part_o, part_l, part_m, wv, ctx, ssum, S);
+  if (C == 64) launch_pdl(k_la_combine<64>, grid, dim3(64), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
+  else launch_pdl(k_la_combine<128>, grid, dim3(64), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
 }
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
@@ -501,6 +505,7 @@ __global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, 
                                                  const float* __restrict__ wq, const float* __restrict__ wout,
                                                  const float* __restrict__ bout, const float* __restrict__ g,
                                                  bf16* __restrict__ weff, float* __restrict__ beff, int C) {
+  pdl_wait();
   __shared__ float cn[4][32][33];
   __shared__ float Ts[8][128];
   const int b = blockIdx.y, co0 = blockIdx.x * 8, tid = threadIdx.x;
@@ -550,7 +555,7 @@ int kernels_global_init() { return 0; }
 void launch_la_weff(const float* ctx, const float* ssum, const float* wq, const float* wout, const float* bout,
                     const float* g, bf16* weff, float* beff, int B, int C, cudaStream_t st) {
   dim3 grid(C / 8, B);
-  k_la_weff<<<grid, 256, 0, st>>>(ctx, ssum, wq, wout, bout, g, weff, beff, C);
+  launch_pdl(k_la_weff, grid, dim3(256), 0, st, ctx, ssum, wq, wout, bout, g, weff, beff, C);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -561,6 +566,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256) k_chan_stats(const bf16* __restrict__ xs, long s_stride, int hi, int lo,
                                                     const float* __restrict__ xf, long f_stride,
                                                     double* __restrict__ stats, int P, int C, int chunk) {
+  pdl_wait();
   __shared__ float red[256][17];
   const int cpt = C / 8;                                      // 16 for C == 128, 8 for C == 64
   const int rows_per_iter = 256 / cpt;
@@ -603,12 +609,12 @@ __global__ void __launch_bounds__(256) k_chan_stats(const bf16* __restrict__ xs,
 void launch_chan_stats_s(SView x, double* stats, int B, int P, int C, cudaStream_t st) {
   const int chunk = 128;                                 // 80 -> 640 blocks at C2: the kernel was latency-bound
   dim3 grid(cdiv(P, chunk), B);
-  k_chan_stats<true><<<grid, 256, 0, st>>>(x.p, x.stride, x.hi, x.lo, nullptr, 0, stats, P, C, chunk);
+  launch_pdl(k_chan_stats<true>, grid, dim3(256), 0, st, x.p, x.stride, x.hi, x.lo, nullptr, 0, stats, P, C, chunk);
 }
 void launch_chan_stats_f(const float* x, long stride, double* stats, int B, int P, int C, cudaStream_t st) {
   const int chunk = 128;                                 // 80 -> 640 blocks at C2: the kernel was latency-bound
   dim3 grid(cdiv(P, chunk), B);
-  k_chan_stats<false><<<grid, 256, 0, st>>>(nullptr, 0, 0, 0, x, stride, stats, P, C, chunk);
+  launch_pdl(k_chan_stats<false>, grid, dim3(256), 0, st, nullptr, 0, 0, 0, x, stride, stats, P, C, chunk);
 }
 
 }  // namespace dexb

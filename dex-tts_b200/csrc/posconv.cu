@@ -245,6 +245,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
 // xe fp32 [b][y][x][D] -> pin [b][g][y][x][hi(32) | lo(32)]  (one 128 B row per pixel and group)
 __global__ void __launch_bounds__(256) k_posconv_pack_in(const float* __restrict__ xe, bf16* __restrict__ pin, int B, int Fq,
                                                          int Wq, int D, int G) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)B * Fq * Wq * (D / 8);
   if (i >= total) return;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256) k_posconv_pack_in(const float* __restrict
   store_split8(row + ci, row + 32 + ci, v);
 }
 void launch_posconv_pack_in(const float* xe, bf16* pin, int B, int Fq, int Wq, int D, int G, cudaStream_t st) {
-  k_posconv_pack_in<<<cdiv((long)B * Fq * Wq * (D / 8), 256), 256, 0, st>>>(xe, pin, B, Fq, Wq, D, G);
+  launch_pdl(k_posconv_pack_in, dim3((unsigned)(cdiv((long)B * Fq * Wq * (D / 8), 256))), dim3(256), 0, st, xe, pin, B, Fq, Wq, D, G);
 }
 
 // W [Co = G*32][Cg = 32][KS][KS] -> pw [g][ky][kg][row = j*32 + n][hi(32 ci) | lo(32 ci)],  kx = 4 kg + j
