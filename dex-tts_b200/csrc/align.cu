@@ -21,6 +21,7 @@ namespace dexb {
 // one thread per utterance walks the tokens in order (same fp32 addition order as torch.cumsum on the CPU)
 __global__ void k_align_len(const float* __restrict__ logw, const float* __restrict__ x_mask, float length_scale,
                             float* __restrict__ cum, long long* __restrict__ y_len, int B, int Tx) {
+  pdl_wait();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float c = 0.f;
@@ -39,6 +40,7 @@ constexpr int ALIGN_FG = 8;
 __global__ void k_align_expand(const float* __restrict__ cum, const float* __restrict__ x_mask, const long long* __restrict__ y_len,
                                const float* __restrict__ mu_x, float* __restrict__ attn, float* __restrict__ y_mask,
                                float* __restrict__ mu_y, int B, int Tx, int F, int Ty) {
+  pdl_wait();
   const long idx = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (idx >= (long)B * Ty) return;
   const int b = (int)(idx / Ty), t = (int)(idx % Ty);
@@ -74,7 +76,7 @@ int dexb_align_lengths(const float* logw_dev, const float* x_mask_dev, int B, in
   DEXB_CHECK(B >= 1 && Tx >= 1 && length_scale > 0.f, "dexb_align_lengths: B = %d, Tx = %d, length_scale = %g", B, Tx, length_scale);
   cudaStream_t st = (cudaStream_t)stream;
   static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
-  k_align_len<<<cdiv(B, 32), 32, 0, st>>>(logw_dev, x_mask_dev, length_scale, cum_dev, reinterpret_cast<long long*>(y_lengths_dev), B, Tx);
+  launch_pdl(k_align_len, dim3((unsigned)(cdiv(B, 32))), dim3(32), 0, st, logw_dev, x_mask_dev, length_scale, cum_dev, reinterpret_cast<long long*>(y_lengths_dev), B, Tx);
   DEXB_CUDA_OK(cudaGetLastError());
   DEXB_CUDA_OK(cudaMemcpyAsync(y_lengths_host, y_lengths_dev, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   DEXB_CUDA_OK(cudaStreamSynchronize(st));          // the reference's own host round trip: int(y_lengths.max()), tts.py:58
@@ -89,7 +91,7 @@ int dexb_align_expand(const float* cum_dev, const float* x_mask_dev, const int64
              "dexb_align_expand: B = %d, Tx = %d, n_feats = %d, Ty = %d", B, Tx, n_feats, Ty);
   cudaStream_t st = (cudaStream_t)stream;
   if (attn_dev != nullptr) DEXB_CUDA_OK(cudaMemsetAsync(attn_dev, 0, (size_t)B * Tx * Ty * sizeof(float), st));
-  k_align_expand<<<dim3(cdiv((long)B * Ty, 256), cdiv(n_feats, ALIGN_FG)), 256, 0, st>>>(cum_dev, x_mask_dev, reinterpret_cast<const long long*>(y_lengths_dev), mu_x_dev,
+  launch_pdl(k_align_expand, dim3(cdiv((long)B * Ty, 256), cdiv(n_feats, ALIGN_FG)), dim3(256), 0, st, cum_dev, x_mask_dev, reinterpret_cast<const long long*>(y_lengths_dev), mu_x_dev,
                                                           attn_dev, y_mask_dev, mu_y_dev, B, Tx, n_feats, Ty);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;

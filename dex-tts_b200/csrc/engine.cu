@@ -951,7 +951,8 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
   const int B = h->B, d = c.dim, mid = 2 * d, hid = c.hidden;
   const int H0 = h->H0, W0 = h->W0, H1 = h->H1, W1 = h->W1, P0 = H0 * W0, P1 = H1 * W1;
   const bool dex = c.variant == 1;
-  DEXB_CUDA_OK(cudaMemsetAsync(h->zero_base, 0, h->zero_bytes, st));
+  // (a kernel, not a memset node: a non-kernel node between two programmatic launches costs a full dependency edge on either side)
+  launch_fill_zero(h->zero_base, h->zero_bytes, st);
   ++h->launches;
   // ---- level 0 ----
   DEXB_TRY(run_resnet(h, h->d00, step, H0, W0, h->mask0, h->raw0, h->A0, 2 * d, h->B0, 2 * d, nullptr, 0, 0, 0, true, st));

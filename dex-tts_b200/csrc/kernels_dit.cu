@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(256) k_small_linear(const float* __restrict__ 
                                                       const float* __restrict__ w, const float* __restrict__ b,
                                                       float* __restrict__ out, long out_stride, int R, int N, int K,
                                                       int act_in, int act_out) {
+  pdl_wait();
   const long gw = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= (long)R * N) return;
@@ -405,13 +406,14 @@ __global__ void __launch_bounds__(256) k_small_linear(const float* __restrict__ 
 }
 void launch_small_linear(const float* in, long in_stride, const float* w, const float* b, float* out, long out_stride,
                          int R, int N, int K, int act_in, int act_out, cudaStream_t st) {
-  k_small_linear<<<cdiv((long)R * N * 32, 256), 256, 0, st>>>(in, in_stride, w, b, out, out_stride, R, N, K, act_in, act_out);
+  launch_pdl(k_small_linear, dim3((unsigned)(cdiv((long)R * N * 32, 256))), dim3(256), 0, st, in, in_stride, w, b, out, out_stride, R, N, K, act_in, act_out);
 }
 
 // mode 0: SinusoidalPosEmb (diffusion.py:113-120): arg = scale * t * exp(-k * ln(1e4)/(half-1)), out = [sin | cos]
 // mode 1: timestep_embedding (dit.py:233-251):      arg = t * exp(-ln(1e4) * k / half),        out = [cos | sin]
 __global__ void k_time_embed(const StepScalars* __restrict__ tab, int steps, float* __restrict__ out, int dim,
                              float scale, int mode, float c0) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = dim / 2;
   if (i >= steps * half) return;
@@ -432,7 +434,7 @@ __global__ void k_time_embed(const StepScalars* __restrict__ tab, int steps, flo
 void launch_time_embed(const StepScalars* tab, int steps, float* out, int dim, float scale, int mode, cudaStream_t st) {
   const int half = dim / 2;
   const float c0 = (mode == 0) ? (float)(log(10000.0) / (double)(half - 1)) : (float)(-log(10000.0));
-  k_time_embed<<<cdiv((long)steps * half, 128), 128, 0, st>>>(tab, steps, out, dim, scale, mode, c0);
+  launch_pdl(k_time_embed, dim3((unsigned)(cdiv((long)steps * half, 128))), dim3(128), 0, st, tab, steps, out, dim, scale, mode, c0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,6 +24,7 @@ bool pdl_enabled() {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ref_stats(const float* __restrict__ ref, float* __restrict__ mean,
                                                    float* __restrict__ stdv, int B, int C, int Tr, int L, int l) {
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * C) return;
   const int b = warp / C, c = warp % C;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) k_ref_stats(const float* __restrict__ ref
   }
 }
 void launch_ref_stats(const float* ref, float* mean, float* stdv, int B, int C, int Tr, int L, int l, cudaStream_t st) {
-  k_ref_stats<<<cdiv((long)B * C * 32, 256), 256, 0, st>>>(ref, mean, stdv, B, C, Tr, L, l);
+  launch_pdl(k_ref_stats, dim3((unsigned)(cdiv((long)B * C * 32, 256))), dim3(256), 0, st, ref, mean, stdv, B, C, Tr, L, l);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -53,6 +54,7 @@ void launch_ref_stats(const float* ref, float* mean, float* stdv, int B, int C, 
 __global__ void __launch_bounds__(128) k_tiv_sap(const float* __restrict__ t_tok, const float* __restrict__ rows,
                                                  const float* __restrict__ W, const float* __restrict__ bias,
                                                  float* __restrict__ out, int B, int C, int L) {
+  pdl_wait();
   __shared__ float logit[16];
   __shared__ float red[4];
   const int step = blockIdx.x / B, b = blockIdx.x % B;
@@ -82,22 +84,24 @@ __global__ void __launch_bounds__(128) k_tiv_sap(const float* __restrict__ t_tok
 }
 void launch_tiv_sap(const float* t_tok, const float* rows, const float* W, const float* bias, float* out, int steps,
                     int B, int C, int L, cudaStream_t st) {
-  k_tiv_sap<<<steps * B, 128, 0, st>>>(t_tok, rows, W, bias, out, B, C, L);
+  launch_pdl(k_tiv_sap, dim3((unsigned)(steps * B)), dim3(128), 0, st, t_tok, rows, W, bias, out, B, C, L);
 }
 
 // out[c][r] = in[r][c] * scale
 __global__ void k_transpose_scale(const float* __restrict__ in, float* __restrict__ out, int R, int Cc, float scale) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)R * Cc) return;
   const int c = (int)(i / R), r = (int)(i % R);
   out[i] = in[(long)r * Cc + c] * scale;
 }
 void launch_transpose_scale(const float* in, float* out, int R, int Cc, float scale, cudaStream_t st) {
-  k_transpose_scale<<<cdiv((long)R * Cc, 256), 256, 0, st>>>(in, out, R, Cc, scale);
+  launch_pdl(k_transpose_scale, dim3((unsigned)(cdiv((long)R * Cc, 256))), dim3(256), 0, st, in, out, R, Cc, scale);
 }
 
 // (B, C, T) -> (B, T, C)
 __global__ void k_bct_to_btc(const float* __restrict__ in, float* __restrict__ out, int B, int C, int T) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)B * C * T) return;
   const int c = (int)(i % C);
@@ -106,11 +110,12 @@ __global__ void k_bct_to_btc(const float* __restrict__ in, float* __restrict__ o
   out[i] = in[((long)b * C + c) * T + t];
 }
 void launch_bct_to_btc(const float* in, float* out, int B, int C, int T, cudaStream_t st) {
-  k_bct_to_btc<<<cdiv((long)B * C * T, 256), 256, 0, st>>>(in, out, B, C, T);
+  launch_pdl(k_bct_to_btc, dim3((unsigned)(cdiv((long)B * C * T, 256))), dim3(256), 0, st, in, out, B, C, T);
 }
 
 // VL rows of the style tokens (j >= 1) -> transposed split operand vlt[b][c][hi(KP)|lo(KP)] at column j
 __global__ void k_tv_vlt_pack(const float* __restrict__ vl, bf16* __restrict__ vlt, int B, int Ts, int C, int KP) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)B * Ts * C) return;
   const int j = (int)(i % Ts);
@@ -120,7 +125,7 @@ __global__ void k_tv_vlt_pack(const float* __restrict__ vl, bf16* __restrict__ v
   split2(vl[((long)b * Ts + j) * C + c], row[j + 1], row[KP + j + 1]);
 }
 void launch_tv_vlt_pack(const float* vl, bf16* vlt, int B, int Ts, int C, int KP, cudaStream_t st) {
-  k_tv_vlt_pack<<<cdiv((long)B * Ts * C, 256), 256, 0, st>>>(vl, vlt, B, Ts, C, KP);
+  launch_pdl(k_tv_vlt_pack, dim3((unsigned)(cdiv((long)B * Ts * C, 256))), dim3(256), 0, st, vl, vlt, B, Ts, C, KP);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@ namespace dexb {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_fill_zero(uint4* p, size_t n16) {
+  pdl_wait();
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
@@ -15,7 +16,7 @@ void launch_fill_zero(void* p, size_t bytes, cudaStream_t st) {
   int blocks = (int)((n16 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  k_fill_zero<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+  launch_pdl(k_fill_zero, dim3(blocks), dim3(256), 0, st, reinterpret_cast<uint4*>(p), n16);
 }
 
 __global__ void k_scale(float* x, long n, float s) {

@@ -81,6 +81,7 @@ __global__ void k_tiv_bn_fold(const float* __restrict__ g, const float* __restri
 // ref (B, c_in, T) channel-major, mask (B, T) -> split rows of ref * mask (columns >= c_in were zeroed by the caller)
 __global__ void k_tiv_in(const float* __restrict__ ref, const float* __restrict__ mask, bf16* __restrict__ xs, int B, int C, int T,
                          int K) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)B * C * T) return;
   const int t = (int)(i % T), c = (int)((i / T) % C), b = (int)(i / ((long)T * C));
@@ -97,6 +98,7 @@ __global__ void k_tiv_in(const float* __restrict__ ref, const float* __restrict_
 __global__ void k_tiv_bn_relu(const float* __restrict__ acc, const float* __restrict__ alpha, const float* __restrict__ beta,
                               const float* __restrict__ mask, bf16* __restrict__ os, float* __restrict__ of,
                               float* __restrict__ ocm, long rows, int C, int T) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long r = i / C;
@@ -119,6 +121,7 @@ __global__ void k_tiv_bn_relu(const float* __restrict__ acc, const float* __rest
 __global__ void __launch_bounds__(256) k_tiv_block_out(const float* __restrict__ acc, float* __restrict__ xf,
                                                        const float* __restrict__ mask, float* __restrict__ skip,
                                                        bf16* __restrict__ xs, int C, int T) {
+  pdl_wait();
   __shared__ float red[8][33];
   const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), tl = threadIdx.x >> 5;
   const long row0 = (long)b * T;
@@ -326,22 +329,22 @@ static int tiv_enqueue(dexb_tiv* h, const float* ref_dev, const float* mask_dev,
   h->launches = 0;
   // in_conv(ref * mask) * mask
   if (h->in_conv.K != h->c_in) DEXB_CUDA_OK(cudaMemsetAsync(h->xs, 0, rows * 2 * h->in_conv.K * sizeof(bf16), st));
-  k_tiv_in<<<cdiv(rows * h->c_in, 256), 256, 0, st>>>(ref_dev, mask_dev, h->xs, B, h->c_in, T, h->in_conv.K);
+  launch_pdl(k_tiv_in, dim3((unsigned)(cdiv(rows * h->c_in, 256))), dim3(256), 0, st, ref_dev, mask_dev, h->xs, B, h->c_in, T, h->in_conv.K);
   DEXB_TRY(gemm_launch(h->in_conv.plan, h->in_conv.plan.p, 0, st));
-  k_tiv_bn_relu<<<cdiv(rows * C, 256), 256, 0, st>>>(h->acc, h->in_conv.alpha, h->in_conv.beta, mask_dev, h->xs, h->xf, nullptr,
+  launch_pdl(k_tiv_bn_relu, dim3((unsigned)(cdiv(rows * C, 256))), dim3(256), 0, st, h->acc, h->in_conv.alpha, h->in_conv.beta, mask_dev, h->xs, h->xf, nullptr,
                                                      rows, C, T);
   h->launches += 3;
   for (int l = 0; l < h->L; ++l) {
     DEXB_TRY(gemm_launch(h->conv_a[l].plan, h->conv_a[l].plan.p, 0, st));
-    k_tiv_bn_relu<<<cdiv(rows * C, 256), 256, 0, st>>>(h->acc, h->conv_a[l].alpha, h->conv_a[l].beta, nullptr, h->hs, nullptr,
+    launch_pdl(k_tiv_bn_relu, dim3((unsigned)(cdiv(rows * C, 256))), dim3(256), 0, st, h->acc, h->conv_a[l].alpha, h->conv_a[l].beta, nullptr, h->hs, nullptr,
                                                        nullptr, rows, C, T);
     DEXB_TRY(gemm_launch(h->conv_b[l].plan, h->conv_b[l].plan.p, 0, st));
-    k_tiv_block_out<<<dim3(C / 32, B), 256, 0, st>>>(h->acc, h->xf, mask_dev, skips_dev[l], h->xs, C, T);
+    launch_pdl(k_tiv_block_out, dim3(C / 32, B), dim3(256), 0, st, h->acc, h->xf, mask_dev, skips_dev[l], h->xs, C, T);
     h->launches += 4;
   }
   if (out_dev != nullptr) {                 // `ref` output of TIVEncoder.forward (unused by DeXTTS.forward, tts.py:50)
     DEXB_TRY(gemm_launch(h->out_conv.plan, h->out_conv.plan.p, 0, st));
-    k_tiv_bn_relu<<<cdiv(rows * h->c_out, 256), 256, 0, st>>>(h->acc, h->out_conv.alpha, h->out_conv.beta, mask_dev, nullptr,
+    launch_pdl(k_tiv_bn_relu, dim3((unsigned)(cdiv(rows * h->c_out, 256))), dim3(256), 0, st, h->acc, h->out_conv.alpha, h->out_conv.beta, mask_dev, nullptr,
                                                               nullptr, out_dev, rows, h->c_out, T);
     h->launches += 2;
   }

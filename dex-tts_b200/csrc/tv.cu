@@ -112,6 +112,7 @@ __global__ void k_tv_bn_fold(const float* __restrict__ g, const float* __restric
 // sty (B, c_in, T) channel-major, mask (B, T) -> split rows of sty * mask (columns >= c_in zeroed by the caller)
 __global__ void k_tv_in(const float* __restrict__ x, const float* __restrict__ mask, bf16* __restrict__ xs, int B, int C, int T,
                         int K) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)B * C * T) return;
   const int t = (int)(i % T), c = (int)((i / T) % C), b = (int)(i / ((long)T * C));
@@ -125,6 +126,7 @@ __global__ void k_tv_in(const float* __restrict__ x, const float* __restrict__ m
 
 // one warp per row (frame): everything between two convolutions
 __global__ void __launch_bounds__(256) k_tv_post(const TvPost p) {
+  pdl_wait();
   const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (r >= p.rows) return;
   const int lane = threadIdx.x & 31;
@@ -189,6 +191,7 @@ constexpr int kVqRows = 4;
 __global__ void __launch_bounds__(256) k_tv_vq(const float* __restrict__ zf, const float* __restrict__ code,
                                                const float* __restrict__ mask, bf16* __restrict__ os, int* __restrict__ idx_out,
                                                double* __restrict__ loss_acc, long rows, int D, int M) {
+  pdl_wait();
   const long r0 = (blockIdx.x * 8L + (threadIdx.x >> 5)) * kVqRows;
   if (r0 >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256) k_tv_vq(const float* __restrict__ zf, con
   }
 }
 __global__ void k_tv_loss(const double* __restrict__ loss_acc, float* __restrict__ out, float commit_w, int D) {
+  pdl_wait();
   // commitment_cost * sum((x*m - q*m)^2) / (sum(m) * D)   (:223-224)
   out[0] = commit_w * (float)(loss_acc[0] / (loss_acc[1] * (double)D));
 }
@@ -384,7 +388,7 @@ static TvPost tv_post(const EncBase* h, const TvConv& c, int relu, int ln_mode, 
   p.C = c.co; p.T = h->T;
   return p;
 }
-static void tv_launch_post(const TvPost& p, cudaStream_t st) { k_tv_post<<<cdiv(p.rows, 8), 256, 0, st>>>(p); }
+static void tv_launch_post(const TvPost& p, cudaStream_t st) { launch_pdl(k_tv_post, dim3((unsigned)(cdiv(p.rows, 8))), dim3(256), 0, st, p); }
 
 }  // namespace dexb
 
@@ -473,7 +477,7 @@ static int tv_enqueue(dexb_tv* h, const float* sty_dev, const float* mask_dev, i
   // in_conv(sty * mask) * mask
   if (h->in_conv.K != h->c_in) DEXB_CUDA_OK(cudaMemsetAsync(h->xs, 0, rows * 2 * h->in_conv.K * sizeof(bf16), st));
   DEXB_CUDA_OK(cudaMemsetAsync(h->loss_acc, 0, 2 * sizeof(double), st));
-  k_tv_in<<<cdiv(rows * h->c_in, 256), 256, 0, st>>>(sty_dev, mask_dev, h->xs, B, h->c_in, T, h->in_conv.K);
+  launch_pdl(k_tv_in, dim3((unsigned)(cdiv(rows * h->c_in, 256))), dim3(256), 0, st, sty_dev, mask_dev, h->xs, B, h->c_in, T, h->in_conv.K);
   DEXB_TRY(gemm_launch(h->in_conv.plan, h->in_conv.plan.p, 0, st));
   {
     TvPost p = tv_post(h, h->in_conv, 1, 1, 1e-5f);
@@ -500,11 +504,11 @@ static int tv_enqueue(dexb_tv* h, const float* sty_dev, const float* mask_dev, i
     tv_launch_post(p, st);
   }
   // vector quantisation -> split operand of proj_0.conv_1, loss
-  k_tv_vq<<<cdiv(cdiv(rows, kVqRows), 8), 256, 0, st>>>(h->xf, h->codebook, mask_dev, h->xs, idx_dev, h->loss_acc, rows, h->c_out,
+  launch_pdl(k_tv_vq, dim3((unsigned)(cdiv(cdiv(rows, kVqRows), 8))), dim3(256), 0, st, h->xf, h->codebook, mask_dev, h->xs, idx_dev, h->loss_acc, rows, h->c_out,
                                                        h->n_emb);
   h->launches += 3;
   if (vq_loss_dev != nullptr) {
-    k_tv_loss<<<1, 1, 0, st>>>(h->loss_acc, vq_loss_dev, h->commit_w, h->c_out);
+    launch_pdl(k_tv_loss, dim3((unsigned)(1)), dim3(1), 0, st, h->loss_acc, vq_loss_dev, h->commit_w, h->c_out);
     h->launches += 1;
   }
   // proj_0: conv_1 -> relu -> norm_1 -> (mask) conv_2 -> relu -> norm_2 -> (mask) proj -> mask
@@ -603,6 +607,7 @@ namespace dexb {
 __global__ void __launch_bounds__(256) k_lf0_in(const float* __restrict__ lf0, const float* __restrict__ mask,
                                                 const float* __restrict__ w, const float* __restrict__ g,
                                                 const float* __restrict__ bta, bf16* __restrict__ os, long rows, int C, int T) {
+  pdl_wait();
   const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -651,6 +656,7 @@ __global__ void __launch_bounds__(3 * H) k_gru_rec(const float* __restrict__ gi,
                                                    const float* __restrict__ bhh_f, const float* __restrict__ whh_b,
                                                    const float* __restrict__ bhh_b, const float* __restrict__ omask,
                                                    bf16* __restrict__ os, int T) {
+  pdl_wait();
   __shared__ __align__(16) float h[H];
   __shared__ float gh[3 * H];
   const int b = blockIdx.x, dir = blockIdx.y, j = threadIdx.x;
@@ -698,6 +704,7 @@ __global__ void __launch_bounds__(3 * H) k_gru_rec(const float* __restrict__ gi,
 
 // rows [2][R][C] -> [2R][C] concatenation helper for the per-layer [forward | backward] input projection
 __global__ void k_cat2(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long na, long nb) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i < na) out[i] = a[i];
   else if (i < na + nb) out[i] = b[i - na];
@@ -706,6 +713,7 @@ __global__ void k_cat2(const float* __restrict__ a, const float* __restrict__ b,
 // time mean used by the fusion: out[b][c] (+)= sum_t x[b][c][t] / sum_t mask[b][t]   (x is already masked; tts.py:45,48)
 __global__ void __launch_bounds__(256) k_time_mean(const float* __restrict__ x, const float* __restrict__ mask,
                                                    float* __restrict__ out, int C, int T, int accumulate) {
+  pdl_wait();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;      // one warp per (b, c)
   const int b = blockIdx.y;
   if (w >= C) return;
@@ -724,6 +732,7 @@ __global__ void __launch_bounds__(256) k_time_mean(const float* __restrict__ x, 
 __global__ void __launch_bounds__(256) k_conv_sty(const float* __restrict__ z, const float* __restrict__ v,
                                                   const float* __restrict__ w, const float* __restrict__ bias,
                                                   float* __restrict__ out, int C, int N, int T) {
+  pdl_wait();
   extern __shared__ float zt[];                  // [C][33]
   const int b = blockIdx.y, t0 = blockIdx.x * 32, tt = threadIdx.x & 31, ng = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < C * 32; i += 256) {
@@ -851,8 +860,8 @@ int dexb_lf0_finalize_weights(dexb_lf0* h, void* stream) {
       DEXB_CUDA_OK(cudaMalloc(&h->ih_w[l], (size_t)6 * H * C * sizeof(float)));
       DEXB_CUDA_OK(cudaMalloc(&h->ih_b[l], (size_t)6 * H * sizeof(float)));
     }
-    k_cat2<<<cdiv(6L * H * C, 256), 256, 0, st>>>(wf, wb, h->ih_w[l], 3L * H * C, 3L * H * C);
-    k_cat2<<<cdiv(6L * H, 256), 256, 0, st>>>(bf, bb, h->ih_b[l], 3L * H, 3L * H);
+    launch_pdl(k_cat2, dim3((unsigned)(cdiv(6L * H * C, 256))), dim3(256), 0, st, wf, wb, h->ih_w[l], 3L * H * C, 3L * H * C);
+    launch_pdl(k_cat2, dim3((unsigned)(cdiv(6L * H, 256))), dim3(256), 0, st, bf, bb, h->ih_b[l], 3L * H, 3L * H);
     TvConv& c = h->ih[l];
     c.ci = C; c.co = 6 * H; c.K = tv_pad64(C); c.taps = 1;
     if (c.w == nullptr) DEXB_CUDA_OK(cudaMalloc(&c.w, (size_t)c.co * 2 * c.K * sizeof(bf16)));
@@ -878,14 +887,14 @@ static int lf0_enqueue(dexb_lf0* h, const float* lf0_dev, const float* mask_dev,
                        cudaStream_t st) {
   const long rows = (long)B * T;
   h->launches = 0;
-  k_lf0_in<<<cdiv(rows, 8), 256, 0, st>>>(lf0_dev, mask_dev, h->in_w, h->in_g, h->in_b, h->xs, rows, h->c_h, T);
+  launch_pdl(k_lf0_in, dim3((unsigned)(cdiv(rows, 8))), dim3(256), 0, st, lf0_dev, mask_dev, h->in_w, h->in_g, h->in_b, h->xs, rows, h->c_h, T);
   h->launches += 1;
   for (int l = 0; l < h->L; ++l) {
     bf16* dst = (l & 1) ? h->xs : h->hs;
     DEXB_TRY(gemm_launch(h->ih[l].plan, h->ih[l].plan.p, 0, st));
-    if (h->c_h == 192) k_gru_rec<96><<<dim3(B, 2), 3 * 96, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
+    if (h->c_h == 192) launch_pdl(k_gru_rec<96>, dim3(B, 2), dim3(3 * 96), 0, st, h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
                                                  l == h->L - 1 ? mask_dev : nullptr, dst, T);
-    else k_gru_rec<128><<<dim3(B, 2), 3 * 128, 0, st>>>(h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
+    else launch_pdl(k_gru_rec<128>, dim3(B, 2), dim3(3 * 128), 0, st, h->gi, h->hh_w[0][l], h->hh_b[0][l], h->hh_w[1][l], h->hh_b[1][l],
                                                  l == h->L - 1 ? mask_dev : nullptr, dst, T);
     h->launches += 2;
   }
@@ -964,11 +973,11 @@ int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const flo
   cudaStream_t st = (cudaStream_t)stream;
   if (sty_enc_dev != nullptr) {                 // text-encoder conditioning (tts.py:45-46): both masked time means added
     DEXB_CHECK(z_before_dev != nullptr && sty_mask_dev != nullptr && lf0_enc_dev != nullptr, "dexb_style_fuse: sty_enc needs its inputs");
-    k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(z_before_dev, sty_mask_dev, sty_enc_dev, C, Ts, 0);
-    k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(lf0_enc_dev, lf0_mask_dev, sty_enc_dev, C, Tl, 1);
+    launch_pdl(k_time_mean, dim3(cdiv(C, 8), B), dim3(256), 0, st, z_before_dev, sty_mask_dev, sty_enc_dev, C, Ts, 0);
+    launch_pdl(k_time_mean, dim3(cdiv(C, 8), B), dim3(256), 0, st, lf0_enc_dev, lf0_mask_dev, sty_enc_dev, C, Tl, 1);
   }
-  k_time_mean<<<dim3(cdiv(C, 8), B), 256, 0, st>>>(lf0_dec_dev, lf0_mask_dev, lf0_mean_scratch_dev, C, Tl, 0);
-  k_conv_sty<<<dim3(cdiv(Ts, 32), B), 256, (size_t)C * 33 * sizeof(float), st>>>(z_dec_dev, lf0_mean_scratch_dev, conv_sty_w_dev,
+  launch_pdl(k_time_mean, dim3(cdiv(C, 8), B), dim3(256), 0, st, lf0_dec_dev, lf0_mask_dev, lf0_mean_scratch_dev, C, Tl, 0);
+  launch_pdl(k_conv_sty, dim3(cdiv(Ts, 32), B), dim3(256), (size_t)C * 33 * sizeof(float), st, z_dec_dev, lf0_mean_scratch_dev, conv_sty_w_dev,
                                                                                  conv_sty_b_dev, sty_dev, C, N, Ts);
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1037,6 +1046,7 @@ struct TxtRow {
 // Ids outside [0, n_vocab) are clamped (upstream raises an IndexError on the host; a device kernel cannot).
 __global__ void k_txt_embed(const long long* __restrict__ ids, const float* __restrict__ emb, const float* __restrict__ mask,
                             float* __restrict__ x0, bf16* __restrict__ xs, long rows, int C, int n_vocab, float scale) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long r = i / C;
@@ -1055,6 +1065,7 @@ __global__ void k_txt_embed(const long long* __restrict__ ids, const float* __re
 // repeats it over all Tx positions) -> the residual stream rows [C0 + S]
 __global__ void k_txt_cat_spk(const float* __restrict__ x, const float* __restrict__ spk, float* __restrict__ out, long rows, int C0, int S,
                               int T) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int C = C0 + S;
   if (i >= rows * C) return;
@@ -1065,6 +1076,7 @@ __global__ void k_txt_cat_spk(const float* __restrict__ x, const float* __restri
 
 // one warp per token: everything between two GEMMs of the text encoder
 __global__ void __launch_bounds__(256) k_txt_row(const TxtRow p) {
+  pdl_wait();
   const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (r >= p.rows) return;
   const int lane = threadIdx.x & 31;
@@ -1149,6 +1161,7 @@ __global__ void __launch_bounds__(256) k_txt_row(const TxtRow p) {
 // AdaLN scale / bias of every layer for this batch: out[m][b][c] = W[m][c][:] . sty[b][:] + bias[m][c]  (base.py:189-190); one warp each
 __global__ void __launch_bounds__(256) k_txt_ada(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ sty,
                                                  float* __restrict__ out, int M, int B, int C) {
+  pdl_wait();
   const long wid = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (wid >= (long)M * B * C) return;
   const int lane = threadIdx.x & 31;
@@ -1166,6 +1179,7 @@ __global__ void __launch_bounds__(256) k_txt_ada(const float* __restrict__ W, co
 // sin / cos(t * angle[i]), angle repeated per pair (retention.py:75-76, 140-142).  One thread per (token, channel pair).
 __global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ angle, long rows, int C, int d, int T,
                            float scaling) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int half = C / 2;
   if (i >= rows * half) return;
@@ -1190,6 +1204,7 @@ __global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const f
 __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                   const float* __restrict__ g, const float* __restrict__ mask, bf16* __restrict__ os,
                                                   int B, int T, int C, int heads) {
+  pdl_wait();
   const long wid = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (wid >= (long)B * heads * T) return;
   const int lane = threadIdx.x & 31;
@@ -1246,6 +1261,7 @@ __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, c
 
 // GLU.forward (retention.py:371-381): gelu(fc1 x) * gate x (exact gelu) -> split rows [rows][hi(F)|lo(F)], the operand of fc2
 __global__ void k_txt_glu(const float* __restrict__ a, const float* __restrict__ gate, bf16* __restrict__ os, long rows, int F) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= rows * F) return;
   const long r = i / F;
@@ -1261,6 +1277,7 @@ __global__ void k_txt_glu(const float* __restrict__ a, const float* __restrict__
 // DurationPredictor.proj (text_encoder.py:94-95): Conv1d(Fd, 1, 1) of the masked rows, * mask; one warp per token
 __global__ void __launch_bounds__(256) k_txt_dp_out(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                     const float* __restrict__ mask, float* __restrict__ logw, long rows, int C) {
+  pdl_wait();
   const long r = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -1343,7 +1360,7 @@ static TxtRow txt_row(const dexb_text* h, const float* in, int C = 0) {
   p.C = C > 0 ? C : h->C; p.T = h->T;
   return p;
 }
-static void txt_launch_row(const TxtRow& p, cudaStream_t st) { k_txt_row<<<cdiv(p.rows, 8), 256, 0, st>>>(p); }
+static void txt_launch_row(const TxtRow& p, cudaStream_t st) { launch_pdl(k_txt_row, dim3((unsigned)(cdiv(p.rows, 8))), dim3(256), 0, st, p); }
 
 }  // namespace dexb
 
@@ -1478,10 +1495,10 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
   const long rows = (long)B * T;
   h->launches = 0;
   if (h->adaln) {
-    k_txt_ada<<<cdiv((long)h->L * 4 * B * C, 8), 256, 0, st>>>(h->adaW, h->adaB, sty_dev, h->ada, h->L * 4, B, C);
+    launch_pdl(k_txt_ada, dim3((unsigned)(cdiv((long)h->L * 4 * B * C, 8))), dim3(256), 0, st, h->adaW, h->adaB, sty_dev, h->ada, h->L * 4, B, C);
     h->launches += 1;
   }
-  k_txt_embed<<<cdiv(rows * C0, 256), 256, 0, st>>>(reinterpret_cast<const long long*>(ids_dev), h->emb, mask_dev, h->x0f, h->xs, rows, C0,
+  launch_pdl(k_txt_embed, dim3((unsigned)(cdiv(rows * C0, 256))), dim3(256), 0, st, reinterpret_cast<const long long*>(ids_dev), h->emb, mask_dev, h->x0f, h->xs, rows, C0,
                                                    h->n_vocab, (float)sqrt((double)C0));
   h->launches += 1;
   // prenet: 3 x (conv5 -> channel LayerNorm -> ReLU), input masked before every conv; then (x + proj(.)) * mask
@@ -1500,7 +1517,7 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
     p.of2 = h->spk_dim > 0 ? h->qf : h->hf;                            // (x + proj(x)) * mask: the residual stream (its first C0 channels)
     txt_launch_row(p, st);
     if (h->spk_dim > 0) {
-      k_txt_cat_spk<<<cdiv(rows * C, 256), 256, 0, st>>>(h->qf, spk_dev, h->hf, rows, C0, h->spk_dim, T);
+      launch_pdl(k_txt_cat_spk, dim3((unsigned)(cdiv(rows * C, 256))), dim3(256), 0, st, h->qf, spk_dev, h->hf, rows, C0, h->spk_dim, T);
       h->launches += 1;
     }
     TxtRow n = txt_row(h, h->hf);
@@ -1516,8 +1533,8 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
     DEXB_TRY(gemm_launch(ly.k.plan, ly.k.plan.p, 0, st));
     DEXB_TRY(gemm_launch(ly.v.plan, ly.v.plan.p, 0, st));
     DEXB_TRY(gemm_launch(ly.g.plan, ly.g.plan.p, 0, st));
-    k_txt_rope<<<cdiv(rows * (C / 2), 256), 256, 0, st>>>(h->qf, h->kf, h->angle, rows, C, d, T, 1.f / sqrtf((float)d));
-    k_txt_attn<<<cdiv((long)B * h->heads * T, 8), 256, 0, st>>>(h->qf, h->kf, h->vf, h->gf, mask_dev, h->hs, B, T, C, h->heads);
+    launch_pdl(k_txt_rope, dim3((unsigned)(cdiv(rows * (C / 2), 256))), dim3(256), 0, st, h->qf, h->kf, h->angle, rows, C, d, T, 1.f / sqrtf((float)d));
+    launch_pdl(k_txt_attn, dim3((unsigned)(cdiv((long)B * h->heads * T, 8))), dim3(256), 0, st, h->qf, h->kf, h->vf, h->gf, mask_dev, h->hs, B, T, C, h->heads);
     DEXB_TRY(gemm_launch(ly.o.plan, ly.o.plan.p, 0, st));
     {
       TxtRow p = txt_row(h, h->acc);                                   // h = adaln_1(h + out_proj(.)); operand = rms(h) * w
@@ -1531,7 +1548,7 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
     }
     DEXB_TRY(gemm_launch(ly.fc1.plan, ly.fc1.plan.p, 0, st));
     DEXB_TRY(gemm_launch(ly.gate.plan, ly.gate.plan.p, 0, st));
-    k_txt_glu<<<cdiv(rows * h->Fc, 256), 256, 0, st>>>(h->f1, h->f2, h->hs, rows, h->Fc);
+    launch_pdl(k_txt_glu, dim3((unsigned)(cdiv(rows * h->Fc, 256))), dim3(256), 0, st, h->f1, h->f2, h->hs, rows, h->Fc);
     DEXB_TRY(gemm_launch(ly.fc2.plan, ly.fc2.plan.p, 0, st));
     {
       const bool last = l == h->L - 1;
@@ -1573,7 +1590,7 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
     p.mask = mask_dev; p.of = h->xf;
     tv_launch_post(p, st);
   }
-  k_txt_dp_out<<<cdiv(rows, 8), 256, 0, st>>>(h->xf, h->dpw, h->dpb, mask_dev, logw_dev, rows, h->Fd);
+  launch_pdl(k_txt_dp_out, dim3((unsigned)(cdiv(rows, 8))), dim3(256), 0, st, h->xf, h->dpw, h->dpb, mask_dev, logw_dev, rows, h->Fd);
   h->launches += 7;
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;

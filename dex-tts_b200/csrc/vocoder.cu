@@ -126,6 +126,7 @@ __global__ void k_voc_pack_post(const float* __restrict__ w, float* __restrict__
 // ---- activations ---------------------------------------------------------------------------------------------------------------
 // mel (B, C, T) channel-major -> split rows [B*T][hi(K)|lo(K)] (columns >= C stay zero: the buffer is cleared once per plan)
 __global__ void k_voc_in(const float* __restrict__ mel, bf16* __restrict__ xs, int B, int C, int T, int K) {
+  pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= (long)B * C * T) return;
   const int t = (int)(i % T), c = (int)((i / T) % C), b = (int)(i / ((long)T * C));
@@ -138,6 +139,7 @@ __global__ void k_voc_in(const float* __restrict__ mel, bf16* __restrict__ xs, i
 // x = (a + b + c) / 3 (models.py:163-168, in that order), y = leaky_relu(x, slope) -> split rows [rows][hi(K)|lo(K)] and / or fp32 rows
 __global__ void k_voc_avg3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, bf16* __restrict__ os,
                            float* __restrict__ of, long rows, int C, int K, float slope) {
+  pdl_wait();
   const long i = (blockIdx.x * (long)blockDim.x + threadIdx.x) * 4;
   if (i >= rows * C) return;
   const float4 va = *reinterpret_cast<const float4*>(a + i), vb = *reinterpret_cast<const float4*>(b + i),
@@ -161,6 +163,7 @@ __global__ void k_voc_avg3(const float* __restrict__ a, const float* __restrict_
 template <int C>
 __global__ void __launch_bounds__(256) k_voc_post(const float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias,
                                                   float* __restrict__ wav, int B, int L) {
+  pdl_wait();
   __shared__ float ws[7 * C];
   for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
   __syncthreads();
@@ -334,7 +337,7 @@ static int voc_plan(dexb_voc* h, int B, int T) {
 static int voc_enqueue(dexb_voc* h, cudaStream_t st) {
   const int B = h->B, T = h->T;
   h->launches = 0;
-  k_voc_in<<<cdiv((long)B * h->n_mels * T, 256), 256, 0, st>>>(h->mel_in, h->mel_s, B, h->n_mels, T, vpad64(h->n_mels));
+  launch_pdl(k_voc_in, dim3((unsigned)(cdiv((long)B * h->n_mels * T, 256))), dim3(256), 0, st, h->mel_in, h->mel_s, B, h->n_mels, T, vpad64(h->n_mels));
   DEXB_TRY(gemm_launch(h->pre.plan, h->pre.plan.p, 0, st));
   h->launches += 2;
   long L = T;
@@ -351,11 +354,11 @@ static int voc_enqueue(dexb_voc* h, cudaStream_t st) {
       }
     const long rows = (long)B * L;
     const bool last = i + 1 == kVocStages;
-    k_voc_avg3<<<cdiv(rows * ch / 4, 256), 256, 0, st>>>(h->xr[i][0], h->xr[i][1], h->xr[i][2], last ? nullptr : h->nxt_s[i],
+    launch_pdl(k_voc_avg3, dim3((unsigned)(cdiv(rows * ch / 4, 256))), dim3(256), 0, st, h->xr[i][0], h->xr[i][1], h->xr[i][2], last ? nullptr : h->nxt_s[i],
                                                          last ? h->yfin : nullptr, rows, ch, vpad64(ch), last ? 0.01f : 0.1f);
     ++h->launches;
   }
-  k_voc_post<32><<<cdiv((long)B * L, 256), 256, 0, st>>>(h->yfin, h->post_w, h->post_b, h->wav_out, B, (int)L);
+  launch_pdl(k_voc_post<32>, dim3((unsigned)(cdiv((long)B * L, 256))), dim3(256), 0, st, h->yfin, h->post_w, h->post_b, h->wav_out, B, (int)L);
   ++h->launches;
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;
