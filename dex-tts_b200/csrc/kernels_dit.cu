@@ -207,25 +207,31 @@ __device__ __forceinline__ void ln_mod_row(float (&v)[PER_LANE], const float* sh
   }
 }
 
+// Two tokens per warp: the pass is latency-bound (one load round trip, two dependent warp reductions, one store per token and ~2 waves of
+// warps per SM), so a warp carries two independent chains.
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) k_ln_mod(const float* __restrict__ x, const float* __restrict__ shift,
                                                 const float* __restrict__ scale, SView out, long M, int D) {
   pdl_wait();
-  const long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+  const long row = ((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5) * 2;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  float v[PER_LANE];
+  const bool two = row + 1 < M;
+  float v[PER_LANE], u[PER_LANE];
   const float* xp = x + row * D;
 #pragma unroll
   for (int g = 0; g < PER_LANE; g += 4) {
     const float4 t = *reinterpret_cast<const float4*>(xp + (g / 4) * 128 + lane * 4);
     v[g] = t.x; v[g + 1] = t.y; v[g + 2] = t.z; v[g + 3] = t.w;
+    const float4 t2 = two ? *reinterpret_cast<const float4*>(xp + D + (g / 4) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    u[g] = t2.x; u[g + 1] = t2.y; u[g + 2] = t2.z; u[g + 3] = t2.w;
   }
   ln_mod_row<PER_LANE>(v, shift, scale, out.p + row * out.stride, out.hi, out.lo, lane, D);
+  if (two) ln_mod_row<PER_LANE>(u, shift, scale, out.p + (row + 1) * out.stride, out.hi, out.lo, lane, D);
 }
 void launch_ln_mod(const float* x, const float* shift, const float* scale, SView out, long M, int D, cudaStream_t st) {
-  if (D == 256) launch_pdl(k_ln_mod<8>, dim3(cdiv(M * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
-  else if (D == 384) launch_pdl(k_ln_mod<12>, dim3(cdiv(M * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
+  if (D == 256) launch_pdl(k_ln_mod<8>, dim3(cdiv(cdiv(M, 2) * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
+  else if (D == 384) launch_pdl(k_ln_mod<12>, dim3(cdiv(cdiv(M, 2) * 32, 256)), dim3(256), 0, st, x, shift, scale, out, M, D);
 }
 
 // pe[b][w][c] = mean over the frequency rows of pg[b][h][w][c] (dit.py:445), summed in a fixed order.  One thread = 4 channels.
