@@ -244,6 +244,12 @@ int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, in
   p.nsplit = nsplit; p.dbg = dbg & 7;
   p.epi.dbg_nostore = (dbg >> 3) & 1;
   if (out_mode & 2) p.epi.act = 1;
+  double* gstats = nullptr;
+  if (out_mode & 4) {                                       // GroupNorm(8, N) sums in the epilogue, as the U-Net convolutions carry them
+    DEXB_CUDA_OK(cudaMalloc(&gstats, (size_t)nimg * 16 * kGnRep * sizeof(double)));
+    DEXB_CUDA_OK(cudaMemset(gstats, 0, (size_t)nimg * 16 * kGnRep * sizeof(double)));
+    p.epi.gn_stats = gstats; p.epi.gn_gs = N / 8;
+  }
   out_mode &= 1;
   p.epi.alpha = 1.f; p.epi.bias = bias; p.epi.out_s_ncols = 1 << 30;
   if (out_mode == 0) { p.epi.out_f32 = (float*)out; p.epi.out_f32_stride = N; }
@@ -270,7 +276,7 @@ int dexb_gemm_bench(int nsplit, int nimg, int H, int W, int K, int N, int KH, in
   cudaEventElapsedTime(&ms, e0, e1);
   *ms_out = ms / iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cudaFree(as); cudaFree(ws); cudaFree(bias); cudaFree(out);
+  cudaFree(as); cudaFree(ws); cudaFree(bias); cudaFree(out); cudaFree(gstats);
   if (r != 0) return r;
   DEXB_CHECK(e == cudaSuccess, "gemm_bench: kernel failed: %s", cudaGetErrorString(e));
   return 0;

@@ -399,7 +399,7 @@ static int plan_block_conv(dexb_handle* h, BlockW& b, const bf16* in, long in_st
   gp_taps(p, 3, 3, -1, -1);
   p.epi.bias = b.bias;
   gp_out_f(p, raw, b.co);
-  p.epi.gn_stats = h->gn_stats + (long)b.slot * h->B * 16;
+  p.epi.gn_stats = h->gn_stats + (long)b.slot * h->B * 16 * kGnRep;
   p.epi.gn_gs = b.co / 8;
   return plan_shared(&b.conv, p);
 }
@@ -450,7 +450,7 @@ static int layout_ws(dexb_handle* h, Arena& ar) {
   }
   // per-step zeroed region
   const size_t z0 = (ar.off + 1023) & ~(size_t)1023;
-  h->gn_stats = ar.get<double>((long)h->n_slots * B * 16);
+  h->gn_stats = ar.get<double>((long)h->n_slots * B * 16 * kGnRep);
   h->gn_done = ar.get<unsigned>((long)h->n_slots * B);
   h->cstats = ar.get<double>(2L * B * mid * 2);
   LinAttW* las[3] = {&h->la0, &h->la1, &h->la2};
@@ -888,7 +888,7 @@ static GnApplyArgs gn_args(dexb_handle* h, const BlockW& b, const float* raw, in
   GnApplyArgs a;
   memset(&a, 0, sizeof(a));
   a.raw = raw; a.C = b.co; a.G = 8;
-  a.stats = h->gn_stats + (long)b.slot * h->B * 16;
+  a.stats = h->gn_stats + (long)b.slot * h->B * 16 * kGnRep;
   a.gamma = b.gamma; a.beta = b.beta;
   a.B = h->B; a.P = P; a.W = W;
   a.mask = mask; a.mask_stride = W;
@@ -924,7 +924,7 @@ static int run_resnet(dexb_handle* h, ResnetW& r, int step, int H, int W, const 
     a.tbias = r.tbias + (long)step * r.co;
     if (first) {
       LAUNCH(launch_conv_in(h->x, h->mu, h->cin == 3 ? h->spk_s : nullptr, mask, h->tab, step, h->conv_in_w, h->conv_in_b, raw,
-                            h->gn_stats + (long)r.b1.slot * h->B * 16, h->B, H, W, r.co, st));
+                            h->gn_stats + (long)r.b1.slot * h->B * 16 * kGnRep, h->B, H, W, r.co, st));
       LAUNCH(launch_gn_apply(a, st));
     } else {
       GEMM_GN(r.b1.conv, r.b1.conv.p, a, r.b1.slot);
@@ -1051,7 +1051,7 @@ static int run_step(dexb_handle* h, int step, float* den_out, cudaStream_t st) {
   DEXB_TRY(run_la(h, h->la2, P1, st));                                  // C1 -> A1 (masked)
   for (int ph = 0; ph < 4; ++ph) GEMM(h->g_up[ph], h->g_up[ph].p);      // A1 -> A0 (masked)
   GEMM(h->fin.conv, h->fin.conv.p);
-  LAUNCH(launch_gn_final(h->raw0, d, 8, h->gn_stats + (long)h->fin.slot * B * 16, h->fin.gamma, h->fin.beta, h->fc_w, h->fc_b,
+  LAUNCH(launch_gn_final(h->raw0, d, 8, h->gn_stats + (long)h->fin.slot * B * 16 * kGnRep, h->fin.gamma, h->fin.beta, h->fc_w, h->fc_b,
                          h->mask0, h->x, den_out, h->tab, step, B, H0, W0, st));
   DEXB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -133,7 +133,7 @@ struct dexb_handle {
   // per-step zeroed region
   char* zero_base = nullptr;
   size_t zero_bytes = 0;
-  double* gn_stats = nullptr;          // [slots][B][8][2]
+  double* gn_stats = nullptr;          // [slots][B][kGnRep][8][2]
   int gn_reverse = 1;                  // stand-alone GroupNorm-apply walks the images backwards (DEXB_GN_REVERSE)
   int gn_lag = 2, gn_mode = 0;         // tuning aids of the fused GroupNorm-apply (DEXB_GN_LAG / DEXB_GN_MODE)
   unsigned* gn_done = nullptr;         // [slots][B] tiles of an image whose raw rows + sums are published (fused GroupNorm-apply)

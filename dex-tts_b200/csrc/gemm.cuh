@@ -169,7 +169,7 @@ __device__ __forceinline__ void epi_apply(const EpiParams& e, int N, int z, int 
       s = warp_sum(s);
       ss = warp_sum(ss);
       if ((threadIdx.x & 31) == 0 && n0 + g0 < N) {
-        double* dst = e.gn_stats + ((long)img * (N / gs) + (n0 + g0) / gs) * 2;
+        double* dst = e.gn_stats + (((long)img * kGnRep + (blockIdx.x & (kGnRep - 1))) * (N / gs) + (n0 + g0) / gs) * 2;
         atomicAdd(dst, (double)s);
         atomicAdd(dst + 1, (double)ss);
       }
@@ -291,7 +291,7 @@ __device__ __forceinline__ void epi_flush_gn(const EpiParams& e, int N, int img,
       gacc[k][g * 2] = 0.f;
       gacc[k][g * 2 + 1] = 0.f;
       if ((threadIdx.x & 31) == 0 && n0 + g * 8 < N) {
-        double* dst = e.gn_stats + ((long)img * (N / gs) + (n0 + g * 8) / gs) * 2;
+        double* dst = e.gn_stats + (((long)img * kGnRep + (blockIdx.x & (kGnRep - 1))) * (N / gs) + (n0 + g * 8) / gs) * 2;
         atomicAdd(dst, (double)s);
         atomicAdd(dst + 1, (double)ss);
       }

@@ -6,6 +6,11 @@
 
 namespace dexb {
 
+// GroupNorm sums are accumulated into kGnRep replicas per (image, group), picked by the writing CTA's index, and summed by the readers:
+// all CTAs of a convolution leave an image at about the same time, and 592 double atomics per address and image change (148 CTAs x 4
+// lane-group warps) serialised in L2 -- the sums cost the 64-channel convolution 21 us of 79 (tools/pair_bench.py, out_mode 4).
+constexpr int kGnRep = 8;
+
 struct EpiParams {
   float alpha;                 // acc *= alpha (before bias)
   const float* bias;           // bias[z * bias_zstride + head * bias_head_stride + n] or null
@@ -37,7 +42,7 @@ struct EpiParams {
   int out_vt_lo;               // lo offset inside a row
   int out_vt_hd;               // head dim: column (n - out_s_ncols) -> head = /hd, d = %hd
   int out_vt_heads;
-  double* gn_stats;            // [img][N/gs][2] (sum, sumsq) accumulated with atomics, or null
+  double* gn_stats;            // [img][kGnRep][N/gs][2] (sum, sumsq) accumulated with atomics, or null
   int gn_gs;                   // channels per group (8 or 16)
   float* colmean;              // atomicAdd(colmean[(img*OW + ow)*colmean_ld + col], v * colmean_scale), or null
   float colmean_scale;

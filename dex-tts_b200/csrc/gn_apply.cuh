@@ -6,6 +6,7 @@
 //     images ago), so the stand-alone pass and its HBM read disappear.
 #pragma once
 #include "common.cuh"
+#include "gemm_host.cuh"
 
 namespace dexb {
 
@@ -22,7 +23,7 @@ struct SView {            // a split-bf16 tensor view: element (row, c) hi at p[
 
 struct GnApplyArgs {
   const float* raw; int C; int G;          // F[M][C]
-  const double* stats;                      // [B][G][2]
+  const double* stats;                      // [B][kGnRep][G][2]
   const float* gamma; const float* beta;
   int B, P, W;                              // P pixels per image, W image width (mask column = pixel % W)
   const float* mask; long mask_stride;      // [B][W]
@@ -66,8 +67,13 @@ __device__ __forceinline__ float mish_fast(float x) {
 template <bool L2 = false>
 __device__ __forceinline__ void gn_thread_stats(const double* __restrict__ stats, int G, double inv_n, int b, int g, float& mean,
                                                 float& rstd) {
-  const double2* sp = reinterpret_cast<const double2*>(stats + ((long)b * G + g) * 2);
-  const double2 s = L2 ? __ldcg(sp) : *sp;
+  const double2* sp = reinterpret_cast<const double2*>(stats + ((long)b * kGnRep * G + g) * 2);
+  double2 s = make_double2(0., 0.);
+#pragma unroll
+  for (int r = 0; r < kGnRep; ++r) {                         // the writers spread their atomics over kGnRep replicas (gemm_host.cuh)
+    const double2 t = L2 ? __ldcg(sp + (long)r * G) : sp[(long)r * G];
+    s.x += t.x; s.y += t.y;
+  }
   const double mean_d = s.x * inv_n;
   double var_d = s.y * inv_n - mean_d * mean_d;
   if (var_d < 0.) var_d = 0.;

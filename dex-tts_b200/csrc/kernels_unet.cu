@@ -125,15 +125,16 @@ __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, co
     double ds = 0., dss = 0.;
     for (int wq = 0; wq < 8; ++wq)
       for (int o = 0; o < OCTS / 8; ++o) { ds += red[wq][g * (OCTS / 8) + o][0]; dss += red[wq][g * (OCTS / 8) + o][1]; }
-    atomicAdd(&stats[((long)b * 8 + g) * 2], ds);
-    atomicAdd(&stats[((long)b * 8 + g) * 2 + 1], dss);
+    double* dst = stats + (((long)b * kGnRep + ((blockIdx.x + blockIdx.y) & (kGnRep - 1))) * 8 + g) * 2;
+    atomicAdd(dst, ds);
+    atomicAdd(dst + 1, dss);
   }
 }
 
 void launch_conv_in(const float* x, const float* mu, const float* spk_s, const float* mask, const StepScalars* tab, int step,
                     const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
                     cudaStream_t st) {
-  // stats layout is [B][8 groups][2]; C = decoder.dim in {64, 128} (engine_finalize rejects other widths)
+  // stats layout is [B][kGnRep][8 groups][2]; C = decoder.dim in {64, 128} (engine_finalize rejects other widths)
   if (C == 64) {
     dim3 grid(cdiv(W, 128), H, B);
     if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);

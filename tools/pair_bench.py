@@ -11,6 +11,7 @@ import torch  # noqa: E402,F401
 from dexb200 import lib as _lib  # noqa: E402
 
 L = _lib.load()
+OUT_MODE = int(os.environ.get('PAIR_BENCH_OUT_MODE', '0'))       # 4 = with GroupNorm sums in the epilogue
 torch.zeros(1).cuda()
 SHAPES = {
     "conv L0 64->64": (8, 80, 512, 64, 64),
@@ -26,6 +27,6 @@ for name, (nimg, H, W, K, N) in SHAPES.items():
     best = 1e9
     for _ in range(3):
         ms = ctypes.c_float(0)
-        _lib.check(L.dexb_gemm_bench(3, nimg, H, W, K, N, 3, 3, -1, -1, 1, 0, 0, 20, ctypes.byref(ms)), "gemm_bench")
+        _lib.check(L.dexb_gemm_bench(3, nimg, H, W, K, N, 3, 3, -1, -1, 1, OUT_MODE, 0, 20, ctypes.byref(ms)), "gemm_bench")
         best = min(best, ms.value)
-    print(f"DEXB_PAIR={os.environ.get('DEXB_PAIR', '1')}  {name:24s} {best*1e3:7.1f} us ({flop/best*1e-9:6.1f} TFLOP/s)")
+    print(f"DEXB_PAIR={os.environ.get('DEXB_PAIR', '1')} out_mode={OUT_MODE}  {name:24s} {best*1e3:7.1f} us ({flop/best*1e-9:6.1f} TFLOP/s)")
