@@ -227,7 +227,7 @@ void launch_gn_apply(const GnApplyArgs& a, cudaStream_t st) {
 // 8 lanes per pixel (C == 64).
 // ------------------------------------------------------------------------------------------------
 template <int ITEMS>
-__global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ raw, int C, int G,
+__global__ void __launch_bounds__(256, 3) k_gn_final(const float* __restrict__ raw, int C, int G,
                                                   const double* __restrict__ stats, const float* __restrict__ gamma,
                                                   const float* __restrict__ beta, const float* __restrict__ fc_w,
                                                   const float* __restrict__ fc_b, const float* __restrict__ mask,
@@ -246,6 +246,9 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
 #pragma unroll
   for (int i = 0; i < 8; ++i) { ga[i] = gamma[c0 + i]; be[i] = beta[c0 + i]; fw[i] = fc_w[c0 + i]; }
   const long img_row0 = (long)b * P;
+  float mean, rstd;                                          // (before the item loads: the replica sums need registers of their own)
+  gn_thread_stats(stats, G, 1.0 / ((double)P * (C / G)), b, g, mean, rstd);
+  gn_thread_scale(rstd, ga);
   float4 r0[ITEMS], r1[ITEMS];
   float xin[ITEMS];
 #pragma unroll
@@ -258,9 +261,6 @@ __global__ void __launch_bounds__(256, 4) k_gn_final(const float* __restrict__ r
   }
   const StepScalars sc = tab[step];
   const float fcb = fc_b[0];
-  float mean, rstd;
-  gn_thread_stats(stats, G, 1.0 / ((double)P * (C / G)), b, g, mean, rstd);
-  gn_thread_scale(rstd, ga);
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     const unsigned gi = base + j * 256 + threadIdx.x;
