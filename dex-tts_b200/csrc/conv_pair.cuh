@@ -94,8 +94,36 @@ __device__ __forceinline__ void mma2_commit(uint64_t* bar) {
 // dx taps -- one `full` wait, 24 MMAs and ONE multicast commit per round in the issuing thread (a multicast commit is not free: with one
 // commit per weight tile plus one per slab the 64-channel convolutions were 12-18 % slower than with this scheme).
 __host__ __device__ constexpr int cp_round_bytes(int block_n) { return 2 * kTcHaloSlab + 3 * block_n * kTcBlockK * 2; }
-__host__ __device__ constexpr int cp_slots(int block_n) { return (kTcSmemMax - 1024 - 512) / cp_round_bytes(block_n); }
-__host__ __device__ constexpr int cp_smem_bytes(int block_n) { return cp_slots(block_n) * cp_round_bytes(block_n) + 1024 + 512; }
+__host__ __device__ constexpr int cp_slots(int block_n) { return (kTcSmemMax - 1024 - 1024) / cp_round_bytes(block_n); }
+// + 1024 alignment slack + 1024: barriers (256 B) and the GroupNorm reduction scratch (16 warps x up to 8 floats)
+__host__ __device__ constexpr int cp_smem_bytes(int block_n) { return cp_slots(block_n) * cp_round_bytes(block_n) + 1024 + 1024; }
+
+// Deferred GroupNorm sums of a CTA leaving image `img`: warp sums -> shared memory -> the four lane-group warps of a column chunk are
+// added by one of them -> one double atomic per (CTA, 8-column group, sum | sum of squares): 16 / 32 instead of 64 / 128 per CTA.
+// (All CTAs leave an image at about the same time; the atomics on its 8 x 2 x kGnRep addresses serialise in L2.)  Called by all 16
+// epilogue warps at the same tile.
+template <int MAXCH>
+__device__ __forceinline__ void cp_flush_gn(const EpiParams& e, int N, int img, int we, int lane, float (&gacc)[MAXCH][8], float* scratch) {
+  constexpr int NV = MAXCH * 4;                              // values per warp: chunk k, group g, (sum, sumsq)
+#pragma unroll
+  for (int k = 0; k < MAXCH; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v = warp_sum(gacc[k][j]);
+      gacc[k][j] = 0.f;
+      if (lane == 0) scratch[we * NV + k * 4 + j] = v;
+    }
+  asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
+  if ((we & 3) == 0 && lane < NV) {
+    const int half = we >> 2, k = lane >> 2, j = lane & 3;
+    const float* sp = scratch + (half * 4) * NV + lane;
+    const float v = (sp[0] + sp[NV]) + (sp[2 * NV] + sp[3 * NV]);
+    const int n0 = (half + kTcEpiPerLG * k) * kTcEpiCW + (j >> 1) * 8;
+    const int gs = e.gn_gs;
+    if (n0 < N) atomicAdd(e.gn_stats + (((long)img * kGnRep + (blockIdx.x & (kGnRep - 1))) * (N / gs) + n0 / gs) * 2 + (j & 1), (double)v);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory");
+}
 
 // grid = 2 x min(#tile pairs, #SMs / 2); pair q walks u = q, q + #pairs, ...: n-tile u % ntn of the m-tiles 2 (u / ntn) + {0, 1}
 template <int BLOCK_N>
@@ -122,6 +150,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* acc_full = empty + AS;                                 // [2]
   uint64_t* acc_empty = acc_full + 2;                              // [2]  (even CTA's copy is the live one)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* gn_scratch = reinterpret_cast<float*>(smem + AS * RB + 256);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -238,7 +267,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const TcTile tl = tc_decode_tile(p, (2 * (u / ntn) + (int)rank) * ntn + u % ntn, ntn, BLOCK_N);
       const int buf = li & 1;
       if (defer_gn && tl.z != gn_img) {
-        if (gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, PLG, gacc);
+        if (gn_img >= 0) cp_flush_gn<MAXCH>(p.epi, p.N, gn_img, warp - 2, lane, gacc, gn_scratch);
         gn_img = tl.z;
       }
       const int ch = tl.ch0 + r / p.BW, cw = tl.cw0 + r % p.BW;
@@ -270,7 +299,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         epi_apply<CW, true>(p.epi, p.N, tl.z, p.nheads, oh, ow, p.OH, p.OW, valid, n0c, v, rpre, defer_gn ? &gacc[k][0] : nullptr);
       }
     }
-    if (defer_gn && gn_img >= 0) epi_flush_gn<MAXCH>(p.epi, p.N, gn_img, half, PLG, gacc);
+    if (defer_gn && gn_img >= 0) cp_flush_gn<MAXCH>(p.epi, p.N, gn_img, warp - 2, lane, gacc, gn_scratch);
   }
   ptx::tc_fence_before();
   __syncthreads();

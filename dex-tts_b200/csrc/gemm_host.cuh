@@ -9,7 +9,7 @@ namespace dexb {
 // GroupNorm sums are accumulated into kGnRep replicas per (image, group), picked by the writing CTA's index, and summed by the readers:
 // all CTAs of a convolution leave an image at about the same time, and 592 double atomics per address and image change (148 CTAs x 4
 // lane-group warps) serialised in L2 -- the sums cost the 64-channel convolution 21 us of 79 (tools/pair_bench.py, out_mode 4).
-constexpr int kGnRep = 8;
+constexpr int kGnRep = 4;
 
 struct EpiParams {
   float alpha;                 // acc *= alpha (before bias)
