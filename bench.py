@@ -413,7 +413,7 @@ def run_workload(args, name, rank, world, local_rank, dist, full):
                 break
             except Exception:
                 pass
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BLOCK_N> / conv2 (tcgen05 implicit GEMM, all conv / linear contractions)",
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel<BLOCK_N> + conv_pair_kernel<BLOCK_N> (tcgen05 implicit GEMM: all linear contractions; 3x3 convolutions on cta_group::2 CTA pairs)",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 "traffic": ncu.get("gemm_tc_kernel", {}).get("avg_dram_bytes_per_launch") if name == "C2" else None,
                 "traffic_source": ncu.get("source") if name == "C2" else None,

@@ -40,79 +40,101 @@ void launch_mask_down(const float* mask, float* mask1, int B, int T, int W1, cud
 // Thread = 8 output channels (one GroupNorm group at C == 64) x 4 x-adjacent pixels: the 144 weights of its channel octet
 // come from shared memory as 36 LDS.128 for 576 FMAs (the one-pixel-per-thread version issued one LDS per FMA and was
 // shared-memory bound: 57 us for 0.75 GFLOP).  8 consecutive lanes write the 256 B row of a pixel.
+// A block walks `rows` consecutive rows of its 128-pixel (C = 64) column strip with a rolling three-row window of the inputs: the
+// weights are staged once, every new row costs one row of loads instead of three, and the GroupNorm sums leave the block once.  (One
+// row per block was bound by the block's own latency chain -- weight staging, loads, reduction, atomics: 2560 blocks in 5.8 waves,
+// 60 us for an 84 MB write.)
 template <int C, int CIN>
 __global__ void __launch_bounds__(256) k_conv_in(const float* __restrict__ x, const float* __restrict__ mu,
                                                  const float* __restrict__ spk_s,
                                                  const float* __restrict__ mask, const StepScalars* __restrict__ tab,
                                                  int step, const float* __restrict__ w, const float* __restrict__ bias,
                                                  float* __restrict__ raw, double* __restrict__ stats, int B, int H,
-                                                 int W) {
+                                                 int W, int rows) {
   static_assert(C == 64 || C == 128, "GroupNorm(8, C): one or two channel octets per group");
   pdl_wait();
   constexpr int KT = 9 * CIN;                                // taps x input channels: [mu | c_in x | speaker channel]
   constexpr int OCTS = C / 8, QUADS = 256 / OCTS;            // a block covers QUADS * 4 pixels of one row: 128 (C = 64) or 64 (C = 128)
   __shared__ __align__(16) float wsT[KT][C];                 // [k][co]
-  __shared__ float red[8][OCTS][2];
+  __shared__ double red[8][OCTS][2];
   for (int i = threadIdx.x; i < C * KT; i += 256) wsT[i % KT][i / KT] = w[i];
   __syncthreads();
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h0 = blockIdx.y * rows, b = blockIdx.z;
   const int oct = threadIdx.x % OCTS, quad = threadIdx.x / OCTS;
   const int c0 = oct * 8;
   const int x0 = blockIdx.x * (QUADS * 4) + quad * 4;
   const float c_in = tab[step].c_in;
-  float va[3][6], vc[3][6], vs[3][6];                        // mu*mask, c_in*x*mask (and spk*mask) at rows h-1..h+1, columns x0-1..x0+4
+  float mk[6];                                               // mask at columns x0-1 .. x0+4 (0 outside the image)
 #pragma unroll
   for (int col = 0; col < 6; ++col) {
     const int ww = x0 + col - 1;
-    const bool cok = ww >= 0 && ww < W;
-    const float m = cok ? mask[(long)b * W + ww] : 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int hh = h + dy - 1;
-      float a = 0.f, c = 0.f, s3 = 0.f;
-      if (cok && hh >= 0 && hh < H) {
-        const long idx = ((long)b * H + hh) * W + ww;
-        a = mu[idx] * m;
-        c = (c_in * x[idx]) * m;
-        if (CIN == 3) s3 = spk_s[b * H + hh] * m;
-      }
-      va[dy][col] = a;
-      vc[dy][col] = c;
-      vs[dy][col] = s3;
-    }
+    mk[col] = (ww >= 0 && ww < W) ? mask[(long)b * W + ww] : 0.f;
   }
-  float acc[4][8];
+  float va[3][6], vc[3][6], vs[3][6];                        // mu*mask, c_in*x*mask (and spk*mask) at rows h-1..h+1, columns x0-1..x0+4
+  auto load_row = [&](int hh, float (&ra)[6], float (&rc)[6], float (&rs)[6]) {
+    const bool rok = hh >= 0 && hh < H;
+    const float sp = (CIN == 3 && rok) ? spk_s[b * H + hh] : 0.f;
+#pragma unroll
+    for (int col = 0; col < 6; ++col) {
+      const int ww = x0 + col - 1;
+      float a = 0.f, c = 0.f;
+      if (rok && ww >= 0 && ww < W) {
+        const long idx = ((long)b * H + hh) * W + ww;
+        a = mu[idx] * mk[col];
+        c = (c_in * x[idx]) * mk[col];
+      }
+      ra[col] = a; rc[col] = c; rs[col] = sp * mk[col];
+    }
+  };
+  load_row(h0 - 1, va[0], vc[0], vs[0]);
+  load_row(h0, va[1], vc[1], vs[1]);
+  float bs[8];
   {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c0)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+  }
+  double s = 0., ss = 0.;                                    // per-row fp32 sums (32 values) are added up in double
+#pragma unroll 1
+  for (int r = 0; r < rows; ++r) {
+    const int h = h0 + r;
+    if (h >= H) break;
+    float sr = 0.f, ssr = 0.f;
+    load_row(h + 1, va[2], vc[2], vs[2]);
+    float acc[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[p][i] = bs[i];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {                           // accumulation order: mu taps, x taps(, speaker taps)
+      const float4 w0 = *reinterpret_cast<const float4*>(&wsT[k][c0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&wsT[k][c0 + 4]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const int dy = (k % 9) / 3, dx = k % 3;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float iv = (k < 9) ? va[dy][p + dx] : ((k < 18) ? vc[dy][p + dx] : vs[dy][p + dx]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(wv[i], iv, acc[p][i]);
+      }
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      acc[p][0] = b0.x; acc[p][1] = b0.y; acc[p][2] = b0.z; acc[p][3] = b0.w;
-      acc[p][4] = b1.x; acc[p][5] = b1.y; acc[p][6] = b1.z; acc[p][7] = b1.w;
+      const int wcol = x0 + p;
+      if (wcol < W) {
+        float* orow = raw + (((long)b * H + h) * W + wcol) * C + c0;
+        *reinterpret_cast<float4*>(orow) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+        *reinterpret_cast<float4*>(orow + 4) = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sr += acc[p][i]; ssr += acc[p][i] * acc[p][i]; }
+      }
     }
-  }
+    s += (double)sr; ss += (double)ssr;
 #pragma unroll
-  for (int k = 0; k < KT; ++k) {                             // accumulation order: mu taps, x taps(, speaker taps)
-    const float4 w0 = *reinterpret_cast<const float4*>(&wsT[k][c0]);
-    const float4 w1 = *reinterpret_cast<const float4*>(&wsT[k][c0 + 4]);
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    const int dy = (k % 9) / 3, dx = k % 3;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const float iv = (k < 9) ? va[dy][p + dx] : ((k < 18) ? vc[dy][p + dx] : vs[dy][p + dx]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[p][i] = fmaf(wv[i], iv, acc[p][i]);
-    }
-  }
-  float s = 0.f, ss = 0.f;
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int wcol = x0 + p;
-    if (wcol < W) {
-      float* orow = raw + (((long)b * H + h) * W + wcol) * C + c0;
-      *reinterpret_cast<float4*>(orow) = make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-      *reinterpret_cast<float4*>(orow + 4) = make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s += acc[p][i]; ss += acc[p][i] * acc[p][i]; }
+    for (int col = 0; col < 6; ++col) {                      // roll the window down one row
+      va[0][col] = va[1][col]; va[1][col] = va[2][col];
+      vc[0][col] = vc[1][col]; vc[1][col] = vc[2][col];
+      vs[0][col] = vs[1][col]; vs[1][col] = vs[2][col];
     }
   }
   if (OCTS == 8) { s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8); }   // lanes of one octet
@@ -135,14 +157,19 @@ void launch_conv_in(const float* x, const float* mu, const float* spk_s, const f
                     const float* w, const float* bias, float* raw, double* stats, int B, int H, int W, int C,
                     cudaStream_t st) {
   // stats layout is [B][kGnRep][8 groups][2]; C = decoder.dim in {64, 128} (engine_finalize rejects other widths)
+  // rows per block: the fewest that let the whole grid be resident at once (2 blocks of 128 registers per SM) -- one wave, no tail
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int strips = cdiv(W, C == 64 ? 128 : 64);
+  int rows = 1;
+  while (rows < H && (long)cdiv(H, rows) * strips * B > 2L * sms) ++rows;
+  dim3 grid(strips, cdiv(H, rows), B);
   if (C == 64) {
-    dim3 grid(cdiv(W, 128), H, B);
-    if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
-    else launch_pdl(k_conv_in<64, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+    if (spk_s == nullptr) launch_pdl(k_conv_in<64, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W, rows);
+    else launch_pdl(k_conv_in<64, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W, rows);
   } else if (C == 128) {
-    dim3 grid(cdiv(W, 64), H, B);
-    if (spk_s == nullptr) launch_pdl(k_conv_in<128, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W);
-    else launch_pdl(k_conv_in<128, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W);
+    if (spk_s == nullptr) launch_pdl(k_conv_in<128, 2>, grid, dim3(256), 0, st, x, mu, nullptr, mask, tab, step, w, bias, raw, stats, B, H, W, rows);
+    else launch_pdl(k_conv_in<128, 3>, grid, dim3(256), 0, st, x, mu, spk_s, mask, tab, step, w, bias, raw, stats, B, H, W, rows);
   }
 }
 

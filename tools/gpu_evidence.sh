@@ -21,7 +21,7 @@ timeout 120 python tools/voc_bench.py 8 512 > "$OUT/${TAG}_voc_bench.json" 2> "$
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/${TAG}_launches_bench.csv" \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > "$OUT/${TAG}_bench_under_ncu.log" 2>&1     # never a bench value
 # the .ncu-rep stays on the box (100 MB: gpurun_out is capped at 64 MiB); only the condensed summary comes back
-timeout 900 ncu --set full --clock-control none -k regex:"gemm_tc_kernel|attn_fwd_kernel|posconv_kernel|k_gn_apply" \
+timeout 900 ncu --set full --clock-control none -k regex:"gemm_tc_kernel|conv_pair_kernel|attn_fwd_kernel|posconv_kernel|k_gn_apply" \
     -s 60 -c 62 -o /tmp/${TAG}_ncu_full python tools/prof_net_call.py C2 2 > "$OUT/${TAG}_ncu_full.log" 2>&1
 ncu -i /tmp/${TAG}_ncu_full.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_summary.py > "$OUT/${TAG}_ncu_summary.csv" 2>> "$OUT/${TAG}_ncu_full.log"
 du -sh "$OUT"

@@ -22,7 +22,7 @@ def sel(pred):
     return [r for r in rows if pred(r["kernel"])]
 
 
-g = sel(lambda k: "gemm_tc_kernel" in k)
+g = sel(lambda k: "gemm_tc_kernel" in k or "conv_pair_kernel" in k)      # the GEMM class: engine + CTA-pair convolutions
 tt = sum(float(r[T]) for r in g)
 out["gemm_tc_kernel"] = {"launches": len(g), "avg_dram_bytes_per_launch": sum((float(r[RD]) + float(r[WR])) * unit for r in g) / len(g),
                          "time_weighted_tensor_pipe_active_pct": sum(float(r[TP]) * float(r[T]) for r in g) / tt, "sum_time_us": tt}
