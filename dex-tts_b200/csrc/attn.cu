@@ -551,12 +551,15 @@ __global__ void __launch_bounds__(256) k_attn_tail_merge(const AttnParams p) {
   const int row = m0 + r;
   if (row >= p.NQ) return;
   const int S = p.tail_splits;
+  // (a chain of L2 round trips on 40 blocks: the maxima of all splits (S <= 8) and the partials of two splits are in flight together)
   float M = -INFINITY;
+#pragma unroll 8
   for (int s = 0; s < S; ++s) M = fmaxf(M, p.part_m[((long)k * S + s) * kAtBM + r]);
   float o[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) o[i] = 0.f;
   float l = 0.f;
+#pragma unroll 2
   for (int s = 0; s < S; ++s) {
     const long pi = ((long)k * S + s) * kAtBM + r;
     const float f = exp2f((p.part_m[pi] - M) * p.scale_log2e);      // exp2(-inf) = 0 for an empty split

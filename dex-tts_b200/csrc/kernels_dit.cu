@@ -110,13 +110,20 @@ void launch_tiv_affine(const double* stats, const float* sc, const float* sh, fl
   launch_pdl(k_tiv_affine, dim3((unsigned)(cdiv((long)B * C, 128))), dim3(128), 0, st, stats, sc, sh, a_out, d_out, B * C, P);
 }
 
-template <bool SPLIT_IN>
+// PS = compile-time patch size (3: DEX-TTS, 7: GeDEX-TTS; 0 = run-time p): the taps of a row are loaded together (out-of-range taps
+// as predicated zero weights) -- as a rolled loop with `continue` every tap was its own dependent round trip (49 of them at p = 7).
+// The depthwise weights are staged transposed ([tap][channel]) in shared memory: two 16 B reads per tap instead of 8 scalar loads.
+template <bool SPLIT_IN, int PS>
 __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin, SView sin,
                                                   const double* __restrict__ stats, const float* __restrict__ tiv_scale,
                                                   const float* __restrict__ tiv_shift, int use_tiv,
                                                   const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                  SView out, int B, int H, int W, int C, int p, int s, int Fq, int Wq) {
+                                                  SView out, int B, int H, int W, int C, int p_rt, int s, int Fq, int Wq) {
   pdl_wait();
+  extern __shared__ __align__(16) float dw_s[];               // [p * p][C]
+  const int p = PS > 0 ? PS : p_rt;
+  for (int i = threadIdx.x; i < C * p * p; i += 256) dw_s[(i % (p * p)) * C + i / (p * p)] = dw_w[i];
+  __syncthreads();
   const int cpt = C / 8;
   const long gid = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)B * Fq * Wq * cpt;
@@ -137,25 +144,39 @@ __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin,
     d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
   }
   const int pad = p / 2;
+  constexpr int KXU = PS > 0 ? PS : 1;                         // taps of a row in flight together
+#pragma unroll 1
   for (int ky = 0; ky < p; ++ky) {
     const int y = hq * s - pad + ky;
-    if (y < 0 || y >= H) continue;
-    for (int kx = 0; kx < p; ++kx) {
-      const int x = wq * s - pad + kx;
-      if (x < 0 || x >= W) continue;                           // conv zero padding and the F.pad zone are both 0
-      float v[8];
-      const long row = ((long)b * H + y) * W + x;
-      if (SPLIT_IN) {
-        const bf16* q = sin.p + row * sin.stride + c0;
-        load_split8(q + sin.hi, q + sin.lo, v);
-      } else {
-        const float* q = xin + row * C + c0;
-        const float4 r0 = *reinterpret_cast<const float4*>(q);
-        const float4 r1 = *reinterpret_cast<const float4*>(q + 4);
-        v[0] = r0.x; v[1] = r0.y; v[2] = r0.z; v[3] = r0.w; v[4] = r1.x; v[5] = r1.y; v[6] = r1.z; v[7] = r1.w;
+    if (y < 0 || y >= H) continue;                             // (uniform enough: whole rows of the padding zone)
+    for (int kx0 = 0; kx0 < p; kx0 += KXU) {
+      float v[KXU][8];
+      bool ok[KXU];
+#pragma unroll
+      for (int u = 0; u < KXU; ++u) {
+        const int x = wq * s - pad + kx0 + u;
+        ok[u] = x >= 0 && x < W;                               // conv zero padding and the F.pad zone are both 0
+        const long row = ((long)b * H + y) * W + (ok[u] ? x : 0);
+        if (SPLIT_IN) {
+          const bf16* q = sin.p + row * sin.stride + c0;
+          load_split8(q + sin.hi, q + sin.lo, v[u]);
+        } else {
+          const float* q = xin + row * C + c0;
+          const float4 r0 = *reinterpret_cast<const float4*>(q);
+          const float4 r1 = *reinterpret_cast<const float4*>(q + 4);
+          v[u][0] = r0.x; v[u][1] = r0.y; v[u][2] = r0.z; v[u][3] = r0.w; v[u][4] = r1.x; v[u][5] = r1.y; v[u][6] = r1.z; v[u][7] = r1.w;
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(dw_w[((c0 + i) * p + ky) * p + kx], fmaf(a[i], v[i], d[i]), acc[i]);
+      for (int u = 0; u < KXU; ++u) {
+        const float* wp = dw_s + (ky * p + kx0 + u) * C + c0;
+        const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        if (ok[u]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv[i], fmaf(a[i], v[u][i], d[i]), acc[i]);
+        }
+      }
     }
   }
 #pragma unroll
@@ -163,19 +184,26 @@ __global__ void __launch_bounds__(256) k_dw_patch(const float* __restrict__ xin,
   bf16* op = out.p + tok * out.stride + c0;
   store_split8(op + out.hi, op + out.lo, acc);
 }
+template <bool SPLIT_IN, class... Args>
+static void launch_dw_patch_p(long total, int C, int p, cudaStream_t st, Args... args) {
+  const size_t smem = (size_t)C * p * p * sizeof(float);      // 4.6 KB (p = 3, C = 128) ... 25 KB (p = 7); < 48 KB checked by the engine's config
+  const dim3 grid((unsigned)cdiv(total, 256));
+  if (p == 3) launch_pdl(k_dw_patch<SPLIT_IN, 3>, grid, dim3(256), smem, st, args...);
+  else if (p == 7) launch_pdl(k_dw_patch<SPLIT_IN, 7>, grid, dim3(256), smem, st, args...);
+  else launch_pdl(k_dw_patch<SPLIT_IN, 0>, grid, dim3(256), smem, st, args...);
+}
 void launch_dw_patch(const float* tv, const double* stats, const float* tiv_scale, const float* tiv_shift, int use_tiv,
                      const float* dw_w, const float* dw_b, SView out, int B, int H, int W, int C, int p, int s, int Fq,
                      int Wq, cudaStream_t st) {
   const long total = (long)B * Fq * Wq * (C / 8);
   SView none = {nullptr, 0, 0, 0};
-  launch_pdl(k_dw_patch<false>, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, tv, none, stats, tiv_scale, tiv_shift, use_tiv, dw_w, dw_b, out, B,
-                                                       H, W, C, p, s, Fq, Wq);
+  launch_dw_patch_p<false>(total, C, p, st, tv, none, stats, tiv_scale, tiv_shift, use_tiv, dw_w, dw_b, out, B, H, W, C, p, s, Fq, Wq);
 }
 void launch_dw_patch_s(SView in, const float* dw_w, const float* dw_b, SView out, int B, int H, int W, int C, int p,
                        int s, int Fq, int Wq, cudaStream_t st) {
   const long total = (long)B * Fq * Wq * (C / 8);
-  launch_pdl(k_dw_patch<true>, dim3((unsigned)(cdiv(total, 256))), dim3(256), 0, st, nullptr, in, nullptr, nullptr, nullptr, 0, dw_w, dw_b, out, B, H, W,
-                                                      C, p, s, Fq, Wq);
+  launch_dw_patch_p<true>(total, C, p, st, (const float*)nullptr, in, (const double*)nullptr, (const float*)nullptr, (const float*)nullptr, 0, dw_w, dw_b,
+                          out, B, H, W, C, p, s, Fq, Wq);
 }
 
 // ------------------------------------------------------------------------------------------------

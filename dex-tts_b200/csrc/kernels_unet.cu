@@ -484,13 +484,26 @@ __global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ par
   const int d = rg * 8 + dl;
   constexpr int CS = C / 8;                                  // columns per thread: 8 or 16
   const int row = h * 32 + d;
+  // The kernel is a chain of dependent L2 round trips (few threads, little data): the weight rows are requested first, and the split
+  // loops are unrolled eight deep so that the partials of eight key ranges are in flight together.
+  {
+    const float4* wsrc = reinterpret_cast<const float4*>(wv + (long)h * 32 * C);         // 32 x C contiguous floats
+#pragma unroll
+    for (int j = 0; j < 32 * C / 4 / 64; ++j) {
+      const int i4 = tid + j * 64;
+      const float4 t = __ldg(wsrc + i4);
+      const int r_ = (i4 * 4) / C, c_ = (i4 * 4) % C;
+      Wvs[r_][c_] = t.x; Wvs[r_][c_ + 1] = t.y; Wvs[r_][c_ + 2] = t.z; Wvs[r_][c_ + 3] = t.w;
+    }
+  }
   float M = -INFINITY;
+#pragma unroll 8
   for (int s = 0; s < S; ++s) M = fmaxf(M, part_m[((long)b * S + s) * 128 + row]);
   float acc[CS];
 #pragma unroll
   for (int j = 0; j < CS; ++j) acc[j] = 0.f;
   float l = 0.f;
-#pragma unroll 4
+#pragma unroll 8
   for (int s = 0; s < S; ++s) {
     const long pi = ((long)b * S + s) * 128 + row;
     const float w = expf(part_m[pi] - M);                    // exp(-inf) = 0 for an empty split
@@ -506,7 +519,6 @@ __global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ par
 #pragma unroll
   for (int j = 0; j < CS; ++j) Gh[dl][seg * CS + j] = acc[j];
   if (seg == 0) ssum[b * 128 + row] = l;
-  for (int i = tid; i < 32 * C; i += 64) Wvs[i / C][i % C] = wv[(long)(h * 32 + i / C) * C + i % C];
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -538,7 +550,10 @@ __global__ void __launch_bounds__(256) k_la_weff(const float* __restrict__ ctx, 
   __shared__ float cn[4][32][33];
   __shared__ float Ts[8][128];
   const int b = blockIdx.y, co0 = blockIdx.x * 8, tid = threadIdx.x;
-  for (int i = tid; i < 4096; i += 256) {
+  // (all 16 loads of a thread in flight at once: as a rolled loop this was 16 dependent round trips, 40 % of the kernel's samples)
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int i = tid + j * 256;
     const int h = i >> 10, d = (i >> 5) & 31, e = i & 31;
     cn[h][d][e] = ctx[(long)b * 4096 + i] / ssum[b * 128 + h * 32 + d];
   }
