@@ -67,7 +67,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   uint64_t* k_full = bars + 1;        // 3
   uint64_t* k_empty = bars + 4;       // 3
   uint64_t* s_full = bars + 7;        // 2
-  uint64_t* s_empty = bars + 9;       // 2
+  // (bars + 9, + 10: formerly s_empty -- not needed, see issue_s)
   uint64_t* p_full = bars + 11;       // 1
   uint64_t* p_empty = bars + 12;      // 1
   uint64_t* o_full = bars + 13;       // 1
@@ -113,7 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(q_full, 256);
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&s_empty[s], 256);
+      ptx::mbar_init(&s_full[s], 1);
     }
     for (int s = 0; s < kAtStages; ++s) {
       ptx::mbar_init(&k_full[s], 1); ptx::mbar_init(&k_empty[s], 1);
@@ -178,7 +178,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       const int st = it % kAtStages, sb = it & 1;
       ptx::mbar_wait(&k_full[st], (it / kAtStages) & 1);
       // S buffer `sb` was last used by tile it - 2, whose P the issuer has already waited for (p_full(it - 2) is only complete once
-      // all softmax warps have read that S tile) -- no wait on s_empty: every mbarrier wait costs this thread ~240 cycles that the
+      // all softmax warps have read that S tile) -- no `s_empty` barrier: every mbarrier wait costs this thread ~240 cycles that the
       // tensor pipe does not hide (profiles/r02_issue_bench.md)
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
@@ -273,8 +273,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       ptx::mbar_wait(&s_full[s], (j >> 1) & 1);
       ptx::tc_fence_after();
       ptx::tmem_ld32(tl + kTmS + s * kAtBN + hf * 32, v);
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&s_empty[s]);
+      ptx::tc_fence_before();                                    // orders the S read before this thread's p_full arrival
       const int nvalid = nkv - (t0 + j) * kAtBN - hf * 32;
       if (kb != nullptr) {
 #pragma unroll

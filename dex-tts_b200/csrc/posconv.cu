@@ -63,7 +63,6 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
   uint64_t* in_empty = bars + 4;       // 4
   uint64_t* w_full = bars + 8;         // 2: weights staged in tensor memory
   uint64_t* d_full = bars + 10;        // 2
-  uint64_t* d_empty = bars + 12;       // 2
   uint64_t* ws_full = bars + 14;       // 2: weight block landed in shared memory
   uint64_t* ws_empty = bars + 16;      // 2
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
@@ -74,7 +73,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
     ptx::prefetch_tmap(&tmW);
     for (int s = 0; s < kPcStages; ++s) { ptx::mbar_init(&in_full[s], 1); ptx::mbar_init(&in_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      ptx::mbar_init(&w_full[s], 128); ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 128);
+      ptx::mbar_init(&w_full[s], 128); ptx::mbar_init(&d_full[s], 1);
       ptx::mbar_init(&ws_full[s], 1); ptx::mbar_init(&ws_empty[s], 128);
     }
     ptx::fence_barrier_init();
@@ -122,7 +121,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
           const int bf = s & 1;
           const uint32_t ph = (s >> 1) & 1;
           // ONE wait per step: w_full(s) is only complete once all four accumulation warps have staged the weights of step s, and each
-          // of them arrived on d_empty(s - 2) one loop iteration earlier (it reads D(s - 2), then stages W(s)) -- so the accumulator
+          // of them has read D(s - 2) one loop iteration earlier (it reads D(s - 2), fences, then stages W(s)) -- so the accumulator
           // buffer of this step is free as well.  A second wait would cost the issuing thread ~240 cycles per step against ~350
           // cycles of MMAs (six N = 96 TS-mode instructions): r01 waited on both and ran 61 % tensor-pipe active.
           ptx::mbar_wait(&w_full[bf], ph);
@@ -209,8 +208,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__
                          : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&d_empty[bf]);
+          ptx::tc_fence_before();                                // orders the tensor-memory reads before this thread's next arrival (w_full)
 #pragma unroll
           for (int i = 0; i < 32; ++i) { acc[i] += v0[i]; acc[32 + i] += v1[i]; }
 #pragma unroll

@@ -26,6 +26,12 @@ CASES = {
     "lin_256_many": (1, 1, 40000, 256, 256, (1, 1), (0, 0), 1),
     "lin_k64_many": (3, 64, 256, 64, 128, (1, 1), (0, 0), 1),
     "conv3_stride2_many": (4, 80, 512, 64, 64, (3, 3), (-1, -1), 2),
+    # an odd number of 128-pixel tiles: the 3x3 convolution stays on single CTAs (halo mode of gemm_tc_kernel); every even case above
+    # runs on CTA pairs (conv_pair_kernel)
+    "conv3_64_odd": (1, 5, 128, 64, 64, (3, 3), (-1, -1), 1),
+    "conv3_128_odd": (3, 7, 100, 128, 128, (3, 3), (-1, -1), 1),
+    # pairs whose two tiles lie in different images (one tile per image row block) and n-tiles > 1
+    "conv3_256_pairs_across_images": (6, 1, 128, 128, 256, (3, 3), (-1, -1), 1),
 }
 
 

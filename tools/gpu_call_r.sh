@@ -1,13 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 ncu --clock-control none --metrics gpu__time_duration.sum -k regex:"k_la_weff|k_la_combine|k_attn_tail_merge|k_dw_patch|k_tok_assemble|k_unpatchify|k_chan_stats|k_freq_mean|k_tv_fold|k_ln_mod|k_posconv_pack_in|k_fill_zero|k_gn_final|k_conv_in" -s 40 -c 40 --csv --log-file gpurun_out/r02z_small.csv python tools/prof_net_call.py C2 3 > /dev/null 2>&1
-python - <<PY
-import csv
-rows=[r for r in csv.reader(open("gpurun_out/r02z_small.csv")) if len(r)>10]
-h=rows[0]; ki=h.index("Kernel Name"); vi=h.index("Metric Value"); ui=h.index("Metric Unit")
-agg={}
-for r in rows[1:]:
-    n=r[ki].split("(")[0][-30:]; v=float(r[vi].replace(",",""))*{"ns":1e-3,"us":1,"ms":1e3}.get(r[ui],1)
-    agg.setdefault(n,[]).append(v)
-for n,v in agg.items(): print(n.ljust(32), len(v), " ".join(f"{x:.1f}" for x in v[:8]))
-PY
+export DEXB_NO_GRAPH=1
+timeout 1200 compute-sanitizer --tool synccheck --error-exitcode 7 python __graft_entry__.py smoke > gpurun_out/r02g_sanitizer_synccheck.log 2>&1
+echo "synccheck: exit $? -- $(grep -E 'ERROR SUMMARY' gpurun_out/r02g_sanitizer_synccheck.log | tail -1)"
+grep "Device Frame" gpurun_out/r02g_sanitizer_synccheck.log | sed 's/(.*//' | sort | uniq -c
+unset DEXB_NO_GRAPH
+timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_decoder_gpu.py -x -q 2>&1 | tail -2
