@@ -471,69 +471,91 @@ void launch_la_ctx(const float* kv, const unsigned* kmax_enc, float* part, float
 // reassociated context:  the kernel produced G = softmax(k)^T x per key range (128 x C, un-normalised), so
 //   M[d] = max_s m_s[d];  G[d][c] = sum_s G_s[d][c] exp(m_s[d] - M[d]);  ssum[b][d] = sum_s l_s[d] exp(m_s[d] - M[d]);
 //   ctx[b][h][d][e] = sum_c G[h*32+d][c] W_v[h*32+e][c]          (= softmax(k)^T v restricted to the 4 diagonal head blocks).
-// One block of 64 threads per (head, group of 8 rows, image); thread = (row d, a contiguous eighth of the C columns).
+// One block of 256 threads per (head, group of 8 rows, image): four thread groups walk the key ranges s = g, g + 4, ... with their own
+// running maximum, then merge in the fixed order g = 0 .. 3 (deterministic); thread = (group, row d, a contiguous eighth of the C columns).
+// (A single utterance is cut into up to 148 key ranges: one group of 64 threads walked them in a chain of dependent L2 round trips --
+// 28 us per call at C1, 7.6 % of its step.)
 template <int C>
-__global__ void __launch_bounds__(64) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
-                                                    const float* __restrict__ part_m, const float* __restrict__ wv,
-                                                    float* __restrict__ ctx, float* __restrict__ ssum, int S) {
+__global__ void __launch_bounds__(256) k_la_combine(const float* __restrict__ part_o, const float* __restrict__ part_l,
+                                                     const float* __restrict__ part_m, const float* __restrict__ wv,
+                                                     float* __restrict__ ctx, float* __restrict__ ssum, int S) {
   pdl_wait();
   __shared__ float Gh[8][C + 1];
   __shared__ float Wvs[32][C + 1];
+  __shared__ float sM[4][8], sL[4][8];
+  __shared__ float sAcc[3][8][C];                             // partial sums of groups 1 .. 3
   const int h = blockIdx.x >> 2, rg = blockIdx.x & 3, b = blockIdx.y, tid = threadIdx.x;
-  const int dl = tid >> 3, seg = tid & 7;
+  const int grp = tid >> 6, t = tid & 63;
+  const int dl = t >> 3, seg = t & 7;
   const int d = rg * 8 + dl;
   constexpr int CS = C / 8;                                  // columns per thread: 8 or 16
   const int row = h * 32 + d;
-  // The kernel is a chain of dependent L2 round trips (few threads, little data): the weight rows are requested first, and the split
-  // loops are unrolled eight deep so that the partials of eight key ranges are in flight together.
   {
-    const float4* wsrc = reinterpret_cast<const float4*>(wv + (long)h * 32 * C);         // 32 x C contiguous floats
+    const float4* wsrc = reinterpret_cast<const float4*>(wv + (long)h * 32 * C);         // 32 x C contiguous floats, requested first
 #pragma unroll
-    for (int j = 0; j < 32 * C / 4 / 64; ++j) {
-      const int i4 = tid + j * 64;
-      const float4 t = __ldg(wsrc + i4);
+    for (int j = 0; j < 32 * C / 4 / 256; ++j) {
+      const int i4 = tid + j * 256;
+      const float4 q = __ldg(wsrc + i4);
       const int r_ = (i4 * 4) / C, c_ = (i4 * 4) % C;
-      Wvs[r_][c_] = t.x; Wvs[r_][c_ + 1] = t.y; Wvs[r_][c_ + 2] = t.z; Wvs[r_][c_ + 3] = t.w;
+      Wvs[r_][c_] = q.x; Wvs[r_][c_ + 1] = q.y; Wvs[r_][c_ + 2] = q.z; Wvs[r_][c_ + 3] = q.w;
     }
   }
   float M = -INFINITY;
 #pragma unroll 8
-  for (int s = 0; s < S; ++s) M = fmaxf(M, part_m[((long)b * S + s) * 128 + row]);
+  for (int s = grp; s < S; s += 4) M = fmaxf(M, part_m[((long)b * S + s) * 128 + row]);
   float acc[CS];
 #pragma unroll
   for (int j = 0; j < CS; ++j) acc[j] = 0.f;
   float l = 0.f;
-#pragma unroll 8
-  for (int s = 0; s < S; ++s) {
-    const long pi = ((long)b * S + s) * 128 + row;
-    const float w = expf(part_m[pi] - M);                    // exp(-inf) = 0 for an empty split
-    l = fmaf(part_l[pi], w, l);
-    const float4* po = reinterpret_cast<const float4*>(part_o + pi * 128 + seg * CS);
+  if (M > -INFINITY) {                                       // (a group whose ranges are all empty contributes nothing)
+#pragma unroll 4
+    for (int s = grp; s < S; s += 4) {
+      const long pi = ((long)b * S + s) * 128 + row;
+      const float w = expf(part_m[pi] - M);                  // exp(-inf) = 0 for an empty split
+      l = fmaf(part_l[pi], w, l);
+      const float4* po = reinterpret_cast<const float4*>(part_o + pi * 128 + seg * CS);
 #pragma unroll
-    for (int j = 0; j < CS / 4; ++j) {
-      const float4 v = po[j];
-      acc[4 * j] = fmaf(v.x, w, acc[4 * j]); acc[4 * j + 1] = fmaf(v.y, w, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(v.z, w, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v.w, w, acc[4 * j + 3]);
+      for (int j = 0; j < CS / 4; ++j) {
+        const float4 v = po[j];
+        acc[4 * j] = fmaf(v.x, w, acc[4 * j]); acc[4 * j + 1] = fmaf(v.y, w, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(v.z, w, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v.w, w, acc[4 * j + 3]);
+      }
     }
   }
-#pragma unroll
-  for (int j = 0; j < CS; ++j) Gh[dl][seg * CS + j] = acc[j];
-  if (seg == 0) ssum[b * 128 + row] = l;
+  if (seg == 0) sM[grp][dl] = M;
   __syncthreads();
+  const float Mt = fmaxf(fmaxf(sM[0][dl], sM[1][dl]), fmaxf(sM[2][dl], sM[3][dl]));
+  const float f = (M > -INFINITY) ? expf(M - Mt) : 0.f;      // rescale this group's sums to the common maximum
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int e = seg * 4 + i;
+  for (int j = 0; j < CS; ++j) acc[j] *= f;
+  l *= f;
+  if (grp > 0) {
+#pragma unroll
+    for (int j = 0; j < CS; ++j) sAcc[grp - 1][dl][seg * CS + j] = acc[j];
+  }
+  if (seg == 0) sL[grp][dl] = l;
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int j = 0; j < CS; ++j)
+      Gh[dl][seg * CS + j] = ((acc[j] + sAcc[0][dl][seg * CS + j]) + sAcc[1][dl][seg * CS + j]) + sAcc[2][dl][seg * CS + j];
+    if (seg == 0) ssum[b * 128 + row] = ((sL[0][dl] + sL[1][dl]) + sL[2][dl]) + sL[3][dl];
+  }
+  __syncthreads();
+  {
+    // 8 rows x 32 columns of the context block: one output per thread
+    const int dd = tid >> 5, e = tid & 31;
     float a = 0.f;
 #pragma unroll 8
-    for (int c = 0; c < C; ++c) a = fmaf(Gh[dl][c], Wvs[e][c], a);
-    ctx[(((long)b * 4 + h) * 32 + d) * 32 + e] = a;
+    for (int c = 0; c < C; ++c) a = fmaf(Gh[dd][c], Wvs[e][c], a);
+    ctx[(((long)b * 4 + h) * 32 + rg * 8 + dd) * 32 + e] = a;
   }
 }
 void launch_la_combine(const float* part_o, const float* part_l, const float* part_m, const float* wv, float* ctx, float* ssum,
                        int B, int S, int C, cudaStream_t st) {
   dim3 grid(16, B);
-  if (C == 64) launch_pdl(k_la_combine<64>, grid, dim3(64), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
-  else launch_pdl(k_la_combine<128>, grid, dim3(64), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
+  if (C == 64) launch_pdl(k_la_combine<64>, grid, dim3(256), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
+  else launch_pdl(k_la_combine<128>, grid, dim3(256), 0, st, part_o, part_l, part_m, wv, ctx, ssum, S);
 }
 
 // W_eff[b][co][ci] = delta(co,ci) + g * sum_{h,e} Wout[co][h*32+e] * sum_d (ctx[b][h][d][e]/ssum[b][h][d]) * Wq[h*32+d][ci]
