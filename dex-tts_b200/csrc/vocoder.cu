@@ -159,34 +159,37 @@ __global__ void k_voc_avg3(const float* __restrict__ a, const float* __restrict_
     *reinterpret_cast<uint2*>(row + K + col) = *reinterpret_cast<const uint2*>(l);
   }
 }
-// wav[b][t] = tanh(bias + sum_{j < 7, c < C} w[j][c] * y[b][t + j - 3][c]), zero padding at both ends of an utterance
+// wav[b][t] = tanh(bias + sum_{j < 7, c < C} w[j][c] * y[b][t + j - 3][c]), zero padding at both ends of an utterance.
+// A block stages its 256 + 6 rows of y in shared memory with coalesced loads (row stride C + 1: conflict-free for the row-per-thread
+// reads); one thread per row reading its seven rows straight from global memory was 32 sectors per load instruction (235 us for 134 MB).
 template <int C>
 __global__ void __launch_bounds__(256) k_voc_post(const float* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias,
                                                   float* __restrict__ wav, int B, int L) {
   pdl_wait();
   __shared__ float ws[7 * C];
+  __shared__ float ys[(256 + 6) * (C + 1)];
   for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
+  const long i0 = blockIdx.x * 256L;                         // first output of the block (blocks never straddle utterances: L % 256 == 0
+  const int b = (int)(i0 / L), t0 = (int)(i0 % L);           //  is checked by the launcher; otherwise rows are clamped per element below)
+  for (int k = threadIdx.x; k < (256 + 6) * (C / 4); k += 256) {
+    const int r = k / (C / 4), c4 = k % (C / 4);
+    const int tt = t0 + r - 3;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt >= 0 && tt < L) q = *reinterpret_cast<const float4*>(y + ((long)b * L + tt) * C + c4 * 4);
+    float* d = ys + r * (C + 1) + c4 * 4;
+    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+  }
   __syncthreads();
-  const long i = blockIdx.x * 256L + threadIdx.x;
-  if (i >= (long)B * L) return;
-  const int t = (int)(i % L);
-  const long row0 = i - t;
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
   float acc = 0.f;
 #pragma unroll
   for (int j = 0; j < 7; ++j) {
-    const int tt = t + j - 3;
-    if (tt < 0 || tt >= L) continue;
-    const float4* yr = reinterpret_cast<const float4*>(y + (row0 + tt) * C);
+    const float* yr = ys + (threadIdx.x + j) * (C + 1);
 #pragma unroll
-    for (int c4 = 0; c4 < C / 4; ++c4) {
-      const float4 q = yr[c4];
-      acc = fmaf(q.x, ws[j * C + c4 * 4], acc);
-      acc = fmaf(q.y, ws[j * C + c4 * 4 + 1], acc);
-      acc = fmaf(q.z, ws[j * C + c4 * 4 + 2], acc);
-      acc = fmaf(q.w, ws[j * C + c4 * 4 + 3], acc);
-    }
+    for (int c = 0; c < C; ++c) acc = fmaf(yr[c], ws[j * C + c], acc);
   }
-  wav[i] = tanhf(acc + bias[0]);
+  wav[i0 + threadIdx.x] = tanhf(acc + bias[0]);
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------------------
@@ -358,6 +361,7 @@ static int voc_enqueue(dexb_voc* h, cudaStream_t st) {
                                                          last ? h->yfin : nullptr, rows, ch, vpad64(ch), last ? 0.01f : 0.1f);
     ++h->launches;
   }
+  DEXB_CHECK(L % 256 == 0, "vocoder: %ld output samples per utterance are not a multiple of the hop size 256", (long)L);
   launch_pdl(k_voc_post<32>, dim3((unsigned)(cdiv((long)B * L, 256))), dim3(256), 0, st, h->yfin, h->post_w, h->post_b, h->wav_out, B, (int)L);
   ++h->launches;
   DEXB_CUDA_OK(cudaGetLastError());
