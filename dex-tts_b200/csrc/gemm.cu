@@ -2,6 +2,7 @@
 // library does not link libcuda), tile-shape selection and launch of either engine.
 #include "gemm.cuh"
 #include "conv_pair.cuh"
+#include "lin_mc.cuh"
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -127,6 +128,8 @@ int gemm_global_init() {
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(lin_mc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
+  DEXB_CUDA_OK(cudaFuncSetAttribute(lin_mc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemMax));
   DEXB_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, cp_smem_bytes(64)));
   DEXB_CUDA_OK(cudaFuncSetAttribute(conv_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cp_smem_bytes(128)));
   return resolve_encode();
@@ -204,6 +207,22 @@ static int launch_tc(const GemmPlan& gp, const GemmParams& p, cudaStream_t st, c
     return 0;
   }
   const int rb = rb_stages_for(p, BN, m_tiles, ntn);
+  if constexpr (FAST && !GNF && (BN == 64 || BN == 128)) {
+    // resident weights + the activation stream shared by the two CTAs of a cluster (lin_mc.cuh): parity-green, measured neutral
+    // (these GEMMs are bound by their stores, not by the activation stream) -- opt-in with DEXB_LINMC=1.
+    static int mc_mode = -1;
+    if (mc_mode < 0) { const char* e = getenv("DEXB_LINMC"); mc_mode = (e != nullptr) ? atoi(e) : 0; }
+    const int nk = p.K / kTcBlockK;
+    if (rb > 0 && mc_mode != 0 && ntn % 2 == 0 && p.N % BN == 0 && p.KH == 1 && p.KW == 1 && p.in_stride == 1 && lm_stages(BN, nk) >= 3) {
+      const int npairs = ntn / 2;
+      const int ncl = (g_num_sms / 2 / npairs) * npairs;       // clusters: a multiple of the n-tile pairs
+      const int nms = ncl / npairs;
+      if (nms >= 1 && m_tiles >= 2L * nms) {
+        launch_pdl(lin_mc_kernel<BN>, dim3(2 * ncl), dim3(kTcThreads), lm_smem_bytes(BN, nk), st, gp.tmA, gp.tmB, p, (int)m_tiles, ntn, nms);
+        return 0;
+      }
+    }
+  }
   if (rb > 0) {
     const int nk = p.KH * p.KW * (p.K / kTcBlockK);
     const int grid = (g_num_sms / ntn) * ntn;            // multiple of ntn: a CTA never changes its n-tile
