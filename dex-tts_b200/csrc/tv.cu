@@ -1006,7 +1006,7 @@ int dexb_style_fuse(const float* z_before_dev, const float* z_dec_dev, const flo
 // =====================================================================================================================
 
 struct TxtLayer {
-  dexb::TvConv q, k, v, g, o, fc1, gate, fc2;
+  dexb::TvConv qkvg, o, ffg, fc2;                   // q | k | v | g and fc1 | gate share their operand: one GEMM each (N = 4 C, 2 Fc)
   const float *rln = nullptr, *fln = nullptr;        // retention_layer_norm.weight, final_layer_norm.weight
 };
 
@@ -1177,8 +1177,9 @@ __global__ void __launch_bounds__(256) k_txt_ada(const float* __restrict__ W, co
 
 // q, k rows [rows][C] in place: k *= d^-0.5 (retention.py:281), then theta_shift on both (retention.py:28-37) with
 // sin / cos(t * angle[i]), angle repeated per pair (retention.py:75-76, 140-142).  One thread per (token, channel pair).
+// q / k are column blocks of the merged projection output: row stride ld (= 4 C)
 __global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const float* __restrict__ angle, long rows, int C, int d, int T,
-                           float scaling) {
+                           float scaling, int ld) {
   pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const int half = C / 2;
@@ -1188,8 +1189,8 @@ __global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const f
   const int t = (int)(r % T);
   const float ph = __fmul_rn((float)t, angle[c0 % d]);
   const float sn = sinf(ph), cs = cosf(ph);
-  float* qp = q + r * C + c0;
-  float* kp = k + r * C + c0;
+  float* qp = q + r * ld + c0;
+  float* kp = k + r * ld + c0;
   const float q0 = qp[0], q1 = qp[1];
   qp[0] = q0 * cs + (-q1) * sn;
   qp[1] = q1 * cs + q0 * sn;
@@ -1203,7 +1204,7 @@ __global__ void k_txt_rope(float* __restrict__ q, float* __restrict__ k, const f
 // -1e4 as upstream (a padded query therefore averages v over ALL keys).  Output: split rows of swish(g) * rms_head(softmax(s) v).
 __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                                   const float* __restrict__ g, const float* __restrict__ mask, bf16* __restrict__ os,
-                                                  int B, int T, int C, int heads) {
+                                                  int B, int T, int C, int heads, int ld) {
   pdl_wait();
   const long wid = blockIdx.x * 8L + (threadIdx.x >> 5);
   if (wid >= (long)B * heads * T) return;
@@ -1215,18 +1216,18 @@ __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, c
   float qv[kTxtMaxDpl], acc[kTxtMaxDpl];
 #pragma unroll
   for (int i = 0; i < kTxtMaxDpl; ++i) {
-    qv[i] = i < dpl ? q[r * C + hd * d + lane + 32 * i] : 0.f;
+    qv[i] = i < dpl ? q[r * ld + hd * d + lane + 32 * i] : 0.f;
     acc[i] = 0.f;
   }
   float mx = -INFINITY, l = 0.f;
-  const float* kb = k + (long)b * T * C + hd * d + lane;
-  const float* vb = v + (long)b * T * C + hd * d + lane;
+  const float* kb = k + (long)b * T * ld + hd * d + lane;
+  const float* vb = v + (long)b * T * ld + hd * d + lane;
   const float* mb = mask + (long)b * T;
   for (int j = 0; j < T; ++j) {
     float part = 0.f;
 #pragma unroll
     for (int i = 0; i < kTxtMaxDpl; ++i)
-      if (i < dpl) part = fmaf(qv[i], kb[(long)j * C + 32 * i], part);
+      if (i < dpl) part = fmaf(qv[i], kb[(long)j * ld + 32 * i], part);
     float s = warp_sum(part);
     if (qm == 0.f || mb[j] == 0.f) s = -1e4f;
     const float mn = fmaxf(mx, s);
@@ -1235,7 +1236,7 @@ __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, c
     l = l * corr + pj;
 #pragma unroll
     for (int i = 0; i < kTxtMaxDpl; ++i)
-      if (i < dpl) acc[i] = acc[i] * corr + pj * vb[(long)j * C + 32 * i];
+      if (i < dpl) acc[i] = acc[i] * corr + pj * vb[(long)j * ld + 32 * i];
     mx = mn;
   }
   const float inv = 1.f / l;
@@ -1250,7 +1251,7 @@ __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, c
   for (int i = 0; i < kTxtMaxDpl; ++i) {
     if (i >= dpl) continue;
     const int c = hd * d + lane + 32 * i;
-    const float gv = g[r * C + c];
+    const float gv = g[r * ld + c];
     const float o = gv / (1.f + expf(-gv)) * (acc[i] * rr);            // swish gate
     bf16 hi, lo;
     split2(o, hi, lo);
@@ -1260,14 +1261,14 @@ __global__ void __launch_bounds__(256) k_txt_attn(const float* __restrict__ q, c
 }
 
 // GLU.forward (retention.py:371-381): gelu(fc1 x) * gate x (exact gelu) -> split rows [rows][hi(F)|lo(F)], the operand of fc2
-__global__ void k_txt_glu(const float* __restrict__ a, const float* __restrict__ gate, bf16* __restrict__ os, long rows, int F) {
+__global__ void k_txt_glu(const float* __restrict__ a, const float* __restrict__ gate, bf16* __restrict__ os, long rows, int F, int ld) {
   pdl_wait();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (i >= rows * F) return;
   const long r = i / F;
   const int c = (int)(i % F);
-  const float x = a[i];
-  const float y = x * 0.5f * (1.f + erff(x * 0.70710678118654752f)) * gate[i];
+  const float x = a[r * ld + c];                            // fc1 | gate are the two column halves of one GEMM output (ld = 2 F)
+  const float y = x * 0.5f * (1.f + erff(x * 0.70710678118654752f)) * gate[r * ld + c];
   bf16 hi, lo;
   split2(y, hi, lo);
   os[r * 2 * F + c] = hi;
@@ -1288,6 +1289,20 @@ __global__ void __launch_bounds__(256) k_txt_dp_out(const float* __restrict__ x,
 }
 
 // Linear (co, ci) or Conv1d (co, ci, taps) weight -> packed split operand (same layout as tv_pack_conv)
+// Several Linear weights with the same input stacked along the output dimension: rows [r0, r0 + co_i) of one packed operand
+static int txt_pack_stacked(EncBase* h, const std::vector<std::string>& wnames, int ci, int co_each, TvConv* c, cudaStream_t st) {
+  const int n = (int)wnames.size();
+  c->ci = ci; c->co = n * co_each; c->K = tv_pad64(ci); c->taps = 1; c->bias = nullptr;
+  if (c->w == nullptr) DEXB_CUDA_OK(cudaMalloc(&c->w, (size_t)c->co * 2 * c->K * sizeof(bf16)));
+  for (int i = 0; i < n; ++i) {
+    const float* w = nullptr;
+    DEXB_TRY(tv_get(h, wnames[i], {co_each, ci}, &w));
+    k_tv_pack_w<<<cdiv((long)co_each * c->K, 256), 256, 0, st>>>(w, c->w + (size_t)i * co_each * 2 * c->K, co_each, ci, c->K, 1);
+  }
+  DEXB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int txt_pack(EncBase* h, const std::string& wname, const std::string& bname, int ci, int co, int taps, bool linear, TvConv* c,
                     cudaStream_t st) {
   c->ci = ci; c->co = co; c->K = tv_pad64(ci); c->taps = taps;
@@ -1304,8 +1319,9 @@ static int txt_pack(EncBase* h, const std::string& wname, const std::string& bna
 
 static void txt_release_plan(dexb_text* h) {
   enc_release_rows(h);
-  float** bufs[] = {&h->hf, &h->x0f, &h->qf, &h->kf, &h->vf, &h->gf, &h->f1, &h->f2, &h->ada};
+  float** bufs[] = {&h->hf, &h->x0f, &h->qf, &h->f1, &h->ada};
   for (float** b : bufs) { cudaFree(*b); *b = nullptr; }
+  h->kf = h->vf = h->gf = h->f2 = nullptr;             // column views of qf / f1
 }
 
 static int txt_plan_build(dexb_text* h, int B, int T) {
@@ -1321,22 +1337,20 @@ static int txt_plan_build(dexb_text* h, int B, int T) {
   DEXB_CUDA_OK(cudaMalloc(&h->hs, rows * 2 * Kmax * sizeof(bf16)));
   DEXB_CUDA_OK(cudaMalloc(&h->acc, rows * Cmax * sizeof(float)));
   DEXB_CUDA_OK(cudaMalloc(&h->xf, rows * Cmax * sizeof(float)));
-  float** cbufs[] = {&h->hf, &h->x0f, &h->qf, &h->kf, &h->vf, &h->gf};
+  float** cbufs[] = {&h->hf, &h->x0f};
   for (float** b : cbufs) DEXB_CUDA_OK(cudaMalloc(b, rows * C * sizeof(float)));
-  DEXB_CUDA_OK(cudaMalloc(&h->f1, rows * h->Fc * sizeof(float)));
-  DEXB_CUDA_OK(cudaMalloc(&h->f2, rows * h->Fc * sizeof(float)));
+  DEXB_CUDA_OK(cudaMalloc(&h->qf, rows * 4 * C * sizeof(float)));      // [rows][q | k | v | g]
+  h->kf = h->qf + C; h->vf = h->qf + 2 * C; h->gf = h->qf + 3 * C;
+  DEXB_CUDA_OK(cudaMalloc(&h->f1, rows * 2 * h->Fc * sizeof(float))); // [rows][fc1 | gate]
+  h->f2 = h->f1 + h->Fc;
   DEXB_CUDA_OK(cudaMalloc(&h->ada, (size_t)h->L * 4 * B * C * sizeof(float)));
   h->B = B; h->T = T;
   for (int i = 0; i < 3; ++i) DEXB_TRY(tv_plan_conv(h, &h->pre[i], h->xs, h->acc));
   DEXB_TRY(tv_plan_conv(h, &h->pre_proj, h->xs, h->acc));
   for (auto& ly : h->layers) {
-    DEXB_TRY(tv_plan_conv(h, &ly.q, h->xs, h->qf));
-    DEXB_TRY(tv_plan_conv(h, &ly.k, h->xs, h->kf));
-    DEXB_TRY(tv_plan_conv(h, &ly.v, h->xs, h->vf));
-    DEXB_TRY(tv_plan_conv(h, &ly.g, h->xs, h->gf));
+    DEXB_TRY(tv_plan_conv(h, &ly.qkvg, h->xs, h->qf));
     DEXB_TRY(tv_plan_conv(h, &ly.o, h->hs, h->acc));
-    DEXB_TRY(tv_plan_conv(h, &ly.fc1, h->xs, h->f1));
-    DEXB_TRY(tv_plan_conv(h, &ly.gate, h->xs, h->f2));
+    DEXB_TRY(tv_plan_conv(h, &ly.ffg, h->xs, h->f1));
     DEXB_TRY(tv_plan_conv(h, &ly.fc2, h->hs, h->acc));
   }
   DEXB_TRY(tv_plan_conv(h, &h->proj_m, h->xs, h->acc));
@@ -1402,7 +1416,7 @@ void dexb_text_destroy(dexb_text* h) {
   TvConv* cs[7] = {&h->pre[0], &h->pre[1], &h->pre[2], &h->pre_proj, &h->proj_m, &h->dp1, &h->dp2};
   for (TvConv* c : cs) tv_free_conv(c);
   for (auto& ly : h->layers) {
-    TvConv* ls[8] = {&ly.q, &ly.k, &ly.v, &ly.g, &ly.o, &ly.fc1, &ly.gate, &ly.fc2};
+    TvConv* ls[4] = {&ly.qkvg, &ly.o, &ly.ffg, &ly.fc2};
     for (TvConv* c : ls) tv_free_conv(c);
   }
   cudaFree(h->adaW); cudaFree(h->adaB);
@@ -1449,13 +1463,10 @@ int dexb_text_finalize_weights(dexb_text* h, void* stream) {
   for (int l = 0; l < h->L; ++l) {
     const std::string p = "encoder.layers." + std::to_string(l) + ".";
     TxtLayer& ly = h->layers[l];
-    DEXB_TRY(txt_pack(h, p + "retention.q_proj.weight", "", C, C, 1, true, &ly.q, st));
-    DEXB_TRY(txt_pack(h, p + "retention.k_proj.weight", "", C, C, 1, true, &ly.k, st));
-    DEXB_TRY(txt_pack(h, p + "retention.v_proj.weight", "", C, C, 1, true, &ly.v, st));
-    DEXB_TRY(txt_pack(h, p + "retention.g_proj.weight", "", C, C, 1, true, &ly.g, st));
+    DEXB_TRY(txt_pack_stacked(h, {p + "retention.q_proj.weight", p + "retention.k_proj.weight", p + "retention.v_proj.weight",
+                                  p + "retention.g_proj.weight"}, C, C, &ly.qkvg, st));
     DEXB_TRY(txt_pack(h, p + "retention.out_proj.weight", "", C, C, 1, true, &ly.o, st));
-    DEXB_TRY(txt_pack(h, p + "ffn.fc1.weight", "", C, h->Fc, 1, true, &ly.fc1, st));
-    DEXB_TRY(txt_pack(h, p + "ffn.gate.weight", "", C, h->Fc, 1, true, &ly.gate, st));
+    DEXB_TRY(txt_pack_stacked(h, {p + "ffn.fc1.weight", p + "ffn.gate.weight"}, C, h->Fc, &ly.ffg, st));
     DEXB_TRY(txt_pack(h, p + "ffn.fc2.weight", "", h->Fc, C, 1, true, &ly.fc2, st));
     DEXB_TRY(tv_get(h, p + "retention_layer_norm.weight", {C}, &ly.rln));
     DEXB_TRY(tv_get(h, p + "final_layer_norm.weight", {C}, &ly.fln));
@@ -1529,12 +1540,9 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
   for (int l = 0; l < h->L; ++l) {
     if (h->layer_limit >= 0 && l >= h->layer_limit) break;
     TxtLayer& ly = h->layers[l];
-    DEXB_TRY(gemm_launch(ly.q.plan, ly.q.plan.p, 0, st));
-    DEXB_TRY(gemm_launch(ly.k.plan, ly.k.plan.p, 0, st));
-    DEXB_TRY(gemm_launch(ly.v.plan, ly.v.plan.p, 0, st));
-    DEXB_TRY(gemm_launch(ly.g.plan, ly.g.plan.p, 0, st));
-    launch_pdl(k_txt_rope, dim3((unsigned)(cdiv(rows * (C / 2), 256))), dim3(256), 0, st, h->qf, h->kf, h->angle, rows, C, d, T, 1.f / sqrtf((float)d));
-    launch_pdl(k_txt_attn, dim3((unsigned)(cdiv((long)B * h->heads * T, 8))), dim3(256), 0, st, h->qf, h->kf, h->vf, h->gf, mask_dev, h->hs, B, T, C, h->heads);
+    DEXB_TRY(gemm_launch(ly.qkvg.plan, ly.qkvg.plan.p, 0, st));          // one C -> 4 C GEMM for q | k | v | g
+    launch_pdl(k_txt_rope, dim3((unsigned)(cdiv(rows * (C / 2), 256))), dim3(256), 0, st, h->qf, h->kf, h->angle, rows, C, d, T, 1.f / sqrtf((float)d), 4 * C);
+    launch_pdl(k_txt_attn, dim3((unsigned)(cdiv((long)B * h->heads * T, 8))), dim3(256), 0, st, h->qf, h->kf, h->vf, h->gf, mask_dev, h->hs, B, T, C, h->heads, 4 * C);
     DEXB_TRY(gemm_launch(ly.o.plan, ly.o.plan.p, 0, st));
     {
       TxtRow p = txt_row(h, h->acc);                                   // h = adaln_1(h + out_proj(.)); operand = rms(h) * w
@@ -1546,9 +1554,8 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
       p.out_f = h->hf; p.rms_w = ly.fln; p.os = h->xs;
       txt_launch_row(p, st);
     }
-    DEXB_TRY(gemm_launch(ly.fc1.plan, ly.fc1.plan.p, 0, st));
-    DEXB_TRY(gemm_launch(ly.gate.plan, ly.gate.plan.p, 0, st));
-    launch_pdl(k_txt_glu, dim3((unsigned)(cdiv(rows * h->Fc, 256))), dim3(256), 0, st, h->f1, h->f2, h->hs, rows, h->Fc);
+    DEXB_TRY(gemm_launch(ly.ffg.plan, ly.ffg.plan.p, 0, st));            // one C -> 2 Fc GEMM for fc1 | gate
+    launch_pdl(k_txt_glu, dim3((unsigned)(cdiv(rows * h->Fc, 256))), dim3(256), 0, st, h->f1, h->f2, h->hs, rows, h->Fc, 2 * h->Fc);
     DEXB_TRY(gemm_launch(ly.fc2.plan, ly.fc2.plan.p, 0, st));
     {
       const bool last = l == h->L - 1;
@@ -1564,7 +1571,7 @@ static int text_enqueue(dexb_text* h, const int64_t* ids_dev, const float* mask_
       p.os = h->xs;
       txt_launch_row(p, st);
     }
-    h->launches += 13;             // 4 projections, rope, attention, out_proj, row, fc1, gate, glu, fc2, row
+    h->launches += 9;              // q|k|v|g projection, rope, attention, out_proj, row, fc1|gate, glu, fc2, row
   }
   if (h->layer_limit >= 0) {                 // unit parity: the residual stream is read back with dexb_text_copy_stream
     DEXB_CUDA_OK(cudaGetLastError());
